@@ -1,0 +1,187 @@
+/*
+ * ranklib_b200.h — C ABI of the B200-native LambdaMART / MART / Random-Forest training path.
+ *
+ * This is the drop-in boundary behind RankLib's Ranker / RankerTrainer plugin API
+ * (reference: src/main/java/ciir/umass/edu/learning/Ranker.java:36-186).  Every entry point
+ * replaces one façade call of the reference's tree learner; the citation after each declaration
+ * names the Java method it stands in for ("R/" = src/main/java/ciir/umass/edu/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All buffers passed in are HOST memory; the
+ *     library copies (host -> device) and returns, the caller may free immediately.  Output
+ *     buffers are caller-allocated.
+ *   - Every function returns an int status: RLB_OK (0) or a negative RLB_E_* code.  The text of
+ *     the last error of a context is available from rlb_last_error(ctx) (or rlb_last_error(NULL)
+ *     for errors raised before a context exists).  The library never aborts the process; the JNI
+ *     shim turns a non-zero status into RankLibError.create(msg) (R/utilities/RankLibError.java:25-42).
+ *   - A context is single-threaded (one caller thread at a time), owns one CUDA device, one
+ *     stream and all device memory it allocates; several contexts may coexist (one per bag for
+ *     Random Forests, one per GPU for query-sharded training).
+ *   - There is NO CPU fallback: if no CUDA device is usable every compute entry point fails with
+ *     RLB_E_CUDA.
+ */
+#ifndef RANKLIB_B200_H
+#define RANKLIB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLB_VERSION 100
+
+/* status codes */
+#define RLB_OK            0
+#define RLB_E_INVALID    -1   /* bad argument / call order */
+#define RLB_E_CUDA       -2   /* CUDA runtime error (message has the CUDA string) */
+#define RLB_E_NCCL       -3   /* NCCL error or NCCL not loadable */
+#define RLB_E_UNSUPPORTED -4  /* e.g. nThreshold == -1 (unbounded bins) */
+#define RLB_E_NOMEM      -5
+
+/* rlb_params.kind — which pseudo-response / leaf-output rule the context runs */
+#define RLB_KIND_LAMBDAMART 0 /* R/learning/tree/LambdaMART.java:331-415 */
+#define RLB_KIND_MART       1 /* R/learning/tree/MART.java:47-65 */
+
+/* rlb_params.metric — the MetricScorer used for swapChange()/score() */
+#define RLB_METRIC_NDCG 0 /* R/metric/NDCGScorer.java:103-160 */
+#define RLB_METRIC_DCG  1 /* R/metric/DCGScorer.java:59-90 */
+
+/* Maximum number of histogram bins per feature: nThreshold(256) candidates + the Float.MAX_VALUE
+ * sentinel (R/learning/tree/LambdaMART.java:39,135-149). */
+#define RLB_MAX_BINS 257
+
+typedef struct rlb_ctx rlb_ctx;
+
+/* Copied from the reference's public static fields at init() time
+ * (R/learning/tree/LambdaMART.java:37-42, R/learning/tree/FeatureHistogram.java:33). */
+typedef struct rlb_params {
+    int32_t n_leaves;              /* LambdaMART.nTreeLeaves (10)                         */
+    int32_t min_leaf_support;      /* LambdaMART.minLeafSupport (1)                       */
+    float   learning_rate;         /* LambdaMART.learningRate (0.1F) — a Java float       */
+    int32_t n_threshold;           /* LambdaMART.nThreshold (256); -1 is RLB_E_UNSUPPORTED */
+    int32_t kind;                  /* RLB_KIND_*                                          */
+    int32_t metric;                /* RLB_METRIC_*                                        */
+    int32_t metric_k;              /* MetricScorer.k (10)                                 */
+    float   feature_sampling_rate; /* FeatureHistogram.samplingRate (1 = no sampling)     */
+    int64_t seed;                  /* seed of the java.util.Random-compatible stream that
+                                      replaces the reference's unseeded `new Random()` in
+                                      FeatureHistogram.java:282                            */
+} rlb_params;
+
+/* One node of a fitted regression tree (R/learning/tree/Split.java:22-38).  Node 0 is the root;
+ * leaves have feature_id == -1.  Enumerating leaves left-first depth-first from node 0 gives the
+ * order of RegressionTree.leaves() (Split.java:100-113). */
+typedef struct rlb_node {
+    int32_t feature_id;     /* RankLib fid (features[featureIdx]); -1 for a leaf        */
+    int32_t feature_idx;    /* index into the features[] array given to rlb_load_dense    */
+    float   threshold;      /* thresholds[featureIdx][thresholdIdx]; go left iff v <= thr  */
+    int32_t threshold_idx;
+    int32_t left;           /* node index, -1 for a leaf                                  */
+    int32_t right;
+    float   output;         /* leaf value (Split.avgLabel after setOutput), 0 for splits  */
+    int32_t count;          /* training samples in the node                              */
+    double  deviance;       /* Split.deviance (root: Float.MAX_VALUE until it is split)  */
+} rlb_node;
+
+/* what rlb_read() copies out (for parity tests; sizes in elements) */
+#define RLB_READ_LAMBDA       1 /* double[N]  pseudoResponses                              */
+#define RLB_READ_WEIGHT       2 /* double[N]  weights                                      */
+#define RLB_READ_SCORE        3 /* double[N]  modelScores                                  */
+#define RLB_READ_LEAF_ID      4 /* int32[N]   leaf ordinal (leaves() order) of each sample in the last tree */
+#define RLB_READ_BINS         5 /* int32[F][N] sampleToThresholdMap                        */
+#define RLB_READ_ROOT_SUM     6 /* double[F][RLB_MAX_BINS] cumulative root sum after rlb_hist_update (padded) */
+#define RLB_READ_ROOT_COUNT   7 /* int32[F][RLB_MAX_BINS]  cumulative root count (padded)   */
+#define RLB_READ_ROOT_STATS   8 /* double[2]  sumResponse, sqSumResponse of the root        */
+#define RLB_READ_NODE_ID      9 /* int32[N]   node index (rlb_node array) of each sample in the last tree */
+
+const char* rlb_last_error(const rlb_ctx* ctx);
+int rlb_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int rlb_device_count(void);
+
+/* Create / destroy a context bound to CUDA device `device`. */
+int rlb_create(int device, rlb_ctx** out);
+int rlb_destroy(rlb_ctx* ctx);
+
+/* Multi-GPU (query-sharded) training: one context per process/GPU.  rank 0 calls
+ * rlb_comm_unique_id and ships the 128 bytes to the other ranks by any means; every rank then
+ * calls rlb_comm_init.  After that each rank loads ITS shard of queries and the histogram of
+ * every node is all-reduced across ranks.  The reference has no counterpart. */
+int rlb_comm_unique_id(uint8_t id_out[128]);
+int rlb_comm_init(rlb_ctx* ctx, int rank, int world, const uint8_t id[128]);
+
+/* Upload the training set: X is row-major float[N][F] holding only the F selected feature
+ * columns (column j = RankLib feature feature_ids[j]); NaN means "unknown" and reads as 0
+ * (R/learning/DenseDataPoint.java:21-32).  label[N] are the relevance labels (float, >= 0,
+ * R/learning/DataPoint.java:70-73), qoff[Q+1] the start offsets of the queries (consecutive
+ * docs of one RankList, R/features/FeatureManager.java:187-245).  Replaces the flattening of
+ * `samples` into martSamples in LambdaMART.init (R/learning/tree/LambdaMART.java:71-91). */
+int rlb_load_dense(rlb_ctx* ctx, const float* X, int64_t N, int32_t F, const int32_t* feature_ids,
+                   const float* label, const int32_t* qoff, int32_t Q);
+
+/* Optional: impose candidate thresholds instead of deriving them from the loaded data (needed
+ * when the data of this context is only a shard: thresholds must come from the whole set).
+ * thr is float[F][RLB_MAX_BINS] (padded), n_thr[f] the number of valid entries of row f. */
+int rlb_set_thresholds(rlb_ctx* ctx, const float* thr, const int32_t* n_thr);
+
+/* LambdaMART.init (R/learning/tree/LambdaMART.java:68-166) + FeatureHistogram.construct
+ * (R/learning/tree/FeatureHistogram.java:54-112): candidate thresholds, sample->bin map,
+ * cumulative root counts; zeroes modelScores. */
+int rlb_lambdamart_init(rlb_ctx* ctx, const rlb_params* params);
+
+/* thresholds[f] (R/learning/tree/LambdaMART.java:108-150): writes n values to out (capacity
+ * RLB_MAX_BINS). */
+int rlb_get_thresholds(rlb_ctx* ctx, int32_t f, float* out, int32_t* n);
+
+/* --- one boosting iteration, step by step (each parity-testable on its own) --- */
+/* LambdaMART.computePseudoResponses (LambdaMART.java:331-396) / MART.java:47-51 */
+int rlb_compute_pseudo_responses(rlb_ctx* ctx);
+/* FeatureHistogram.update (FeatureHistogram.java:114-146) */
+int rlb_hist_update(rlb_ctx* ctx);
+/* RegressionTree.fit (RegressionTree.java:58-87) incl. FeatureHistogram.findBestSplit
+ * (FeatureHistogram.java:236-359).  nodes_out has capacity `cap` >= 2*n_leaves-1. */
+int rlb_tree_fit(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
+/* LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.java:54-65; fills node.output */
+int rlb_update_tree_output(rlb_ctx* ctx, rlb_node* nodes_inout, int32_t n_nodes);
+/* modelScores[k] += learningRate * leaf output (LambdaMART.java:203-210) */
+int rlb_update_scores(rlb_ctx* ctx);
+/* LambdaMART.computeModelScoreOnTraining (LambdaMART.java:442-483) */
+int rlb_train_metric(rlb_ctx* ctx, float* out);
+
+/* The production call: one pass of the loop body LambdaMART.java:180-251 (no validation) in a
+ * single boundary crossing.  Writes the fitted tree (with leaf outputs) and NDCG@k-T. */
+int rlb_boost_iter(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes,
+                   float* train_metric);
+
+/* n_iters passes of the same loop body with no host round trip in between; results land in
+ * nodes_out[n_iters][cap], n_nodes_out[n_iters], train_metric_out[n_iters] at the end. */
+int rlb_boost_iters(rlb_ctx* ctx, int32_t n_iters, rlb_node* nodes_out, int32_t cap,
+                    int32_t* n_nodes_out, float* train_metric_out);
+
+/* Copy internal state out for parity tests (see RLB_READ_*). `bytes` is the size of dst. */
+int rlb_read(rlb_ctx* ctx, int32_t what, void* dst, int64_t bytes);
+
+/* Counters of the last rlb_tree_fit/rlb_boost_iter: [0] rows fed to child-histogram builds,
+ * [1] splits done, [2] leaf float-chain segments that took the serial path, [3] reserved. */
+int rlb_stats(rlb_ctx* ctx, int64_t out[4]);
+
+/* Ensemble.eval (R/learning/tree/Ensemble.java:110-116) for a batch of data points:
+ *   out[i] = float chain  s += (double)tree_t.eval(x_i) * (double)weight[t]  over t.
+ * nodes is the concatenation of the trees' node arrays, tree_off[n_trees+1] their offsets.
+ * X is row-major float[N][n_cols] indexed by RankLib fid directly (column 0 unused, NaN -> 0,
+ * fid >= n_cols reads 0 like -missingZero, R/learning/DenseDataPoint.java:21-32). */
+int rlb_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* tree_off,
+                      int32_t n_trees, const float* weights, const float* X, int64_t N,
+                      int32_t n_cols, float* out);
+
+/* MetricScorer.score(List<RankList>) on caller-provided scores (R/metric/MetricScorer.java:46-52
+ * + NDCGScorer.java:103-129): ranks each query by score (stable, descending) and returns the
+ * double mean of NDCG@k (or DCG@k). */
+int rlb_score_metric(rlb_ctx* ctx, const double* scores, const float* label, const int32_t* qoff,
+                     int32_t Q, int32_t metric, int32_t k, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANKLIB_B200_H */
