@@ -1,0 +1,412 @@
+// rlb_api.cu — the C ABI of include/ranklib_b200.h, NCCL plumbing, state read-back.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "rlb_internal.cuh"
+
+static std::string g_last_error;
+static std::mutex g_err_mutex;
+
+const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* detail) {
+    char buf[1024];
+    snprintf(buf, sizeof(buf), "ranklib_b200 error %d in %s: %s", code, what ? what : "?", detail ? detail : "");
+    if (ctx) {
+        ctx->err = buf;
+        return ctx->err.c_str();
+    }
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = buf;
+    return g_last_error.c_str();
+}
+
+// ---- all-reduce helpers ----------------------------------------------------------------------
+int rlb_allreduce_i64(rlb_ctx* c, long long* buf, size_t n) {
+    if (c->world <= 1) return RLB_OK;
+    RLB_NCCL(c, ncclAllReduce(buf, buf, n, ncclInt64, ncclSum, c->comm, c->stream));
+    return RLB_OK;
+}
+int rlb_allreduce_i32(rlb_ctx* c, int32_t* buf, size_t n) {
+    if (c->world <= 1) return RLB_OK;
+    RLB_NCCL(c, ncclAllReduce(buf, buf, n, ncclInt32, ncclSum, c->comm, c->stream));
+    return RLB_OK;
+}
+int rlb_allreduce_max_u64(rlb_ctx* c, unsigned long long* buf, size_t n) {
+    if (c->world <= 1) return RLB_OK;
+    RLB_NCCL(c, ncclAllReduce(buf, buf, n, ncclUint64, ncclMax, c->comm, c->stream));
+    return RLB_OK;
+}
+
+// Cross-rank float chains: leaf sums and the NDCG-T sum run in GLOBAL doc / query
+// order, i.e. rank r continues where rank r-1 stopped.  begin: receive the carries from rank-1 into
+// dCarry (zeros on rank 0); end: pass this rank's results on to rank+1, then broadcast the final
+// values from the last rank so that every rank holds the same leaf outputs.
+int rlb_chain_carry_begin(rlb_ctx* c, int nfloats) {
+    if (c->rank == 0) {
+        RLB_CUDA(c, cudaMemsetAsync(c->dCarry, 0, nfloats * sizeof(float), c->stream));
+    } else {
+        RLB_NCCL(c, ncclRecv(c->dCarry, nfloats, ncclFloat, c->rank - 1, c->comm, c->stream));
+    }
+    return RLB_OK;
+}
+int rlb_chain_carry_end(rlb_ctx* c, float* dOutVals, int nfloats) {
+    if (c->rank + 1 < c->world) RLB_NCCL(c, ncclSend(dOutVals, nfloats, ncclFloat, c->rank + 1, c->comm, c->stream));
+    RLB_NCCL(c, ncclBroadcast(dOutVals, dOutVals, nfloats, ncclFloat, c->world - 1, c->comm, c->stream));
+    return RLB_OK;
+}
+
+long long rlb_q_total(rlb_ctx* c) { return c->Q_total > 0 ? c->Q_total : c->Q; }
+
+static int check_ready(rlb_ctx* c, const char* fn) {
+    if (!c) return RLB_E_INVALID;
+    if (!c->inited) {
+        rlb_set_error(c, RLB_E_INVALID, fn, "rlb_lambdamart_init has not been called");
+        return RLB_E_INVALID;
+    }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) {
+        rlb_set_error(c, RLB_E_CUDA, fn, cudaGetErrorString(e));
+        return RLB_E_CUDA;
+    }
+    return RLB_OK;
+}
+
+extern "C" {
+
+const char* rlb_last_error(const rlb_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    return g_last_error.c_str();
+}
+
+int rlb_version(void) { return RLB_VERSION; }
+
+int rlb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rlb_create(int device, rlb_ctx** out) {
+    if (!out) return RLB_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        rlb_set_error(nullptr, RLB_E_CUDA, "rlb_create",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device (this library has no CPU fallback)");
+        return RLB_E_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        rlb_set_error(nullptr, RLB_E_INVALID, "rlb_create", "device index out of range");
+        return RLB_E_INVALID;
+    }
+    rlb_ctx* c = new rlb_ctx();
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        rlb_set_error(nullptr, RLB_E_CUDA, "rlb_create", cudaGetErrorString(e));
+        delete c;
+        return RLB_E_CUDA;
+    }
+    *out = c;
+    return RLB_OK;
+}
+
+int rlb_destroy(rlb_ctx* c) {
+    if (!c) return RLB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    rlb_impl_free(c);
+    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RLB_OK;
+}
+
+int rlb_comm_unique_id(uint8_t id_out[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) {
+        rlb_set_error(nullptr, RLB_E_NCCL, "ncclGetUniqueId", ncclGetErrorString(r));
+        return RLB_E_NCCL;
+    }
+    memcpy(id_out, &id, 128);
+    return RLB_OK;
+}
+
+int rlb_comm_init(rlb_ctx* c, int rank, int world, const uint8_t id[128]) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return RLB_E_INVALID;
+    RLB_CUDA(c, cudaSetDevice(c->device));
+    if (world == 1) {
+        c->rank = 0;
+        c->world = 1;
+        return RLB_OK;
+    }
+    ncclUniqueId nid;
+    memcpy(&nid, id, 128);
+    RLB_NCCL(c, ncclCommInitRank(&c->comm, world, nid, rank));
+    c->rank = rank;
+    c->world = world;
+    return RLB_OK;
+}
+
+int rlb_load_dense(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
+                   const int32_t* qoff, int32_t Q) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_load(c, X, N, F, feature_ids, label, qoff, Q);
+}
+
+int rlb_set_thresholds(rlb_ctx* c, const float* thr, const int32_t* n_thr) {
+    if (!c || !c->loaded || !thr || !n_thr) {
+        if (c) rlb_set_error(c, RLB_E_INVALID, "rlb_set_thresholds", "load the training set first");
+        return RLB_E_INVALID;
+    }
+    for (int f = 0; f < c->F; f++)
+        if (n_thr[f] < 1 || n_thr[f] > RLB_MAX_BINS) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_set_thresholds", "n_thr out of range");
+            return RLB_E_INVALID;
+        }
+    c->h_thr.assign(thr, thr + (size_t)c->F * RLB_T);
+    c->h_nthr.assign(n_thr, n_thr + c->F);
+    c->have_thr = true;
+    return RLB_OK;
+}
+
+int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
+    if (!c || !params) return RLB_E_INVALID;
+    int rc = rlb_impl_init(c, params);
+    if (rc) return rc;
+    // global query count for the NDCG-T mean
+    long long q = c->Q;
+    if (c->world > 1) {
+        long long* d = nullptr;
+        RLB_CUDA(c, cudaMalloc(&d, 8));
+        RLB_CUDA(c, cudaMemcpyAsync(d, &q, 8, cudaMemcpyHostToDevice, c->stream));
+        RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt64, ncclSum, c->comm, c->stream));
+        RLB_CUDA(c, cudaMemcpyAsync(&q, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
+    c->Q_total = q;
+    return RLB_OK;
+}
+
+int rlb_get_thresholds(rlb_ctx* c, int32_t f, float* out, int32_t* n) {
+    if (!c || !c->have_thr || f < 0 || f >= c->F || !out || !n) return RLB_E_INVALID;
+    *n = c->h_nthr[f];
+    memcpy(out, &c->h_thr[(size_t)f * RLB_T], sizeof(float) * c->h_nthr[f]);
+    return RLB_OK;
+}
+
+int rlb_compute_pseudo_responses(rlb_ctx* c) {
+    if (int rc = check_ready(c, "rlb_compute_pseudo_responses")) return rc;
+    if (int rc = rlb_impl_pseudo(c)) return rc;
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+int rlb_hist_update(rlb_ctx* c) {
+    if (int rc = check_ready(c, "rlb_hist_update")) return rc;
+    if (int rc = rlb_impl_hist_update(c)) return rc;
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+int rlb_tree_fit(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes) {
+    if (int rc = check_ready(c, "rlb_tree_fit")) return rc;
+    if (int rc = rlb_impl_tree_fit(c)) return rc;
+    // node assignment of every doc is available right after the fit (no score change)
+    if (nodes_out) return rlb_impl_export_tree(c, nodes_out, cap, n_nodes);
+    return RLB_OK;
+}
+
+int rlb_update_tree_output(rlb_ctx* c, rlb_node* nodes_inout, int32_t n_nodes) {
+    if (int rc = check_ready(c, "rlb_update_tree_output")) return rc;
+    if (int rc = rlb_impl_tree_output(c)) return rc;
+    if (nodes_inout) {
+        int32_t n = 0;
+        return rlb_impl_export_tree(c, nodes_inout, n_nodes, &n);
+    }
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+int rlb_update_scores(rlb_ctx* c) {
+    if (int rc = check_ready(c, "rlb_update_scores")) return rc;
+    if (int rc = rlb_impl_update_scores(c)) return rc;
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+int rlb_train_metric(rlb_ctx* c, float* out) {
+    if (int rc = check_ready(c, "rlb_train_metric")) return rc;
+    if (int rc = rlb_impl_train_metric(c)) return rc;
+    RLB_CUDA(c, cudaMemcpyAsync(&c->hState->train_metric, &c->dState->train_metric, sizeof(float), cudaMemcpyDeviceToHost,
+                                c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (out) *out = c->hState->train_metric;
+    return RLB_OK;
+}
+
+static int boost_one(rlb_ctx* c) {
+    if (int rc = rlb_impl_pseudo(c)) return rc;
+    if (int rc = rlb_impl_hist_update(c)) return rc;
+    if (int rc = rlb_impl_tree_fit(c)) return rc;
+    if (int rc = rlb_impl_tree_output(c)) return rc;
+    if (int rc = rlb_impl_update_scores(c)) return rc;
+    if (int rc = rlb_impl_train_metric(c)) return rc;
+    return RLB_OK;
+}
+
+int rlb_boost_iter(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes, float* train_metric) {
+    if (int rc = check_ready(c, "rlb_boost_iter")) return rc;
+    if (int rc = boost_one(c)) return rc;
+    if (nodes_out) {
+        if (int rc = rlb_impl_export_tree(c, nodes_out, cap, n_nodes)) return rc;
+    } else {
+        RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (n_nodes) *n_nodes = c->hState->n_nodes;
+    }
+    if (train_metric) *train_metric = c->hState->train_metric;
+    return RLB_OK;
+}
+
+int rlb_boost_iters(rlb_ctx* c, int32_t n_iters, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes_out,
+                    float* train_metric_out) {
+    if (int rc = check_ready(c, "rlb_boost_iters")) return rc;
+    for (int i = 0; i < n_iters; i++) {
+        int32_t n = 0;
+        float m = 0.f;
+        int rc = rlb_boost_iter(c, nodes_out ? nodes_out + (size_t)i * cap : nullptr, cap, &n, &m);
+        if (rc) return rc;
+        if (n_nodes_out) n_nodes_out[i] = n;
+        if (train_metric_out) train_metric_out[i] = m;
+    }
+    return RLB_OK;
+}
+
+__global__ void k_node_to_leaf(const DevState* __restrict__ st, const int32_t* __restrict__ nodeOf, int32_t* __restrict__ out,
+                               int64_t N) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = st->nodes[nodeOf[i]].leaf_ord;
+}
+
+int rlb_read(rlb_ctx* c, int32_t what, void* dst, int64_t bytes) {
+    if (int rc = check_ready(c, "rlb_read")) return rc;
+    if (!dst) return RLB_E_INVALID;
+    const int64_t N = c->N;
+    const int F = c->F;
+    auto need = [&](int64_t b) -> bool {
+        if (bytes < b) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_read", "destination buffer too small");
+            return false;
+        }
+        return true;
+    };
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    switch (what) {
+        case RLB_READ_LAMBDA:
+        case RLB_READ_WEIGHT:
+        case RLB_READ_SCORE: {
+            if (!need(N * 8)) return RLB_E_INVALID;
+            const double* src = what == RLB_READ_LAMBDA ? c->dLambda : what == RLB_READ_WEIGHT ? c->dWeight : c->dScore;
+            RLB_CUDA(c, cudaMemcpy(dst, src, N * 8, cudaMemcpyDeviceToHost));
+            return RLB_OK;
+        }
+        case RLB_READ_NODE_ID:
+        case RLB_READ_LEAF_ID: {
+            if (!need(N * 4)) return RLB_E_INVALID;
+            if (!c->tree_ready) {
+                rlb_set_error(c, RLB_E_INVALID, "rlb_read", "no fitted tree");
+                return RLB_E_INVALID;
+            }
+            // (re)derive the node of every doc from the leaf segments of the last tree
+            extern int rlb_impl_assign_nodes(rlb_ctx*);
+            if (int rc = rlb_impl_assign_nodes(c)) return rc;
+            if (what == RLB_READ_NODE_ID) {
+                RLB_CUDA(c, cudaMemcpy(dst, c->dNodeOf, N * 4, cudaMemcpyDeviceToHost));
+            } else {
+                int32_t* tmp = nullptr;
+                RLB_CUDA(c, cudaMalloc(&tmp, N * 4));
+                k_node_to_leaf<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dNodeOf, tmp, N);
+                RLB_CHECK_LAUNCH(c);
+                RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+                RLB_CUDA(c, cudaMemcpy(dst, tmp, N * 4, cudaMemcpyDeviceToHost));
+                cudaFree(tmp);
+            }
+            return RLB_OK;
+        }
+        case RLB_READ_BINS: {
+            if (!need((int64_t)F * N * 4)) return RLB_E_INVALID;
+            std::vector<uint16_t> h((size_t)N * c->Fp);
+            RLB_CUDA(c, cudaMemcpy(h.data(), c->dBins, h.size() * 2, cudaMemcpyDeviceToHost));
+            int32_t* d = (int32_t*)dst;
+            for (int f = 0; f < F; f++)
+                for (int64_t k = 0; k < N; k++) d[(size_t)f * N + k] = h[(size_t)k * c->Fp + f];
+            return RLB_OK;
+        }
+        case RLB_READ_ROOT_SUM: {
+            if (!need((int64_t)F * RLB_T * 8)) return RLB_E_INVALID;
+            std::vector<long long> h(c->hist_stride);
+            RLB_CUDA(c, cudaMemcpy(h.data(), c->dHistSum, h.size() * 8, cudaMemcpyDeviceToHost));
+            int se = 0;
+            RLB_CUDA(c, cudaMemcpy(&se, &c->dState->scale_exp, 4, cudaMemcpyDeviceToHost));
+            double* d = (double*)dst;
+            for (size_t i = 0; i < h.size(); i++) d[i] = std::scalbn((double)h[i], -se);
+            return RLB_OK;
+        }
+        case RLB_READ_ROOT_COUNT: {
+            if (!need((int64_t)F * RLB_T * 4)) return RLB_E_INVALID;
+            RLB_CUDA(c, cudaMemcpy(dst, c->dHistCnt, c->hist_stride * 4, cudaMemcpyDeviceToHost));
+            return RLB_OK;
+        }
+        case RLB_READ_ROOT_STATS: {
+            if (!need(16)) return RLB_E_INVALID;
+            long long tot = 0, sq = 0;
+            int se[2];
+            RLB_CUDA(c, cudaMemcpy(&tot, c->dHistSum + (RLB_T - 1), 8, cudaMemcpyDeviceToHost));
+            RLB_CUDA(c, cudaMemcpy(&sq, &c->dState->root_sq_fix, 8, cudaMemcpyDeviceToHost));
+            RLB_CUDA(c, cudaMemcpy(se, &c->dState->scale_exp, 8, cudaMemcpyDeviceToHost));
+            ((double*)dst)[0] = std::scalbn((double)tot, -se[0]);
+            ((double*)dst)[1] = std::scalbn((double)sq, -se[1]);
+            return RLB_OK;
+        }
+        default:
+            rlb_set_error(c, RLB_E_INVALID, "rlb_read", "unknown selector");
+            return RLB_E_INVALID;
+    }
+}
+
+int rlb_stats(rlb_ctx* c, int64_t out[4]) {
+    if (!c || !out) return RLB_E_INVALID;
+    out[0] = c->stats[0];
+    out[1] = c->stats[1];
+    out[2] = 0;
+    out[3] = c->launches;
+    if (c->inited) {
+        long long s = 0;
+        if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess) out[2] = s;
+    }
+    return RLB_OK;
+}
+
+int rlb_ensemble_eval(rlb_ctx* c, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees, const float* weights,
+                      const float* X, int64_t N, int32_t n_cols, float* out) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_ensemble_eval(c, nodes, tree_off, n_trees, weights, X, N, n_cols, out);
+}
+
+int rlb_score_metric(rlb_ctx* c, const double* scores, const float* label, const int32_t* qoff, int32_t Q, int32_t metric,
+                     int32_t k, double* out) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_score_metric(c, scores, label, qoff, Q, metric, k, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,1195 @@
+// rlb_boost.cu — one boosting iteration of LambdaMART / MART on the device (sm_100a).
+//
+// Reference loop body: R/learning/tree/LambdaMART.java:180-251.  Kernels and the reference code
+// each one replaces are listed in DESIGN.md.  Design points that differ from a translation:
+//   * histograms accumulate in 64-bit FIXED POINT (v = rint(lambda * 2^s), s chosen per iteration
+//     from max|lambda| and the global sample count).  Integer sums are order independent, so the
+//     result is bit-identical for any grid shape or GPU count, sibling subtraction is exact, and the
+//     histogram of the SMALLER child can be scanned instead of always the left one.
+//   * tree growth (RegressionTree.fit's deviance-ordered queue) runs as a device-resident state
+//     machine: every kernel of a split step reads its arguments from DevState, so an iteration is
+//     a fixed launch sequence with no host round trip.
+//   * the float32 sequential sums of the reference (leaf outputs, NDCG-T) are reproduced exactly by
+//     a block-parallel scan of per-element quanta inside one float binade (chain_block).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "rlb_internal.cuh"
+
+#define QCAP 1024   // queries up to this size are ranked out of shared memory
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fix2d(long long v, int scale_exp) { return scalbn((double)v, -scale_exp); }
+
+__device__ __forceinline__ long long warp_incl_scan_ll(long long v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// java.util.Random.next / nextInt on the 48-bit state kept in DevState
+__device__ int32_t jr_next(DevState* st, int bits) {
+    st->rng_seed = (long long)(((unsigned long long)st->rng_seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1));
+    return (int32_t)(st->rng_seed >> (48 - bits));
+}
+__device__ int32_t jr_next_int(DevState* st, int32_t bound) {
+    int32_t r = jr_next(st, 31);
+    int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((long long)bound * (long long)r) >> 31);
+    for (int32_t u = r; (int32_t)((uint32_t)u - (uint32_t)(r = u % bound) + (uint32_t)m) < 0; u = jr_next(st, 31)) {
+    }
+    return r;
+}
+
+struct TreeParams {
+    int32_t F, n_leaves, mls;
+    float frate;
+};
+
+// FeatureHistogram.findBestSplit's feature sub-sampling (FeatureHistogram.java:271-294); `pool` is
+// scratch of F ints.  Runs in one thread.
+__device__ void draw_features(DevState* st, const TreeParams& tp, int32_t* used, int32_t* pool) {
+    if (tp.frate < 1.f) {
+        int size = (int)(tp.frate * (float)tp.F);
+        int np = tp.F;
+        for (int i = 0; i < np; i++) pool[i] = i;
+        for (int i = 0; i < size; i++) {
+            int sel = jr_next_int(st, np);
+            used[i] = pool[sel];
+            for (int j = sel; j + 1 < np; j++) pool[j] = pool[j + 1];
+            np--;
+        }
+        st->n_used = size;
+    } else {
+        st->n_used = tp.F;  // identity order; `used` is not consulted
+    }
+}
+
+// RegressionTree.insert (RegressionTree.java:147-157)
+__device__ void queue_insert(DevState* st, int node) {
+    int i = 0;
+    const double d = st->nodes[node].deviance;
+    while (i < st->qlen) {
+        if (st->nodes[st->queue[i]].deviance > d)
+            i++;
+        else
+            break;
+    }
+    for (int j = st->qlen; j > i; j--) st->queue[j] = st->queue[j - 1];
+    st->queue[i] = node;
+    st->qlen++;
+}
+
+// the head of RegressionTree.fit's while loop (RegressionTree.java:69-77) up to the point where a
+// histogram scan is needed; the cheap rejections are consumed here.
+__device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, int32_t* pool) {
+    while (true) {
+        if (!(st->taken + st->qlen < tp.n_leaves) || st->qlen == 0) {
+            st->cur = -1;
+            st->done = 1;
+            return;
+        }
+        const int leaf = st->queue[0];
+        for (int j = 0; j + 1 < st->qlen; j++) st->queue[j] = st->queue[j + 1];
+        st->qlen--;
+        if (st->nodes[leaf].count < 2 * tp.mls) {
+            st->taken++;
+            continue;
+        }
+        const double dev = st->nodes[leaf].deviance;
+        if (dev >= 0.0 && dev <= 0.0) {  // FeatureHistogram.java:267-269
+            st->taken++;
+            continue;
+        }
+        draw_features(st, tp, used, pool);
+        st->cur = leaf;
+        return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K9: per-query ranking, NDCG@k and pairwise lambdas
+//   LambdaMART.computePseudoResponses (LambdaMART.java:361-396), NDCGScorer.swapChange
+//   (NDCGScorer.java:132-160), NDCGScorer.score (:103-129), MergeSorter.sort (stable, descending).
+// One CTA per query (grid-stride).  rank(i) = #{j : s_j > s_i or (s_j == s_i and j < i)} is the
+// position MergeSorter gives doc i.  Thread p then owns the doc at rank p and accumulates ITS lambda
+// and weight privately in the reference's visit order: no atomics, and the
+// same double additions in the same order as the Java loop.
+// ------------------------------------------------------------------------------------------------
+template <bool LAMBDA>
+__global__ void __launch_bounds__(128) k_query(const double* __restrict__ score, const float* __restrict__ label,
+                                                const int32_t* __restrict__ qoff, int Q, int cutoff, int metric,
+                                                const double* __restrict__ disc, const double* __restrict__ idealIn,
+                                                int32_t* __restrict__ rankDoc, double* __restrict__ lambda,
+                                                double* __restrict__ weight, double* __restrict__ qmetric,
+                                                DevState* __restrict__ st) {
+    __shared__ double sRaw[QCAP];
+    __shared__ double sScore[QCAP];
+    __shared__ float sLabel[QCAP];
+    __shared__ double sIdeal;
+    __shared__ unsigned long long sMax;
+    const int tid = threadIdx.x;
+    double thrMax = 0.0;
+    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+        const int lo = qoff[q];
+        const int n = qoff[q + 1] - lo;
+        if (n <= 0) {
+            if (tid == 0 && qmetric) qmetric[q] = 0.0;
+            continue;
+        }
+        const bool small = n <= QCAP;
+        __syncthreads();  // previous query's shared arrays are free
+        if (small)
+            for (int i = tid; i < n; i += blockDim.x) sRaw[i] = score[lo + i];
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {
+            const double si = small ? sRaw[i] : score[lo + i];
+            int r = 0;
+            if (small) {
+                for (int j = 0; j < n; j++) {
+                    const double sj = sRaw[j];
+                    r += (sj > si) || (sj == si && j < i);
+                }
+            } else {
+                for (int j = 0; j < n; j++) {
+                    const double sj = score[lo + j];
+                    r += (sj > si) || (sj == si && j < i);
+                }
+            }
+            rankDoc[lo + r] = i;
+            if (small) {
+                sScore[r] = si;
+                sLabel[r] = label[lo + i];
+            }
+        }
+        __syncthreads();
+        auto S = [&](int r) -> double { return small ? sScore[r] : score[lo + rankDoc[lo + r]]; };
+        auto L = [&](int r) -> float { return small ? sLabel[r] : label[lo + rankDoc[lo + r]]; };
+        if (tid == 0) {
+            int size = cutoff;
+            if (cutoff > n || cutoff <= 0) size = n;
+            double ideal = 0.0;
+            if (metric == RLB_METRIC_NDCG) {
+                if (idealIn) {
+                    ideal = idealIn[q];
+                } else {  // NDCGScorer.getIdealDCG (NDCGScorer.java:167-174)
+                    int cnt[RLB_MAX_LABEL + 1];
+                    for (int i = 0; i <= RLB_MAX_LABEL; i++) cnt[i] = 0;
+                    for (int i = 0; i < n; i++) {
+                        int r = (int)L(i);
+                        r = r < 0 ? 0 : (r > RLB_MAX_LABEL ? RLB_MAX_LABEL : r);
+                        cnt[r]++;
+                    }
+                    int pos = 0;
+                    for (int r = RLB_MAX_LABEL; r >= 0 && pos < size; r--) {
+                        const double g = (double)((1 << r) - 1);
+                        for (int c = cnt[r]; c > 0 && pos < size; c--, pos++) ideal += g * disc[pos];
+                    }
+                }
+            }
+            sIdeal = ideal;
+            if (qmetric) {
+                double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
+                for (int i = 0; i < size; i++) dcg += (double)((1 << (int)L(i)) - 1) * disc[i];
+                double m = dcg;
+                if (metric == RLB_METRIC_NDCG) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
+                qmetric[q] = m;
+            }
+        }
+        if (LAMBDA) {
+            __syncthreads();
+            const double ideal = sIdeal;
+            const bool ndcg = (metric == RLB_METRIC_NDCG);
+            const bool have = !ndcg || ideal > 0.0;
+            const int size = (n > cutoff) ? cutoff : n;  // swapChange (NDCGScorer.java:133)
+            for (int p = tid; p < n; p += blockDim.x) {
+                double lam = 0.0, w = 0.0;
+                if (have) {
+                    const float lp = L(p);
+                    const double sp = S(p);
+                    const double gp = (double)((1 << (int)lp) - 1);
+                    const double dp = disc[p];
+                    // |changes[a][b]| for a < b, a < size
+                    auto delta = [&](int a, int b, double ga, double gb) -> double {
+                        double ch = (disc[a] - disc[b]) * (ga - gb);
+                        if (ndcg) ch = ch / ideal;
+                        return fabs(ch);
+                    };
+                    (void)dp;
+                    // (1) outer j < p, inner k == p: p is the loser when label_j > label_p
+                    const int j1 = (p > cutoff) ? min(p, cutoff + 1) : p;
+                    for (int j = 0; j < j1; j++) {
+                        const float lj = L(j);
+                        if (lj > lp && j < size) {
+                            const double d = delta(j, p, (double)((1 << (int)lj) - 1), gp);
+                            if (d > 0) {
+                                const double rho = 1.0 / (1 + exp(S(j) - sp));
+                                lam -= rho * d;
+                                w += rho * (1.0 - rho) * d;
+                            }
+                        }
+                    }
+                    // (2) outer j == p: p is the winner over every k with label_p > label_k
+                    const int k2 = (p > cutoff) ? min(n, cutoff + 1) : n;
+                    for (int k = 0; k < k2; k++) {
+                        const float lk = L(k);
+                        if (lp > lk) {
+                            const int a = min(p, k), b = max(p, k);
+                            if (a < size) {
+                                const double gk = (double)((1 << (int)lk) - 1);
+                                const double d = (p < k) ? delta(a, b, gp, gk) : delta(a, b, gk, gp);
+                                if (d > 0) {
+                                    const double rho = 1.0 / (1 + exp(sp - S(k)));
+                                    lam += rho * d;
+                                    w += rho * (1.0 - rho) * d;
+                                }
+                            }
+                        }
+                    }
+                    // (3) outer j > p, inner k == p: visited only while p <= cutoff
+                    if (p <= cutoff && p < size) {
+                        for (int j = p + 1; j < n; j++) {
+                            const float lj = L(j);
+                            if (lj > lp) {
+                                const double d = delta(p, j, gp, (double)((1 << (int)lj) - 1));
+                                if (d > 0) {
+                                    const double rho = 1.0 / (1 + exp(S(j) - sp));
+                                    lam -= rho * d;
+                                    w += rho * (1.0 - rho) * d;
+                                }
+                            }
+                        }
+                    }
+                }
+                const int doc = lo + rankDoc[lo + p];
+                lambda[doc] = lam;
+                weight[doc] = w;
+                thrMax = fmax(thrMax, fabs(lam));
+            }
+        }
+    }
+    if (LAMBDA) {
+        if (tid == 0) sMax = 0ull;
+        __syncthreads();
+        unsigned long long b = (unsigned long long)__double_as_longlong(thrMax);
+        for (int d = 16; d > 0; d >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, b, d);
+            b = o > b ? o : b;
+        }
+        if ((tid & 31) == 0) atomicMax(&sMax, b);
+        __syncthreads();
+        if (tid == 0 && sMax) atomicMax(&st->max_abs_bits, sMax);
+    }
+}
+
+// MART.computePseudoResponses (R/learning/tree/MART.java:47-51)
+__global__ void __launch_bounds__(256) k_mart_pseudo(const double* __restrict__ score, const float* __restrict__ label,
+                                                      int64_t N, double* __restrict__ lambda, DevState* __restrict__ st) {
+    double mx = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)label[i] - score[i];
+        lambda[i] = v;
+        mx = fmax(mx, fabs(v));
+    }
+    unsigned long long b = (unsigned long long)__double_as_longlong(mx);
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, b, d);
+        b = o > b ? o : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(&st->max_abs_bits, b);
+}
+
+// fixed-point scales of the iteration from max|lambda| and the global sample count
+__global__ void k_scale(DevState* st, long long n_total) {
+    const double m = __longlong_as_double((long long)st->max_abs_bits);
+    int nb = 64 - __clzll(n_total);
+    int se = 0, s2 = 0;
+    if (m > 0.0 && isfinite(m)) {
+        const int e = ilogb(m) + 1;  // m < 2^e
+        se = 61 - nb - e;
+        s2 = 61 - nb - 2 * e;
+        se = max(-1000, min(1000, se));
+        s2 = max(-1000, min(1000, s2));
+    }
+    st->scale_exp = se;
+    st->scale2_exp = s2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / K3: histogram accumulation (FeatureHistogram.update :126-140, construct(parent,soi,labels)
+// :176-187).  v0: one warp per row, lanes over features, native 64-bit global reductions (REDG).
+// ------------------------------------------------------------------------------------------------
+template <bool CHILD>
+__global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ bins, int Fp, int F,
+                                                    const double* __restrict__ lambda, int64_t N,
+                                                    const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
+                                                    long long* __restrict__ histSum, int32_t* __restrict__ histCnt,
+                                                    size_t hist_stride, DevState* __restrict__ st) {
+    int64_t lo = 0, hi = N;
+    const int32_t* samples = nullptr;
+    long long* sum = histSum;
+    int32_t* cnt = histCnt;
+    if (CHILD) {
+        if (!st->split_active) return;
+        const NodeRec& r = st->nodes[st->small_id];
+        lo = r.lo;
+        hi = r.hi;
+        samples = r.buf ? samples1 : samples0;
+        // histSum / histCnt point at the STAGING slot for child builds (fixed address: the
+        // all-reduce that follows is enqueued by a host that does not know small_id)
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
+    }
+    const double sc = scalbn(1.0, st->scale_exp);
+    const double sc2 = scalbn(1.0, st->scale2_exp);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    long long sq = 0;
+    for (int64_t i = lo + warp; i < hi; i += nwarps) {
+        const int64_t row = CHILD ? (int64_t)samples[i] : i;
+        const double lam = lambda[row];
+        const long long v = __double2ll_rn(lam * sc);
+        if (lane == 0) sq += __double2ll_rn((lam * lam) * sc2);
+        const uint16_t* b = bins + row * Fp;
+        for (int f = lane; f < F; f += 32) {
+            const int t = b[f];
+            atomicAdd((unsigned long long*)&sum[(size_t)f * RLB_T + t], (unsigned long long)v);
+            if (CHILD) atomicAdd(&cnt[(size_t)f * RLB_T + t], 1);
+        }
+    }
+    if (lane == 0 && sq != 0)
+        atomicAdd((unsigned long long*)(CHILD ? &st->small_sq_fix : &st->root_sq_fix), (unsigned long long)sq);
+}
+
+// per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan
+__global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum) {
+    __shared__ long long wt[9];
+    long long* s = sum + (size_t)blockIdx.x * RLB_T;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    long long v = (t < RLB_T) ? s[t] : 0;
+    v = warp_incl_scan_ll(v, lane);
+    if (lane == 31) wt[w] = v;
+    __syncthreads();
+    long long off = 0;
+    for (int i = 0; i < w; i++) off += wt[i];
+    if (t < RLB_T) s[t] = v + off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tree controller kernels
+// ------------------------------------------------------------------------------------------------
+// every tree starts from the identity sample list (RegressionTree.java:49-52)
+__global__ void __launch_bounds__(256) k_identity(int32_t* __restrict__ a, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)i;
+}
+
+__global__ void k_tree_begin(DevState* st, TreeParams tp, const long long* __restrict__ histSum, int64_t N_local,
+                             long long N_total, int32_t* used, int32_t* pool) {
+    st->n_nodes = 1;
+    NodeRec& r = st->nodes[0];
+    r.feature_idx = -1;
+    r.thr_idx = -1;
+    r.left = r.right = -1;
+    r.lo = 0;
+    r.hi = (int32_t)N_local;
+    r.buf = 0;
+    r.count = (int32_t)N_total;
+    r.sum_fix = histSum[RLB_T - 1];  // cumulative total of feature 0
+    r.sq_fix = st->root_sq_fix;
+    r.deviance = (double)FLT_MAX;    // RegressionTree.java:60
+    r.output = 0.f;
+    r.leaf_ord = -1;
+    st->qlen = 0;
+    st->taken = 0;
+    st->done = 0;
+    st->incomplete = 0;
+    st->split_active = 0;
+    st->rows_hist = 0;
+    st->n_splits = 0;
+    st->chain_serial = 0;
+    st->small_sq_fix = 0;
+    st->ticket_scan = st->ticket_part = st->ticket_finish = 0;
+    draw_features(st, tp, used, pool);
+    st->cur = 0;
+}
+
+// K5: FeatureHistogram.findBestSplit(usedFeatures, mls, start, end) (FeatureHistogram.java:236-264).
+// One CTA per feature; thread t evaluates threshold t; argmax keeps the lowest t among equal S.
+// The last CTA to finish merges the features in usedFeatures order with strict '<' (first wins) and
+// takes the split decision of FeatureHistogram.findBestSplit(sp, ...) (:311-326, :348-352).
+__global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreeParams tp, const long long* __restrict__ histSum,
+                                               const int32_t* __restrict__ histCnt, size_t hist_stride,
+                                               const int32_t* __restrict__ nthr, double* __restrict__ featS,
+                                               int32_t* __restrict__ featT, int32_t* used, int32_t* pool) {
+    const int node = st->cur;
+    if (node < 0 || st->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->split_active = 0;
+        return;
+    }
+    __shared__ double sS[9];
+    __shared__ int sT[9];
+    __shared__ bool amLast;
+    const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const NodeRec& rec = st->nodes[node];
+    const int se = st->scale_exp;
+    const long long* sum = histSum + (size_t)node * hist_stride + (size_t)f * RLB_T;
+    const int32_t* cnt = histCnt + (size_t)node * hist_stride + (size_t)f * RLB_T;
+    const int total = rec.count;
+    const double sumResponse = fix2d(rec.sum_fix, se);
+    double S = -1.0;
+    int bt = 0x7fffffff;
+    if (t < nthr[f]) {
+        const int cL = cnt[t];
+        const int cR = total - cL;
+        if (!(cL < tp.mls || cR < tp.mls)) {
+            const double sL = fix2d(sum[t], se);
+            const double sR = sumResponse - sL;
+            const double v = sL * sL / cL + sR * sR / cR;
+            if (v > -1.0) {  // false for NaN, like `cfg.S < S`
+                S = v;
+                bt = t;
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const double oS = __shfl_xor_sync(0xffffffffu, S, d);
+        const int oT = __shfl_xor_sync(0xffffffffu, bt, d);
+        if (oS > S || (oS == S && oT < bt)) {
+            S = oS;
+            bt = oT;
+        }
+    }
+    if (lane == 0) {
+        sS[w] = S;
+        sT[w] = bt;
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int i = 1; i < 9; i++)
+            if (sS[i] > S || (sS[i] == S && sT[i] < bt)) {
+                S = sS[i];
+                bt = sT[i];
+            }
+        featS[f] = S;
+        featT[f] = bt;
+        __threadfence();
+        const unsigned int tk = atomicAdd(&st->ticket_scan, 1u);
+        amLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast || t != 0) return;
+    __threadfence();
+    st->ticket_scan = 0;
+    double bestS = -1.0;
+    int bestF = -1, bestT = -1;
+    const int nu = st->n_used;
+    for (int i = 0; i < nu; i++) {
+        const int ff = (tp.frate < 1.f) ? used[i] : i;
+        const double s = ((volatile double*)featS)[ff];
+        if (bestS < s) {
+            bestS = s;
+            bestF = ff;
+            bestT = ((volatile int32_t*)featT)[ff];
+        }
+    }
+    if (bestS == -1.0) {  // FeatureHistogram.java:311-313 -> RegressionTree.java:79-80
+        st->taken++;
+        st->split_active = 0;
+        select_next(st, tp, used, pool);
+        return;
+    }
+    NodeRec& sp = st->nodes[node];
+    const int nl = histCnt[(size_t)node * hist_stride + (size_t)bestF * RLB_T + bestT];
+    const int nr = total - nl;
+    const int li = st->n_nodes, ri = li + 1;
+    st->n_nodes += 2;
+    st->split_active = 1;
+    st->split_node = node;
+    st->best_f = bestF;
+    st->best_t = bestT;
+    st->best_S = bestS;
+    st->n_left_g = nl;
+    st->n_right_g = nr;
+    st->small_is_left = (nl <= nr) ? 1 : 0;
+    st->small_id = st->small_is_left ? li : ri;
+    st->other_id = st->small_is_left ? ri : li;
+    st->small_sq_fix = 0;
+    st->n_splits++;
+    const double sq = fix2d(sp.sq_fix, st->scale2_exp);
+    sp.deviance = sq - sumResponse * sumResponse / total;  // Split.set(..., var) (FeatureHistogram.java:348,352)
+    sp.feature_idx = bestF;
+    sp.thr_idx = bestT;
+    sp.left = li;
+    sp.right = ri;
+    st->cur = -1;
+}
+
+// K6a: count the rows of every tile that go left (FeatureHistogram.java:334-341); zero the
+// histogram slot of the child that will be scanned; the last CTA turns tile counts into offsets and
+// creates the two child records.
+__global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, const uint16_t* __restrict__ bins, int Fp,
+                                                     const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
+                                                     int32_t* __restrict__ tileCnt, long long* __restrict__ histSum,
+                                                     int32_t* __restrict__ histCnt, size_t hist_stride) {
+    if (!st->split_active) return;
+    __shared__ int sw[8];
+    __shared__ bool amLast;
+    const NodeRec& rec = st->nodes[st->split_node];
+    const int lo = rec.lo, n = rec.hi - rec.lo;
+    const int32_t* src = rec.buf ? samples1 : samples0;
+    const int bf = st->best_f, btv = st->best_t;
+    const int tiles = (n + RLB_PART_TILE - 1) / RLB_PART_TILE;
+    // zero the staging slot the scanned child's raw histogram is accumulated in
+    {
+        long long* zs = histSum;
+        int32_t* zc = histCnt;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hist_stride; i += (size_t)gridDim.x * blockDim.x) {
+            zs[i] = 0;
+            zc[i] = 0;
+        }
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int base = tile * RLB_PART_TILE + threadIdx.x * 8;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = base + k;
+            if (i < n) c += (bins[(size_t)src[lo + i] * Fp + bf] <= btv) ? 1 : 0;
+        }
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int i = 0; i < 8; i++) s += sw[i];
+            tileCnt[tile] = s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(&st->ticket_part, 1u);
+        amLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast) return;
+    __threadfence();
+    // exclusive scan of the tile counts by one CTA (chunked)
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 256) {
+        const int i = base + threadIdx.x;
+        const int v = (i < tiles) ? ((volatile int32_t*)tileCnt)[i] : 0;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int inc = warp_incl_scan_i(v, lane);
+        if (lane == 31) sw[w] = inc;
+        __syncthreads();
+        int off = carry;
+        for (int k = 0; k < w; k++) off += sw[k];
+        if (i < tiles) tileCnt[i] = off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = off + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int nl = carry;
+        st->ticket_part = 0;
+        st->n_left_l = nl;
+        st->n_right_l = n - nl;
+        const int li = rec.left, ri = rec.right;
+        NodeRec& l = st->nodes[li];
+        NodeRec& r = st->nodes[ri];
+        l.feature_idx = r.feature_idx = -1;
+        l.thr_idx = r.thr_idx = -1;
+        l.left = l.right = r.left = r.right = -1;
+        l.buf = r.buf = 1 - rec.buf;
+        l.lo = lo;
+        l.hi = lo + nl;
+        r.lo = lo + nl;
+        r.hi = rec.hi;
+        l.count = st->n_left_g;
+        r.count = st->n_right_g;
+        l.output = r.output = 0.f;
+        l.leaf_ord = r.leaf_ord = -1;
+        l.deviance = r.deviance = 0.0;
+    }
+}
+
+// K6b: stable scatter of the node's segment into the other sample buffer (left rows first).
+__global__ void __launch_bounds__(256) k_part_scatter(DevState* __restrict__ st, const uint16_t* __restrict__ bins, int Fp,
+                                                       int32_t* __restrict__ samples0, int32_t* __restrict__ samples1,
+                                                       const int32_t* __restrict__ tileOff) {
+    if (!st->split_active) return;
+    __shared__ int sw[8];
+    const NodeRec& rec = st->nodes[st->split_node];
+    const int lo = rec.lo, n = rec.hi - rec.lo;
+    const int32_t* src = rec.buf ? samples1 : samples0;
+    int32_t* dst = rec.buf ? samples0 : samples1;
+    const int bf = st->best_f, btv = st->best_t;
+    const int nl = st->n_left_l;
+    const int tiles = (n + RLB_PART_TILE - 1) / RLB_PART_TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int tbase = tile * RLB_PART_TILE;
+        const int base = tbase + threadIdx.x * 8;
+        int doc[8];
+        unsigned int mask = 0;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = base + k;
+            doc[k] = (i < n) ? src[lo + i] : -1;
+            if (i < n && bins[(size_t)doc[k] * Fp + bf] <= btv) {
+                mask |= 1u << k;
+                c++;
+            }
+        }
+        const int inc = warp_incl_scan_i(c, lane);
+        if (lane == 31) sw[w] = inc;
+        __syncthreads();
+        int off = 0;
+        for (int k = 0; k < w; k++) off += sw[k];
+        __syncthreads();
+        const int leftBefore = off + inc - c;                  // lefts of this tile before this thread
+        const int toff = tileOff[tile];                        // lefts before this tile
+        int lpos = lo + toff + leftBefore;
+        int rpos = lo + nl + (tbase - toff) + (threadIdx.x * 8 - leftBefore);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (doc[k] >= 0) {
+                if (mask & (1u << k))
+                    dst[lpos++] = doc[k];
+                else
+                    dst[rpos++] = doc[k];
+            }
+        }
+    }
+}
+
+// K4 + bookkeeping: prefix the scanned child's histogram over t (FeatureHistogram.java:189-194),
+// derive the sibling by subtraction from the parent (:222-234, exact in fixed point), then the last
+// CTA computes the children's deviances (:349-350), inserts them in the queue and selects the next
+// node (RegressionTree.java:69-85).
+__global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeParams tp, long long* __restrict__ histSum,
+                                                 int32_t* __restrict__ histCnt, size_t hist_stride,
+                                                 const long long* __restrict__ stageSum,
+                                                 const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool) {
+    if (!st->split_active) return;
+    __shared__ long long wtS[9];
+    __shared__ int wtC[9];
+    __shared__ bool amLast;
+    const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int parent = st->split_node, small = st->small_id, other = st->other_id;
+    const size_t o = (size_t)f * RLB_T + t;
+    long long vS = 0;
+    int vC = 0;
+    if (t < RLB_T) {
+        vS = stageSum[o];
+        vC = stageCnt[o];
+    }
+    vS = warp_incl_scan_ll(vS, lane);
+    vC = warp_incl_scan_i(vC, lane);
+    if (lane == 31) {
+        wtS[w] = vS;
+        wtC[w] = vC;
+    }
+    __syncthreads();
+    for (int i = 0; i < w; i++) {
+        vS += wtS[i];
+        vC += wtC[i];
+    }
+    if (t < RLB_T) {
+        const long long pS = histSum[(size_t)parent * hist_stride + o];
+        const int pC = histCnt[(size_t)parent * hist_stride + o];
+        histSum[(size_t)small * hist_stride + o] = vS;
+        histCnt[(size_t)small * hist_stride + o] = vC;
+        histSum[(size_t)other * hist_stride + o] = pS - vS;
+        histCnt[(size_t)other * hist_stride + o] = pC - vC;
+        if (f == 0 && t == RLB_T - 1) {
+            st->nodes[small].sum_fix = vS;
+            st->nodes[other].sum_fix = pS - vS;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(&st->ticket_finish, 1u);
+        amLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!amLast || t != 0) return;
+    __threadfence();
+    st->ticket_finish = 0;
+    volatile NodeRec* ns = &st->nodes[small];
+    volatile NodeRec* no = &st->nodes[other];
+    const long long sqS = st->small_sq_fix;
+    const long long sqP = st->nodes[parent].sq_fix;
+    ns->sq_fix = sqS;
+    no->sq_fix = sqP - sqS;
+    const int se = st->scale_exp, s2 = st->scale2_exp;
+    {
+        const double s = fix2d(ns->sum_fix, se);
+        ns->deviance = fix2d(sqS, s2) - s * s / ns->count;
+    }
+    {
+        const double s = fix2d(no->sum_fix, se);
+        no->deviance = fix2d(sqP - sqS, s2) - s * s / no->count;
+    }
+    __threadfence();
+    queue_insert(st, st->nodes[parent].left);   // RegressionTree.java:82-83: left first, then right
+    queue_insert(st, st->nodes[parent].right);
+    st->split_active = 0;
+    select_next(st, tp, used, pool);
+}
+
+// end of RegressionTree.fit: leaves() in left-first DFS order (Split.java:100-113)
+__global__ void k_tree_end(DevState* st, int64_t N_local) {
+    if (!st->done && st->cur >= 0) {
+        st->incomplete = 1;
+        return;
+    }
+    st->incomplete = 0;
+    int stack[64];
+    int sp = 0, nl = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const int n = stack[--sp];
+        NodeRec& r = st->nodes[n];
+        if (r.feature_idx == -1) {
+            r.leaf_ord = nl;
+            st->leaf_nodes[nl] = n;
+            st->leaf_lo[nl] = r.lo;
+            nl++;
+        } else {
+            if (sp + 2 > 64) break;  // depth bound: cannot happen for n_leaves <= RLB_MAX_LEAVES in practice
+            stack[sp++] = r.right;
+            stack[sp++] = r.left;
+        }
+    }
+    st->leaf_lo[nl] = (int32_t)N_local;
+    st->n_leaves_out = nl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// float32 sequential chain  s = (float)((double)s + x_i), i ascending — exact, block parallel.
+// While s stays strictly inside one binade [2^e, 2^(e+1)) every step adds an integer number of
+// float ulps u = 2^(e-23):  fl32(fl64(s + x)) = s + u * rn(rn_v(x) / u), v = 2^(e-52) (the double
+// grid in that binade).  A chunk is therefore an integer prefix scan; the first element whose
+// running mantissa would leave (2^23, 2^24), or that is an exact half-ulp tie (needs the parity of
+// the mantissa), is applied with the real float/double arithmetic by one thread and the rest of the
+// chunk is re-quantised from the new binade.
+// ------------------------------------------------------------------------------------------------
+__device__ float chain_block(const double* __restrict__ val, const int32_t* __restrict__ idx, int64_t n, float s0,
+                             long long* serialCount) {
+    __shared__ long long wTot[32];
+    __shared__ int sFirstBad;
+    __shared__ long long sM;
+    __shared__ float sS;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int CH = RLB_CHAIN_THREADS * RLB_CHAIN_PER_THREAD;
+    float s = s0;
+    long long nserial = 0;
+    for (int64_t base = 0; base < n; base += CH) {
+        const int m = (int)min((int64_t)CH, n - base);
+        double x[RLB_CHAIN_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < RLB_CHAIN_PER_THREAD; k++) {
+            const int j = tid * RLB_CHAIN_PER_THREAD + k;
+            x[k] = 0.0;
+            if (j < m) x[k] = val[idx ? (int64_t)idx[base + j] : base + j];
+        }
+        int start = 0;
+        while (start < m) {
+            const unsigned int bits = __float_as_uint(s);
+            const int ebits = (bits >> 23) & 0xff;
+            const bool normal = (ebits != 0 && ebits != 0xff);
+            if (tid == 0) sFirstBad = m;
+            __syncthreads();
+            long long Q[RLB_CHAIN_PER_THREAD];
+            bool bad[RLB_CHAIN_PER_THREAD];
+            long long M = 0;
+            int e = 0;
+            double sg = 1.0;
+            if (normal) {
+                e = ebits - 127;
+                sg = (bits >> 31) ? -1.0 : 1.0;
+                M = (long long)((bits & 0x7fffffu) | 0x800000u);
+                const double scale_v = scalbn(1.0, 52 - e);
+#pragma unroll
+                for (int k = 0; k < RLB_CHAIN_PER_THREAD; k++) {
+                    const int j = tid * RLB_CHAIN_PER_THREAD + k;
+                    Q[k] = 0;
+                    bad[k] = false;
+                    if (j >= start && j < m && x[k] != 0.0) {
+                        const double a = sg * x[k] * scale_v;
+                        const double ya = rint(a);
+                        if (!(fabs(ya) < 2305843009213693952.0)) {  // 2^61; also NaN / inf
+                            bad[k] = true;
+                        } else {
+                            const double qd = ya * (1.0 / 536870912.0);  // / 2^29
+                            const double Qd = rint(qd);
+                            if (fabs(qd - Qd) == 0.5) bad[k] = true;
+                            Q[k] = (long long)Qd;
+                        }
+                    }
+                }
+            } else {
+                // s is 0, subnormal, inf or NaN: zeros are absorbed (0 + 0 = 0), anything else is exact-serial
+#pragma unroll
+                for (int k = 0; k < RLB_CHAIN_PER_THREAD; k++) {
+                    const int j = tid * RLB_CHAIN_PER_THREAD + k;
+                    Q[k] = 0;
+                    bad[k] = (j >= start && j < m && !(x[k] == 0.0 && s == 0.f));
+                }
+            }
+            // inclusive prefix of Q over the chunk
+            long long run = 0, P[RLB_CHAIN_PER_THREAD];
+#pragma unroll
+            for (int k = 0; k < RLB_CHAIN_PER_THREAD; k++) {
+                run += Q[k];
+                P[k] = run;
+            }
+            const long long inc = warp_incl_scan_ll(run, lane);
+            if (lane == 31) wTot[w] = inc;
+            __syncthreads();
+            long long off = inc - run;
+            for (int i = 0; i < w; i++) off += wTot[i];
+            int myBad = m;
+#pragma unroll
+            for (int k = RLB_CHAIN_PER_THREAD - 1; k >= 0; k--) {
+                const int j = tid * RLB_CHAIN_PER_THREAD + k;
+                if (j >= start && j < m) {
+                    bool b = bad[k];
+                    if (normal && !b) {
+                        const long long Mi = M + off + P[k];
+                        b = !(Mi > 8388608LL && Mi < 16777216LL);
+                    }
+                    if (b) myBad = j;
+                }
+            }
+            if (myBad < m) atomicMin(&sFirstBad, myBad);
+            __syncthreads();
+            const int fb = sFirstBad;
+            // commit elements [start, fb)
+            if (normal && fb > start) {
+                const int last = fb - 1;
+                if (last / RLB_CHAIN_PER_THREAD == tid) sM = M + off + P[last % RLB_CHAIN_PER_THREAD];
+            }
+            __syncthreads();
+            if (normal && fb > start) {
+                const long long Mi = sM;  // in (2^23, 2^24): same sign and exponent as s
+                s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mi & 0x7fffffu));
+            }
+            if (fb < m) {
+                if (fb / RLB_CHAIN_PER_THREAD == tid) sS = (float)((double)s + x[fb % RLB_CHAIN_PER_THREAD]);
+                __syncthreads();
+                s = sS;
+                nserial++;
+                start = fb + 1;
+            } else {
+                start = m;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && serialCount && nserial) atomicAdd((unsigned long long*)serialCount, (unsigned long long)nserial);
+    return s;
+}
+
+// K7: LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.updateTreeOutput (MART.java:54-65):
+// blockIdx.x = leaf ordinal, blockIdx.y = 0 -> sum of pseudo responses, 1 -> sum of weights.
+__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __restrict__ st, const double* __restrict__ lambda,
+                                                                    const double* __restrict__ weight,
+                                                                    const int32_t* __restrict__ samples0,
+                                                                    const int32_t* __restrict__ samples1,
+                                                                    const float* __restrict__ carryIn) {
+    const int l = blockIdx.x;
+    if (l >= st->n_leaves_out) return;
+    const NodeRec& r = st->nodes[st->leaf_nodes[l]];
+    const int32_t* src = (r.buf ? samples1 : samples0) + r.lo;
+    const int which = blockIdx.y;
+    const float c0 = carryIn ? carryIn[which * (RLB_MAX_LEAVES + 1) + l] : 0.f;
+    const float s = chain_block(which ? weight : lambda, src, (int64_t)(r.hi - r.lo), c0, &st->chain_serial);
+    if (threadIdx.x == 0) (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
+}
+
+__global__ void k_leaf_finalize(DevState* st, int kind) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= st->n_leaves_out) return;
+    NodeRec& r = st->nodes[st->leaf_nodes[l]];
+    const float s1 = st->leaf_s1[l];
+    float out;
+    if (kind == RLB_KIND_MART) {
+        out = s1 / (float)r.count;  // MART.java:63: s1 / idx.length
+    } else {
+        const float s2 = st->leaf_s2[l];
+        out = (s2 == 0.f) ? 0.f : s1 / s2;
+    }
+    r.output = out;
+}
+
+// K8: modelScores[k] += learningRate * leaf output (LambdaMART.java:203-210); also records the node
+// of every doc for rlb_read.
+__global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st, const int32_t* __restrict__ samples0,
+                                                       const int32_t* __restrict__ samples1, double* __restrict__ score,
+                                                       int32_t* __restrict__ nodeOf, int64_t N, float lr, int apply) {
+    const int nl = st->n_leaves_out;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = nl - 1;  // last leaf with leaf_lo <= p
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (st->leaf_lo[mid] <= p)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        // leaves with an empty local segment share their lo with the next one: walk forward
+        while (lo + 1 < nl && st->leaf_lo[lo + 1] <= p) lo++;
+        const int node = st->leaf_nodes[lo];
+        const NodeRec& r = st->nodes[node];
+        const int doc = (r.buf ? samples1 : samples0)[p];
+        if (apply) score[doc] += (double)lr * (double)r.output;
+        nodeOf[doc] = node;
+    }
+}
+
+// K9 tail: float chain over the per-query metric values (LambdaMART.java:474-483)
+__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const double* __restrict__ qmetric,
+                                                                      int Q, const float* __restrict__ carryIn) {
+    const float s = chain_block(qmetric, nullptr, (int64_t)Q, carryIn ? carryIn[0] : 0.f, &st->chain_serial);
+    if (threadIdx.x == 0) st->chain_out[0] = s;
+}
+
+__global__ void k_metric_final(DevState* st, long long Q_total) {
+    st->train_metric = st->chain_out[0] / (float)(int)Q_total;  // LambdaMART.java:470
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static TreeParams tree_params(const rlb_ctx* c) {
+    TreeParams tp;
+    tp.F = c->F;
+    tp.n_leaves = c->prm.n_leaves;
+    tp.mls = c->prm.min_leaf_support;
+    tp.frate = c->prm.feature_sampling_rate;
+    return tp;
+}
+
+int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* dLabel, const int32_t* dQoff, int32_t Q,
+                                int64_t N, int32_t metric, int32_t k, const double* dDisc, double* dOut) {
+    int32_t* dRank = nullptr;
+    RLB_CUDA(c, cudaMalloc(&dRank, std::max<int64_t>(N, 1) * 4));
+    const int grid = std::min(Q, 148 * 16);
+    k_query<false><<<grid, 128, 0, c->stream>>>(dScores, dLabel, dQoff, Q, k, metric, dDisc, nullptr, dRank, nullptr, nullptr,
+                                                dOut, nullptr);
+    RLB_CHECK_LAUNCH(c);
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dRank);
+    return RLB_OK;
+}
+
+int rlb_impl_pseudo(rlb_ctx* c) {
+    RLB_CUDA(c, cudaMemsetAsync(&c->dState->max_abs_bits, 0, sizeof(unsigned long long), c->stream));
+    if (c->prm.kind == RLB_KIND_MART) {
+        k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
+    } else {
+        const int grid = std::min(c->Q, c->sm_count * 16);
+        k_query<true><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->Q, c->prm.metric_k, c->prm.metric, c->dDisc,
+                                                   c->dIdeal, c->dRankDoc, c->dLambda, c->dWeight, nullptr, c->dState);
+    }
+    RLB_CHECK_LAUNCH(c);
+    if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
+    k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+int rlb_impl_hist_update(rlb_ctx* c) {
+    RLB_CUDA(c, cudaMemsetAsync(c->dHistSum, 0, c->hist_stride * sizeof(long long), c->stream));
+    RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
+    k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, nullptr, nullptr,
+                                                            c->dHistSum, c->dHistCnt, c->hist_stride, c->dState);
+    RLB_CHECK_LAUNCH(c);
+    if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
+    if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
+    k_root_cumsum<<<c->F, 288, 0, c->stream>>>(c->dHistSum);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+static int enqueue_split_steps(rlb_ctx* c, int steps) {
+    const TreeParams tp = tree_params(c);
+    for (int s = 0; s < steps; s++) {
+        k_scan<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, c->dNThr, c->dFeatS, c->dFeatT,
+                                            c->dUsed, c->dUsed + c->F);
+        RLB_CHECK_LAUNCH(c);
+        long long* stageSum = c->dHistSum + (size_t)c->max_nodes * c->hist_stride;
+        int32_t* stageCnt = c->dHistCnt + (size_t)c->max_nodes * c->hist_stride;
+        k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
+                                                          stageSum, stageCnt, c->hist_stride);
+        RLB_CHECK_LAUNCH(c);
+        k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
+        RLB_CHECK_LAUNCH(c);
+        k_hist_rows<true><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, c->dSamples[0], c->dSamples[1],
+                                                               stageSum, stageCnt, c->hist_stride, c->dState);
+        RLB_CHECK_LAUNCH(c);
+        if (c->world > 1) {
+            // one all-reduce per node split: raw sums + counts of the scanned child
+            // and its squared-sum scalar, at fixed addresses
+            if (int rc = rlb_allreduce_i64(c, stageSum, c->hist_stride)) return rc;
+            if (int rc = rlb_allreduce_i32(c, stageCnt, c->hist_stride)) return rc;
+            if (int rc = rlb_allreduce_i64(c, &c->dState->small_sq_fix, 1)) return rc;
+        }
+        k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
+                                              c->dUsed + c->F);
+        RLB_CHECK_LAUNCH(c);
+    }
+    return RLB_OK;
+}
+
+static int sync_state_header(rlb_ctx* c) {
+    RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+int rlb_impl_tree_fit(rlb_ctx* c) {
+    const TreeParams tp = tree_params(c);
+    k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
+    RLB_CHECK_LAUNCH(c);
+    k_tree_begin<<<1, 1, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F);
+    RLB_CHECK_LAUNCH(c);
+    int steps = c->prm.n_leaves - 1;
+    for (int round = 0; round < 4 * c->prm.n_leaves + 8; round++) {
+        if (int rc = enqueue_split_steps(c, steps)) return rc;
+        k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);
+        RLB_CHECK_LAUNCH(c);
+        if (int rc = sync_state_header(c)) return rc;
+        if (!c->hState->incomplete) break;
+        steps = 2;  // failed scans used up steps: keep going
+    }
+    if (c->hState->incomplete) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_tree_fit", "tree controller did not terminate");
+        return RLB_E_INVALID;
+    }
+    c->stats[0] = c->hState->rows_hist;
+    c->stats[1] = c->hState->n_splits;
+    c->tree_ready = true;
+    c->tree_output_ready = false;
+    return RLB_OK;
+}
+
+extern int rlb_chain_carry_begin(rlb_ctx* c, int nfloats);
+extern int rlb_chain_carry_end(rlb_ctx* c, float* dOutVals, int nfloats);
+
+int rlb_impl_tree_output(rlb_ctx* c) {
+    if (!c->tree_ready) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_update_tree_output", "no fitted tree");
+        return RLB_E_INVALID;
+    }
+    const int nl = c->prm.n_leaves;
+    const float* carry = nullptr;
+    if (c->world > 1) {
+        if (int rc = rlb_chain_carry_begin(c, 2 * (RLB_MAX_LEAVES + 1))) return rc;
+        carry = c->dCarry;
+    }
+    dim3 grid(nl, c->prm.kind == RLB_KIND_MART ? 1 : 2);
+    k_leaf_chain<<<grid, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dLambda, c->dWeight, c->dSamples[0], c->dSamples[1], carry);
+    RLB_CHECK_LAUNCH(c);
+    if (c->world > 1) {
+        // leaf_s1 and leaf_s2 are adjacent in DevState: one carry message
+        if (int rc = rlb_chain_carry_end(c, c->dState->leaf_s1, 2 * (RLB_MAX_LEAVES + 1))) return rc;
+    }
+    k_leaf_finalize<<<(nl + 127) / 128, 128, 0, c->stream>>>(c->dState, c->prm.kind);
+    RLB_CHECK_LAUNCH(c);
+    c->tree_output_ready = true;
+    return RLB_OK;
+}
+
+int rlb_impl_update_scores(rlb_ctx* c) {
+    if (!c->tree_output_ready) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_update_scores", "leaf outputs not computed");
+        return RLB_E_INVALID;
+    }
+    k_score_update<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N,
+                                                        c->prm.learning_rate, 1);
+    RLB_CHECK_LAUNCH(c);
+    c->tree_output_ready = false;  // a second call must not add the tree twice
+    return RLB_OK;
+}
+
+// node id of every doc of the last tree without touching the scores (rlb_read)
+int rlb_impl_assign_nodes(rlb_ctx* c) {
+    k_score_update<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N,
+                                                        c->prm.learning_rate, 0);
+    RLB_CHECK_LAUNCH(c);
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+extern long long rlb_q_total(rlb_ctx* c);
+
+int rlb_impl_train_metric(rlb_ctx* c) {
+    const int grid = std::min(c->Q, c->sm_count * 16);
+    k_query<false><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->Q, c->prm.metric_k, c->prm.metric, c->dDisc,
+                                                c->dIdeal, c->dRankDoc, nullptr, nullptr, c->dQMetric, c->dState);
+    RLB_CHECK_LAUNCH(c);
+    const float* carry = nullptr;
+    if (c->world > 1) {
+        if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
+        carry = c->dCarry;
+    }
+    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dQMetric, c->Q, carry);
+    RLB_CHECK_LAUNCH(c);
+    if (c->world > 1) {
+        if (int rc = rlb_chain_carry_end(c, c->dState->chain_out, 1)) return rc;
+    }
+    k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, rlb_q_total(c));
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+int rlb_impl_export_tree(rlb_ctx* c, rlb_node* out, int32_t cap, int32_t* n_nodes) {
+    RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const DevState* st = c->hState;
+    const int n = st->n_nodes;
+    if (n_nodes) *n_nodes = n;
+    if (cap < n || !out) {
+        rlb_set_error(c, RLB_E_INVALID, "tree export", "node buffer too small");
+        return RLB_E_INVALID;
+    }
+    for (int i = 0; i < n; i++) {
+        const NodeRec& r = st->nodes[i];
+        rlb_node& o = out[i];
+        o.feature_idx = r.feature_idx;
+        o.feature_id = (r.feature_idx >= 0) ? c->feature_ids[r.feature_idx] : -1;
+        o.threshold_idx = r.thr_idx;
+        o.threshold = (r.feature_idx >= 0) ? c->h_thr[(size_t)r.feature_idx * RLB_T + r.thr_idx] : 0.f;
+        o.left = r.left;
+        o.right = r.right;
+        o.output = (r.feature_idx == -1) ? r.output : 0.f;
+        o.count = r.count;
+        o.deviance = r.deviance;
+    }
+    return RLB_OK;
+}

@@ -1,0 +1,182 @@
+// rlb_internal.cuh — context, device-resident tree state and shared helpers of the B200 LambdaMART path.
+// Nothing here is part of the ABI (see include/ranklib_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ranklib_b200.h"
+
+#define RLB_T RLB_MAX_BINS          // bins per feature in every padded table (257)
+#define RLB_MAX_LEAVES 1024          // n_leaves limit of the device tree controller
+#define RLB_MAX_NODES (2 * RLB_MAX_LEAVES)
+#define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
+#define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
+#define RLB_CHAIN_THREADS 1024
+#define RLB_CHAIN_PER_THREAD 4
+
+// One tree node as the device controller sees it.  Node ids follow creation order: root = 0, the
+// k-th successful split creates ids 2k+1 (left) and 2k+2 (right) — the oracle numbers the same way.
+struct NodeRec {
+    int32_t feature_idx;   // -1 while a leaf
+    int32_t thr_idx;
+    int32_t left, right;
+    int32_t lo, hi;        // LOCAL segment [lo,hi) of the sample list (this rank's docs of the node)
+    int32_t buf;           // which ping-pong sample buffer holds the segment
+    int32_t count;         // GLOBAL number of samples (all ranks)
+    long long sum_fix;     // fixed-point sum of pseudo responses (global)
+    long long sq_fix;      // fixed-point sum of squared pseudo responses (global)
+    double deviance;
+    float output;
+    int32_t leaf_ord;      // ordinal in leaves() order once the tree is finished, else -1
+};
+
+struct DevState {
+    // fixed-point scales of this iteration: v = rint(lambda * 2^scale_exp), q = rint(lambda^2 * 2^scale2_exp)
+    unsigned long long max_abs_bits;  // max |pseudo response| as a double bit pattern (atomicMax)
+    int32_t scale_exp, scale2_exp;
+    long long root_sq_fix;
+    // best-first controller (RegressionTree.fit)
+    int32_t n_nodes;
+    int32_t qlen, taken;
+    int32_t cur;            // node to scan at the next split step, -1 = none
+    int32_t done;           // growth finished
+    int32_t incomplete;     // ran out of split steps before the loop of RegressionTree.fit ended
+    int32_t split_active;   // the current step performs a split (set by the scan, read by partition/hist/finish)
+    int32_t split_node, best_f, best_t;
+    int32_t small_is_left, small_id, other_id;
+    int32_t n_left_g, n_right_g;      // global child sizes (from the histogram)
+    int32_t n_left_l, n_right_l;      // local child sizes (from the partition)
+    double best_S;
+    // last-block tickets
+    uint32_t ticket_scan, ticket_part, ticket_finish;
+    // feature sampling (FeatureHistogram.java:271-294)
+    long long rng_seed;     // java.util.Random state
+    int32_t n_used;
+    // leaves
+    int32_t n_leaves_out;
+    // statistics
+    long long rows_hist;    // rows fed to child histogram builds (local)
+    long long n_splits;
+    long long chain_serial; // float-chain elements that took the exact serial path
+    long long small_sq_fix; // scratch: squared-sum of the scanned child (local, then all-reduced)
+    float train_metric;
+    float chain_out[4];
+    int32_t queue[RLB_MAX_NODES];
+    int32_t leaf_nodes[RLB_MAX_LEAVES + 1];   // node ids of the leaves in leaves() order
+    int32_t leaf_lo[RLB_MAX_LEAVES + 1];      // their segment starts (ascending) + N sentinel
+    float leaf_s1[RLB_MAX_LEAVES + 1], leaf_s2[RLB_MAX_LEAVES + 1];
+    NodeRec nodes[RLB_MAX_NODES];
+};
+
+struct rlb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    // data
+    int64_t N = 0, N_total = 0, Q_total = 0;
+    int32_t F = 0, Fp = 0, Q = 0, max_query = 0;
+    bool loaded = false, inited = false, have_thr = false, tree_ready = false, tree_output_ready = false;
+    rlb_params prm{};
+    std::vector<int32_t> feature_ids;
+    std::vector<float> h_thr;       // [F][RLB_T]
+    std::vector<int32_t> h_nthr;    // [F]
+    float* dX = nullptr;            // [N][F] raw values (kept for re-binning)
+    float* dLabel = nullptr;
+    int32_t* dQoff = nullptr;
+    int32_t* dQidOfDoc = nullptr;
+    uint16_t* dBins = nullptr;      // [N][Fp]
+    float* dThr = nullptr;          // [F][RLB_T]
+    int32_t* dNThr = nullptr;       // [F]
+    double* dDisc = nullptr;        // discount table [max_query + 1]
+    double* dIdeal = nullptr;       // ideal DCG@k per query
+    double* dScore = nullptr;
+    double* dLambda = nullptr;
+    double* dWeight = nullptr;
+    double* dQMetric = nullptr;     // per-query NDCG
+    // per-query ranking scratch (positions inside the query, sorted by score)
+    int32_t* dRankDoc = nullptr;
+    // tree state
+    int32_t max_nodes = 0;
+    size_t hist_stride = 0;         // elements per node: F*RLB_T
+    long long* dHistSum = nullptr;  // [max_nodes][F][RLB_T]
+    int32_t* dHistCnt = nullptr;    // [max_nodes][F][RLB_T]
+    int32_t* dSamples[2] = {nullptr, nullptr};
+    int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
+    int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
+    int32_t n_tiles = 0;
+    double* dFeatS = nullptr;       // per-feature best S
+    int32_t* dFeatT = nullptr;      // per-feature best t
+    int32_t* dUsed = nullptr;       // usedFeatures order
+    DevState* dState = nullptr;
+    DevState* hState = nullptr;     // pinned mirror (partial copies)
+    float* dCarry = nullptr;        // cross-rank float-chain carries
+    int32_t grid_rows = 0;          // CTAs of the row-oriented kernels (multiple of the SM count)
+    int32_t sm_count = 0;
+    int64_t stats[4] = {0, 0, 0, 0};
+    int64_t launches = 0;           // kernels launched by this context (bench: gpu_launches)
+};
+
+const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* detail);
+
+#define RLB_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            rlb_set_error((ctx), RLB_E_CUDA, #call, cudaGetErrorString(e__));            \
+            return RLB_E_CUDA;                                                           \
+        }                                                                                \
+    } while (0)
+
+#define RLB_NCCL(ctx, call)                                                              \
+    do {                                                                                 \
+        ncclResult_t r__ = (call);                                                       \
+        if (r__ != ncclSuccess) {                                                        \
+            rlb_set_error((ctx), RLB_E_NCCL, #call, ncclGetErrorString(r__));            \
+            return RLB_E_NCCL;                                                           \
+        }                                                                                \
+    } while (0)
+
+#define RLB_CHECK_LAUNCH(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            rlb_set_error((ctx), RLB_E_CUDA, "kernel launch", cudaGetErrorString(e__));  \
+            return RLB_E_CUDA;                                                           \
+        }                                                                                \
+    } while (0)
+
+// ---- rlb_init.cu ----
+int rlb_impl_load(rlb_ctx* ctx, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
+                  const int32_t* qoff, int32_t Q);
+int rlb_impl_init(rlb_ctx* ctx, const rlb_params* params);
+int rlb_impl_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees,
+                           const float* weights, const float* X, int64_t N, int32_t n_cols, float* out);
+int rlb_impl_score_metric(rlb_ctx* ctx, const double* scores, const float* label, const int32_t* qoff, int32_t Q,
+                          int32_t metric, int32_t k, double* out);
+void rlb_impl_free(rlb_ctx* ctx);
+
+// ---- rlb_boost.cu ----
+int rlb_impl_pseudo(rlb_ctx* ctx);
+int rlb_impl_hist_update(rlb_ctx* ctx);
+int rlb_impl_tree_fit(rlb_ctx* ctx);
+int rlb_impl_tree_output(rlb_ctx* ctx);
+int rlb_impl_update_scores(rlb_ctx* ctx);
+int rlb_impl_train_metric(rlb_ctx* ctx);
+int rlb_impl_assign_nodes(rlb_ctx* ctx);
+int rlb_impl_export_tree(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
+int rlb_impl_launch_rank_metric(rlb_ctx* ctx, const double* dScores, const float* dLabel, const int32_t* dQoff,
+                                int32_t Q, int64_t N, int32_t metric, int32_t k, const double* dDisc, double* dOut);
+
+// all-reduce helpers (no-ops when world == 1)
+int rlb_allreduce_i64(rlb_ctx* ctx, long long* buf, size_t n);
+int rlb_allreduce_i32(rlb_ctx* ctx, int32_t* buf, size_t n);
+int rlb_allreduce_max_u64(rlb_ctx* ctx, unsigned long long* buf, size_t n);

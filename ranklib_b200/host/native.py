@@ -1,0 +1,217 @@
+"""ctypes binding of libranklib_b200.so — the C ABI declared in include/ranklib_b200.h.
+
+This is what the JNI shim (jni/ranklib_b200_jni.c) calls from Java; Python drives the very same
+entry points.  There is no fallback: if the shared library is missing, or no CUDA device is
+visible when a context is created, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+LIB_PATH = os.path.join(CSRC, "libranklib_b200.so")
+
+RLB_OK = 0
+KIND_LAMBDAMART, KIND_MART = 0, 1
+METRIC_NDCG, METRIC_DCG = 0, 1
+MAX_BINS = 257
+
+READ = dict(LAMBDA=1, WEIGHT=2, SCORE=3, LEAF_ID=4, BINS=5, ROOT_SUM=6, ROOT_COUNT=7, ROOT_STATS=8, NODE_ID=9)
+
+# every symbol include/ranklib_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "rlb_destroy", "rlb_comm_unique_id",
+           "rlb_comm_init", "rlb_load_dense", "rlb_set_thresholds", "rlb_lambdamart_init", "rlb_get_thresholds",
+           "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
+           "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
+           "rlb_ensemble_eval", "rlb_score_metric"]
+
+
+class RankLibError(RuntimeError):
+    """Mirror of ciir.umass.edu.utilities.RankLibError (R/utilities/RankLibError.java:9-42): the one
+    unchecked error type of the boundary."""
+
+
+class Params(C.Structure):
+    _fields_ = [("n_leaves", C.c_int32), ("min_leaf_support", C.c_int32), ("learning_rate", C.c_float),
+                ("n_threshold", C.c_int32), ("kind", C.c_int32), ("metric", C.c_int32), ("metric_k", C.c_int32),
+                ("feature_sampling_rate", C.c_float), ("seed", C.c_int64)]
+
+
+NODE_DTYPE = np.dtype([("feature_id", "<i4"), ("feature_idx", "<i4"), ("threshold", "<f4"), ("threshold_idx", "<i4"),
+                       ("left", "<i4"), ("right", "<i4"), ("output", "<f4"), ("count", "<i4"), ("deviance", "<f8")],
+                      align=True)
+assert NODE_DTYPE.itemsize == 40
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RankLibError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rlb_last_error.restype = C.c_char_p
+        _lib.rlb_last_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+def device_count():
+    return lib().rlb_device_count()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(n_leaves=10, mls=1, lr=0.1, n_threshold=256, kind=KIND_LAMBDAMART, metric=METRIC_NDCG, k=10, frate=1.0,
+                seed=0):
+    return Params(n_leaves, mls, lr, n_threshold, kind, metric, k, frate, seed)
+
+
+class Context:
+    """One rlb_ctx: one CUDA device, one stream, one training set."""
+
+    def __init__(self, device=0):
+        self.lib = lib()
+        h = C.c_void_p()
+        rc = self.lib.rlb_create(device, C.byref(h))
+        if rc != RLB_OK:
+            raise RankLibError(self.lib.rlb_last_error(None).decode())
+        self.h = h
+        self.N = self.F = self.Q = 0
+        self.params = None
+
+    def _ck(self, rc):
+        if rc != RLB_OK:
+            raise RankLibError(self.lib.rlb_last_error(self.h).decode() or f"ranklib_b200 status {rc}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rlb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        rc = lib().rlb_comm_unique_id(buf)
+        if rc != RLB_OK:
+            raise RankLibError(lib().rlb_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, world, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.rlb_comm_init(self.h, rank, world, buf))
+
+    # ---- data / init ----
+    def load_dense(self, X, label, qoff, feature_ids=None):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        label = np.ascontiguousarray(label, dtype=np.float32)
+        qoff = np.ascontiguousarray(qoff, dtype=np.int32)
+        N, F = X.shape
+        fids = (np.arange(1, F + 1, dtype=np.int32) if feature_ids is None
+                else np.ascontiguousarray(feature_ids, np.int32))
+        self._ck(self.lib.rlb_load_dense(self.h, _p(X), C.c_int64(N), F, _p(fids), _p(label), _p(qoff), len(qoff) - 1))
+        self.N, self.F, self.Q = N, F, len(qoff) - 1
+
+    def set_thresholds(self, thr, n_thr):
+        thr = np.ascontiguousarray(thr, np.float32)
+        n_thr = np.ascontiguousarray(n_thr, np.int32)
+        self._ck(self.lib.rlb_set_thresholds(self.h, _p(thr), _p(n_thr)))
+
+    def init(self, params=None):
+        self.params = params or make_params()
+        self._ck(self.lib.rlb_lambdamart_init(self.h, C.byref(self.params)))
+        self.cap = 2 * self.params.n_leaves + 1
+
+    def thresholds(self, f):
+        out = np.zeros(MAX_BINS, np.float32)
+        n = C.c_int32()
+        self._ck(self.lib.rlb_get_thresholds(self.h, f, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- stepwise iteration ----
+    def compute_pseudo_responses(self):
+        self._ck(self.lib.rlb_compute_pseudo_responses(self.h))
+
+    def hist_update(self):
+        self._ck(self.lib.rlb_hist_update(self.h))
+
+    def tree_fit(self):
+        nodes = np.zeros(self.cap, NODE_DTYPE)
+        n = C.c_int32()
+        self._ck(self.lib.rlb_tree_fit(self.h, _p(nodes), self.cap, C.byref(n)))
+        return nodes[:n.value].copy()
+
+    def update_tree_output(self, nodes):
+        nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+        self._ck(self.lib.rlb_update_tree_output(self.h, _p(nodes), len(nodes)))
+        return nodes
+
+    def update_scores(self):
+        self._ck(self.lib.rlb_update_scores(self.h))
+
+    def train_metric(self):
+        m = C.c_float()
+        self._ck(self.lib.rlb_train_metric(self.h, C.byref(m)))
+        return m.value
+
+    def boost_iter(self, want_tree=True):
+        n = C.c_int32()
+        m = C.c_float()
+        if want_tree:
+            nodes = np.zeros(self.cap, NODE_DTYPE)
+            self._ck(self.lib.rlb_boost_iter(self.h, _p(nodes), self.cap, C.byref(n), C.byref(m)))
+            return nodes[:n.value].copy(), m.value
+        self._ck(self.lib.rlb_boost_iter(self.h, None, 0, C.byref(n), C.byref(m)))
+        return None, m.value
+
+    def boost_iters(self, n_iters):
+        nodes = np.zeros((n_iters, self.cap), NODE_DTYPE)
+        nn = np.zeros(n_iters, np.int32)
+        mm = np.zeros(n_iters, np.float32)
+        self._ck(self.lib.rlb_boost_iters(self.h, n_iters, _p(nodes), self.cap, _p(nn), _p(mm)))
+        return [nodes[i, :nn[i]].copy() for i in range(n_iters)], mm
+
+    def read(self, what):
+        w = READ[what]
+        N, F = self.N, self.F
+        shape, dt = {1: ((N,), np.float64), 2: ((N,), np.float64), 3: ((N,), np.float64), 4: ((N,), np.int32),
+                     5: ((F, N), np.int32), 6: ((F, MAX_BINS), np.float64), 7: ((F, MAX_BINS), np.int32),
+                     8: ((2,), np.float64), 9: ((N,), np.int32)}[w]
+        out = np.zeros(shape, dt)
+        self._ck(self.lib.rlb_read(self.h, w, _p(out), C.c_int64(out.nbytes)))
+        return out
+
+    def stats(self):
+        out = np.zeros(4, np.int64)
+        self._ck(self.lib.rlb_stats(self.h, _p(out)))
+        return out
+
+    # ---- scoring ----
+    def ensemble_eval(self, nodes, tree_off, weights, X):
+        nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+        tree_off = np.ascontiguousarray(tree_off, np.int32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        X = np.ascontiguousarray(X, np.float32)
+        out = np.zeros(X.shape[0], np.float32)
+        self._ck(self.lib.rlb_ensemble_eval(self.h, _p(nodes), _p(tree_off), len(tree_off) - 1, _p(weights), _p(X),
+                                            C.c_int64(X.shape[0]), X.shape[1], _p(out)))
+        return out
+
+    def score_metric(self, scores, label, qoff, metric=METRIC_NDCG, k=10):
+        scores = np.ascontiguousarray(scores, np.float64)
+        label = np.ascontiguousarray(label, np.float32)
+        qoff = np.ascontiguousarray(qoff, np.int32)
+        out = C.c_double()
+        self._ck(self.lib.rlb_score_metric(self.h, _p(scores), _p(label), _p(qoff), len(qoff) - 1, metric, k, C.byref(out)))
+        return out.value

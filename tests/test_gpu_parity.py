@@ -1,0 +1,178 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bins / thresholds / leaf assignment bit-exact; split (feature,
+threshold) identical, or — where the reference itself resolves a tie by rounding noise (SURVEY.md
+F10/H1) — equivalent (same partition of the training samples); lambdas 1e-12 relative (exp is the
+only non-identical operation); leaf values and scores 1e-5 relative; NDCG@10 equal at 4 decimals.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from ranklib_b200.host import native, synth
+from tests.util import compare_tree, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(X, label, qoff, **kw):
+    po = orc.make_params(**kw)
+    pg = native.make_params(**kw)
+    o = orc.Oracle(X, label, qoff, po)
+    g = native.Context(0)
+    g.load_dense(X, label, qoff)
+    g.init(pg)
+    return o, g
+
+
+def test_thresholds_and_bins_c1(built):
+    X, label, qoff = synth.c1()
+    o, g = _pair(X, label, qoff)
+    for f in range(X.shape[1]):
+        np.testing.assert_array_equal(o.thresholds(f), g.thresholds(f))
+    np.testing.assert_array_equal(o.read("BINS"), g.read("BINS"))
+    np.testing.assert_array_equal(o.read("ROOT_COUNT"), g.read("ROOT_COUNT"))
+
+
+def test_thresholds_and_bins_mslr_shaped(built):
+    X, label, qoff = synth.c2(0.02)
+    X = X.copy()
+    X[::97, 3] = np.nan      # unknown values read as 0 (DenseDataPoint.java:28-30)
+    X[::89, 5] = -0.0
+    o, g = _pair(X, label, qoff)
+    for f in range(X.shape[1]):
+        np.testing.assert_array_equal(o.thresholds(f), g.thresholds(f))
+    np.testing.assert_array_equal(o.read("BINS"), g.read("BINS"))
+    np.testing.assert_array_equal(o.read("ROOT_COUNT"), g.read("ROOT_COUNT"))
+
+
+def test_stagewise_first_iterations_c1(built):
+    X, label, qoff = synth.c1()
+    o, g = _pair(X, label, qoff)
+    for it in range(3):
+        o.compute_pseudo_responses()
+        g.compute_pseudo_responses()
+        np.testing.assert_allclose(g.read("LAMBDA"), o.read("LAMBDA"), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(g.read("WEIGHT"), o.read("WEIGHT"), rtol=1e-12, atol=1e-15)
+        o.hist_update()
+        g.hist_update()
+        os_, gs_ = o.read("ROOT_SUM"), g.read("ROOT_SUM")
+        assert np.max(np.abs(os_ - gs_)) <= 1e-9 * max(1.0, np.max(np.abs(os_)))
+        np.testing.assert_allclose(g.read("ROOT_STATS"), o.read("ROOT_STATS"), rtol=1e-9, atol=1e-9)
+        on = o.tree_fit()
+        gn = g.tree_fit()
+        ng, no = g.read("NODE_ID"), o.read("NODE_ID")
+        identical, equivalent = compare_tree(gn, on, ng, no)
+        assert equivalent, f"iteration {it}: different partition\n{gn}\n{on}"
+        if identical:
+            np.testing.assert_array_equal(ng, no)
+            np.testing.assert_array_equal(g.read("LEAF_ID"), o.read("LEAF_ID"))
+        on = o.update_tree_output(on)
+        gn = g.update_tree_output(gn)
+        assert np.max(rel_err(gn["output"][ng], on["output"][no])) <= 1e-5   # leaf value seen by every doc
+        o.update_scores()
+        g.update_scores()
+        assert np.max(rel_err(g.read("SCORE"), o.read("SCORE"), floor=1e-12)) <= 1e-5
+        mo, mg = o.train_metric(), g.train_metric()
+        assert round(mo, 4) == round(mg, 4), (mo, mg)
+
+
+def _run_lockstep(X, label, qoff, n_trees, **kw):
+    o, g = _pair(X, label, qoff, **kw)
+    n_ident = n_equiv = 0
+    for it in range(n_trees):
+        on, mo = o.boost_iter()
+        gn, mg = g.boost_iter()
+        ng, no = g.read("NODE_ID"), o.read("NODE_ID")
+        identical, equivalent = compare_tree(gn, on, ng, no)
+        assert equivalent, f"tree {it}: partitions differ"
+        n_ident += identical
+        n_equiv += equivalent
+        assert np.max(rel_err(gn["output"][ng], on["output"][no])) <= 1e-5, f"tree {it}"
+        assert abs(mo - mg) <= 5e-5 and round(mo, 4) == round(mg, 4), (it, mo, mg)
+    so, sg = o.read("SCORE"), g.read("SCORE")
+    assert np.max(rel_err(sg, so, floor=1e-9)) <= 1e-5
+    return n_ident, n_equiv, o, g
+
+
+def test_c1_20_trees_lockstep(built):
+    """BASELINE.json configs[0]: 20 trees on the 1k-doc / 50-feature set."""
+    X, label, qoff = synth.c1()
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 20)
+    assert n_equiv == 20
+    assert n_ident >= 15, f"only {n_ident}/20 trees have identical split ids"
+
+
+def test_mslr_shaped_small_lockstep(built):
+    X, label, qoff = synth.c2(0.03)
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 8)
+    assert n_equiv == 8
+
+
+def test_mart_lockstep(built):
+    X, label, qoff = synth.c1()
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 6, kind=1)
+    assert n_equiv == 6
+
+
+def test_min_leaf_support_and_small_leaves(built):
+    X, label, qoff = synth.c1()
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 4, mls=25, n_leaves=6)
+    assert n_equiv == 4
+
+
+def test_feature_sampling_seeded(built):
+    """Random-Forest style per-split feature sampling with a shared java.util.Random stream."""
+    X, label, qoff = synth.c1()
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 3, kind=1, frate=0.3, seed=12345, n_leaves=20)
+    assert n_equiv == 3
+
+
+def test_ragged_and_degenerate_queries(built):
+    rng = np.random.default_rng(7)
+    sizes = np.array([1, 2, 1, 37, 3, 1200, 5, 1, 64, 11])     # singletons, one query larger than the smem cap
+    qoff = np.zeros(len(sizes) + 1, np.int32)
+    qoff[1:] = np.cumsum(sizes)
+    N = int(qoff[-1])
+    X = rng.standard_normal((N, 7)).astype(np.float32)
+    X[:, 6] = 3.0                                               # constant feature: a single threshold
+    label = rng.integers(0, 5, N).astype(np.float32)
+    label[qoff[4]:qoff[5]] = 2.0                                # a query whose labels are all equal: lambdas 0
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 5)
+    assert n_equiv == 5
+
+
+def test_ensemble_eval_and_score_metric(built):
+    X, label, qoff = synth.c1()
+    o, g = _pair(X, label, qoff)
+    trees, offs = [], [0]
+    for _ in range(10):
+        gn, _m = g.boost_iter()
+        o.boost_iter()
+        trees.append(gn)
+        offs.append(offs[-1] + len(gn))
+    nodes = np.concatenate(trees)
+    w = np.full(len(trees), 0.1, np.float32)
+    Xe = np.zeros((X.shape[0], X.shape[1] + 1), np.float32)     # column 0 unused: fids are 1-based
+    Xe[:, 1:] = X
+    Xe[5, 3] = np.nan
+    se = g.ensemble_eval(nodes, offs, w, Xe)
+    so = orc.ensemble_eval(nodes, offs, w, Xe)
+    np.testing.assert_array_equal(se, so)                        # float chain reproduced bit for bit
+    m_g = g.score_metric(se.astype(np.float64), label, qoff)
+    m_o = orc.score_metric(so.astype(np.float64), label, qoff)
+    assert m_g == m_o
+
+
+def test_errors(built):
+    g = native.Context(0)
+    with pytest.raises(native.RankLibError):
+        g.init()                                                 # nothing loaded
+    X, label, qoff = synth.c1()
+    bad = label.copy()
+    bad[3] = -1
+    with pytest.raises(native.RankLibError, match="negative"):
+        g.load_dense(X, bad, qoff)
+    g.load_dense(X, label, qoff)
+    with pytest.raises(native.RankLibError):
+        g.init(native.make_params(n_threshold=-1))
