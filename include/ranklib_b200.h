@@ -166,6 +166,19 @@ int rlb_read(rlb_ctx* ctx, int32_t what, void* dst, int64_t bytes);
  * [1] splits done, [2] leaf float-chain segments that took the serial path, [3] reserved. */
 int rlb_stats(rlb_ctx* ctx, int64_t out[4]);
 
+/* Measurement hooks (no reference counterpart; RankerTrainer only prints wall time,
+ * R/learning/RankerTrainer.java:31-34,53-55).  rlb_stream returns the cudaStream_t every kernel of
+ * the context is launched on, so that a caller can bracket calls with its own CUDA events.
+ * rlb_profile(1) makes the context record CUDA events around each histogram kernel;
+ * rlb_profile_read returns, accumulated since the last rlb_profile(1):
+ *   out[0] ms inside the root-histogram kernel (FeatureHistogram.update), out[1] its launches,
+ *   out[2] rows it processed; out[3..5] the same for the child-histogram kernel
+ *   (FeatureHistogram.construct(parent, soi, labels)); out[6] ms inside the lambda kernel, out[7]
+ *   its launches. */
+int rlb_stream(rlb_ctx* ctx, void** stream_out);
+int rlb_profile(rlb_ctx* ctx, int32_t enable);
+int rlb_profile_read(rlb_ctx* ctx, double out[8]);
+
 /* Ensemble.eval (R/learning/tree/Ensemble.java:110-116) for a batch of data points:
  *   out[i] = float chain  s += (double)tree_t.eval(x_i) * (double)weight[t]  over t.
  * nodes is the concatenation of the trees' node arrays, tree_off[n_trees+1] their offsets.

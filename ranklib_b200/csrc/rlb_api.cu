@@ -56,6 +56,40 @@ int rlb_chain_carry_end(rlb_ctx* c, float* dOutVals, int nfloats) {
     return RLB_OK;
 }
 
+// ---- per-kernel event timing ------------------------------------------------------------------
+void rlb_prof_begin(rlb_ctx* c, int kind) {
+    if (!c->profile) return;
+    if ((size_t)(2 * c->ev_used + 2) > c->ev_pool.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        c->ev_pool.push_back(a);
+        c->ev_pool.push_back(b);
+        c->ev_kind.push_back(kind);
+    }
+    c->ev_kind[c->ev_used] = kind;
+    cudaEventRecord(c->ev_pool[2 * c->ev_used], c->stream);
+}
+void rlb_prof_end(rlb_ctx* c) {
+    if (!c->profile) return;
+    cudaEventRecord(c->ev_pool[2 * c->ev_used + 1], c->stream);
+    c->ev_used++;
+}
+// call after a stream synchronize
+void rlb_prof_collect(rlb_ctx* c) {
+    if (!c->profile) return;
+    for (int i = 0; i < c->ev_used; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) == cudaSuccess) {
+            const int k = c->ev_kind[i];
+            if (k == 0) { c->prof[0] += ms; c->prof[1] += 1; }
+            else if (k == 1) { c->prof[3] += ms; c->prof[4] += 1; }
+            else { c->prof[6] += ms; c->prof[7] += 1; }
+        }
+    }
+    c->ev_used = 0;
+}
+
 long long rlb_q_total(rlb_ctx* c) { return c->Q_total > 0 ? c->Q_total : c->Q; }
 
 static int check_ready(rlb_ctx* c, const char* fn) {
@@ -275,6 +309,9 @@ int rlb_boost_iter(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_node
         if (n_nodes) *n_nodes = c->hState->n_nodes;
     }
     if (train_metric) *train_metric = c->hState->train_metric;
+    rlb_prof_collect(c);
+    c->prof[2] += (double)c->N;
+    c->prof[5] += (double)c->stats[0];
     return RLB_OK;
 }
 
@@ -394,6 +431,31 @@ int rlb_stats(rlb_ctx* c, int64_t out[4]) {
         long long s = 0;
         if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess) out[2] = s;
     }
+    return RLB_OK;
+}
+
+int rlb_stream(rlb_ctx* c, void** stream_out) {
+    if (!c || !stream_out) return RLB_E_INVALID;
+    *stream_out = (void*)c->stream;
+    return RLB_OK;
+}
+
+int rlb_profile(rlb_ctx* c, int32_t enable) {
+    if (!c) return RLB_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->profile = enable != 0;
+    c->ev_used = 0;
+    for (double& v : c->prof) v = 0;
+    return RLB_OK;
+}
+
+int rlb_profile_read(rlb_ctx* c, double out[8]) {
+    if (!c || !out) return RLB_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    rlb_prof_collect(c);
+    for (int i = 0; i < 8; i++) out[i] = c->prof[i];
     return RLB_OK;
 }
 

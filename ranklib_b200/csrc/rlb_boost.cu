@@ -1013,8 +1013,10 @@ int rlb_impl_pseudo(rlb_ctx* c) {
         k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
     } else {
         const int grid = std::min(c->Q, c->sm_count * 16);
+        rlb_prof_begin(c, 2);
         k_query<true><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->Q, c->prm.metric_k, c->prm.metric, c->dDisc,
                                                    c->dIdeal, c->dRankDoc, c->dLambda, c->dWeight, nullptr, c->dState);
+        rlb_prof_end(c);
     }
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
@@ -1026,8 +1028,10 @@ int rlb_impl_pseudo(rlb_ctx* c) {
 int rlb_impl_hist_update(rlb_ctx* c) {
     RLB_CUDA(c, cudaMemsetAsync(c->dHistSum, 0, c->hist_stride * sizeof(long long), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
+    rlb_prof_begin(c, 0);
     k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, nullptr, nullptr,
                                                             c->dHistSum, c->dHistCnt, c->hist_stride, c->dState);
+    rlb_prof_end(c);
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
     if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
@@ -1049,8 +1053,10 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         RLB_CHECK_LAUNCH(c);
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
+        rlb_prof_begin(c, 1);
         k_hist_rows<true><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, c->dSamples[0], c->dSamples[1],
                                                                stageSum, stageCnt, c->hist_stride, c->dState);
+        rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
         if (c->world > 1) {
             // one all-reduce per node split: raw sums + counts of the scanned child

@@ -122,6 +122,12 @@ struct rlb_ctx {
     int32_t sm_count = 0;
     int64_t stats[4] = {0, 0, 0, 0};
     int64_t launches = 0;           // kernels launched by this context (bench: gpu_launches)
+    // optional per-kernel event timing (rlb_profile)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;      // pairs: [2i] start, [2i+1] stop
+    std::vector<int> ev_kind;              // 0 root hist, 1 child hist, 2 lambda
+    int ev_used = 0;
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* detail);
@@ -175,6 +181,11 @@ int rlb_impl_assign_nodes(rlb_ctx* ctx);
 int rlb_impl_export_tree(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
 int rlb_impl_launch_rank_metric(rlb_ctx* ctx, const double* dScores, const float* dLabel, const int32_t* dQoff,
                                 int32_t Q, int64_t N, int32_t metric, int32_t k, const double* dDisc, double* dOut);
+
+// event-timing helpers (rlb_api.cu)
+void rlb_prof_begin(rlb_ctx* ctx, int kind);
+void rlb_prof_end(rlb_ctx* ctx);
+void rlb_prof_collect(rlb_ctx* ctx);
 
 // all-reduce helpers (no-ops when world == 1)
 int rlb_allreduce_i64(rlb_ctx* ctx, long long* buf, size_t n);

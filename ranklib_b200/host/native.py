@@ -24,7 +24,7 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_comm_init", "rlb_load_dense", "rlb_set_thresholds", "rlb_lambdamart_init", "rlb_get_thresholds",
            "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
-           "rlb_ensemble_eval", "rlb_score_metric"]
+           "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read"]
 
 
 class RankLibError(RuntimeError):
@@ -195,6 +195,20 @@ class Context:
     def stats(self):
         out = np.zeros(4, np.int64)
         self._ck(self.lib.rlb_stats(self.h, _p(out)))
+        return out
+
+    # ---- measurement ----
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.lib.rlb_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def profile(self, enable=True):
+        self._ck(self.lib.rlb_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        out = np.zeros(8, np.float64)
+        self._ck(self.lib.rlb_profile_read(self.h, _p(out)))
         return out
 
     # ---- scoring ----
