@@ -331,41 +331,67 @@ __global__ void k_scale(DevState* st, long long n_total) {
     st->scale2_exp = s2;
 }
 
+// fixed-point images of the pseudo responses: v = rint(lambda * 2^s), q = rint(lambda^2 * 2^s2); also the
+// root's squared sum (FeatureHistogram.update's sqSumResponse, FeatureHistogram.java:134-137)
+__global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lambda, int64_t N, long long* __restrict__ vfix,
+                                                   long long* __restrict__ sqfix, DevState* __restrict__ st) {
+    const double sc = scalbn(1.0, st->scale_exp);
+    const double sc2 = scalbn(1.0, st->scale2_exp);
+    long long sq = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const double lam = lambda[i];
+        vfix[i] = __double2ll_rn(lam * sc);
+        const long long q = __double2ll_rn((lam * lam) * sc2);
+        sqfix[i] = q;
+        sq += q;
+    }
+    for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    if ((threadIdx.x & 31) == 0 && sq != 0) atomicAdd((unsigned long long*)&st->root_sq_fix, (unsigned long long)sq);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 / K3: histogram accumulation (FeatureHistogram.update :126-140, construct(parent,soi,labels)
-// :176-187).  v0: one warp per row, lanes over features, native 64-bit global reductions (REDG).
+// :176-187).
+//
+// k_hist_rows: small nodes.  One warp per row, lanes over features, native 64-bit global
+// reductions (REDG.64).  Cost ~ rows x F atomics; used below hist_min_rows rows.
+//
+// k_hist_priv: everything else.  Shared-memory atomics are native only for 32-bit integers on
+// sm_100a (64-bit and floating point ones are CAS loops), and at ~0.5 updates/clk/SM even those
+// are an order of magnitude short of HBM speed.  So no atomics at all: every THREAD owns a private
+// 257-bin histogram in shared memory, laid out [bin][thread] so that lane l always hits bank pair
+// l mod 16 whatever its bin — conflict free by construction.  A CTA covers a group of 16 adjacent
+// features (one 32-byte sector of a bins row) x PH row phases; thread (fi, ph) walks rows
+// ph, ph+PH, ... of the CTA's row range, 4 rows per batch with register forwarding between equal
+// bins so the 4 read-modify-writes overlap.  At the end the PH phases are summed in shared memory
+// and each CTA issues one global reduction per non-empty (feature, bin).  Sums are 64-bit fixed
+// point, so the result does not depend on the decomposition.
 // ------------------------------------------------------------------------------------------------
 template <bool CHILD>
 __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ bins, int Fp, int F,
-                                                    const double* __restrict__ lambda, int64_t N,
-                                                    const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
-                                                    long long* __restrict__ histSum, int32_t* __restrict__ histCnt,
-                                                    size_t hist_stride, DevState* __restrict__ st) {
+                                                    const long long* __restrict__ vfix, const long long* __restrict__ sqfix,
+                                                    int64_t N, const int32_t* __restrict__ samples0,
+                                                    const int32_t* __restrict__ samples1, long long* __restrict__ sum,
+                                                    int32_t* __restrict__ cnt, DevState* __restrict__ st, int minRows) {
     int64_t lo = 0, hi = N;
     const int32_t* samples = nullptr;
-    long long* sum = histSum;
-    int32_t* cnt = histCnt;
     if (CHILD) {
         if (!st->split_active) return;
         const NodeRec& r = st->nodes[st->small_id];
         lo = r.lo;
         hi = r.hi;
+        if (hi - lo >= minRows) return;  // k_hist_priv's regime
         samples = r.buf ? samples1 : samples0;
-        // histSum / histCnt point at the STAGING slot for child builds (fixed address: the
-        // all-reduce that follows is enqueued by a host that does not know small_id)
         if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
     }
-    const double sc = scalbn(1.0, st->scale_exp);
-    const double sc2 = scalbn(1.0, st->scale2_exp);
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     long long sq = 0;
     for (int64_t i = lo + warp; i < hi; i += nwarps) {
         const int64_t row = CHILD ? (int64_t)samples[i] : i;
-        const double lam = lambda[row];
-        const long long v = __double2ll_rn(lam * sc);
-        if (lane == 0) sq += __double2ll_rn((lam * lam) * sc2);
+        const long long v = vfix[row];
+        if (CHILD && lane == 0) sq += sqfix[row];
         const uint16_t* b = bins + row * Fp;
         for (int f = lane; f < F; f += 32) {
             const int t = b[f];
@@ -373,8 +399,237 @@ __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ 
             if (CHILD) atomicAdd(&cnt[(size_t)f * RLB_T + t], 1);
         }
     }
-    if (lane == 0 && sq != 0)
-        atomicAdd((unsigned long long*)(CHILD ? &st->small_sq_fix : &st->root_sq_fix), (unsigned long long)sq);
+    if (CHILD && lane == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
+}
+
+#define HG 16        // features per CTA group = one 32-byte sector of a bins row
+#define HSTAGES 8    // depth of the bulk-copy ring
+
+// ---- mbarrier / bulk-copy (TMA engine, SASS UBLKCP) primitives -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cpasync16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpasync8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier gets one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cpasync_arrive(void* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One 4-row batch of private read-modify-writes with forwarding between equal bins.
+template <bool CHILD, int T>
+__device__ __forceinline__ void hist_batch4(long long* Hme, unsigned short* Cme, int b0, int b1, int b2, int b3, long long v0,
+                                            long long v1, long long v2, long long v3) {
+    long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
+    h0 += v0;
+    Hme[b0 * T] = h0;
+    if (b1 == b0) h1 = h0;
+    h1 += v1;
+    Hme[b1 * T] = h1;
+    if (b2 == b1) h2 = h1; else if (b2 == b0) h2 = h0;
+    h2 += v2;
+    Hme[b2 * T] = h2;
+    if (b3 == b2) h3 = h2; else if (b3 == b1) h3 = h1; else if (b3 == b0) h3 = h0;
+    h3 += v3;
+    Hme[b3 * T] = h3;
+    if (CHILD) {  // counts: sequential read-modify-writes (program order keeps equal bins correct)
+        Cme[b0 * T] += 1;
+        Cme[b1 * T] += 1;
+        Cme[b2 * T] += 1;
+        Cme[b3 * T] += 1;
+    }
+}
+
+// k_hist_priv<CHILD, PH>: CTA = ceil(16*PH/32) consumer warps + 1 producer warp.
+//   producer: per stage, one 32-byte bulk copy per row (the 16 bins of this CTA's feature group) and
+//             the rows' fixed-point responses, completion tracked by an mbarrier ("full"); HSTAGES
+//             stages in flight hide the HBM latency that 3 resident warps could not.
+//   consumer: thread (fi, ph) owns histogram column tid of H[bin][tid] and the rows ph, ph+PH, ... of
+//             each stage.
+template <bool CHILD, int PH>
+__global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
+    k_hist_priv(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfix,
+                const long long* __restrict__ sqfix, int64_t N, const int32_t* __restrict__ samples0,
+                const int32_t* __restrict__ samples1, long long* __restrict__ sum, int32_t* __restrict__ cnt,
+                DevState* __restrict__ st, int nGroups, int minRows) {
+    constexpr int T = HG * PH;           // consumer threads = private histograms
+    constexpr int R = HG * PH;           // rows per stage (16 per consumer thread)
+    constexpr int CW = (T + 31) / 32;    // consumer warps
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    long long* H = reinterpret_cast<long long*>(smem_raw);                         // [RLB_T][T]
+    size_t off = (size_t)RLB_T * T * 8;
+    unsigned short* Cn = reinterpret_cast<unsigned short*>(smem_raw + off);        // [RLB_T][T] (CHILD)
+    if (CHILD) off += (size_t)RLB_T * T * 2;
+    off = (off + 127) & ~(size_t)127;
+    unsigned char* tiles = smem_raw + off;                                         // HSTAGES x (R*32 + R*8)
+    constexpr int STAGE_BYTES = R * 32 + R * 8;
+    off += (size_t)HSTAGES * STAGE_BYTES;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    unsigned long long* empty = full + HSTAGES;
+
+    int64_t lo = 0, hi = N;
+    const int32_t* samples = nullptr;
+    if (CHILD) {
+        if (!st->split_active) return;
+        const NodeRec& r = st->nodes[st->small_id];
+        lo = r.lo;
+        hi = r.hi;
+        if (hi - lo < minRows) return;  // k_hist_rows' regime
+        samples = r.buf ? samples1 : samples0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x % nGroups;
+    const int idx = blockIdx.x / nGroups;
+    const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
+    const int64_t n = hi - lo;
+    // even split points keep the 16-byte alignment the bulk copy of the response tile needs
+    int64_t r0 = lo + ((n * idx / nCta) & ~(int64_t)1), r1 = lo + ((n * (idx + 1) / nCta) & ~(int64_t)1);
+    if (idx == nCta - 1) r1 = hi;
+    if (idx == 0) r0 = lo;
+    const int nst = (int)((r1 - r0 + R - 1) / R);
+
+    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if (CHILD)
+        for (int i = tid; i < RLB_T * T; i += blockDim.x) Cn[i] = 0;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < HSTAGES; s2++) {
+            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
+            mbar_init(&empty[s2], (uint32_t)CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CW) {
+        // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
+        long long sq = 0;
+        int32_t nxt[(R + 31) / 32];   // CHILD: sample indices of the next stage, fetched one stage ahead
+        if (CHILD) {
+#pragma unroll
+            for (int u = 0; u < (R + 31) / 32; u++) {
+                const int64_t pos = r0 + lane + 32 * u;
+                nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+            }
+        }
+        for (int k = 0; k < nst; k++) {
+            const int s2 = k % HSTAGES;
+            if (k >= HSTAGES) mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
+            const int64_t base = r0 + (int64_t)k * R;
+            const int nr = (int)min((int64_t)R, r1 - base);
+            unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
+            long long* vt = reinterpret_cast<long long*>(bt + R * 32);
+            if (CHILD) {
+                int32_t cur[(R + 31) / 32];
+#pragma unroll
+                for (int u = 0; u < (R + 31) / 32; u++) {
+                    cur[u] = nxt[u];
+                    const int64_t pos = base + R + lane + 32 * u;
+                    nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < (R + 31) / 32; u++) {
+                    const int j = lane + 32 * u;
+                    if (j < nr) {
+                        const int64_t row = cur[u];
+                        const uint16_t* src = bins + row * Fp + g * HG;
+                        cpasync16(bt + j * 32, src);
+                        cpasync16(bt + j * 32 + 16, src + 8);
+                        cpasync8(vt + j, vfix + row);
+                        if (g == 0) sq += sqfix[row];
+                    }
+                }
+            } else {
+                for (int c2 = lane; c2 < 2 * nr; c2 += 32) {
+                    const int j = c2 >> 1, half = c2 & 1;
+                    cpasync16(bt + j * 32 + half * 16, bins + (base + j) * Fp + g * HG + half * 8);
+                }
+                for (int c2 = lane; c2 < (nr + 1) / 2; c2 += 32) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
+            }
+            cpasync_arrive(&full[s2]);
+        }
+        if (CHILD && g == 0) {
+            for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+            if (lane == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
+        }
+    } else {
+        // ===== consumer warps =====
+        const int fi = tid & (HG - 1), ph = tid / HG;
+        const bool active = (tid < T) && (g * HG + fi < F);
+        long long* Hme = H + tid;
+        unsigned short* Cme = Cn + tid;
+        for (int k = 0; k < nst; k++) {
+            const int s2 = k % HSTAGES;
+            mbar_wait(&full[s2], (k / HSTAGES) & 1);
+            const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
+            const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
+            const long long* vt = reinterpret_cast<const long long*>(bt + R * 32);
+            const int nr = (int)min((int64_t)R, r1 - (r0 + (int64_t)k * R));
+            if (active) {
+                if (nr == R) {
+#pragma unroll
+                    for (int kk = 0; kk < 16; kk += 4) {
+                        const int ra = kk * PH + ph, rb = ra + PH, rc = rb + PH, rd = rc + PH;
+                        hist_batch4<CHILD, T>(Hme, Cme, btile[ra * HG + fi], btile[rb * HG + fi], btile[rc * HG + fi],
+                                              btile[rd * HG + fi], vt[ra], vt[rb], vt[rc], vt[rd]);
+                    }
+                } else {
+                    for (int rr = ph; rr < nr; rr += PH) {
+                        const int b = btile[rr * HG + fi];
+                        Hme[b * T] += vt[rr];
+                        if (CHILD) Cme[b * T] += 1;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s2]);
+        }
+    }
+    __syncthreads();
+    // sum the PH phases and publish: one global reduction per non-empty (feature, bin) of this CTA
+    for (int p = tid; p < RLB_T * HG; p += blockDim.x) {
+        const int bin = p / HG, ff = p % HG;
+        const int fo = g * HG + ff;
+        if (fo >= F) continue;
+        long long sacc = 0;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < PH; q++) {
+            sacc += H[bin * T + q * HG + ff];
+            if (CHILD) c += Cn[bin * T + q * HG + ff];
+        }
+        if (sacc != 0) atomicAdd((unsigned long long*)&sum[(size_t)fo * RLB_T + bin], (unsigned long long)sacc);
+        if (CHILD && c != 0) atomicAdd(&cnt[(size_t)fo * RLB_T + bin], c);
+    }
 }
 
 // per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan
@@ -1025,12 +1280,40 @@ int rlb_impl_pseudo(rlb_ctx* c) {
     return RLB_OK;
 }
 
+#define PH_ROOT 6    // 96 private histograms x 257 bins x 8 B = 197 KB + 8 stages x 3840 B
+#define PH_CHILD 5   // 80 private histograms x 257 bins x (8 + 2) B = 206 KB + 8 stages x 3200 B
+
+static constexpr size_t hist_smem(bool child, int ph) {
+    size_t t = (size_t)HG * ph;
+    size_t off = (size_t)RLB_T * t * 8 + (child ? (size_t)RLB_T * t * 2 : 0);
+    off = (off + 127) & ~(size_t)127;
+    return off + (size_t)HSTAGES * (t * 40) + 2 * HSTAGES * 8 + HSTAGES * 4;
+}
+
+static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
+static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
+
 int rlb_impl_hist_update(rlb_ctx* c) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)hist_smem(false, PH_ROOT)));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<true, PH_CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)hist_smem(true, PH_CHILD)));
+        attr_done = true;
+    }
     RLB_CUDA(c, cudaMemsetAsync(c->dHistSum, 0, c->hist_stride * sizeof(long long), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
+    k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dSqfix, c->dState);
+    RLB_CHECK_LAUNCH(c);
     rlb_prof_begin(c, 0);
-    k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, nullptr, nullptr,
-                                                            c->dHistSum, c->dHistCnt, c->hist_stride, c->dState);
+    if (c->N >= c->hist_min_rows) {
+        k_hist_priv<false, PH_ROOT><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+            c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+    } else {
+        k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr,
+                                                                c->dHistSum, c->dHistCnt, c->dState, 0);
+    }
     rlb_prof_end(c);
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
@@ -1054,8 +1337,12 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
         rlb_prof_begin(c, 1);
-        k_hist_rows<true><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dLambda, c->N, c->dSamples[0], c->dSamples[1],
-                                                               stageSum, stageCnt, c->hist_stride, c->dState);
+        k_hist_rows<true><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0],
+                                                               c->dSamples[1], stageSum, stageCnt, c->dState, c->hist_min_rows);
+        RLB_CHECK_LAUNCH(c);
+        k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
+            c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
+            hist_groups(c), c->hist_min_rows);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
         if (c->world > 1) {

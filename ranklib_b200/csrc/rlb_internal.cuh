@@ -101,6 +101,9 @@ struct rlb_ctx {
     double* dLambda = nullptr;
     double* dWeight = nullptr;
     double* dQMetric = nullptr;     // per-query NDCG
+    long long* dVfix = nullptr;     // fixed-point pseudo responses of the iteration
+    long long* dSqfix = nullptr;    // fixed-point squared pseudo responses
+    int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
     // tree state
