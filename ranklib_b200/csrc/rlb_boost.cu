@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
                                                 const double* __restrict__ disc, const double* __restrict__ idealIn,
                                                 int32_t* __restrict__ rankDoc, double* __restrict__ lambda,
                                                 double* __restrict__ weight, double* __restrict__ qmetric,
-                                                DevState* __restrict__ st) {
+                                                DevState* __restrict__ st, const int32_t* __restrict__ qlist) {
     __shared__ double sRaw[QCAP];
     __shared__ double sScore[QCAP];
     __shared__ float sLabel[QCAP];
@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
     __shared__ unsigned long long sMax;
     const int tid = threadIdx.x;
     double thrMax = 0.0;
-    for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    for (int qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+        const int q = qlist ? qlist[qi] : qi;
         const int lo = qoff[q];
         const int n = qoff[q + 1] - lo;
         if (n <= 0) {
@@ -296,6 +297,181 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
         __syncthreads();
         if (tid == 0 && sMax) atomicMax(&st->max_abs_bits, sMax);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast path.  Same arithmetic and the same per-document accumulation order as k_query, but the
+// pair terms are produced pair-parallel: every pair (a, b), a < size = min(k, n), b > a is evaluated
+// ONCE (one exp) into a shared-memory table [size][n]; afterwards the thread that owns rank p
+// adds its terms in the reference's visit order.  G threads cooperate on one query: a warp for
+// queries of up to 64 documents (no block barrier at all), a CTA for larger ones.  Queries whose
+// table does not fit fall back to k_query.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if (G == 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+template <int G>
+__device__ __forceinline__ void query_fast(int q, int gt, const double* __restrict__ score, const float* __restrict__ label,
+                                           const int32_t* __restrict__ qoff, int cutoff, int metric,
+                                           const double* __restrict__ disc, const double* __restrict__ idealIn,
+                                           double* __restrict__ lambda, double* __restrict__ weight,
+                                           double* __restrict__ qmetric, double* sRaw, double* sScore, float* sLabel,
+                                           int* sDoc, double* tL, double* tW, double& thrMax) {
+    const int lo = qoff[q];
+    const int n = qoff[q + 1] - lo;
+    if (n <= 0) {
+        if (gt == 0 && qmetric) qmetric[q] = 0.0;
+        return;
+    }
+    for (int i = gt; i < n; i += G) sRaw[i] = score[lo + i];
+    group_sync<G>();
+    for (int i = gt; i < n; i += G) {
+        const double si = sRaw[i];
+        int r = 0;
+        for (int j = 0; j < n; j++) {
+            const double sj = sRaw[j];
+            r += (sj > si) || (sj == si && j < i);
+        }
+        sScore[r] = si;
+        sLabel[r] = label[lo + i];
+        sDoc[r] = i;
+    }
+    group_sync<G>();
+    const bool ndcg = (metric == RLB_METRIC_NDCG);
+    const double ideal = ndcg ? idealIn[q] : 0.0;
+    if (qmetric && gt == 0) {
+        int sz = cutoff;
+        if (cutoff > n || cutoff <= 0) sz = n;
+        double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
+        for (int i = 0; i < sz; i++) dcg += (double)((1 << (int)sLabel[i]) - 1) * disc[i];
+        double m = dcg;
+        if (ndcg) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
+        qmetric[q] = m;
+    }
+    if (lambda) {
+        const int size = (n > cutoff) ? cutoff : n;  // swapChange (NDCGScorer.java:133)
+        const bool have = !ndcg || ideal > 0.0;
+        const int np = size > 0 ? size * n : 0;
+        for (int e = gt; e < np; e += G) {
+            const int a = e / n, b = e - a * n;
+            double l = 0.0, w = 0.0;
+            if (b > a && have) {
+                const float la = sLabel[a], lb = sLabel[b];
+                if (la != lb) {
+                    double ch = (disc[a] - disc[b]) * ((double)((1 << (int)la) - 1) - (double)((1 << (int)lb) - 1));
+                    if (ndcg) ch = ch / ideal;
+                    const double d = fabs(ch);
+                    if (d > 0) {
+                        const double diff = (la > lb) ? (sScore[a] - sScore[b]) : (sScore[b] - sScore[a]);
+                        const double rho = 1.0 / (1 + exp(diff));
+                        l = rho * d;
+                        w = rho * (1.0 - rho) * d;
+                    }
+                }
+            }
+            tL[e] = l;
+            tW[e] = w;
+        }
+        group_sync<G>();
+        for (int p = gt; p < n; p += G) {
+            const float lp = sLabel[p];
+            double lam = 0.0, w = 0.0;
+            if (size > 0) {
+                const int j1 = min(p, size);
+                for (int j = 0; j < j1; j++)  // (1) outer j < p: p loses to every better-labelled j in the top `size`
+                    if (sLabel[j] > lp) {
+                        lam -= tL[j * n + p];
+                        w += tW[j * n + p];
+                    }
+                if (p < size) {
+                    for (int k = 0; k < n; k++)  // (2) outer j == p: p wins over every worse-labelled k
+                        if (lp > sLabel[k]) {
+                            const int t = (k < p) ? k * n + p : p * n + k;
+                            lam += tL[t];
+                            w += tW[t];
+                        }
+                    for (int j = p + 1; j < n; j++)  // (3) outer j > p
+                        if (sLabel[j] > lp) {
+                            lam -= tL[p * n + j];
+                            w += tW[p * n + j];
+                        }
+                } else {
+                    for (int k = 0; k < size; k++)
+                        if (lp > sLabel[k]) {
+                            lam += tL[k * n + p];
+                            w += tW[k * n + p];
+                        }
+                }
+            }
+            const int doc = lo + sDoc[p];
+            lambda[doc] = lam;
+            weight[doc] = w;
+            thrMax = fmax(thrMax, fabs(lam));
+        }
+    }
+    group_sync<G>();
+}
+
+#define QA_N 64      // warp path: documents per query
+#define QA_T 640     // warp path: table entries (min(k, n) * n)
+#define QA_WARP_BYTES (QA_N * (8 + 8 + 4 + 4) + QA_T * 16)
+
+__device__ __forceinline__ void publish_max(double thrMax, DevState* st) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(thrMax);
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, b, d);
+        b = o > b ? o : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(&st->max_abs_bits, b);
+}
+
+__global__ void __launch_bounds__(256) k_query_warp(const double* __restrict__ score, const float* __restrict__ label,
+                                                     const int32_t* __restrict__ qoff, const int32_t* __restrict__ qlist, int nq,
+                                                     int cutoff, int metric, const double* __restrict__ disc,
+                                                     const double* __restrict__ idealIn, double* __restrict__ lambda,
+                                                     double* __restrict__ weight, double* __restrict__ qmetric,
+                                                     DevState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* base = qsm + (size_t)warp * QA_WARP_BYTES;
+    double* sRaw = reinterpret_cast<double*>(base);
+    double* sScore = sRaw + QA_N;
+    double* tL = sScore + QA_N;
+    double* tW = tL + QA_T;
+    float* sLabel = reinterpret_cast<float*>(tW + QA_T);
+    int* sDoc = reinterpret_cast<int*>(sLabel + QA_N);
+    double thrMax = 0.0;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
+    for (int i = gw; i < nq; i += nw)
+        query_fast<32>(qlist[i], lane, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw, sScore,
+                       sLabel, sDoc, tL, tW, thrMax);
+    if (lambda) publish_max(thrMax, st);
+}
+
+template <int G>
+__global__ void __launch_bounds__(G) k_query_block(const double* __restrict__ score, const float* __restrict__ label,
+                                                    const int32_t* __restrict__ qoff, const int32_t* __restrict__ qlist, int nq,
+                                                    int cutoff, int metric, const double* __restrict__ disc,
+                                                    const double* __restrict__ idealIn, double* __restrict__ lambda,
+                                                    double* __restrict__ weight, double* __restrict__ qmetric,
+                                                    DevState* __restrict__ st, int capN, int capT) {
+    extern __shared__ __align__(16) unsigned char qsm[];
+    double* sRaw = reinterpret_cast<double*>(qsm);
+    double* sScore = sRaw + capN;
+    double* tL = sScore + capN;
+    double* tW = tL + capT;
+    float* sLabel = reinterpret_cast<float*>(tW + capT);
+    int* sDoc = reinterpret_cast<int*>(sLabel + capN);
+    double thrMax = 0.0;
+    for (int i = blockIdx.x; i < nq; i += gridDim.x)
+        query_fast<G>(qlist[i], threadIdx.x, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw,
+                      sScore, sLabel, sDoc, tL, tW, thrMax);
+    if (lambda) publish_max(thrMax, st);
 }
 
 // MART.computePseudoResponses (R/learning/tree/MART.java:47-51)
@@ -450,22 +626,34 @@ template <bool CHILD, int T>
 __device__ __forceinline__ void hist_batch4(long long* Hme, unsigned short* Cme, int b0, int b1, int b2, int b3, long long v0,
                                             long long v1, long long v2, long long v3) {
     long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
+    unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (CHILD) {
+        c0 = Cme[b0 * T];
+        c1 = Cme[b1 * T];
+        c2 = Cme[b2 * T];
+        c3 = Cme[b3 * T];
+    }
+    const bool e10 = b1 == b0, e21 = b2 == b1, e20 = b2 == b0, e32 = b3 == b2, e31 = b3 == b1, e30 = b3 == b0;
     h0 += v0;
+    c0 += 1;
     Hme[b0 * T] = h0;
-    if (b1 == b0) h1 = h0;
+    if (e10) { h1 = h0; c1 = c0; }
     h1 += v1;
+    c1 += 1;
     Hme[b1 * T] = h1;
-    if (b2 == b1) h2 = h1; else if (b2 == b0) h2 = h0;
+    if (e21) { h2 = h1; c2 = c1; } else if (e20) { h2 = h0; c2 = c0; }
     h2 += v2;
+    c2 += 1;
     Hme[b2 * T] = h2;
-    if (b3 == b2) h3 = h2; else if (b3 == b1) h3 = h1; else if (b3 == b0) h3 = h0;
+    if (e32) { h3 = h2; c3 = c2; } else if (e31) { h3 = h1; c3 = c1; } else if (e30) { h3 = h0; c3 = c0; }
     h3 += v3;
+    c3 += 1;
     Hme[b3 * T] = h3;
-    if (CHILD) {  // counts: sequential read-modify-writes (program order keeps equal bins correct)
-        Cme[b0 * T] += 1;
-        Cme[b1 * T] += 1;
-        Cme[b2 * T] += 1;
-        Cme[b3 * T] += 1;
+    if (CHILD) {  // later stores win, and they carry the forwarded running counts
+        Cme[b0 * T] = (unsigned short)c0;
+        Cme[b1 * T] = (unsigned short)c1;
+        Cme[b2 * T] = (unsigned short)c2;
+        Cme[b3 * T] = (unsigned short)c3;
     }
 }
 
@@ -748,20 +936,49 @@ __global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreePar
         amLast = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (!amLast || t != 0) return;
+    if (!amLast) return;
     __threadfence();
-    st->ticket_scan = 0;
+    // merge the per-feature winners in usedFeatures order: strict '<' keeps the FIRST maximum
+    // (FeatureHistogram.java:255,302-308) == the lowest position among equal S.  Block-parallel.
+    __shared__ double mS[9];
+    __shared__ int mP[9];
     double bestS = -1.0;
-    int bestF = -1, bestT = -1;
+    int bestPos = 0x7fffffff;
     const int nu = st->n_used;
-    for (int i = 0; i < nu; i++) {
+    for (int i = t; i < nu; i += blockDim.x) {
         const int ff = (tp.frate < 1.f) ? used[i] : i;
-        const double s = ((volatile double*)featS)[ff];
-        if (bestS < s) {
-            bestS = s;
-            bestF = ff;
-            bestT = ((volatile int32_t*)featT)[ff];
+        const double sv = ((volatile double*)featS)[ff];
+        if (sv > bestS) {  // positions ascend within a thread: first maximum kept
+            bestS = sv;
+            bestPos = i;
         }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const double oS = __shfl_xor_sync(0xffffffffu, bestS, d);
+        const int oP = __shfl_xor_sync(0xffffffffu, bestPos, d);
+        if (oS > bestS || (oS == bestS && oP < bestPos)) {
+            bestS = oS;
+            bestPos = oP;
+        }
+    }
+    if (lane == 0) {
+        mS[w] = bestS;
+        mP[w] = bestPos;
+    }
+    __syncthreads();
+    if (t != 0) return;
+    for (int i = 1; i < 9; i++)
+        if (mS[i] > bestS || (mS[i] == bestS && mP[i] < bestPos)) {
+            bestS = mS[i];
+            bestPos = mP[i];
+        }
+    st->ticket_scan = 0;
+    int bestF = -1, bestT = -1;
+    if (bestS > -1.0) {
+        bestF = (tp.frate < 1.f) ? used[bestPos] : bestPos;
+        bestT = ((volatile int32_t*)featT)[bestF];
+    } else {
+        bestS = -1.0;
     }
     if (bestS == -1.0) {  // FeatureHistogram.java:311-313 -> RegressionTree.java:79-80
         st->taken++;
@@ -1053,7 +1270,7 @@ __global__ void k_tree_end(DevState* st, int64_t N_local) {
 // chunk is re-quantised from the new binade.
 // ------------------------------------------------------------------------------------------------
 __device__ float chain_block(const double* __restrict__ val, const int32_t* __restrict__ idx, int64_t n, float s0,
-                             long long* serialCount) {
+                             long long* serialCount, int64_t valOff = 0) {
     __shared__ long long wTot[32];
     __shared__ int sFirstBad;
     __shared__ long long sM;
@@ -1069,7 +1286,7 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
         for (int k = 0; k < RLB_CHAIN_PER_THREAD; k++) {
             const int j = tid * RLB_CHAIN_PER_THREAD + k;
             x[k] = 0.0;
-            if (j < m) x[k] = val[idx ? (int64_t)idx[base + j] : base + j];
+            if (j < m) x[k] = val[idx ? (int64_t)idx[base + j] : valOff + base + j];
         }
         int start = 0;
         while (start < m) {
@@ -1169,20 +1386,289 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
     return s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-level float chains.  chain_block alone walks a leaf of 900 k samples chunk after chunk.  The
+// chunks are made independent by SPECULATING the binade the running float is in when a chunk starts:
+//   k_chain_sum   exact double sum of every 1024-element chunk (parallel)
+//   k_chain_pred  prefix of those sums per chain = predicted float at every chunk start (the float
+//                 chain stays within ~1e-3 relative of the exact sum, so the predicted exponent is
+//                 right except next to a power of two)
+//   k_chain_summ  per chunk, under the predicted exponent/sign: total quanta, min/max prefix quanta,
+//                 tie/overflow flag (parallel)
+//   k_*_chain     one CTA per chain walks the chunk summaries: a chunk whose summary is valid for
+//                 the ACTUAL running float (same sign and exponent, mantissa stays inside
+//                 (2^23, 2^24), no tie) costs O(1); any other chunk is redone exactly by chain_block.
+// The result is bit-identical to the sequential chain in every case; speculation only buys time.
+// ------------------------------------------------------------------------------------------------
+#define CK 1024   // elements per chunk (256 threads x 4)
+
+struct ChainBufs {
+    double* sumD;       // [2][maxChunks] exact chunk sums, then (in place) predicted start values
+    long long* Qtot;    // [2][maxChunks]
+    long long* Pmin;
+    long long* Pmax;
+    int32_t* ef;        // [2][maxChunks] bit0 valid, bit1 all-zero chunk, bit2 sign, bits 8.. biased exponent
+    int32_t maxChunks;
+};
+
+struct ChainView {
+    const double* val;
+    const int32_t* idx;
+    int64_t n;
+};
+
+// mode 0: chain (l, which) = leaf l of the last tree, which ? weights : pseudo responses
+// mode 1: the single chain of per-query metric values
+__device__ __forceinline__ ChainView chain_view(int mode, const DevState* st, int l, int which, const double* a0,
+                                                const double* a1, const int32_t* s0, const int32_t* s1, int64_t nMetric) {
+    ChainView v;
+    if (mode == 1) {
+        v.val = a0;
+        v.idx = nullptr;
+        v.n = nMetric;
+    } else {
+        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
+        v.val = which ? a1 : a0;
+        v.idx = (r.buf ? s1 : s0) + r.lo;
+        v.n = r.hi - r.lo;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int chain_of_chunk(const int32_t* chunk0, int nCh, int b) {
+    int lo = 0, hi = nCh - 1;  // last chain with chunk0 <= b
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (chunk0[mid] <= b)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_chain_sum(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                    int nChIn, const double* __restrict__ a0, const double* __restrict__ a1,
+                                                    const int32_t* __restrict__ s0, const int32_t* __restrict__ s1,
+                                                    int64_t nMetric, ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    (void)nChIn;
+    const int b = blockIdx.x, which = blockIdx.y;
+    if (b >= chunk0[nCh]) return;
+    const int l = chain_of_chunk(chunk0, nCh, b);
+    const ChainView v = chain_view(mode, st, l, which, a0, a1, s0, s1, nMetric);
+    const int64_t off = (int64_t)(b - chunk0[l]) * CK;
+    __shared__ double ws[8];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t j = off + threadIdx.x * 4 + k;
+        if (j < v.n) acc += v.val[v.idx ? (int64_t)v.idx[j] : j];
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += ws[i];
+        cb.sumD[(size_t)which * cb.maxChunks + b] = t;
+    }
+}
+
+// one warp per (chain, which): exclusive prefix of the chunk sums, starting from the carry
+__global__ void __launch_bounds__(32) k_chain_pred(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                    const float* __restrict__ carryIn, ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int l = blockIdx.x, which = blockIdx.y;
+    if (l >= nCh) return;
+    const int c0 = chunk0[l], c1 = chunk0[l + 1];
+    double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
+    double* sd = cb.sumD + (size_t)which * cb.maxChunks;
+    const int lane = threadIdx.x;
+    for (int base = c0; base < c1; base += 32) {
+        const int i = base + lane;
+        const double v = (i < c1) ? sd[i] : 0.0;
+        double inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (i < c1) sd[i] = run + inc - v;  // predicted running value at the start of chunk i
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// quanta of x when added to a float with sign sg (+-1) and exponent e: Q = rn(rn_v(x) / u); bad on ties / overflow
+__device__ __forceinline__ long long chain_quantum(double x, double sg, double scale_v, bool& bad) {
+    const double a = sg * x * scale_v;
+    const double ya = rint(a);
+    if (!(fabs(ya) < 2305843009213693952.0)) {  // 2^61; also NaN / inf
+        bad = true;
+        return 0;
+    }
+    const double qd = ya * (1.0 / 536870912.0);  // / 2^29
+    const double Qd = rint(qd);
+    if (fabs(qd - Qd) == 0.5) bad = true;
+    return (long long)Qd;
+}
+
+__global__ void __launch_bounds__(256) k_chain_summ(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                     const double* __restrict__ a0, const double* __restrict__ a1,
+                                                     const int32_t* __restrict__ s0, const int32_t* __restrict__ s1,
+                                                     int64_t nMetric, ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int b = blockIdx.x, which = blockIdx.y;
+    if (b >= chunk0[nCh]) return;
+    const int l = chain_of_chunk(chunk0, nCh, b);
+    const ChainView v = chain_view(mode, st, l, which, a0, a1, s0, s1, nMetric);
+    const int64_t off = (int64_t)(b - chunk0[l]) * CK;
+    const size_t o = (size_t)which * cb.maxChunks + b;
+    const float pred = (float)cb.sumD[o];
+    const unsigned int bits = __float_as_uint(pred);
+    const int ebits = (bits >> 23) & 0xff;
+    const bool normal = (ebits != 0 && ebits != 0xff);
+    const double sg = (bits >> 31) ? -1.0 : 1.0;
+    const double scale_v = scalbn(1.0, 52 - (ebits - 127));
+    __shared__ long long wT[8], wMin[8], wMax[8];
+    __shared__ int sBad, sNonZero;
+    if (threadIdx.x == 0) {
+        sBad = 0;
+        sNonZero = 0;
+    }
+    __syncthreads();
+    long long Q[4];
+    bool bad = false, nz = false;
+    long long run = 0, mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t j = off + threadIdx.x * 4 + k;
+        Q[k] = 0;
+        if (j < v.n) {
+            const double x = v.val[v.idx ? (int64_t)v.idx[j] : j];
+            if (x != 0.0) {
+                nz = true;
+                if (normal) Q[k] = chain_quantum(x, sg, scale_v, bad);
+            }
+        }
+        run += Q[k];
+        Q[k] = run;  // thread-local inclusive prefix
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long inc = warp_incl_scan_ll(run, lane);
+    if (lane == 31) wT[w] = inc;
+    __syncthreads();
+    long long offp = inc - run;
+    for (int i = 0; i < w; i++) offp += wT[i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t j = off + threadIdx.x * 4 + k;
+        if (j < v.n) {
+            const long long P = offp + Q[k];
+            mn = min(mn, P);
+            mx = max(mx, P);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if (lane == 0) {
+        wMin[w] = mn;
+        wMax[w] = mx;
+    }
+    if (bad) atomicOr(&sBad, 1);
+    if (nz) atomicOr(&sNonZero, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int i = 0; i < 8; i++) {
+            tot += wT[i];
+            mn = min(mn, wMin[i]);
+            mx = max(mx, wMax[i]);
+        }
+        cb.Qtot[o] = tot;
+        cb.Pmin[o] = mn;
+        cb.Pmax[o] = mx;
+        int ef = 0;
+        if (!sNonZero) ef |= 2;
+        if (normal && !sBad) ef |= 1;
+        if (bits >> 31) ef |= 4;
+        ef |= ebits << 8;
+        cb.ef[o] = ef;
+    }
+}
+
+// Walk the chunk summaries of one chain (all threads of a 1024-thread CTA call this).  Summaries are
+// staged through shared memory 1024 chunks at a time so that the walking thread never waits on HBM.
+__device__ float chain_two_level(const ChainView v, int c0, int c1, int which, float carry, const ChainBufs& cb,
+                                 long long* serialCount) {
+    __shared__ float sCur;
+    __shared__ int sStop;
+    __shared__ long long bQ[RLB_CHAIN_THREADS], bMin[RLB_CHAIN_THREADS], bMax[RLB_CHAIN_THREADS];
+    __shared__ int bEf[RLB_CHAIN_THREADS];
+    const int tid = threadIdx.x;
+    const size_t o = (size_t)which * cb.maxChunks;
+    if (tid == 0) sCur = carry;
+    for (int cbase = c0; cbase < c1; cbase += RLB_CHAIN_THREADS) {
+        const int cend = min(c1, cbase + RLB_CHAIN_THREADS);
+        __syncthreads();
+        if (cbase + tid < cend) {
+            bQ[tid] = cb.Qtot[o + cbase + tid];
+            bMin[tid] = cb.Pmin[o + cbase + tid];
+            bMax[tid] = cb.Pmax[o + cbase + tid];
+            bEf[tid] = cb.ef[o + cbase + tid];
+        }
+        __syncthreads();
+        int c = cbase;
+        while (c < cend) {
+            if (tid == 0) {
+                float s = sCur;
+                int i = c;
+                for (; i < cend; i++) {
+                    const int ef = bEf[i - cbase];
+                    if (ef & 2) continue;  // nothing but zeros: s + 0 = s
+                    const unsigned int bits = __float_as_uint(s);
+                    if (!(ef & 1) || (int)((bits >> 23) & 0xff) != (ef >> 8) || (int)(bits >> 31) != ((ef >> 2) & 1)) break;
+                    const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
+                    if (!(M + bMin[i - cbase] > 8388608LL && M + bMax[i - cbase] < 16777216LL)) break;
+                    s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)(M + bQ[i - cbase]) & 0x7fffffu));
+                }
+                sCur = s;
+                sStop = i;
+            }
+            __syncthreads();
+            const int stop = sStop;
+            const float s = sCur;
+            if (stop >= cend) break;
+            const int64_t off = (int64_t)(stop - c0) * CK;
+            const int64_t len = min((int64_t)CK, v.n - off);
+            const float s2 = chain_block(v.val, v.idx ? v.idx + off : nullptr, len, s, serialCount, v.idx ? 0 : off);
+            __syncthreads();
+            if (tid == 0) sCur = s2;
+            c = stop + 1;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const float r = sCur;
+    __syncthreads();
+    return r;
+}
+
 // K7: LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.updateTreeOutput (MART.java:54-65):
 // blockIdx.x = leaf ordinal, blockIdx.y = 0 -> sum of pseudo responses, 1 -> sum of weights.
-__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __restrict__ st, const double* __restrict__ lambda,
+__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                                    const double* __restrict__ lambda,
                                                                     const double* __restrict__ weight,
                                                                     const int32_t* __restrict__ samples0,
                                                                     const int32_t* __restrict__ samples1,
-                                                                    const float* __restrict__ carryIn) {
+                                                                    const float* __restrict__ carryIn, ChainBufs cb) {
     const int l = blockIdx.x;
     if (l >= st->n_leaves_out) return;
-    const NodeRec& r = st->nodes[st->leaf_nodes[l]];
-    const int32_t* src = (r.buf ? samples1 : samples0) + r.lo;
     const int which = blockIdx.y;
+    const ChainView v = chain_view(0, st, l, which, lambda, weight, samples0, samples1, 0);
     const float c0 = carryIn ? carryIn[which * (RLB_MAX_LEAVES + 1) + l] : 0.f;
-    const float s = chain_block(which ? weight : lambda, src, (int64_t)(r.hi - r.lo), c0, &st->chain_serial);
+    const float s = chain_two_level(v, chunk0[l], chunk0[l + 1], which, c0, cb, &st->chain_serial);
     if (threadIdx.x == 0) (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
 }
 
@@ -1227,10 +1713,27 @@ __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st,
 }
 
 // K9 tail: float chain over the per-query metric values (LambdaMART.java:474-483)
-__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const double* __restrict__ qmetric,
-                                                                      int Q, const float* __restrict__ carryIn) {
-    const float s = chain_block(qmetric, nullptr, (int64_t)Q, carryIn ? carryIn[0] : 0.f, &st->chain_serial);
+__global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                                      const double* __restrict__ qmetric, int Q,
+                                                                      const float* __restrict__ carryIn, ChainBufs cb) {
+    ChainView v;
+    v.val = qmetric;
+    v.idx = nullptr;
+    v.n = Q;
+    const float s = chain_two_level(v, chunk0[0], chunk0[1], 0, carryIn ? carryIn[0] : 0.f, cb, &st->chain_serial);
     if (threadIdx.x == 0) st->chain_out[0] = s;
+}
+
+// chunk table of the leaf chains (after k_tree_end): chunk0[l] = first chunk of leaf l
+__global__ void k_leaf_chunks(const DevState* __restrict__ st, int32_t* __restrict__ chunk0) {
+    int run = 0;
+    const int nl = st->n_leaves_out;
+    for (int l = 0; l < nl; l++) {
+        chunk0[l] = run;
+        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
+        run += (r.hi - r.lo + CK - 1) / CK;
+    }
+    chunk0[nl] = run;
 }
 
 __global__ void k_metric_final(DevState* st, long long Q_total) {
@@ -1255,10 +1758,57 @@ int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* 
     RLB_CUDA(c, cudaMalloc(&dRank, std::max<int64_t>(N, 1) * 4));
     const int grid = std::min(Q, 148 * 16);
     k_query<false><<<grid, 128, 0, c->stream>>>(dScores, dLabel, dQoff, Q, k, metric, dDisc, nullptr, dRank, nullptr, nullptr,
-                                                dOut, nullptr);
+                                                dOut, nullptr, nullptr);
     RLB_CHECK_LAUNCH(c);
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(dRank);
+    return RLB_OK;
+}
+
+// One pass over all training queries: NDCG@k per query (qmetric != null) and / or lambdas + weights
+// (want_lambda).  Queries are routed by size class (lists built at init).
+static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
+    static bool attr_done = false;
+    const int B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
+    const size_t smA = (size_t)8 * QA_WARP_BYTES, smB1 = (size_t)B1N * 24 + (size_t)B1T * 16, smB2 = (size_t)B2N * 24 + (size_t)B2T * 16;
+    if (!attr_done) {
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB1));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB2));
+        attr_done = true;
+    }
+    double* lam = want_lambda ? c->dLambda : nullptr;
+    double* wgt = want_lambda ? c->dWeight : nullptr;
+    const int k = c->prm.metric_k, m = c->prm.metric;
+    if (c->nqA > 0) {
+        const int grid = std::min((c->nqA + 7) / 8, c->sm_count * 2);
+        k_query_warp<<<grid, 256, smA, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList, c->nqA, k, m, c->dDisc, c->dIdeal, lam, wgt,
+                                                    qmetric, c->dState);
+        RLB_CHECK_LAUNCH(c);
+    }
+    if (c->nqB1 > 0) {
+        const int grid = std::min(c->nqB1, c->sm_count * 4);
+        k_query_block<128><<<grid, 128, smB1, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB1, k, m, c->dDisc,
+                                                           c->dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
+        RLB_CHECK_LAUNCH(c);
+    }
+    if (c->nqB2 > 0) {
+        const int grid = std::min(c->nqB2, c->sm_count);
+        k_query_block<256><<<grid, 256, smB2, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB1, c->nqB2, k, m,
+                                                           c->dDisc, c->dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
+        RLB_CHECK_LAUNCH(c);
+    }
+    if (c->nqC > 0) {
+        const int grid = std::min(c->nqC, c->sm_count * 8);
+        const int32_t* ql = c->dQList + c->nqA + c->nqB1 + c->nqB2;
+        if (want_lambda)
+            k_query<true><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, lam,
+                                                       wgt, qmetric, c->dState, ql);
+        else
+            k_query<false><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc,
+                                                        nullptr, nullptr, qmetric, c->dState, ql);
+        RLB_CHECK_LAUNCH(c);
+    }
     return RLB_OK;
 }
 
@@ -1266,14 +1816,12 @@ int rlb_impl_pseudo(rlb_ctx* c) {
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->max_abs_bits, 0, sizeof(unsigned long long), c->stream));
     if (c->prm.kind == RLB_KIND_MART) {
         k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
+        RLB_CHECK_LAUNCH(c);
     } else {
-        const int grid = std::min(c->Q, c->sm_count * 16);
         rlb_prof_begin(c, 2);
-        k_query<true><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->Q, c->prm.metric_k, c->prm.metric, c->dDisc,
-                                                   c->dIdeal, c->dRankDoc, c->dLambda, c->dWeight, nullptr, c->dState);
+        if (int rc = launch_queries(c, true, nullptr)) return rc;
         rlb_prof_end(c);
     }
-    RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
     k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
     RLB_CHECK_LAUNCH(c);
@@ -1405,8 +1953,21 @@ int rlb_impl_tree_output(rlb_ctx* c) {
         if (int rc = rlb_chain_carry_begin(c, 2 * (RLB_MAX_LEAVES + 1))) return rc;
         carry = c->dCarry;
     }
-    dim3 grid(nl, c->prm.kind == RLB_KIND_MART ? 1 : 2);
-    k_leaf_chain<<<grid, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dLambda, c->dWeight, c->dSamples[0], c->dSamples[1], carry);
+    const int nw = c->prm.kind == RLB_KIND_MART ? 1 : 2;
+    ChainBufs cb{c->dChainSum, c->dChainQ, c->dChainMin, c->dChainMax, c->dChainEf, c->chain_max_chunks};
+    k_leaf_chunks<<<1, 1, 0, c->stream>>>(c->dState, c->dChunk0);
+    RLB_CHECK_LAUNCH(c);
+    const int gchunks = (int)(c->N / CK) + nl + 1;
+    k_chain_sum<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
+                                                          c->dSamples[1], 0, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_summ<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, c->dLambda, c->dWeight, c->dSamples[0],
+                                                           c->dSamples[1], 0, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, c->dLambda, c->dWeight, c->dSamples[0],
+                                                                    c->dSamples[1], carry, cb);
     RLB_CHECK_LAUNCH(c);
     if (c->world > 1) {
         // leaf_s1 and leaf_s2 are adjacent in DevState: one carry message
@@ -1442,17 +2003,25 @@ int rlb_impl_assign_nodes(rlb_ctx* c) {
 extern long long rlb_q_total(rlb_ctx* c);
 
 int rlb_impl_train_metric(rlb_ctx* c) {
-    const int grid = std::min(c->Q, c->sm_count * 16);
-    k_query<false><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->Q, c->prm.metric_k, c->prm.metric, c->dDisc,
-                                                c->dIdeal, c->dRankDoc, nullptr, nullptr, c->dQMetric, c->dState);
-    RLB_CHECK_LAUNCH(c);
+    if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
     const float* carry = nullptr;
     if (c->world > 1) {
         if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
         carry = c->dCarry;
     }
-    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dQMetric, c->Q, carry);
-    RLB_CHECK_LAUNCH(c);
+    {
+        ChainBufs cb{c->dChainSum, c->dChainQ, c->dChainMin, c->dChainMax, c->dChainEf, c->chain_max_chunks};
+        int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2;  // static table of the metric chain: {0, ceil(Q / CK)}
+        const int gchunks = (c->Q + CK - 1) / CK;
+        k_chain_sum<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, carry, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_summ<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, c->dState, ch0, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, c->dQMetric, c->Q, carry, cb);
+        RLB_CHECK_LAUNCH(c);
+    }
     if (c->world > 1) {
         if (int rc = rlb_chain_carry_end(c, c->dState->chain_out, 1)) return rc;
     }

@@ -160,7 +160,8 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
-    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dSqfix);
+    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dSqfix); fr(c->dQList);
+    fr(c->dChainSum); fr(c->dChainQ); fr(c->dChainMin); fr(c->dChainMax); fr(c->dChainEf); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
     c->loaded = c->inited = false;
@@ -388,6 +389,18 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dUsed, 2 * F * sizeof(int32_t)));  // usedFeatures + sampling pool
     RLB_CUDA(c, alloc(c->dState, sizeof(DevState)));
     RLB_CUDA(c, alloc(c->dCarry, 4 * (RLB_MAX_LEAVES + 1) * sizeof(float)));
+    c->chain_max_chunks = (int)(std::max<int64_t>(N, Q) / 1024) + RLB_MAX_LEAVES + 2;
+    RLB_CUDA(c, alloc(c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
+    RLB_CUDA(c, alloc(c->dChainQ, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
+    RLB_CUDA(c, alloc(c->dChainMin, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
+    RLB_CUDA(c, alloc(c->dChainMax, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
+    RLB_CUDA(c, alloc(c->dChainEf, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dChunk0, (size_t)(RLB_MAX_LEAVES + 4) * sizeof(int32_t)));
+    {
+        const int32_t mc[2] = {0, (Q + 1023) / 1024};
+        RLB_CUDA(c, cudaMemcpyAsync(c->dChunk0 + RLB_MAX_LEAVES + 2, mc, sizeof(mc), cudaMemcpyHostToDevice, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     if (!c->hState) RLB_CUDA(c, cudaMallocHost(&c->hState, sizeof(DevState)));
     RLB_CUDA(c, cudaMemsetAsync(c->dState, 0, sizeof(DevState), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(c->dScore, 0, N * sizeof(double), c->stream));   // modelScores = 0 (LambdaMART.java:86)
@@ -419,6 +432,27 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         RLB_CUDA(c, alloc(c->dDisc, disc.size() * sizeof(double)));
         RLB_CUDA(c, cudaMemcpyAsync(c->dDisc, disc.data(), disc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    // ---- query size classes of the lambda / NDCG kernels (table = min(k, n) * n pair terms) ----
+    {
+        std::vector<int32_t> qoffh((size_t)Q + 1);
+        RLB_CUDA(c, cudaMemcpy(qoffh.data(), c->dQoff, ((size_t)Q + 1) * 4, cudaMemcpyDeviceToHost));
+        std::vector<int32_t> la, lb1, lb2, lc;
+        for (int q = 0; q < Q; q++) {
+            const int64_t n = qoffh[q + 1] - qoffh[q];
+            const int64_t sz = (p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0;
+            const int64_t terms = sz * n;
+            if (n <= 64 && terms <= 640) la.push_back(q);
+            else if (n <= 256 && terms <= 2560) lb1.push_back(q);
+            else if (n <= 1024 && terms <= 10240) lb2.push_back(q);
+            else lc.push_back(q);
+        }
+        c->nqA = (int)la.size(); c->nqB1 = (int)lb1.size(); c->nqB2 = (int)lb2.size(); c->nqC = (int)lc.size();
+        la.insert(la.end(), lb1.begin(), lb1.end());
+        la.insert(la.end(), lb2.begin(), lb2.end());
+        la.insert(la.end(), lc.begin(), lc.end());
+        RLB_CUDA(c, alloc(c->dQList, (size_t)Q * 4));
+        RLB_CUDA(c, cudaMemcpy(c->dQList, la.data(), (size_t)Q * 4, cudaMemcpyHostToDevice));
     }
     k_ideal_dcg<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->dLabel, c->dQoff, Q, p->metric_k, c->dDisc, c->dIdeal);
     RLB_CHECK_LAUNCH(c);

@@ -106,6 +106,9 @@ struct rlb_ctx {
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
+    // query ids grouped by size class: [A: warp path | B1: 128-thread CTA | B2: 256-thread CTA | C: fallback]
+    int32_t* dQList = nullptr;
+    int32_t nqA = 0, nqB1 = 0, nqB2 = 0, nqC = 0;
     // tree state
     int32_t max_nodes = 0;
     size_t hist_stride = 0;         // elements per node: F*RLB_T
@@ -121,6 +124,11 @@ struct rlb_ctx {
     DevState* dState = nullptr;
     DevState* hState = nullptr;     // pinned mirror (partial copies)
     float* dCarry = nullptr;        // cross-rank float-chain carries
+    // two-level float chains (rlb_boost.cu)
+    double* dChainSum = nullptr;
+    long long *dChainQ = nullptr, *dChainMin = nullptr, *dChainMax = nullptr;
+    int32_t *dChainEf = nullptr, *dChunk0 = nullptr;
+    int32_t chain_max_chunks = 0;
     int32_t grid_rows = 0;          // CTAs of the row-oriented kernels (multiple of the SM count)
     int32_t sm_count = 0;
     int64_t stats[4] = {0, 0, 0, 0};
