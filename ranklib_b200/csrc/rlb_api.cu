@@ -1,6 +1,7 @@
 // rlb_api.cu — the C ABI of include/ranklib_b200.h, NCCL plumbing, state read-back.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -68,11 +69,17 @@ void rlb_prof_begin(rlb_ctx* c, int kind) {
         c->ev_kind.push_back(kind);
     }
     c->ev_kind[c->ev_used] = kind;
-    cudaEventRecord(c->ev_pool[2 * c->ev_used], c->stream);
+    if (c->capturing)
+        cudaEventRecordWithFlags(c->ev_pool[2 * c->ev_used], c->stream, cudaEventRecordExternal);
+    else
+        cudaEventRecord(c->ev_pool[2 * c->ev_used], c->stream);
 }
 void rlb_prof_end(rlb_ctx* c) {
     if (!c->profile) return;
-    cudaEventRecord(c->ev_pool[2 * c->ev_used + 1], c->stream);
+    if (c->capturing)
+        cudaEventRecordWithFlags(c->ev_pool[2 * c->ev_used + 1], c->stream, cudaEventRecordExternal);
+    else
+        cudaEventRecord(c->ev_pool[2 * c->ev_used + 1], c->stream);
     c->ev_used++;
 }
 // call after a stream synchronize
@@ -88,6 +95,15 @@ void rlb_prof_collect(rlb_ctx* c) {
         }
     }
     c->ev_used = 0;
+}
+
+void rlb_trace_mark(rlb_ctx* c, const char* file, int line) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->tr_ev.push_back(e);
+    c->tr_line.push_back(line);
+    c->tr_file.push_back(file);
 }
 
 long long rlb_q_total(rlb_ctx* c) { return c->Q_total > 0 ? c->Q_total : c->Q; }
@@ -156,6 +172,9 @@ int rlb_destroy(rlb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     rlb_impl_free(c);
+    for (int i = 0; i < 2; i++)
+        if (c->iter_graph[i]) cudaGraphExecDestroy(c->iter_graph[i]);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -228,7 +247,18 @@ int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
         cudaFree(d);
     }
     c->Q_total = q;
-    return RLB_OK;
+    if (const char* e = getenv("RLB_NO_GRAPH")) c->use_graph = (atoi(e) == 0);
+    if (const char* e = getenv("RLB_TRACE")) {
+        c->trace = atoi(e) != 0;
+        if (c->trace) c->use_graph = false;
+    }
+    for (int i = 0; i < 2; i++)
+        if (c->iter_graph[i]) {
+            cudaGraphExecDestroy(c->iter_graph[i]);
+            c->iter_graph[i] = nullptr;
+        }
+    c->launches_per_iter = 0;
+    return rlb_impl_prepare(c);
 }
 
 int rlb_get_thresholds(rlb_ctx* c, int32_t f, float* out, int32_t* n) {
@@ -288,25 +318,49 @@ int rlb_train_metric(rlb_ctx* c, float* out) {
     return RLB_OK;
 }
 
+// One iteration = one CUDA-graph launch (captured on first use) + one stream synchronisation.
 static int boost_one(rlb_ctx* c) {
-    if (int rc = rlb_impl_pseudo(c)) return rc;
-    if (int rc = rlb_impl_hist_update(c)) return rc;
-    if (int rc = rlb_impl_tree_fit(c)) return rc;
-    if (int rc = rlb_impl_tree_output(c)) return rc;
-    if (int rc = rlb_impl_update_scores(c)) return rc;
-    if (int rc = rlb_impl_train_metric(c)) return rc;
-    return RLB_OK;
+    const int gi = c->profile ? 1 : 0;
+    if (!c->use_graph || c->world > 1) {
+        if (int rc = rlb_impl_enqueue_iter(c)) return rc;
+    } else {
+        if (!c->iter_graph[gi]) {
+            cudaGraph_t g = nullptr;
+            c->ev_used = 0;
+            RLB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            c->capturing = true;
+            int rc = rlb_impl_enqueue_iter(c);
+            c->capturing = false;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) {
+                rlb_set_error(c, RLB_E_CUDA, "cudaStreamEndCapture", cudaGetErrorString(e));
+                return RLB_E_CUDA;
+            }
+            RLB_CUDA(c, cudaGraphInstantiate(&c->iter_graph[gi], g, 0));
+            cudaGraphDestroy(g);
+            c->graph_events[gi] = c->ev_used;
+        }
+        c->ev_used = c->graph_events[gi];
+        RLB_CUDA(c, cudaGraphLaunch(c->iter_graph[gi], c->stream));
+        c->launches += 0;  // kernel launches inside the graph were counted at capture time; see rlb_stats
+    }
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return rlb_impl_finish_iter(c);
 }
 
 int rlb_boost_iter(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes, float* train_metric) {
     if (int rc = check_ready(c, "rlb_boost_iter")) return rc;
+    const int64_t l0 = c->launches;
     if (int rc = boost_one(c)) return rc;
+    if (c->launches == l0) c->launches += c->launches_per_iter; else if (c->launches_per_iter == 0) c->launches_per_iter = c->launches - l0;
     if (nodes_out) {
         if (int rc = rlb_impl_export_tree(c, nodes_out, cap, n_nodes)) return rc;
-    } else {
-        RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
-        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (n_nodes) *n_nodes = c->hState->n_nodes;
+    } else if (n_nodes) {
+        *n_nodes = c->hState->n_nodes;
     }
     if (train_metric) *train_metric = c->hState->train_metric;
     rlb_prof_collect(c);
@@ -429,8 +483,31 @@ int rlb_stats(rlb_ctx* c, int64_t out[4]) {
     out[3] = c->launches;
     if (c->inited) {
         long long s = 0;
-        if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess) out[2] = s;
+        long long fb = 0;
+        if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+            cudaMemcpy(&fb, &c->dState->chain_fallback, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            out[2] = s + (fb << 32);
     }
+    return RLB_OK;
+}
+
+/* development aid (not in the public header): dumps "file:line ms-since-previous-mark" of the traced launches */
+int rlb_trace_dump(rlb_ctx* c, const char* path) {
+    if (!c || !path) return RLB_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    FILE* f = fopen(path, "w");
+    if (!f) return RLB_E_INVALID;
+    for (size_t i = 1; i < c->tr_ev.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->tr_ev[i - 1], c->tr_ev[i]);
+        fprintf(f, "%s:%d %.3f\n", c->tr_file[i], c->tr_line[i], ms * 1000.0);
+    }
+    fclose(f);
+    for (cudaEvent_t e : c->tr_ev) cudaEventDestroy(e);
+    c->tr_ev.clear();
+    c->tr_line.clear();
+    c->tr_file.clear();
     return RLB_OK;
 }
 

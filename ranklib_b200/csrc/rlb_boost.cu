@@ -498,7 +498,9 @@ __global__ void k_scale(DevState* st, long long n_total) {
     int se = 0, s2 = 0;
     if (m > 0.0 && isfinite(m)) {
         const int e = ilogb(m) + 1;  // m < 2^e
-        se = 61 - nb - e;
+        // |v| < 2^min(61-nb, 39): the global sum fits 62 bits, and 2^11 rows of a private bin fit the
+        // 52-bit sum field of the packed (count, sum) accumulators of the child-histogram kernel
+        se = min(61 - nb, 39) - e;
         s2 = 61 - nb - 2 * e;
         se = max(-1000, min(1000, se));
         s2 = max(-1000, min(1000, s2));
@@ -509,14 +511,21 @@ __global__ void k_scale(DevState* st, long long n_total) {
 
 // fixed-point images of the pseudo responses: v = rint(lambda * 2^s), q = rint(lambda^2 * 2^s2); also the
 // root's squared sum (FeatureHistogram.update's sqSumResponse, FeatureHistogram.java:134-137)
+#define CNT_SHIFT 52                      // packed private accumulator of child builds: count << 52 | 52-bit signed sum
+#define CNT_ONE (1LL << CNT_SHIFT)
+#define FLUSH_STAGES 127                  // 127 stages x 16 rows per thread = 2032 rows < 2^11 per private bin
+
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lambda, int64_t N, long long* __restrict__ vfix,
-                                                   long long* __restrict__ sqfix, DevState* __restrict__ st) {
+                                                   long long* __restrict__ vfixc, long long* __restrict__ sqfix,
+                                                   DevState* __restrict__ st) {
     const double sc = scalbn(1.0, st->scale_exp);
     const double sc2 = scalbn(1.0, st->scale2_exp);
     long long sq = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const double lam = lambda[i];
-        vfix[i] = __double2ll_rn(lam * sc);
+        const long long v = __double2ll_rn(lam * sc);
+        vfix[i] = v;
+        vfixc[i] = v + CNT_ONE;
         const long long q = __double2ll_rn((lam * lam) * sc2);
         sqfix[i] = q;
         sq += q;
@@ -567,7 +576,6 @@ __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ 
     for (int64_t i = lo + warp; i < hi; i += nwarps) {
         const int64_t row = CHILD ? (int64_t)samples[i] : i;
         const long long v = vfix[row];
-        if (CHILD && lane == 0) sq += sqfix[row];
         const uint16_t* b = bins + row * Fp;
         for (int f = lane; f < F; f += 32) {
             const int t = b[f];
@@ -575,7 +583,8 @@ __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ 
             if (CHILD) atomicAdd(&cnt[(size_t)f * RLB_T + t], 1);
         }
     }
-    if (CHILD && lane == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
+    (void)sq;
+    (void)sqfix;
 }
 
 #define HG 16        // features per CTA group = one 32-byte sector of a bins row
@@ -621,40 +630,56 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// One 4-row batch of private read-modify-writes with forwarding between equal bins.
-template <bool CHILD, int T>
-__device__ __forceinline__ void hist_batch4(long long* Hme, unsigned short* Cme, int b0, int b1, int b2, int b3, long long v0,
-                                            long long v1, long long v2, long long v3) {
+// One 4-row batch of private read-modify-writes with forwarding between equal bins.  For child
+// builds v already carries the count increment (v + CNT_ONE).
+template <int T>
+__device__ __forceinline__ void hist_batch4(long long* Hme, int b0, int b1, int b2, int b3, long long v0, long long v1,
+                                            long long v2, long long v3) {
     long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
-    unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if (CHILD) {
-        c0 = Cme[b0 * T];
-        c1 = Cme[b1 * T];
-        c2 = Cme[b2 * T];
-        c3 = Cme[b3 * T];
-    }
-    const bool e10 = b1 == b0, e21 = b2 == b1, e20 = b2 == b0, e32 = b3 == b2, e31 = b3 == b1, e30 = b3 == b0;
     h0 += v0;
-    c0 += 1;
     Hme[b0 * T] = h0;
-    if (e10) { h1 = h0; c1 = c0; }
+    if (b1 == b0) h1 = h0;
     h1 += v1;
-    c1 += 1;
     Hme[b1 * T] = h1;
-    if (e21) { h2 = h1; c2 = c1; } else if (e20) { h2 = h0; c2 = c0; }
+    if (b2 == b1) h2 = h1; else if (b2 == b0) h2 = h0;
     h2 += v2;
-    c2 += 1;
     Hme[b2 * T] = h2;
-    if (e32) { h3 = h2; c3 = c2; } else if (e31) { h3 = h1; c3 = c1; } else if (e30) { h3 = h0; c3 = c0; }
+    if (b3 == b2) h3 = h2; else if (b3 == b1) h3 = h1; else if (b3 == b0) h3 = h0;
     h3 += v3;
-    c3 += 1;
     Hme[b3 * T] = h3;
-    if (CHILD) {  // later stores win, and they carry the forwarded running counts
-        Cme[b0 * T] = (unsigned short)c0;
-        Cme[b1 * T] = (unsigned short)c1;
-        Cme[b2 * T] = (unsigned short)c2;
-        Cme[b3 * T] = (unsigned short)c3;
+}
+
+// Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
+// per non-empty entry and clear the private copies.  Consumer threads only (named barrier 1).
+template <bool CHILD, int PH>
+__device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, long long* __restrict__ sum,
+                                           int32_t* __restrict__ cnt) {
+    constexpr int T = HG * PH;
+    constexpr int NC = 32 * ((T + 31) / 32);
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    for (int p = tid; p < RLB_T * HG; p += NC) {
+        const int bin = p / HG, ff = p % HG;
+        const int fo = g * HG + ff;
+        long long sacc = 0;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < PH; q++) {
+            const long long pk = H[bin * T + q * HG + ff];
+            H[bin * T + q * HG + ff] = 0;
+            if (CHILD) {
+                const long long sv = ((pk + (1LL << (CNT_SHIFT - 1))) & (CNT_ONE - 1)) - (1LL << (CNT_SHIFT - 1));
+                sacc += sv;
+                c += (int)((pk - sv) >> CNT_SHIFT);
+            } else {
+                sacc += pk;
+            }
+        }
+        if (fo < F) {
+            if (sacc != 0) atomicAdd((unsigned long long*)&sum[(size_t)fo * RLB_T + bin], (unsigned long long)sacc);
+            if (CHILD && c != 0) atomicAdd(&cnt[(size_t)fo * RLB_T + bin], c);
+        }
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
 }
 
 // k_hist_priv<CHILD, PH>: CTA = ceil(16*PH/32) consumer warps + 1 producer warp.
@@ -675,8 +700,6 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     long long* H = reinterpret_cast<long long*>(smem_raw);                         // [RLB_T][T]
     size_t off = (size_t)RLB_T * T * 8;
-    unsigned short* Cn = reinterpret_cast<unsigned short*>(smem_raw + off);        // [RLB_T][T] (CHILD)
-    if (CHILD) off += (size_t)RLB_T * T * 2;
     off = (off + 127) & ~(size_t)127;
     unsigned char* tiles = smem_raw + off;                                         // HSTAGES x (R*32 + R*8)
     constexpr int STAGE_BYTES = R * 32 + R * 8;
@@ -707,8 +730,6 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     const int nst = (int)((r1 - r0 + R - 1) / R);
 
     for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
-    if (CHILD)
-        for (int i = tid; i < RLB_T * T; i += blockDim.x) Cn[i] = 0;
     if (tid == 0) {
         for (int s2 = 0; s2 < HSTAGES; s2++) {
             mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
@@ -720,7 +741,6 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
 
     if (warp == CW) {
         // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
-        long long sq = 0;
         int32_t nxt[(R + 31) / 32];   // CHILD: sample indices of the next stage, fetched one stage ahead
         if (CHILD) {
 #pragma unroll
@@ -753,7 +773,6 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
                         cpasync16(bt + j * 32, src);
                         cpasync16(bt + j * 32 + 16, src + 8);
                         cpasync8(vt + j, vfix + row);
-                        if (g == 0) sq += sqfix[row];
                     }
                 }
             } else {
@@ -765,18 +784,15 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
             }
             cpasync_arrive(&full[s2]);
         }
-        if (CHILD && g == 0) {
-            for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-            if (lane == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
-        }
     } else {
         // ===== consumer warps =====
         const int fi = tid & (HG - 1), ph = tid / HG;
         const bool active = (tid < T) && (g * HG + fi < F);
         long long* Hme = H + tid;
-        unsigned short* Cme = Cn + tid;
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
+            // the packed (count, sum) accumulators of a child build hold at most 2^11 rows
+            if (CHILD && k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<CHILD, PH>(H, tid, g, F, sum, cnt);
             mbar_wait(&full[s2], (k / HSTAGES) & 1);
             const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
@@ -787,36 +803,20 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
 #pragma unroll
                     for (int kk = 0; kk < 16; kk += 4) {
                         const int ra = kk * PH + ph, rb = ra + PH, rc = rb + PH, rd = rc + PH;
-                        hist_batch4<CHILD, T>(Hme, Cme, btile[ra * HG + fi], btile[rb * HG + fi], btile[rc * HG + fi],
-                                              btile[rd * HG + fi], vt[ra], vt[rb], vt[rc], vt[rd]);
+                        hist_batch4<T>(Hme, btile[ra * HG + fi], btile[rb * HG + fi], btile[rc * HG + fi], btile[rd * HG + fi],
+                                       vt[ra], vt[rb], vt[rc], vt[rd]);
                     }
                 } else {
                     for (int rr = ph; rr < nr; rr += PH) {
                         const int b = btile[rr * HG + fi];
                         Hme[b * T] += vt[rr];
-                        if (CHILD) Cme[b * T] += 1;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s2]);
         }
-    }
-    __syncthreads();
-    // sum the PH phases and publish: one global reduction per non-empty (feature, bin) of this CTA
-    for (int p = tid; p < RLB_T * HG; p += blockDim.x) {
-        const int bin = p / HG, ff = p % HG;
-        const int fo = g * HG + ff;
-        if (fo >= F) continue;
-        long long sacc = 0;
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < PH; q++) {
-            sacc += H[bin * T + q * HG + ff];
-            if (CHILD) c += Cn[bin * T + q * HG + ff];
-        }
-        if (sacc != 0) atomicAdd((unsigned long long*)&sum[(size_t)fo * RLB_T + bin], (unsigned long long)sacc);
-        if (CHILD && c != 0) atomicAdd(&cnt[(size_t)fo * RLB_T + bin], c);
+        hist_flush<CHILD, PH>(H, tid, g, F, sum, cnt);
     }
 }
 
@@ -866,6 +866,7 @@ __global__ void k_tree_begin(DevState* st, TreeParams tp, const long long* __res
     st->rows_hist = 0;
     st->n_splits = 0;
     st->chain_serial = 0;
+    st->chain_fallback = 0;
     st->small_sq_fix = 0;
     st->ticket_scan = st->ticket_part = st->ticket_finish = 0;
     draw_features(st, tp, used, pool);
@@ -1018,7 +1019,8 @@ __global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreePar
 __global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, const uint16_t* __restrict__ bins, int Fp,
                                                      const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
                                                      int32_t* __restrict__ tileCnt, long long* __restrict__ histSum,
-                                                     int32_t* __restrict__ histCnt, size_t hist_stride) {
+                                                     int32_t* __restrict__ histCnt, size_t hist_stride,
+                                                     const long long* __restrict__ sqfix) {
     if (!st->split_active) return;
     __shared__ int sw[8];
     __shared__ bool amLast;
@@ -1039,12 +1041,23 @@ __global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, c
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int base = tile * RLB_PART_TILE + threadIdx.x * 8;
         int c = 0;
+        long long sq = 0;  // squared responses of the rows going left (FeatureHistogram.java:183-184)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int i = base + k;
-            if (i < n) c += (bins[(size_t)src[lo + i] * Fp + bf] <= btv) ? 1 : 0;
+            if (i < n) {
+                const int doc = src[lo + i];
+                if (bins[(size_t)doc * Fp + bf] <= btv) {
+                    c++;
+                    sq += sqfix[doc];
+                }
+            }
         }
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, d);
+            sq += __shfl_xor_sync(0xffffffffu, sq, d);
+        }
+        if ((threadIdx.x & 31) == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
         if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1212,8 +1225,9 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     st->ticket_finish = 0;
     volatile NodeRec* ns = &st->nodes[small];
     volatile NodeRec* no = &st->nodes[other];
-    const long long sqS = st->small_sq_fix;
     const long long sqP = st->nodes[parent].sq_fix;
+    const long long sqLeft = st->small_sq_fix;  // accumulated by the partition: squared sum of the LEFT rows
+    const long long sqS = st->small_is_left ? sqLeft : sqP - sqLeft;
     ns->sq_fix = sqS;
     no->sq_fix = sqP - sqS;
     const int se = st->scale_exp, s2 = st->scale2_exp;
@@ -1236,6 +1250,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
 __global__ void k_tree_end(DevState* st, int64_t N_local) {
     if (!st->done && st->cur >= 0) {
         st->incomplete = 1;
+        st->n_leaves_out = 0;  // the leaf / score kernels that follow become no-ops
         return;
     }
     st->incomplete = 0;
@@ -1275,6 +1290,8 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
     __shared__ int sFirstBad;
     __shared__ long long sM;
     __shared__ float sS;
+    __shared__ int sNext;
+    __shared__ double xs[RLB_CHAIN_THREADS * RLB_CHAIN_PER_THREAD];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int CH = RLB_CHAIN_THREADS * RLB_CHAIN_PER_THREAD;
     float s = s0;
@@ -1287,6 +1304,7 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
             const int j = tid * RLB_CHAIN_PER_THREAD + k;
             x[k] = 0.0;
             if (j < m) x[k] = val[idx ? (int64_t)idx[base + j] : valOff + base + j];
+            xs[j] = x[k];
         }
         int start = 0;
         while (start < m) {
@@ -1371,11 +1389,27 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
                 s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mi & 0x7fffffu));
             }
             if (fb < m) {
-                if (fb / RLB_CHAIN_PER_THREAD == tid) sS = (float)((double)s + x[fb % RLB_CHAIN_PER_THREAD]);
+                // exact serial steps by one thread.  Where the running sum is small against the elements
+                // (start of a chain, zero crossings) nearly every step changes binade: keep going
+                // serially until 8 consecutive steps stayed inside one binade, then resume in parallel.
+                if (tid == 0) {
+                    float cur = s;
+                    int j = fb, stable = 0;
+                    while (j < m && stable < 8) {
+                        const float nxt = (float)((double)cur + xs[j]);
+                        const unsigned int b0 = __float_as_uint(cur), b1 = __float_as_uint(nxt);
+                        const bool same = ((b0 ^ b1) & 0xff800000u) == 0 && ((b0 >> 23) & 0xff) != 0 && ((b0 >> 23) & 0xff) != 0xff;
+                        stable = same ? stable + 1 : 0;
+                        cur = nxt;
+                        j++;
+                    }
+                    sS = cur;
+                    sNext = j;
+                }
                 __syncthreads();
                 s = sS;
-                nserial++;
-                start = fb + 1;
+                nserial += sNext - fb;
+                start = sNext;
             } else {
                 start = m;
             }
@@ -1644,7 +1678,10 @@ __device__ float chain_two_level(const ChainView v, int c0, int c1, int which, f
             const int64_t len = min((int64_t)CK, v.n - off);
             const float s2 = chain_block(v.val, v.idx ? v.idx + off : nullptr, len, s, serialCount, v.idx ? 0 : off);
             __syncthreads();
-            if (tid == 0) sCur = s2;
+            if (tid == 0) {
+                sCur = s2;
+                atomicAdd((unsigned long long*)(serialCount + 1), 1ull);  // chain_fallback follows chain_serial
+            }
             c = stop + 1;
             __syncthreads();
         }
@@ -1693,6 +1730,7 @@ __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st,
                                                        const int32_t* __restrict__ samples1, double* __restrict__ score,
                                                        int32_t* __restrict__ nodeOf, int64_t N, float lr, int apply) {
     const int nl = st->n_leaves_out;
+    if (nl == 0) return;  // unfinished tree (see k_tree_end)
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nl - 1;  // last leaf with leaf_lo <= p
         while (lo < hi) {
@@ -1768,15 +1806,8 @@ int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* 
 // One pass over all training queries: NDCG@k per query (qmetric != null) and / or lambdas + weights
 // (want_lambda).  Queries are routed by size class (lists built at init).
 static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
-    static bool attr_done = false;
     const int B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
     const size_t smA = (size_t)8 * QA_WARP_BYTES, smB1 = (size_t)B1N * 24 + (size_t)B1T * 16, smB2 = (size_t)B2N * 24 + (size_t)B2T * 16;
-    if (!attr_done) {
-        RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB1));
-        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB2));
-        attr_done = true;
-    }
     double* lam = want_lambda ? c->dLambda : nullptr;
     double* wgt = want_lambda ? c->dWeight : nullptr;
     const int k = c->prm.metric_k, m = c->prm.metric;
@@ -1829,11 +1860,12 @@ int rlb_impl_pseudo(rlb_ctx* c) {
 }
 
 #define PH_ROOT 6    // 96 private histograms x 257 bins x 8 B = 197 KB + 8 stages x 3840 B
-#define PH_CHILD 5   // 80 private histograms x 257 bins x (8 + 2) B = 206 KB + 8 stages x 3200 B
+#define PH_CHILD 6   // same shape: child builds pack the row count into the top 12 bits of each accumulator
 
 static constexpr size_t hist_smem(bool child, int ph) {
     size_t t = (size_t)HG * ph;
-    size_t off = (size_t)RLB_T * t * 8 + (child ? (size_t)RLB_T * t * 2 : 0);
+    (void)child;
+    size_t off = (size_t)RLB_T * t * 8;
     off = (off + 127) & ~(size_t)127;
     return off + (size_t)HSTAGES * (t * 40) + 2 * HSTAGES * 8 + HSTAGES * 4;
 }
@@ -1842,17 +1874,9 @@ static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
 static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
 
 int rlb_impl_hist_update(rlb_ctx* c) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)hist_smem(false, PH_ROOT)));
-        RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<true, PH_CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)hist_smem(true, PH_CHILD)));
-        attr_done = true;
-    }
     RLB_CUDA(c, cudaMemsetAsync(c->dHistSum, 0, c->hist_stride * sizeof(long long), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
-    k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dSqfix, c->dState);
+    k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dVfixC, c->dSqfix, c->dState);
     RLB_CHECK_LAUNCH(c);
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
@@ -1880,7 +1904,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         long long* stageSum = c->dHistSum + (size_t)c->max_nodes * c->hist_stride;
         int32_t* stageCnt = c->dHistCnt + (size_t)c->max_nodes * c->hist_stride;
         k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
-                                                          stageSum, stageCnt, c->hist_stride);
+                                                          stageSum, stageCnt, c->hist_stride, c->dSqfix);
         RLB_CHECK_LAUNCH(c);
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
@@ -1889,7 +1913,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
                                                                c->dSamples[1], stageSum, stageCnt, c->dState, c->hist_min_rows);
         RLB_CHECK_LAUNCH(c);
         k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
-            c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
+            c->dBins, c->Fp, c->F, c->dVfixC, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
             hist_groups(c), c->hist_min_rows);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
@@ -1913,20 +1937,30 @@ static int sync_state_header(rlb_ctx* c) {
     return RLB_OK;
 }
 
-int rlb_impl_tree_fit(rlb_ctx* c) {
+// RegressionTree.fit as a fixed launch sequence: n_leaves-1 split steps cover every tree whose scans
+// all succeed; a failed scan (no admissible threshold in a popped node) uses up a step, which
+// k_tree_end reports as `incomplete` — rlb_impl_tree_check then adds steps.
+int rlb_impl_tree_enqueue(rlb_ctx* c) {
     const TreeParams tp = tree_params(c);
     k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
     RLB_CHECK_LAUNCH(c);
     k_tree_begin<<<1, 1, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F);
     RLB_CHECK_LAUNCH(c);
-    int steps = c->prm.n_leaves - 1;
-    for (int round = 0; round < 4 * c->prm.n_leaves + 8; round++) {
-        if (int rc = enqueue_split_steps(c, steps)) return rc;
+    if (int rc = enqueue_split_steps(c, c->prm.n_leaves - 1)) return rc;
+    k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+// needs hState's header of the finished enqueue; returns 1 in *recovered if extra steps were run
+int rlb_impl_tree_check(rlb_ctx* c, int* recovered) {
+    if (recovered) *recovered = 0;
+    for (int round = 0; c->hState->incomplete && round < 4 * c->prm.n_leaves + 8; round++) {
+        if (recovered) *recovered = 1;
+        if (int rc = enqueue_split_steps(c, 2)) return rc;
         k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);
         RLB_CHECK_LAUNCH(c);
         if (int rc = sync_state_header(c)) return rc;
-        if (!c->hState->incomplete) break;
-        steps = 2;  // failed scans used up steps: keep going
     }
     if (c->hState->incomplete) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_tree_fit", "tree controller did not terminate");
@@ -1935,6 +1969,52 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
     c->stats[0] = c->hState->rows_hist;
     c->stats[1] = c->hState->n_splits;
     c->tree_ready = true;
+    c->tree_output_ready = false;
+    return RLB_OK;
+}
+
+int rlb_impl_tree_fit(rlb_ctx* c) {
+    if (int rc = rlb_impl_tree_enqueue(c)) return rc;
+    if (int rc = sync_state_header(c)) return rc;
+    return rlb_impl_tree_check(c, nullptr);
+}
+
+// one-time kernel attributes (must not happen inside a stream capture)
+int rlb_impl_prepare(rlb_ctx* c) {
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(false, PH_ROOT)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<true, PH_CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(true, PH_CHILD)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 24 + 2560 * 16));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 24 + 10240 * 16));
+    return RLB_OK;
+}
+
+// the whole loop body of LambdaMART.learn (LambdaMART.java:180-251) as one launch sequence without
+// any host synchronisation; ends with the copy of the state header (tree size, NDCG-T, flags)
+int rlb_impl_enqueue_iter(rlb_ctx* c) {
+    if (int rc = rlb_impl_pseudo(c)) return rc;
+    if (int rc = rlb_impl_hist_update(c)) return rc;
+    if (int rc = rlb_impl_tree_enqueue(c)) return rc;
+    c->tree_ready = true;
+    if (int rc = rlb_impl_tree_output(c)) return rc;
+    if (int rc = rlb_impl_update_scores(c)) return rc;
+    if (int rc = rlb_impl_train_metric(c)) return rc;
+    RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
+    return RLB_OK;
+}
+
+// after the stream has been synchronised: finish trees that needed more split steps
+int rlb_impl_finish_iter(rlb_ctx* c) {
+    int recovered = 0;
+    if (int rc = rlb_impl_tree_check(c, &recovered)) return rc;
+    if (recovered) {  // the leaf / score / metric kernels of the sequence were no-ops on the unfinished tree
+        if (int rc = rlb_impl_tree_output(c)) return rc;
+        if (int rc = rlb_impl_update_scores(c)) return rc;
+        if (int rc = rlb_impl_train_metric(c)) return rc;
+        if (int rc = sync_state_header(c)) return rc;
+    }
     c->tree_output_ready = false;
     return RLB_OK;
 }

@@ -160,7 +160,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
-    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dSqfix); fr(c->dQList);
+    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList);
     fr(c->dChainSum); fr(c->dChainQ); fr(c->dChainMin); fr(c->dChainMax); fr(c->dChainEf); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
@@ -375,6 +375,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dWeight, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dQMetric, (size_t)Q * sizeof(double)));
     RLB_CUDA(c, alloc(c->dVfix, (N + 2) * sizeof(long long)));  // +2: the bulk copy of a tile rounds up to 16 bytes
+    RLB_CUDA(c, alloc(c->dVfixC, (N + 2) * sizeof(long long)));
     RLB_CUDA(c, alloc(c->dSqfix, N * sizeof(long long)));
     if (const char* e = getenv("RLB_HIST_MIN_ROWS")) c->hist_min_rows = atoi(e);
     RLB_CUDA(c, alloc(c->dIdeal, (size_t)Q * sizeof(double)));

@@ -16,7 +16,7 @@
 #define RLB_MAX_NODES (2 * RLB_MAX_LEAVES)
 #define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
 #define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
-#define RLB_CHAIN_THREADS 1024
+#define RLB_CHAIN_THREADS 256
 #define RLB_CHAIN_PER_THREAD 4
 
 // One tree node as the device controller sees it.  Node ids follow creation order: root = 0, the
@@ -63,7 +63,8 @@ struct DevState {
     long long rows_hist;    // rows fed to child histogram builds (local)
     long long n_splits;
     long long chain_serial; // float-chain elements that took the exact serial path
-    long long small_sq_fix; // scratch: squared-sum of the scanned child (local, then all-reduced)
+    long long chain_fallback; // float-chain chunks redone exactly (speculation miss or binade crossing)
+    long long small_sq_fix; // scratch: squared-sum of the rows going LEFT (local, then all-reduced)
     float train_metric;
     float chain_out[4];
     int32_t queue[RLB_MAX_NODES];
@@ -102,6 +103,7 @@ struct rlb_ctx {
     double* dWeight = nullptr;
     double* dQMetric = nullptr;     // per-query NDCG
     long long* dVfix = nullptr;     // fixed-point pseudo responses of the iteration
+    long long* dVfixC = nullptr;    // the same + (1 << 52): response and row count in one accumulator
     long long* dSqfix = nullptr;    // fixed-point squared pseudo responses
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
@@ -139,6 +141,17 @@ struct rlb_ctx {
     std::vector<int> ev_kind;              // 0 root hist, 1 child hist, 2 lambda
     int ev_used = 0;
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // CUDA graph of one boosting iteration (index 1: with event-timing nodes)
+    cudaGraphExec_t iter_graph[2] = {nullptr, nullptr};
+    int graph_events[2] = {0, 0};
+    bool capturing = false;
+    bool use_graph = true;
+    int64_t launches_per_iter = 0;
+    // development trace: one event after every kernel launch (RLB_TRACE=1, disables the graph)
+    bool trace = false;
+    std::vector<cudaEvent_t> tr_ev;
+    std::vector<int> tr_line;
+    std::vector<const char*> tr_file;
 };
 
 const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* detail);
@@ -161,9 +174,12 @@ const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* 
         }                                                                                \
     } while (0)
 
+void rlb_trace_mark(rlb_ctx* ctx, const char* file, int line);
+
 #define RLB_CHECK_LAUNCH(ctx)                                                            \
     do {                                                                                 \
         (ctx)->launches++;                                                               \
+        if ((ctx)->trace) rlb_trace_mark((ctx), __FILE__, __LINE__);                     \
         cudaError_t e__ = cudaGetLastError();                                            \
         if (e__ != cudaSuccess) {                                                        \
             rlb_set_error((ctx), RLB_E_CUDA, "kernel launch", cudaGetErrorString(e__));  \
@@ -185,6 +201,9 @@ void rlb_impl_free(rlb_ctx* ctx);
 int rlb_impl_pseudo(rlb_ctx* ctx);
 int rlb_impl_hist_update(rlb_ctx* ctx);
 int rlb_impl_tree_fit(rlb_ctx* ctx);
+int rlb_impl_prepare(rlb_ctx* ctx);
+int rlb_impl_enqueue_iter(rlb_ctx* ctx);
+int rlb_impl_finish_iter(rlb_ctx* ctx);
 int rlb_impl_tree_output(rlb_ctx* ctx);
 int rlb_impl_update_scores(rlb_ctx* ctx);
 int rlb_impl_train_metric(rlb_ctx* ctx);
