@@ -310,7 +310,7 @@ int rlb_update_scores(rlb_ctx* c) {
 
 int rlb_train_metric(rlb_ctx* c, float* out) {
     if (int rc = check_ready(c, "rlb_train_metric")) return rc;
-    if (int rc = rlb_impl_train_metric(c)) return rc;
+    if (int rc = rlb_impl_train_metric(c, false)) return rc;
     RLB_CUDA(c, cudaMemcpyAsync(&c->hState->train_metric, &c->dState->train_metric, sizeof(float), cudaMemcpyDeviceToHost,
                                 c->stream));
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -324,6 +324,9 @@ static int boost_one(rlb_ctx* c) {
     if (!c->use_graph || c->world > 1) {
         if (int rc = rlb_impl_enqueue_iter(c)) return rc;
     } else {
+        if (!c->lambda_fresh) {  // the captured sequence is the steady state: pseudo responses already fresh
+            if (int rc = rlb_impl_pseudo(c)) return rc;
+        }
         if (!c->iter_graph[gi]) {
             cudaGraph_t g = nullptr;
             c->ev_used = 0;
@@ -346,6 +349,8 @@ static int boost_one(rlb_ctx* c) {
         }
         c->ev_used = c->graph_events[gi];
         RLB_CUDA(c, cudaGraphLaunch(c->iter_graph[gi], c->stream));
+        c->tree_ready = true;
+        c->lambda_fresh = true;
         c->launches += 0;  // kernel launches inside the graph were counted at capture time; see rlb_stats
     }
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -1843,7 +1843,10 @@ static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
     return RLB_OK;
 }
 
+// pseudo responses for the CURRENT scores.  A no-op when the previous iteration's fused metric pass
+// already produced them (lambda_fresh).
 int rlb_impl_pseudo(rlb_ctx* c) {
+    if (c->lambda_fresh) return RLB_OK;
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->max_abs_bits, 0, sizeof(unsigned long long), c->stream));
     if (c->prm.kind == RLB_KIND_MART) {
         k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
@@ -1856,6 +1859,7 @@ int rlb_impl_pseudo(rlb_ctx* c) {
     if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
     k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
     RLB_CHECK_LAUNCH(c);
+    c->lambda_fresh = true;
     return RLB_OK;
 }
 
@@ -1909,7 +1913,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
         rlb_prof_begin(c, 1);
-        k_hist_rows<true><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0],
+        k_hist_rows<true><<<c->sm_count, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0],
                                                                c->dSamples[1], stageSum, stageCnt, c->dState, c->hist_min_rows);
         RLB_CHECK_LAUNCH(c);
         k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
@@ -2000,7 +2004,7 @@ int rlb_impl_enqueue_iter(rlb_ctx* c) {
     c->tree_ready = true;
     if (int rc = rlb_impl_tree_output(c)) return rc;
     if (int rc = rlb_impl_update_scores(c)) return rc;
-    if (int rc = rlb_impl_train_metric(c)) return rc;
+    if (int rc = rlb_impl_train_metric(c, true)) return rc;
     RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
     return RLB_OK;
 }
@@ -2012,7 +2016,7 @@ int rlb_impl_finish_iter(rlb_ctx* c) {
     if (recovered) {  // the leaf / score / metric kernels of the sequence were no-ops on the unfinished tree
         if (int rc = rlb_impl_tree_output(c)) return rc;
         if (int rc = rlb_impl_update_scores(c)) return rc;
-        if (int rc = rlb_impl_train_metric(c)) return rc;
+        if (int rc = rlb_impl_train_metric(c, true)) return rc;
         if (int rc = sync_state_header(c)) return rc;
     }
     c->tree_output_ready = false;
@@ -2068,6 +2072,7 @@ int rlb_impl_update_scores(rlb_ctx* c) {
                                                         c->prm.learning_rate, 1);
     RLB_CHECK_LAUNCH(c);
     c->tree_output_ready = false;  // a second call must not add the tree twice
+    c->lambda_fresh = false;       // the pseudo responses belong to the old scores
     return RLB_OK;
 }
 
@@ -2082,8 +2087,28 @@ int rlb_impl_assign_nodes(rlb_ctx* c) {
 
 extern long long rlb_q_total(rlb_ctx* c);
 
-int rlb_impl_train_metric(rlb_ctx* c) {
-    if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
+// LambdaMART.computeModelScoreOnTraining (LambdaMART.java:442-483).  with_pseudo: the same ranking pass
+// also produces the pseudo responses of the NEXT iteration (both need the stable descending order of
+// the current scores), which saves one full pass over the queries per iteration.
+int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
+    if (with_pseudo && !c->lambda_fresh) {
+        RLB_CUDA(c, cudaMemsetAsync(&c->dState->max_abs_bits, 0, sizeof(unsigned long long), c->stream));
+        if (c->prm.kind == RLB_KIND_MART) {
+            if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
+            k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
+            RLB_CHECK_LAUNCH(c);
+        } else {
+            rlb_prof_begin(c, 2);
+            if (int rc = launch_queries(c, true, c->dQMetric)) return rc;
+            rlb_prof_end(c);
+        }
+        if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
+        k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
+        RLB_CHECK_LAUNCH(c);
+        c->lambda_fresh = true;
+    } else {
+        if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
+    }
     const float* carry = nullptr;
     if (c->world > 1) {
         if (int rc = rlb_chain_carry_begin(c, 1)) return rc;

@@ -462,6 +462,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->inited = true;
     c->tree_ready = c->tree_output_ready = false;
+    c->lambda_fresh = false;
     return RLB_OK;
 }
 

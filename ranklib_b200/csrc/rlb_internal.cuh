@@ -85,6 +85,7 @@ struct rlb_ctx {
     int64_t N = 0, N_total = 0, Q_total = 0;
     int32_t F = 0, Fp = 0, Q = 0, max_query = 0;
     bool loaded = false, inited = false, have_thr = false, tree_ready = false, tree_output_ready = false;
+    bool lambda_fresh = false;      // dLambda / dWeight / scales belong to the current dScore
     rlb_params prm{};
     std::vector<int32_t> feature_ids;
     std::vector<float> h_thr;       // [F][RLB_T]
@@ -206,7 +207,7 @@ int rlb_impl_enqueue_iter(rlb_ctx* ctx);
 int rlb_impl_finish_iter(rlb_ctx* ctx);
 int rlb_impl_tree_output(rlb_ctx* ctx);
 int rlb_impl_update_scores(rlb_ctx* ctx);
-int rlb_impl_train_metric(rlb_ctx* ctx);
+int rlb_impl_train_metric(rlb_ctx* ctx, bool with_pseudo);
 int rlb_impl_assign_nodes(rlb_ctx* ctx);
 int rlb_impl_export_tree(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
 int rlb_impl_launch_rank_metric(rlb_ctx* ctx, const double* dScores, const float* dLabel, const int32_t* dQoff,
