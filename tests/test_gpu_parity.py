@@ -184,3 +184,85 @@ def test_errors(built):
     g.load_dense(X, label, qoff)
     with pytest.raises(native.RankLibError):
         g.init(native.make_params(n_threshold=-1))
+
+
+def test_gpu_matches_committed_golden_c1(built):
+    """The CUDA path against tests/golden/c1_oracle.npz (oracle outputs, scripts/make_golden.py) — no oracle call."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_oracle.npz"))
+    X, label, qoff = synth.c1()
+    ctx = native.Context(0)
+    ctx.load_dense(X, label, qoff)
+    ctx.init(native.make_params())
+    np.testing.assert_array_equal(g["thr_n"], [len(ctx.thresholds(f)) for f in range(X.shape[1])])
+    np.testing.assert_array_equal(g["thr0"], ctx.thresholds(0))
+    assert int(g["bins_checksum"][0]) == int(ctx.read("BINS").astype(np.int64).sum())
+    off = 0
+    for it in range(20):
+        nodes, m = ctx.boost_iter()
+        if it == 0:
+            np.testing.assert_allclose(ctx.read("LAMBDA"), g["lambda_iter1"], rtol=1e-12, atol=1e-15)
+        n = int(g["n_nodes"][it])
+        ref = g["nodes"][off:off + n]
+        off += n
+        assert len(nodes) == n
+        np.testing.assert_array_equal(np.sort(nodes["count"][nodes["feature_id"] == -1]), np.sort(ref["count"][ref["feature_id"] == -1]))
+        assert round(float(m), 4) == round(float(g["metrics"][it]), 4)
+    assert np.max(rel_err(ctx.read("SCORE"), g["scores"], floor=1e-9)) <= 1e-5
+
+
+def test_behavioural_separable_feature_gpu(built):
+    """EvaluatorTest.testLambdaMART's data and assertion through the C ABI (train, then Ensemble.eval)."""
+    rng = np.random.default_rng(0)
+    X = np.zeros((200, 2), np.float32)
+    X[:100, 0] = 1.0
+    X[100:, 0] = 0.9
+    X[:, 1] = rng.choice([-1.0, 1.0], 200)
+    label = np.r_[np.ones(100), np.zeros(100)].astype(np.float32)
+    perm = rng.permutation(200)
+    X, label = X[perm], label[perm]
+    qoff = np.array([0, 200], np.int32)
+    ctx = native.Context(0)
+    ctx.load_dense(X, label, qoff)
+    ctx.init(native.make_params())
+    trees, offs = [], [0]
+    for _ in range(10):
+        nodes, m = ctx.boost_iter()
+        trees.append(nodes)
+        offs.append(offs[-1] + len(nodes))
+    Xe = np.zeros((200, 3), np.float32)
+    Xe[:, 1:] = X
+    s = ctx.ensemble_eval(np.concatenate(trees), offs, np.full(10, 0.1, np.float32), Xe)
+    assert np.all(np.isfinite(s))
+    assert s[label == 1].min() > s[label == 0].max()
+    assert m == 1.0
+
+
+def test_full_size_properties(built):
+    """BASELINE.json configs[1] at full size: size-independent invariants instead of the (too slow) oracle.
+    Root histogram: every feature's cumulative sum ends at the same total = sum of all pseudo responses, and
+    the last cumulative count is N; leaf sizes of every tree add up to N; NDCG@10-T rises."""
+    X, label, qoff = synth.c2(1.0)
+    ctx = native.Context(0)
+    ctx.load_dense(X, label, qoff)
+    ctx.init(native.make_params())
+    N = X.shape[0]
+    ctx.compute_pseudo_responses()
+    ctx.hist_update()
+    rs = ctx.read("ROOT_SUM")
+    rc = ctx.read("ROOT_COUNT")
+    lam = ctx.read("LAMBDA")
+    assert np.all(rc[:, -1] == N)
+    assert np.all(rs[:, -1] == rs[0, -1])                        # fixed point: bit-identical totals
+    assert abs(rs[0, -1] - lam.sum()) <= 1e-6 * np.abs(lam).sum()
+    b = ctx.read("BINS")
+    f = 17
+    direct = np.bincount(b[f], weights=lam, minlength=257).cumsum()
+    np.testing.assert_allclose(rs[f], direct, rtol=0, atol=1e-6 * np.abs(lam).sum())
+    metrics = []
+    for _ in range(12):
+        nodes, m = ctx.boost_iter()
+        leaves = nodes[nodes["feature_id"] == -1]
+        assert leaves["count"].sum() == N and len(leaves) == 10
+        metrics.append(m)
+    assert metrics[-1] > metrics[0]

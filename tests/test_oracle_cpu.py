@@ -1,0 +1,191 @@
+"""CPU-only tests (run with -m "not gpu"): the oracle against its independent Python transliteration, the
+committed golden vectors and the ported behavioural test of the reference; host logic; and that the
+C-ABI library loads and exports every symbol include/ranklib_b200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.pyref import PyLambdaMART, merge_sort
+from ranklib_b200.host import native, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_merge_sorter_is_a_stable_argsort():
+    """R/utilities/MergeSorter.java:134-217 transliterated vs numpy's stable argsort, incl. heavy ties."""
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(1, 60))
+        a = list(rng.integers(0, 5, n).astype(float))
+        assert merge_sort(a, 0, n - 1, False) == list(np.argsort(-np.array(a), kind="stable"))
+        assert merge_sort(a, 0, n - 1, True) == list(np.argsort(np.array(a), kind="stable"))
+
+
+def test_java_random_known_answers():
+    """java.util.Random(42): nextInt(10) starts 0, 3, 8, 4, 0 (JDK specification)."""
+    assert list(orc.java_random_ints(42, 10, 5)) == [0, 3, 8, 4, 0]
+    v = orc.java_random_ints(7, 16, 64)          # power-of-two bound path
+    assert v.min() >= 0 and v.max() < 16
+
+
+def _small_problem(seed=3, Q=8, F=6):
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(1, 30, Q)
+    qoff = np.zeros(Q + 1, np.int32)
+    qoff[1:] = np.cumsum(sizes)
+    N = int(qoff[-1])
+    X = rng.standard_normal((N, F)).astype(np.float32)
+    X[:, F - 2] = rng.integers(0, 4, N)
+    X[:, F - 1] = np.where(rng.random(N) < 0.8, 0, X[:, F - 1])
+    label = rng.integers(0, 5, N).astype(np.float32)
+    return X, label, qoff
+
+
+@pytest.mark.parametrize("seed,nthr", [(3, 16), (11, 256), (5, 4)])
+def test_oracle_matches_python_transliteration(built, seed, nthr):
+    """Two restatements written separately from the Java source agree bit for bit."""
+    X, label, qoff = _small_problem(seed)
+    p = PyLambdaMART(X, label, qoff, n_leaves=6, n_threshold=nthr)
+    o = orc.Oracle(X, label, qoff, orc.make_params(n_leaves=6, n_threshold=nthr))
+    for f in range(X.shape[1]):
+        np.testing.assert_array_equal(np.array(p.thresholds[f], np.float32), o.thresholds(f))
+    np.testing.assert_array_equal(np.array(p.stmap), o.read("BINS"))
+    for it in range(4):
+        root, leaves, m = p.boost_iter()
+        on, mo = o.boost_iter()
+        np.testing.assert_array_equal(np.array(p.lam), o.read("LAMBDA"))
+        np.testing.assert_array_equal(np.array(p.w), o.read("WEIGHT"))
+        np.testing.assert_array_equal(np.array(p.scores), o.read("SCORE"))
+        assert m == mo
+        assert [lf.output for lf in leaves] == [float(v) for v in on["output"][_leaves_dfs(on)]]
+
+
+def _leaves_dfs(nodes):
+    out, stack = [], [0]
+    while stack:
+        n = stack.pop()
+        if nodes["feature_id"][n] == -1:
+            out.append(n)
+        else:
+            stack.append(int(nodes["right"][n]))
+            stack.append(int(nodes["left"][n]))
+    return out
+
+
+def test_oracle_thread_count_does_not_change_results(built):
+    """the reference's decomposition has one writer per (feature, bin) and per query."""
+    X, label, qoff = synth.c2(0.004)
+    a = orc.Oracle(X, label, qoff, orc.make_params(), nthreads=1)
+    b = orc.Oracle(X, label, qoff, orc.make_params(), nthreads=5)
+    for _ in range(3):
+        na, ma = a.boost_iter()
+        nb, mb = b.boost_iter()
+        np.testing.assert_array_equal(na, nb)
+        assert ma == mb
+    np.testing.assert_array_equal(a.read("SCORE"), b.read("SCORE"))
+
+
+def test_oracle_matches_golden_c1(built):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_oracle.npz"))
+    X, label, qoff = synth.c1()
+    o = orc.Oracle(X, label, qoff, orc.make_params())
+    np.testing.assert_array_equal(g["thr_n"], [len(o.thresholds(f)) for f in range(X.shape[1])])
+    np.testing.assert_array_equal(g["thr0"], o.thresholds(0))
+    assert int(g["bins_checksum"][0]) == int(o.read("BINS").astype(np.int64).sum())
+    off = 0
+    for it in range(20):
+        nodes, m = o.boost_iter()
+        if it == 0:
+            np.testing.assert_array_equal(g["lambda_iter1"], o.read("LAMBDA"))
+        n = int(g["n_nodes"][it])
+        np.testing.assert_array_equal(g["nodes"][off:off + n], nodes)
+        off += n
+        assert np.float32(m) == g["metrics"][it]
+    np.testing.assert_array_equal(g["scores"], o.read("SCORE"))
+    assert g["metrics"][-1] > g["metrics"][0] + 0.05          # the model learns
+
+
+def test_behavioural_separable_feature_oracle(built):
+    """Port of EvaluatorTest.testLambdaMART's data and assertion (src/test/java/.../EvaluatorTest.java:65-76,
+    244-255): one query, positives have feature 1 = 1.0, negatives 0.9, feature 2 = +-1 noise; after training
+    every positive must outrank every negative and all scores must be finite."""
+    rng = np.random.default_rng(0)
+    X = np.zeros((200, 2), np.float32)
+    X[:100, 0] = 1.0
+    X[100:, 0] = 0.9
+    X[:, 1] = rng.choice([-1.0, 1.0], 200)
+    label = np.r_[np.ones(100), np.zeros(100)].astype(np.float32)
+    perm = rng.permutation(200)
+    X, label = X[perm], label[perm]
+    qoff = np.array([0, 200], np.int32)
+    o = orc.Oracle(X, label, qoff, orc.make_params())
+    trees, offs = [], [0]
+    for _ in range(10):
+        nodes, m = o.boost_iter()
+        trees.append(nodes)
+        offs.append(offs[-1] + len(nodes))
+    Xe = np.zeros((200, 3), np.float32)
+    Xe[:, 1:] = X
+    s = orc.ensemble_eval(np.concatenate(trees), offs, np.full(10, 0.1, np.float32), Xe)
+    assert np.all(np.isfinite(s))
+    assert s[label == 1].min() > s[label == 0].max()
+    np.testing.assert_allclose(s, o.read("SCORE"), rtol=1e-5, atol=1e-7)   # float ensemble vs double training scores
+    assert m == 1.0
+
+
+def test_metric_scorer_edge_cases(built):
+    # all-zero labels: ideal DCG 0 -> NDCG 0 (NDCGScorer.java:124-126); a one-document query; k > n
+    scores = np.array([0.3, 0.1, 0.2, 5.0, 1.0, 2.0, 0.0], np.float64)
+    label = np.array([0, 0, 0, 2, 1, 0, 3], np.float32)
+    qoff = np.array([0, 3, 4, 7], np.int32)
+    v = orc.score_metric(scores, label, qoff, 0, 10)
+    from oracle.pyref import ndcg_score
+    exp = (0.0 + ndcg_score([2], 10) + ndcg_score([0, 1, 3], 10)) / 3
+    assert v == exp
+
+
+def test_synth_is_deterministic_and_shaped():
+    X, label, qoff = synth.c2(0.01)
+    X2, label2, qoff2 = synth.c2(0.01)
+    np.testing.assert_array_equal(X, X2)
+    np.testing.assert_array_equal(label, label2)
+    assert X.shape == (12000, 136) and qoff[-1] == 12000 and len(qoff) == 311
+    assert set(np.unique(label)) <= {0.0, 1.0, 2.0, 3.0, 4.0}
+    X1, l1, q1 = synth.c1()
+    assert X1.shape == (1000, 50) and len(q1) == 26
+
+
+def test_library_exports_every_declared_symbol(built):
+    """include/ranklib_b200.h <-> libranklib_b200.so <-> the ctypes binding."""
+    hdr = open(os.path.join(ROOT, "include", "ranklib_b200.h")).read()
+    declared = set(re.findall(r"\b(rlb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (rlb_[a-z_0-9]+)\b", out))
+    assert declared <= exported
+    assert lib.rlb_version() == 100
+
+
+def test_product_library_does_not_link_the_oracle(built):
+    out = subprocess.run(["ldd", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "liboracle" not in out
+    src = "".join(open(os.path.join(ROOT, "ranklib_b200", d, f)).read()
+                  for d in ("csrc", "host") for f in os.listdir(os.path.join(ROOT, "ranklib_b200", d))
+                  if f.endswith((".cu", ".cuh", ".py")))
+    assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("oracle numbers", "").replace("oracle uses", ""), \
+        "the product package must not reference oracle/"
+
+
+def test_no_cpu_fallback_without_a_gpu(built):
+    if native.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(native.RankLibError):
+        native.Context(0)
