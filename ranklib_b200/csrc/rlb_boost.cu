@@ -800,12 +800,18 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
             const int nr = (int)min((int64_t)R, r1 - (r0 + (int64_t)k * R));
             if (active) {
                 if (nr == R) {
+                    // all 16 (bin, response) pairs of the stage first: the tile reads then overlap the
+                    // read-modify-write chains instead of sitting in front of each of them
+                    int bb[16];
+                    long long vv[16];
 #pragma unroll
-                    for (int kk = 0; kk < 16; kk += 4) {
-                        const int ra = kk * PH + ph, rb = ra + PH, rc = rb + PH, rd = rc + PH;
-                        hist_batch4<T>(Hme, btile[ra * HG + fi], btile[rb * HG + fi], btile[rc * HG + fi], btile[rd * HG + fi],
-                                       vt[ra], vt[rb], vt[rc], vt[rd]);
+                    for (int kk = 0; kk < 16; kk++) {
+                        bb[kk] = btile[(kk * PH + ph) * HG + fi];
+                        vv[kk] = vt[kk * PH + ph];
                     }
+#pragma unroll
+                    for (int kk = 0; kk < 16; kk += 4)
+                        hist_batch4<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2], vv[kk + 3]);
                 } else {
                     for (int rr = ph; rr < nr; rr += PH) {
                         const int b = btile[rr * HG + fi];

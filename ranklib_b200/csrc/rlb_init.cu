@@ -201,7 +201,7 @@ int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_
     rlb_impl_free(c);
     c->N = N;
     c->F = F;
-    c->Fp = (F + 7) & ~7;  // 16-byte rows of uint16 bins
+    c->Fp = (F + 15) & ~15;  // rows of uint16 bins padded to whole 32-byte sectors: a 16-feature group never straddles two
     c->Q = Q;
     c->max_query = maxq;
     c->feature_ids.assign(feature_ids, feature_ids + F);
