@@ -7,6 +7,42 @@
 
 #include "rlb_internal.cuh"
 
+#include <dlfcn.h>
+
+NcclApi g_nccl = {};
+
+bool rlb_nccl_load(std::string* why) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (g_nccl.loaded) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // whatever the process already uses
+    if (!h) {
+        const char* env = getenv("RLB_NCCL_LIB");
+        if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        if (why) *why = dlerror() ? dlerror() : "libnccl.so.2 not found";
+        return false;
+    }
+    struct { const char* name; void** dst; } syms[] = {
+        {"ncclGetUniqueId", (void**)&g_nccl.GetUniqueId}, {"ncclCommInitRank", (void**)&g_nccl.CommInitRank},
+        {"ncclCommDestroy", (void**)&g_nccl.CommDestroy}, {"ncclAllReduce", (void**)&g_nccl.AllReduce},
+        {"ncclAllGather", (void**)&g_nccl.AllGather},     {"ncclBroadcast", (void**)&g_nccl.Broadcast},
+        {"ncclSend", (void**)&g_nccl.Send},               {"ncclRecv", (void**)&g_nccl.Recv},
+        {"ncclGroupStart", (void**)&g_nccl.GroupStart},   {"ncclGroupEnd", (void**)&g_nccl.GroupEnd},
+        {"ncclGetErrorString", (void**)&g_nccl.GetErrorString}};
+    for (auto& sm : syms) {
+        *sm.dst = dlsym(h, sm.name);
+        if (!*sm.dst) {
+            if (why) *why = std::string("symbol missing in libnccl: ") + sm.name;
+            return false;
+        }
+    }
+    g_nccl.loaded = true;
+    return true;
+}
+
 static std::string g_last_error;
 static std::mutex g_err_mutex;
 
@@ -183,6 +219,11 @@ int rlb_destroy(rlb_ctx* c) {
 
 int rlb_comm_unique_id(uint8_t id_out[128]) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::string why;
+    if (!rlb_nccl_load(&why)) {
+        rlb_set_error(nullptr, RLB_E_NCCL, "NCCL not loadable", why.c_str());
+        return RLB_E_NCCL;
+    }
     ncclUniqueId id;
     ncclResult_t r = ncclGetUniqueId(&id);
     if (r != ncclSuccess) {
@@ -201,11 +242,24 @@ int rlb_comm_init(rlb_ctx* c, int rank, int world, const uint8_t id[128]) {
         c->world = 1;
         return RLB_OK;
     }
+    std::string why;
+    if (!rlb_nccl_load(&why)) {
+        rlb_set_error(c, RLB_E_NCCL, "NCCL not loadable", why.c_str());
+        return RLB_E_NCCL;
+    }
     ncclUniqueId nid;
     memcpy(&nid, id, 128);
     RLB_NCCL(c, ncclCommInitRank(&c->comm, world, nid, rank));
     c->rank = rank;
     c->world = world;
+    {   // connect the rings now (first collective) rather than inside the first training call
+        int* d = nullptr;
+        RLB_CUDA(c, cudaMalloc(&d, 4));
+        RLB_CUDA(c, cudaMemsetAsync(d, 0, 4, c->stream));
+        RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt32, ncclSum, c->comm, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
     return RLB_OK;
 }
 

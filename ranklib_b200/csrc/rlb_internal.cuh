@@ -11,6 +11,37 @@
 
 #include "../../include/ranklib_b200.h"
 
+// NCCL is bound at run time (dlopen) the first time a communicator is needed: a single-GPU user never loads
+// it, and a process that already carries a NCCL (e.g. PyTorch's bundled 2.28) keeps exactly that one
+// instead of having a second, older libnccl.so.2 pulled in by our DT_NEEDED and shadowing it.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+    bool loaded;
+};
+extern NcclApi g_nccl;
+bool rlb_nccl_load(std::string* why);
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclBroadcast g_nccl.Broadcast
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
+
 #define RLB_T RLB_MAX_BINS          // bins per feature in every padded table (257)
 #define RLB_MAX_LEAVES 1024          // n_leaves limit of the device tree controller
 #define RLB_MAX_NODES (2 * RLB_MAX_LEAVES)

@@ -1,0 +1,515 @@
+"""Host-side mirror of the reference's plugin API for the tree rankers, on top of the C ABI.
+
+The reference is Java; no JDK exists in this image, so the façades the JNI shim would sit
+behind are mirrored here with the same names, argument meaning and error behaviour:
+
+    Ranker (R/learning/Ranker.java:36-186)            init / learn / eval / rank / model / loadFromString / name
+    LambdaMART, MART, RFRanker (R/learning/tree/*)    public static parameter fields, getEnsemble()
+    Ensemble, RegressionTree (flat node arrays)       add / treeCount / getWeight / eval / toString / parse
+    RankerTrainer.train, RankerFactory.createRanker   (R/learning/RankerTrainer.java:29-47, RankerFactory.java:60-70)
+    RankList / DataPoint as arrays, FeatureManager.readInput for LETOR text (R/features/FeatureManager.java:187-245)
+
+All numeric work happens in libranklib_b200.so (CUDA); nothing here computes a histogram, a lambda or a
+tree on the CPU.
+"""
+import re
+
+import numpy as np
+
+from . import native
+from .native import RankLibError
+
+R_LAMBDAMART, R_MART, R_RF = 6, 0, 8          # Evaluator's -ranker ids (R/eval/Evaluator.java:71-73)
+
+
+# ---------------------------------------------------------------------------------------------------
+# data model: a List<RankList> flattened the way LambdaMART.init flattens it (LambdaMART.java:71-91)
+# ---------------------------------------------------------------------------------------------------
+class RankLists:
+    """samples: X[N][F] (column j = feature id features[j]), label[N], qoff[Q+1], qids[Q]."""
+
+    def __init__(self, X, label, qoff, features=None, qids=None):
+        self.X = np.ascontiguousarray(X, np.float32)
+        self.label = np.ascontiguousarray(label, np.float32)
+        self.qoff = np.ascontiguousarray(qoff, np.int32)
+        self.features = (np.arange(1, self.X.shape[1] + 1, dtype=np.int32) if features is None
+                         else np.ascontiguousarray(features, np.int32))
+        self.qids = list(qids) if qids is not None else [str(i + 1) for i in range(len(self.qoff) - 1)]
+
+    def size(self):
+        return len(self.qoff) - 1
+
+    def select(self, query_indices):
+        """The List<RankList> obtained by picking whole queries (Sampler.doSampling, R/learning/Sampler.java:21-38)."""
+        rows = np.concatenate([np.arange(self.qoff[q], self.qoff[q + 1]) for q in query_indices]) if len(query_indices) else \
+            np.zeros(0, np.int64)
+        sizes = [int(self.qoff[q + 1] - self.qoff[q]) for q in query_indices]
+        qoff = np.zeros(len(sizes) + 1, np.int32)
+        qoff[1:] = np.cumsum(sizes)
+        return RankLists(self.X[rows], self.label[rows], qoff, self.features, [self.qids[q] for q in query_indices])
+
+    def dense_with_fid_columns(self):
+        """float[N][maxFid+1] indexed by feature id directly (DataPoint.fVals layout, column 0 unused)."""
+        out = np.full((self.X.shape[0], int(self.features.max()) + 1), np.nan, np.float32)
+        out[:, self.features] = self.X
+        return out
+
+
+def read_letor(path):
+    """FeatureManager.readInput (R/features/FeatureManager.java:187-245) + DataPoint.parse
+    (R/learning/DataPoint.java:58-110): `<label> qid:<id> <fid>:<val> ... # comment`; consecutive lines with the
+    same qid form one RankList; missing features are NaN (= unknown, read as 0)."""
+    labels, qids, rows, maxf = [], [], [], 0
+    with open(path) as fh:
+        for line in fh:
+            line = line.split("#", 1)[0].strip()
+            if not line:
+                continue
+            parts = line.split()
+            lab = float(parts[0])
+            if lab < 0:
+                raise RankLibError("Relevance label cannot be negative. System will now exit.")
+            qids.append(parts[1].split(":", 1)[1])
+            feats = {}
+            for tok in parts[2:]:
+                k, v = tok.rsplit(":", 1)
+                f = int(k)
+                if f <= 0:
+                    raise RankLibError("Cannot use feature numbering less than or equal to zero. Start your features at 1.")
+                feats[f] = float(v)
+                maxf = max(maxf, f)
+            labels.append(lab)
+            rows.append(feats)
+    X = np.full((len(rows), maxf), np.nan, np.float32)
+    for i, feats in enumerate(rows):
+        for f, v in feats.items():
+            X[i, f - 1] = v
+    qoff, names = [0], []
+    for i, q in enumerate(qids):
+        if i > 0 and q != qids[i - 1]:
+            qoff.append(i)
+            names.append(qids[i - 1])
+    qoff.append(len(qids))
+    if qids:
+        names.append(qids[-1])
+    return RankLists(X, np.array(labels, np.float32), np.array(qoff, np.int32), None, names)
+
+
+# ---------------------------------------------------------------------------------------------------
+# java.util.Random (JDK specification) — replaces the reference's unseeded `new Random()`
+# ---------------------------------------------------------------------------------------------------
+class JavaRandom:
+    def __init__(self, seed):
+        self.seed = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def next(self, bits):
+        self.seed = (self.seed * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        v = self.seed >> (48 - bits)
+        return v - (1 << 32) if v >= (1 << 31) else v
+
+    def next_int(self, bound):
+        r = self.next(31)
+        m = bound - 1
+        if bound & m == 0:
+            return (bound * r) >> 31
+        u = r
+        while True:
+            r = u % bound
+            if u - r + m < (1 << 31):
+                return r
+            u = self.next(31)
+
+
+# ---------------------------------------------------------------------------------------------------
+# metric (R/metric/NDCGScorer.java, DCGScorer.java) — evaluated by the library (rlb_score_metric)
+# ---------------------------------------------------------------------------------------------------
+class NDCGScorer:
+    metric = native.METRIC_NDCG
+
+    def __init__(self, k=10):
+        self.k = k
+
+    def name(self):
+        return f"NDCG@{self.k}"
+
+    def getK(self):
+        return self.k
+
+
+class DCGScorer(NDCGScorer):
+    metric = native.METRIC_DCG
+
+    def name(self):
+        return f"DCG@{self.k}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Java number formatting for the model text (Float.toString / Double.toString)
+# ---------------------------------------------------------------------------------------------------
+def _java_fmt(digits, exp10):
+    """digits: shortest decimal digits d1d2.. (no dot), value = 0.d1d2.. * 10^exp10"""
+    if -3 < exp10 <= 7:  # 1e-3 <= |x| < 1e7: plain decimal with at least one fractional digit
+        if exp10 <= 0:
+            return "0." + "0" * (-exp10) + digits
+        if len(digits) <= exp10:
+            return digits + "0" * (exp10 - len(digits)) + ".0"
+        return digits[:exp10] + "." + digits[exp10:]
+    mant = digits[0] + "." + (digits[1:] or "0")
+    return f"{mant}E{exp10 - 1}"
+
+
+def java_float_str(x, single=True):
+    x = np.float32(x) if single else float(x)
+    if x != x:
+        return "NaN"
+    if x == 0:
+        return "-0.0" if np.signbit(x) else "0.0"
+    if np.isinf(x):
+        return "-Infinity" if x < 0 else "Infinity"
+    s = np.format_float_scientific(x, unique=True, trim="-")  # shortest round-trip digits
+    m, e = s.split("e")
+    neg = m.startswith("-")
+    digits = m.lstrip("-").replace(".", "")
+    out = _java_fmt(digits, int(e) + 1)
+    return "-" + out if neg else out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ensemble / RegressionTree over flat node arrays (R/learning/tree/Ensemble.java, Split.java)
+# ---------------------------------------------------------------------------------------------------
+class RegressionTree:
+    def __init__(self, nodes):
+        self.nodes = np.ascontiguousarray(nodes, native.NODE_DTYPE)
+
+    def leaves(self):
+        """Split.leaves(): left-first depth-first (R/learning/tree/Split.java:100-113)."""
+        out, stack = [], [0]
+        while stack:
+            n = stack.pop()
+            if self.nodes["feature_id"][n] == -1:
+                out.append(n)
+            else:
+                stack.append(int(self.nodes["right"][n]))
+                stack.append(int(self.nodes["left"][n]))
+        return out
+
+    def toString(self, indent=""):
+        return self._split_str(0, indent)
+
+    def _split_str(self, n, indent):
+        return indent + "<split>\n" + self._body(n, indent + "\t") + indent + "</split>\n"
+
+    def _body(self, n, indent):  # Split.getString (Split.java:139-155)
+        nd = self.nodes[n]
+        if nd["feature_id"] == -1:
+            return f"{indent}<output>{java_float_str(float(np.float32(nd['output'])), single=False)} </output>\n"
+        s = f"{indent}<feature>{int(nd['feature_id'])} </feature>\n"
+        s += f"{indent}<threshold> {java_float_str(nd['threshold'])} </threshold>\n"
+        s += f"{indent}<split pos=\"left\">\n" + self._body(int(nd["left"]), indent + "\t") + f"{indent}</split>\n"
+        s += f"{indent}<split pos=\"right\">\n" + self._body(int(nd["right"]), indent + "\t") + f"{indent}</split>\n"
+        return s
+
+
+class Ensemble:
+    def __init__(self, text=None):
+        self.trees, self.weights = [], []
+        if text is not None:
+            self._parse(text)
+
+    def add(self, tree, weight):
+        self.trees.append(tree)
+        self.weights.append(np.float32(weight))
+
+    def getTree(self, k):
+        return self.trees[k]
+
+    def getWeight(self, k):
+        return float(self.weights[k])
+
+    def treeCount(self):
+        return len(self.trees)
+
+    def remove(self, k):
+        self.trees.pop(k)
+        self.weights.pop(k)
+
+    def leafCount(self):
+        return sum(len(t.leaves()) for t in self.trees)
+
+    def getFeatures(self):
+        f = set()
+        for t in self.trees:
+            f.update(int(v) for v in t.nodes["feature_id"] if v != -1)
+        return sorted(f)
+
+    def flat(self):
+        offs = np.zeros(len(self.trees) + 1, np.int32)
+        offs[1:] = np.cumsum([len(t.nodes) for t in self.trees])
+        nodes = np.concatenate([t.nodes for t in self.trees]) if self.trees else np.zeros(0, native.NODE_DTYPE)
+        return nodes, offs, np.array(self.weights, np.float32)
+
+    def eval(self, ctx, X_fid):
+        """Ensemble.eval (Ensemble.java:110-116) for a batch: X_fid[N][maxFid+1] indexed by feature id."""
+        nodes, offs, w = self.flat()
+        return ctx.ensemble_eval(nodes, offs, w, X_fid)
+
+    def toString(self):  # Ensemble.toString (Ensemble.java:119-130)
+        buf = ["<ensemble>\n"]
+        for i, t in enumerate(self.trees):
+            buf.append(f"\t<tree id=\"{i + 1}\" weight=\"{java_float_str(self.weights[i])}\">\n")
+            buf.append(t.toString("\t\t"))
+            buf.append("\t</tree>\n")
+        buf.append("</ensemble>\n")
+        return "".join(buf)
+
+    def _parse(self, text):  # Ensemble(String) (Ensemble.java:45-70) + Split construction from XML
+        import xml.etree.ElementTree as ET
+        root = ET.fromstring(text[text.index("<ensemble>"):])
+        for tr in root.findall("tree"):
+            nodes = []
+
+            def walk(el):
+                idx = len(nodes)
+                nodes.append(None)
+                out = el.find("output")
+                if out is not None:
+                    nodes[idx] = (-1, -1, 0.0, -1, -1, -1, float(out.text), 0, 0.0)
+                    return idx
+                fid = int(el.find("feature").text)
+                thr = float(el.find("threshold").text)
+                kids = {k.get("pos"): k for k in el.findall("split")}
+                li = walk(kids["left"])
+                ri = walk(kids["right"])
+                nodes[idx] = (fid, -1, thr, -1, li, ri, 0.0, 0, 0.0)
+                return idx
+
+            walk(tr.find("split"))
+            self.add(RegressionTree(np.array(nodes, native.NODE_DTYPE)), float(tr.get("weight")))
+
+
+# ---------------------------------------------------------------------------------------------------
+# rankers
+# ---------------------------------------------------------------------------------------------------
+class Ranker:
+    def __init__(self, samples=None, features=None, scorer=None):
+        self.samples, self.scorer = samples, scorer or NDCGScorer(10)
+        self.features = features
+        self.validationSamples = None
+        self.scoreOnTrainingData = 0.0
+        self.bestScoreOnValidationData = 0.0
+        self.device = 0
+
+    def setTrainingSet(self, samples):
+        self.samples = samples
+
+    def setFeatures(self, features):
+        self.features = features
+
+    def setValidationSet(self, samples):
+        self.validationSamples = samples
+
+    def setMetricScorer(self, scorer):
+        self.scorer = scorer
+
+    def getScoreOnTrainingData(self):
+        return self.scoreOnTrainingData
+
+    def getScoreOnValidationData(self):
+        return self.bestScoreOnValidationData
+
+
+class LambdaMART(Ranker):
+    # public static parameters (R/learning/tree/LambdaMART.java:37-42)
+    nTrees = 1000
+    learningRate = 0.1
+    nThreshold = 256
+    nRoundToStopEarly = 100
+    nTreeLeaves = 10
+    minLeafSupport = 1
+    KIND = native.KIND_LAMBDAMART
+    # feature sampling is FeatureHistogram.samplingRate in the reference (FeatureHistogram.java:33)
+    samplingRate = 1.0
+    seed = 0
+
+    def name(self):
+        return "LambdaMART"
+
+    def createNew(self):
+        return type(self)()
+
+    def init(self):
+        if self.samples is None or self.samples.size() == 0:
+            raise RankLibError("Error in LambdaMART::init(): no training data")
+        s = self.samples
+        cols = np.arange(s.X.shape[1]) if self.features is None else \
+            np.array([int(np.nonzero(s.features == f)[0][0]) for f in self.features])
+        self.features = s.features[cols]
+        self.ctx = native.Context(self.device)
+        self.ctx.load_dense(s.X[:, cols], s.label, s.qoff, self.features)
+        self.ctx.init(native.make_params(n_leaves=type(self).nTreeLeaves, mls=type(self).minLeafSupport,
+                                         lr=type(self).learningRate, n_threshold=type(self).nThreshold, kind=self.KIND,
+                                         metric=self.scorer.metric, k=self.scorer.getK(), frate=type(self).samplingRate,
+                                         seed=type(self).seed))
+        self.ensemble = Ensemble()
+        self.trainLog = []
+
+    def learn(self):
+        """LambdaMART.learn (LambdaMART.java:169-272): boosting loop, validation-based best-model tracking and early
+        stopping, roll-back, final score on the training data from Ensemble.eval."""
+        cls = type(self)
+        v = self.validationSamples
+        best_model, best_v = (1 << 31) - 3, -1.0
+        v_scores = None if v is None else np.zeros(v.X.shape[0], np.float64)
+        v_fid = None if v is None else v.dense_with_fid_columns()
+        for m in range(cls.nTrees):
+            nodes, metric = self.ctx.boost_iter()
+            rt = RegressionTree(nodes)
+            self.ensemble.add(rt, cls.learningRate)
+            self.scoreOnTrainingData = metric
+            row = [m + 1, round(float(metric), 4)]
+            if v is not None:
+                # modelScoresOnValidation += learningRate * rt.eval(dp) (LambdaMART.java:228-234), double accumulation
+                leaf = self.ctx.ensemble_eval(nodes, [0, len(nodes)], [1.0], v_fid).astype(np.float64)
+                v_scores += float(np.float32(cls.learningRate)) * leaf
+                score = np.float32(self.ctx.score_metric(v_scores, v.label, v.qoff, self.scorer.metric, self.scorer.getK()))
+                row.append(round(float(score), 4))
+                if score > best_v:
+                    best_v, best_model = float(score), self.ensemble.treeCount() - 1
+            self.trainLog.append(row)
+            if m - best_model > cls.nRoundToStopEarly:
+                break
+        while self.ensemble.treeCount() > best_model + 1:
+            self.ensemble.remove(self.ensemble.treeCount() - 1)
+        self.scoreOnTrainingData = self._score(self.samples)
+        if v is not None:
+            self.bestScoreOnValidationData = self._score(v)
+
+    def _score(self, rl):  # scorer.score(rank(samples)) (LambdaMART.java:259, Ranker.java:88-103)
+        s = self.ensemble.eval(self.ctx, rl.dense_with_fid_columns()).astype(np.float64)
+        return self.ctx.score_metric(s, rl.label, rl.qoff, self.scorer.metric, self.scorer.getK())
+
+    def eval(self, rl):
+        """Ranker.eval for every data point of `rl` (batched Ensemble.eval)."""
+        return self.ensemble.eval(self.ctx, rl.dense_with_fid_columns())
+
+    def rank(self, rl):
+        """Ranker.rank (Ranker.java:88-103): per query, stable descending order of the scores."""
+        s = self.eval(rl).astype(np.float64)
+        return [rl.qoff[q] + np.argsort(-s[rl.qoff[q]:rl.qoff[q + 1]], kind="stable") for q in range(rl.size())]
+
+    def getEnsemble(self):
+        return self.ensemble
+
+    def toString(self):
+        return self.ensemble.toString()
+
+    def model(self):  # LambdaMART.model (LambdaMART.java:290-301)
+        cls = type(self)
+        return (f"## {self.name()}\n## No. of trees = {cls.nTrees}\n## No. of leaves = {cls.nTreeLeaves}\n"
+                f"## No. of threshold candidates = {cls.nThreshold}\n## Learning rate = {java_float_str(cls.learningRate)}\n"
+                f"## Stop early = {cls.nRoundToStopEarly}\n\n" + self.toString())
+
+    def loadFromString(self, fullText):  # LambdaMART.loadFromString (LambdaMART.java:303-310) + ModelLineProducer
+        body = "\n".join(ln.strip() for ln in fullText.splitlines() if not ln.startswith("##"))
+        self.ensemble = Ensemble(body)
+        self.features = np.array(self.ensemble.getFeatures(), np.int32)
+        if not hasattr(self, "ctx"):
+            self.ctx = native.Context(self.device)
+
+
+class MART(LambdaMART):
+    KIND = native.KIND_MART
+
+    def name(self):
+        return "MART"
+
+
+class RFRanker(Ranker):
+    # R/learning/tree/RFRanker.java:35-44
+    nBag = 300
+    subSamplingRate = 1.0
+    featureSamplingRate = 0.3
+    rType = R_MART
+    nTrees = 1
+    nTreeLeaves = 100
+    learningRate = 0.1
+    nThreshold = 256
+    minLeafSupport = 1
+    seed = 0            # seeds the java.util.Random streams that replace the reference's unseeded ones
+
+    def name(self):
+        return "Random Forests"
+
+    def init(self):
+        self.ensembles = []
+
+    def bag_queries(self, rnd):
+        """Sampler.doSampling(samples, subSamplingRate, withReplacement=true) (R/learning/Sampler.java:21-38)."""
+        n = self.samples.size()
+        size = int(np.float32(type(self).subSamplingRate) * np.float32(n))
+        return [rnd.next_int(n) for _ in range(size)]
+
+    def learn(self, bags=None):
+        cls = type(self)
+        base = MART if cls.rType == R_MART else LambdaMART
+        rnd = JavaRandom(cls.seed)
+        self.ensembles = []
+        bag_ids = range(cls.nBag) if bags is None else bags
+        for i in range(cls.nBag):
+            picks = self.bag_queries(rnd)          # every bag consumes its draws, also when another GPU trains it
+            if i not in bag_ids:
+                continue
+
+            class _Bag(base):
+                nTrees, nTreeLeaves, learningRate = cls.nTrees, cls.nTreeLeaves, cls.learningRate
+                nThreshold, minLeafSupport, nRoundToStopEarly = cls.nThreshold, cls.minLeafSupport, -1
+                samplingRate, seed = cls.featureSamplingRate, cls.seed + 1 + i
+
+            r = _Bag(self.samples.select(picks), self.features, self.scorer)
+            r.device = self.device
+            r.init()
+            r.nRoundToStopEarly = -1
+            # RFRanker.init sets nRoundToStopEarly = -1 (RFRanker.java:66): with no validation set the loop runs nTrees times
+            _Bag.nRoundToStopEarly = (1 << 30)
+            r.learn()
+            self.ensembles.append(r.getEnsemble())
+            self._ctx = r.ctx
+
+    def eval(self, rl):
+        """RFRanker.eval (RFRanker.java:117-123): double mean of the bag ensembles' float scores."""
+        Xf = rl.dense_with_fid_columns()
+        s = np.zeros(rl.X.shape[0], np.float64)
+        for e in self.ensembles:
+            s += e.eval(self._ctx, Xf).astype(np.float64)
+        return s / len(self.ensembles)
+
+    def model(self):
+        return "".join(f"## {self.name()}\n## No. of bags = {type(self).nBag}\n\n" if i == 0 else "" for i in range(1)) + \
+            "".join(e.toString() for e in self.ensembles)
+
+
+class RankerFactory:
+    """RankerFactory.createRanker (R/learning/RankerFactory.java:60-70) for the tree rankers."""
+    _types = {R_LAMBDAMART: LambdaMART, R_MART: MART, R_RF: RFRanker}
+
+    def createRanker(self, rtype, samples=None, features=None, scorer=None):
+        if rtype not in self._types:
+            raise RankLibError(f"ranker type {rtype} is outside the accelerated path (only 0 MART, 6 LambdaMART, 8 Random Forests)")
+        return self._types[rtype](samples, features, scorer)
+
+
+class RankerTrainer:
+    """RankerTrainer.train (R/learning/RankerTrainer.java:29-47)."""
+
+    def __init__(self):
+        self.trainingTime = 0.0
+
+    def train(self, rtype, train, validation=None, features=None, scorer=None):
+        import time
+        ranker = RankerFactory().createRanker(rtype, train, features, scorer)
+        ranker.setValidationSet(validation)
+        t0 = time.perf_counter()
+        ranker.init()
+        ranker.learn()
+        self.trainingTime = time.perf_counter() - t0
+        return ranker

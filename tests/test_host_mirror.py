@@ -1,0 +1,109 @@
+"""The Python mirror of the reference's Ranker / RankerTrainer / Ensemble API (ranklib_b200/host/rankers.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from ranklib_b200.host import native, synth
+from ranklib_b200.host import rankers as R
+from tests.util import compare_tree, rel_err
+
+
+def test_java_number_formatting():
+    f = R.java_float_str
+    assert [f(x) for x in [0.1, 1.0, 1234567.0, 1e7, 1.5e-4, 3.4028235e38, 0.001, 100.0, -2.5, 0.0]] == \
+        ["0.1", "1.0", "1234567.0", "1.0E7", "1.5E-4", "3.4028235E38", "0.001", "100.0", "-2.5", "0.0"]
+    assert f(float(np.float32(0.3)), single=False) == "0.30000001192092896"
+
+
+def test_java_random_mirror_matches_oracle_stream(built):
+    for seed, bound in [(42, 10), (7, 16), (123456789, 31000), (0, 136)]:
+        r = R.JavaRandom(seed)
+        assert [r.next_int(bound) for _ in range(50)] == list(orc.java_random_ints(seed, bound, 50))
+
+
+def test_letor_reader_round_trip(tmp_path):
+    X, label, qoff = synth.c1()
+    X = X[:120, :7].copy()
+    label, qoff = label[:120], qoff[:4]
+    p = tmp_path / "train.txt"
+    synth.write_letor(str(p), X, label, qoff)
+    rl = R.read_letor(str(p))
+    np.testing.assert_array_equal(rl.X, X)
+    np.testing.assert_array_equal(rl.label, label)
+    np.testing.assert_array_equal(rl.qoff, qoff)
+    assert rl.qids == ["1", "2", "3"]
+    (tmp_path / "bad.txt").write_text("-1 qid:1 1:0.5\n")
+    with pytest.raises(R.RankLibError, match="negative"):
+        R.read_letor(str(tmp_path / "bad.txt"))
+
+
+def test_ensemble_text_round_trip():
+    nodes = np.zeros(3, native.NODE_DTYPE)
+    nodes[0] = (3, 2, 0.5, 7, 1, 2, 0, 10, 1.0)
+    nodes[1] = (-1, -1, 0, -1, -1, -1, 0.25, 4, 0)
+    nodes[2] = (-1, -1, 0, -1, -1, -1, -1.5, 6, 0)
+    e = R.Ensemble()
+    e.add(R.RegressionTree(nodes), 0.1)
+    txt = e.toString()
+    assert "<feature>3 </feature>" in txt and "<threshold> 0.5 </threshold>" in txt and 'weight="0.1"' in txt
+    e2 = R.Ensemble(txt)
+    assert e2.treeCount() == 1 and e2.getFeatures() == [3]
+    for k in ("feature_id", "threshold", "left", "right", "output"):
+        np.testing.assert_array_equal(e2.trees[0].nodes[k], nodes[k])
+    assert e2.toString() == txt
+
+
+@pytest.mark.gpu
+def test_trainer_validation_early_stop_and_model_reload(built):
+    """-ranker 6 with -validate and -estop: best-model roll-back (LambdaMART.java:240-256), then save / load / rank."""
+    X, label, qoff = synth.c1()
+    train = R.RankLists(X[:800], label[:800], qoff[:21])
+    valid = R.RankLists(X[800:], label[800:], (qoff[20:] - qoff[20]).astype(np.int32))
+    R.LambdaMART.nTrees, R.LambdaMART.nRoundToStopEarly = 40, 5
+    try:
+        ranker = R.RankerTrainer().train(R.R_LAMBDAMART, train, valid, None, R.NDCGScorer(10))
+    finally:
+        R.LambdaMART.nTrees, R.LambdaMART.nRoundToStopEarly = 1000, 100
+    log = ranker.trainLog
+    best = int(np.argmax([r[2] for r in log]))                 # first maximum of the rounded? no: of the raw float score
+    assert ranker.ensemble.treeCount() <= len(log)
+    assert len(log) < 40 or ranker.ensemble.treeCount() <= 40
+    assert 0.0 < ranker.getScoreOnValidationData() <= 1.0
+    text = ranker.model()
+    assert text.startswith("## LambdaMART\n## No. of trees = ")
+    again = R.LambdaMART()
+    again.loadFromString(text)
+    assert again.ensemble.treeCount() == ranker.ensemble.treeCount()
+    np.testing.assert_array_equal(again.eval(valid), ranker.eval(valid))   # thresholds / outputs survive the text form
+    order = ranker.rank(valid)
+    assert len(order) == valid.size() and sorted(order[0] - valid.qoff[0]) == list(range(valid.qoff[1] - valid.qoff[0]))
+    assert best >= 0
+
+
+@pytest.mark.gpu
+def test_random_forest_bags_match_oracle(built):
+    """-ranker 8: bootstrap bags of queries (seeded java.util.Random), one MART tree of 20 leaves per bag with per-split
+    feature sampling 0.3 — the CUDA path against the oracle run on the very same bags."""
+    X, label, qoff = synth.c1()
+    samples = R.RankLists(X, label, qoff)
+    R.RFRanker.nBag, R.RFRanker.nTreeLeaves, R.RFRanker.seed = 3, 20, 99
+    try:
+        rf = R.RFRanker(samples, None, R.NDCGScorer(10))
+        rf.init()
+        rf.learn()
+        rnd = R.JavaRandom(99)
+        for i in range(3):
+            picks = rf.bag_queries(rnd)
+            bag = samples.select(picks)
+            o = orc.Oracle(bag.X, bag.label, bag.qoff, orc.make_params(n_leaves=20, kind=1, frate=0.3, seed=99 + 1 + i))
+            on, _ = o.boost_iter()
+            gn = rf.ensembles[i].trees[0].nodes
+            assert len(gn) == len(on)
+            np.testing.assert_array_equal(np.sort(gn["count"][gn["feature_id"] == -1]), np.sort(on["count"][on["feature_id"] == -1]))
+            assert np.max(rel_err(np.sort(gn["output"]), np.sort(on["output"]))) <= 1e-5
+        s = rf.eval(samples)
+        assert np.all(np.isfinite(s)) and s.shape == (1000,)
+    finally:
+        R.RFRanker.nBag, R.RFRanker.nTreeLeaves, R.RFRanker.seed = 300, 100, 0
