@@ -714,7 +714,6 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
         const NodeRec& r = st->nodes[st->small_id];
         lo = r.lo;
         hi = r.hi;
-        if (hi - lo < minRows) return;  // k_hist_rows' regime
         samples = r.buf ? samples1 : samples0;
         if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
     }
@@ -728,6 +727,7 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     if (idx == nCta - 1) r1 = hi;
     if (idx == 0) r0 = lo;
     const int nst = (int)((r1 - r0 + R - 1) / R);
+    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
 
     for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
     if (tid == 0) {
@@ -826,10 +826,64 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     }
 }
 
-// per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan
-__global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum) {
+// Best threshold of ONE feature for one node, from the cumulative (sum, count) every thread t holds for
+// threshold t: S = sL^2/cL + sR^2/cR, largest S, lowest t among equals (FeatureHistogram.java:243-261).
+// Result (S, t) is written by thread 0; S = -1 when no threshold is admissible.
+__device__ __forceinline__ void feature_best(long long cumS, int cumC, int t, int nthr_f, int total, long long totalSumFix,
+                                             int mls, int se, double* sS, int* sT, double* outS, int32_t* outT) {
+    const int lane = t & 31, w = t >> 5;
+    double S = -1.0;
+    int bt = 0x7fffffff;
+    if (t < nthr_f) {
+        const int cL = cumC, cR = total - cumC;
+        if (!(cL < mls || cR < mls)) {
+            const double sumResponse = fix2d(totalSumFix, se);
+            const double sL = fix2d(cumS, se);
+            const double sR = sumResponse - sL;
+            const double v = sL * sL / cL + sR * sR / cR;
+            if (v > -1.0) {  // false for NaN, like `cfg.S < S`
+                S = v;
+                bt = t;
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const double oS = __shfl_xor_sync(0xffffffffu, S, d);
+        const int oT = __shfl_xor_sync(0xffffffffu, bt, d);
+        if (oS > S || (oS == S && oT < bt)) {
+            S = oS;
+            bt = oT;
+        }
+    }
+    __syncthreads();  // sS / sT may still be read from a previous call
+    if (lane == 0) {
+        sS[w] = S;
+        sT[w] = bt;
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int i = 1; i < 9; i++)
+            if (sS[i] > S || (sS[i] == S && sT[i] < bt)) {
+                S = sS[i];
+                bt = sT[i];
+            }
+        *outS = S;
+        *outT = bt;
+    }
+}
+
+// per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan; also the root's
+// best threshold of this feature (the split scan of every node is done where its histogram is produced)
+__global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum, const int32_t* __restrict__ cnt,
+                                                      const int32_t* __restrict__ nthr, const DevState* __restrict__ st, int mls,
+                                                      long long N_total, double* __restrict__ nodeFeatS,
+                                                      int32_t* __restrict__ nodeFeatT) {
     __shared__ long long wt[9];
-    long long* s = sum + (size_t)blockIdx.x * RLB_T;
+    __shared__ double sS[9];
+    __shared__ int sT[9];
+    __shared__ long long sTot;
+    const int f = blockIdx.x;
+    long long* s = sum + (size_t)f * RLB_T;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     long long v = (t < RLB_T) ? s[t] : 0;
     v = warp_incl_scan_ll(v, lane);
@@ -837,7 +891,12 @@ __global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum
     __syncthreads();
     long long off = 0;
     for (int i = 0; i < w; i++) off += wt[i];
-    if (t < RLB_T) s[t] = v + off;
+    v += off;
+    if (t < RLB_T) s[t] = v;
+    if (t == RLB_T - 1) sTot = v;
+    __syncthreads();
+    const int c = (t < RLB_T) ? cnt[(size_t)f * RLB_T + t] : 0;
+    feature_best(v, c, t, nthr[f], (int)N_total, sTot, mls, st->scale_exp, sS, sT, &nodeFeatS[f], &nodeFeatT[f]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -848,8 +907,101 @@ __global__ void __launch_bounds__(256) k_identity(int32_t* __restrict__ a, int64
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)i;
 }
 
-__global__ void k_tree_begin(DevState* st, TreeParams tp, const long long* __restrict__ histSum, int64_t N_local,
-                             long long N_total, int32_t* used, int32_t* pool) {
+// K5 (merge): FeatureHistogram.findBestSplit(sp, ...) for node st->cur (FeatureHistogram.java:296-326, 348-352), run
+// by ONE CTA.  The per-feature winners were computed when the node's histogram was produced (k_root_cumsum /
+// k_finish); here they are merged in usedFeatures order with the strict-'<' first-wins rule (= largest S,
+// lowest position) and the split decision is taken.  Loops while the selected node has no admissible split
+// (S == -1 -> RegressionTree.java:79-80 takes the leaf), so a failed scan does not use up a split step.
+__device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp, const int32_t* __restrict__ histCnt,
+                                size_t hist_stride, const double* __restrict__ nodeFeatS,
+                                const int32_t* __restrict__ nodeFeatT, int32_t* used, int32_t* pool) {
+    __shared__ double zS[9];
+    __shared__ int zP[9];
+    __shared__ int zCur;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    while (true) {
+        __syncthreads();
+        if (t == 0) zCur = (st->done ? -1 : st->cur);
+        __syncthreads();
+        const int node = zCur;
+        if (node < 0) {
+            if (t == 0) st->split_active = 0;
+            return;
+        }
+        const int nu = st->n_used;
+        double bestS = -1.0;
+        int bestPos = 0x7fffffff;
+        for (int i = t; i < nu; i += blockDim.x) {
+            const int ff = (tp.frate < 1.f) ? used[i] : i;
+            const double sv = __ldcg(&nodeFeatS[(size_t)node * tp.F + ff]);
+            if (sv > bestS) {  // positions ascend within a thread: the first maximum is kept
+                bestS = sv;
+                bestPos = i;
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            const double oS = __shfl_xor_sync(0xffffffffu, bestS, d);
+            const int oP = __shfl_xor_sync(0xffffffffu, bestPos, d);
+            if (oS > bestS || (oS == bestS && oP < bestPos)) {
+                bestS = oS;
+                bestPos = oP;
+            }
+        }
+        if (lane == 0) {
+            zS[w] = bestS;
+            zP[w] = bestPos;
+        }
+        __syncthreads();
+        if (t == 0) {
+            for (int i = 1; i < (int)(blockDim.x >> 5); i++)
+                if (zS[i] > bestS || (zS[i] == bestS && zP[i] < bestPos)) {
+                    bestS = zS[i];
+                    bestPos = zP[i];
+                }
+            if (!(bestS > -1.0)) {  // FeatureHistogram.java:311-313 -> RegressionTree.java:79-80
+                st->taken++;
+                st->split_active = 0;
+                select_next(st, tp, used, pool);
+            } else {
+                const int bestF = (tp.frate < 1.f) ? used[bestPos] : bestPos;
+                const int bestT = __ldcg(&nodeFeatT[(size_t)node * tp.F + bestF]);
+                NodeRec& sp = st->nodes[node];
+                const int total = sp.count;
+                const double sumResponse = fix2d(((const volatile NodeRec*)&sp)->sum_fix, st->scale_exp);
+                const int nl = __ldcg(&histCnt[(size_t)node * hist_stride + (size_t)bestF * RLB_T + bestT]);
+                const int nr = total - nl;
+                const int li = st->n_nodes, ri = li + 1;
+                st->n_nodes += 2;
+                st->split_active = 1;
+                st->split_node = node;
+                st->best_f = bestF;
+                st->best_t = bestT;
+                st->best_S = bestS;
+                st->n_left_g = nl;
+                st->n_right_g = nr;
+                st->small_is_left = (nl <= nr) ? 1 : 0;
+                st->small_id = st->small_is_left ? li : ri;
+                st->other_id = st->small_is_left ? ri : li;
+                st->small_sq_fix = 0;
+                st->n_splits++;
+                const double sq = fix2d(sp.sq_fix, st->scale2_exp);
+                sp.deviance = sq - sumResponse * sumResponse / total;  // Split.set(..., var) (FeatureHistogram.java:348,352)
+                sp.feature_idx = bestF;
+                sp.thr_idx = bestT;
+                sp.left = li;
+                sp.right = ri;
+                st->cur = -1;
+            }
+        }
+        __syncthreads();
+        if (st->split_active) return;   // written by thread 0 before the barrier
+    }
+}
+
+__global__ void __launch_bounds__(288) k_tree_begin(DevState* st, TreeParams tp, const long long* __restrict__ histSum, int64_t N_local,
+                             long long N_total, int32_t* used, int32_t* pool, const int32_t* __restrict__ histCnt,
+                             size_t hist_stride, const double* __restrict__ nodeFeatS, const int32_t* __restrict__ nodeFeatT) {
+    if (threadIdx.x == 0) {
     st->n_nodes = 1;
     NodeRec& r = st->nodes[0];
     r.feature_idx = -1;
@@ -877,9 +1029,13 @@ __global__ void k_tree_begin(DevState* st, TreeParams tp, const long long* __res
     st->ticket_scan = st->ticket_part = st->ticket_finish = 0;
     draw_features(st, tp, used, pool);
     st->cur = 0;
+    }
+    __syncthreads();
+    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool);  // the root's split
 }
 
-// K5: FeatureHistogram.findBestSplit(usedFeatures, mls, start, end) (FeatureHistogram.java:236-264).
+// K5 (stand-alone form, kept for reference / debugging; the step sequence uses scan_and_decide):
+// FeatureHistogram.findBestSplit(usedFeatures, mls, start, end) (FeatureHistogram.java:236-264).
 // One CTA per feature; thread t evaluates threshold t; argmax keeps the lowest t among equal S.
 // The last CTA to finish merges the features in usedFeatures order with strict '<' (first wins) and
 // takes the split decision of FeatureHistogram.findBestSplit(sp, ...) (:311-326, :348-352).
@@ -1181,16 +1337,21 @@ __global__ void __launch_bounds__(256) k_part_scatter(DevState* __restrict__ st,
 __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeParams tp, long long* __restrict__ histSum,
                                                  int32_t* __restrict__ histCnt, size_t hist_stride,
                                                  const long long* __restrict__ stageSum,
-                                                 const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool) {
+                                                 const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool,
+                                                 const int32_t* __restrict__ nthr, double* __restrict__ nodeFeatS,
+                                                 int32_t* __restrict__ nodeFeatT) {
     if (!st->split_active) return;
     __shared__ long long wtS[9];
     __shared__ int wtC[9];
     __shared__ bool amLast;
+    __shared__ double sS[9];
+    __shared__ int sT[9];
+    __shared__ long long sTotS, sTotO;
     const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int parent = st->split_node, small = st->small_id, other = st->other_id;
     const size_t o = (size_t)f * RLB_T + t;
-    long long vS = 0;
-    int vC = 0;
+    long long vS = 0, oS = 0;
+    int vC = 0, oC = 0;
     if (t < RLB_T) {
         vS = stageSum[o];
         vC = stageCnt[o];
@@ -1213,6 +1374,12 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         histCnt[(size_t)small * hist_stride + o] = vC;
         histSum[(size_t)other * hist_stride + o] = pS - vS;
         histCnt[(size_t)other * hist_stride + o] = pC - vC;
+        oS = pS - vS;
+        oC = pC - vC;
+        if (t == RLB_T - 1) {
+            sTotS = vS;
+            sTotO = pS - vS;
+        }
         if (f == 0 && t == RLB_T - 1) {
             st->nodes[small].sum_fix = vS;
             st->nodes[other].sum_fix = pS - vS;
@@ -1220,36 +1387,50 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         }
     }
     __syncthreads();
+    {   // the split scan of both children for this feature, while their cumulative histograms are in registers
+        const int cntS = st->small_is_left ? st->n_left_g : st->n_right_g;
+        const int cntO = st->small_is_left ? st->n_right_g : st->n_left_g;
+        const int se = st->scale_exp;
+        feature_best(vS, vC, t, nthr[f], cntS, sTotS, tp.mls, se, sS, sT, &nodeFeatS[(size_t)small * tp.F + f],
+                     &nodeFeatT[(size_t)small * tp.F + f]);
+        feature_best(oS, oC, t, nthr[f], cntO, sTotO, tp.mls, se, sS, sT, &nodeFeatS[(size_t)other * tp.F + f],
+                     &nodeFeatT[(size_t)other * tp.F + f]);
+    }
     if (t == 0) {
         __threadfence();
         const unsigned int tk = atomicAdd(&st->ticket_finish, 1u);
         amLast = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (!amLast || t != 0) return;
+    if (!amLast) return;
     __threadfence();
-    st->ticket_finish = 0;
-    volatile NodeRec* ns = &st->nodes[small];
-    volatile NodeRec* no = &st->nodes[other];
-    const long long sqP = st->nodes[parent].sq_fix;
-    const long long sqLeft = st->small_sq_fix;  // accumulated by the partition: squared sum of the LEFT rows
-    const long long sqS = st->small_is_left ? sqLeft : sqP - sqLeft;
-    ns->sq_fix = sqS;
-    no->sq_fix = sqP - sqS;
-    const int se = st->scale_exp, s2 = st->scale2_exp;
-    {
-        const double s = fix2d(ns->sum_fix, se);
-        ns->deviance = fix2d(sqS, s2) - s * s / ns->count;
+    if (t == 0) {
+        st->ticket_finish = 0;
+        volatile NodeRec* ns = &st->nodes[small];
+        volatile NodeRec* no = &st->nodes[other];
+        const long long sqP = st->nodes[parent].sq_fix;
+        const long long sqLeft = st->small_sq_fix;  // accumulated by the partition: squared sum of the LEFT rows
+        const long long sqS = st->small_is_left ? sqLeft : sqP - sqLeft;
+        ns->sq_fix = sqS;
+        no->sq_fix = sqP - sqS;
+        const int se = st->scale_exp, s2 = st->scale2_exp;
+        {
+            const double sv = fix2d(ns->sum_fix, se);
+            ns->deviance = fix2d(sqS, s2) - sv * sv / ns->count;
+        }
+        {
+            const double sv = fix2d(no->sum_fix, se);
+            no->deviance = fix2d(sqP - sqS, s2) - sv * sv / no->count;
+        }
+        __threadfence();
+        queue_insert(st, st->nodes[parent].left);   // RegressionTree.java:82-83: left first, then right
+        queue_insert(st, st->nodes[parent].right);
+        st->split_active = 0;
+        select_next(st, tp, used, pool);
     }
-    {
-        const double s = fix2d(no->sum_fix, se);
-        no->deviance = fix2d(sqP - sqS, s2) - s * s / no->count;
-    }
-    __threadfence();
-    queue_insert(st, st->nodes[parent].left);   // RegressionTree.java:82-83: left first, then right
-    queue_insert(st, st->nodes[parent].right);
-    st->split_active = 0;
-    select_next(st, tp, used, pool);
+    __syncthreads();
+    // the scan of the node just selected, by this (last) CTA: the next step starts with its partition
+    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool);
 }
 
 // end of RegressionTree.fit: leaves() in left-first DFS order (Split.java:100-113)
@@ -1900,7 +2081,8 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
     if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
-    k_root_cumsum<<<c->F, 288, 0, c->stream>>>(c->dHistSum);
+    k_root_cumsum<<<c->F, 288, 0, c->stream>>>(c->dHistSum, c->dHistCnt, c->dNThr, c->dState, c->prm.min_leaf_support,
+                                               (long long)c->N_total, c->dNodeFeatS, c->dNodeFeatT);
     RLB_CHECK_LAUNCH(c);
     return RLB_OK;
 }
@@ -1908,9 +2090,6 @@ int rlb_impl_hist_update(rlb_ctx* c) {
 static int enqueue_split_steps(rlb_ctx* c, int steps) {
     const TreeParams tp = tree_params(c);
     for (int s = 0; s < steps; s++) {
-        k_scan<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, c->dNThr, c->dFeatS, c->dFeatT,
-                                            c->dUsed, c->dUsed + c->F);
-        RLB_CHECK_LAUNCH(c);
         long long* stageSum = c->dHistSum + (size_t)c->max_nodes * c->hist_stride;
         int32_t* stageCnt = c->dHistCnt + (size_t)c->max_nodes * c->hist_stride;
         k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
@@ -1919,9 +2098,6 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
         rlb_prof_begin(c, 1);
-        k_hist_rows<true><<<c->sm_count, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, c->dSamples[0],
-                                                               c->dSamples[1], stageSum, stageCnt, c->dState, c->hist_min_rows);
-        RLB_CHECK_LAUNCH(c);
         k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
             c->dBins, c->Fp, c->F, c->dVfixC, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
             hist_groups(c), c->hist_min_rows);
@@ -1935,7 +2111,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             if (int rc = rlb_allreduce_i64(c, &c->dState->small_sq_fix, 1)) return rc;
         }
         k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F);
+                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;
@@ -1954,7 +2130,8 @@ int rlb_impl_tree_enqueue(rlb_ctx* c) {
     const TreeParams tp = tree_params(c);
     k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
     RLB_CHECK_LAUNCH(c);
-    k_tree_begin<<<1, 1, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F);
+    k_tree_begin<<<1, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F,
+                                           c->dHistCnt, c->hist_stride, c->dNodeFeatS, c->dNodeFeatT);
     RLB_CHECK_LAUNCH(c);
     if (int rc = enqueue_split_steps(c, c->prm.n_leaves - 1)) return rc;
     k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);

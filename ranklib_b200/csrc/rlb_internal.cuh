@@ -152,6 +152,8 @@ struct rlb_ctx {
     int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
     int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
     int32_t n_tiles = 0;
+    double* dNodeFeatS = nullptr;   // [max_nodes][F] best S of every (node, feature), computed with the node's histogram
+    int32_t* dNodeFeatT = nullptr;  // [max_nodes][F] its threshold index
     double* dFeatS = nullptr;       // per-feature best S
     int32_t* dFeatT = nullptr;      // per-feature best t
     int32_t* dUsed = nullptr;       // usedFeatures order
