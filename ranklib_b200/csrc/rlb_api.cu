@@ -199,6 +199,11 @@ int rlb_create(int device, rlb_ctx** out) {
         delete c;
         return RLB_E_CUDA;
     }
+    for (int i = 0; i < 3; i++) {
+        cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     *out = c;
     return RLB_OK;
 }
@@ -212,6 +217,11 @@ int rlb_destroy(rlb_ctx* c) {
         if (c->iter_graph[i]) cudaGraphExecDestroy(c->iter_graph[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
+    for (int i = 0; i < 3; i++) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RLB_OK;

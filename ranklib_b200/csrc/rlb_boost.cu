@@ -1998,34 +1998,54 @@ static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
     double* lam = want_lambda ? c->dLambda : nullptr;
     double* wgt = want_lambda ? c->dWeight : nullptr;
     const int k = c->prm.metric_k, m = c->prm.metric;
+    // The size classes are independent: run them as parallel branches (fork / join with events; inside a stream
+    // capture this becomes parallel graph branches).  The warp-path kernel stays on the main stream.
+    int nside = 0;
+    const bool fork = !c->trace;
+    if (fork && (c->nqB1 > 0 || c->nqB2 > 0 || c->nqC > 0)) RLB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    auto branch = [&](int i) -> cudaStream_t {
+        if (!fork) return c->stream;
+        cudaStreamWaitEvent(c->side[i], c->ev_fork, 0);
+        nside = std::max(nside, i + 1);
+        return c->side[i];
+    };
+    if (c->nqB1 > 0) {
+        const int grid = std::min(c->nqB1, c->sm_count * 4);
+        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB1, k, m, c->dDisc,
+                                                           c->dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
+        RLB_CHECK_LAUNCH(c);
+        if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
+    }
+    if (c->nqB2 > 0) {
+        const int grid = std::min(c->nqB2, c->sm_count);
+        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB1, c->nqB2, k, m,
+                                                           c->dDisc, c->dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
+        RLB_CHECK_LAUNCH(c);
+        if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
+    }
+    if (c->nqC > 0) {
+        const int grid = std::min(c->nqC, c->sm_count * 8);
+        const int32_t* ql = c->dQList + c->nqA + c->nqB1 + c->nqB2;
+        cudaStream_t sC = branch(2);
+        if (want_lambda)
+            k_query<true><<<grid, 128, 0, sC>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, lam, wgt,
+                                                qmetric, c->dState, ql);
+        else
+            k_query<false><<<grid, 128, 0, sC>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, nullptr,
+                                                 nullptr, qmetric, c->dState, ql);
+        RLB_CHECK_LAUNCH(c);
+        if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[2], c->side[2]));
+    }
     if (c->nqA > 0) {
         const int grid = std::min((c->nqA + 7) / 8, c->sm_count * 2);
         k_query_warp<<<grid, 256, smA, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList, c->nqA, k, m, c->dDisc, c->dIdeal, lam, wgt,
                                                     qmetric, c->dState);
         RLB_CHECK_LAUNCH(c);
     }
-    if (c->nqB1 > 0) {
-        const int grid = std::min(c->nqB1, c->sm_count * 4);
-        k_query_block<128><<<grid, 128, smB1, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB1, k, m, c->dDisc,
-                                                           c->dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
-        RLB_CHECK_LAUNCH(c);
-    }
-    if (c->nqB2 > 0) {
-        const int grid = std::min(c->nqB2, c->sm_count);
-        k_query_block<256><<<grid, 256, smB2, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB1, c->nqB2, k, m,
-                                                           c->dDisc, c->dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
-        RLB_CHECK_LAUNCH(c);
-    }
-    if (c->nqC > 0) {
-        const int grid = std::min(c->nqC, c->sm_count * 8);
-        const int32_t* ql = c->dQList + c->nqA + c->nqB1 + c->nqB2;
-        if (want_lambda)
-            k_query<true><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, lam,
-                                                       wgt, qmetric, c->dState, ql);
-        else
-            k_query<false><<<grid, 128, 0, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc,
-                                                        nullptr, nullptr, qmetric, c->dState, ql);
-        RLB_CHECK_LAUNCH(c);
+    if (fork) {
+        if (c->nqB1 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+        if (c->nqB2 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+        if (c->nqC > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[2], 0));
     }
     return RLB_OK;
 }

@@ -108,6 +108,8 @@ struct DevState {
 struct rlb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // fork/join branches for independent kernels (query size classes)
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     std::string err;
     // comm
     ncclComm_t comm = nullptr;
