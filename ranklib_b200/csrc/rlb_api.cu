@@ -312,6 +312,7 @@ int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
     }
     c->Q_total = q;
     if (const char* e = getenv("RLB_NO_GRAPH")) c->use_graph = (atoi(e) == 0);
+    if (const char* e = getenv("RLB_GRAPH_MULTI")) c->graph_multi = (atoi(e) != 0);
     if (const char* e = getenv("RLB_TRACE")) {
         c->trace = atoi(e) != 0;
         if (c->trace) c->use_graph = false;
@@ -385,7 +386,7 @@ int rlb_train_metric(rlb_ctx* c, float* out) {
 // One iteration = one CUDA-graph launch (captured on first use) + one stream synchronisation.
 static int boost_one(rlb_ctx* c) {
     const int gi = c->profile ? 1 : 0;
-    if (!c->use_graph || c->world > 1) {
+    if (!c->use_graph || (c->world > 1 && !c->graph_multi)) {
         if (int rc = rlb_impl_enqueue_iter(c)) return rc;
     } else {
         if (!c->lambda_fresh) {  // the captured sequence is the steady state: pseudo responses already fresh

@@ -1182,7 +1182,7 @@ __global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, c
                                                      const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
                                                      int32_t* __restrict__ tileCnt, long long* __restrict__ histSum,
                                                      int32_t* __restrict__ histCnt, size_t hist_stride,
-                                                     const long long* __restrict__ sqfix) {
+                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq) {
     if (!st->split_active) return;
     __shared__ int sw[8];
     __shared__ bool amLast;
@@ -1219,7 +1219,7 @@ __global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, c
             c += __shfl_xor_sync(0xffffffffu, c, d);
             sq += __shfl_xor_sync(0xffffffffu, sq, d);
         }
-        if ((threadIdx.x & 31) == 0 && sq != 0) atomicAdd((unsigned long long*)&st->small_sq_fix, (unsigned long long)sq);
+        if ((threadIdx.x & 31) == 0 && sq != 0) atomicAdd((unsigned long long*)stageSq, (unsigned long long)sq);
         if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1339,7 +1339,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
                                                  const long long* __restrict__ stageSum,
                                                  const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool,
                                                  const int32_t* __restrict__ nthr, double* __restrict__ nodeFeatS,
-                                                 int32_t* __restrict__ nodeFeatT) {
+                                                 int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq) {
     if (!st->split_active) return;
     __shared__ long long wtS[9];
     __shared__ int wtC[9];
@@ -1409,7 +1409,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         volatile NodeRec* ns = &st->nodes[small];
         volatile NodeRec* no = &st->nodes[other];
         const long long sqP = st->nodes[parent].sq_fix;
-        const long long sqLeft = st->small_sq_fix;  // accumulated by the partition: squared sum of the LEFT rows
+        const long long sqLeft = *(volatile long long*)stageSq;  // accumulated by the partition: squared sum of the LEFT rows
+        *stageSq = 0;                                           // ready for the next split step
         const long long sqS = st->small_is_left ? sqLeft : sqP - sqLeft;
         ns->sq_fix = sqS;
         no->sq_fix = sqP - sqS;
@@ -2110,10 +2111,14 @@ int rlb_impl_hist_update(rlb_ctx* c) {
 static int enqueue_split_steps(rlb_ctx* c, int steps) {
     const TreeParams tp = tree_params(c);
     for (int s = 0; s < steps; s++) {
-        long long* stageSum = c->dHistSum + (size_t)c->max_nodes * c->hist_stride;
-        int32_t* stageCnt = c->dHistCnt + (size_t)c->max_nodes * c->hist_stride;
+        // staging block of the scanned child, contiguous so that ONE all-reduce covers it:
+        //   [F*257 x i64 raw sums][F*257 x i32 raw counts, viewed as i64 pairs][1 x i64 left squared-sum]
+        // (adding two packed non-negative i32 as one i64 never carries across the halves: counts sum to < 2^31)
+        long long* stageSum = c->dStage;
+        int32_t* stageCnt = reinterpret_cast<int32_t*>(c->dStage + c->hist_stride);
+        long long* stageSq = c->dStage + c->hist_stride + (c->hist_stride + 1) / 2;
         k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
-                                                          stageSum, stageCnt, c->hist_stride, c->dSqfix);
+                                                          stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
         RLB_CHECK_LAUNCH(c);
         k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
         RLB_CHECK_LAUNCH(c);
@@ -2126,12 +2131,10 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         if (c->world > 1) {
             // one all-reduce per node split: raw sums + counts of the scanned child
             // and its squared-sum scalar, at fixed addresses
-            if (int rc = rlb_allreduce_i64(c, stageSum, c->hist_stride)) return rc;
-            if (int rc = rlb_allreduce_i32(c, stageCnt, c->hist_stride)) return rc;
-            if (int rc = rlb_allreduce_i64(c, &c->dState->small_sq_fix, 1)) return rc;
+            if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
         k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT);
+                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;
@@ -2148,6 +2151,7 @@ static int sync_state_header(rlb_ctx* c) {
 // k_tree_end reports as `incomplete` — rlb_impl_tree_check then adds steps.
 int rlb_impl_tree_enqueue(rlb_ctx* c) {
     const TreeParams tp = tree_params(c);
+    RLB_CUDA(c, cudaMemsetAsync(c->dStage + c->hist_stride + (c->hist_stride + 1) / 2, 0, sizeof(long long), c->stream));
     k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
     RLB_CHECK_LAUNCH(c);
     k_tree_begin<<<1, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F,

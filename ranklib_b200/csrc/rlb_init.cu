@@ -160,7 +160,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
-    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT);
+    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage);
     fr(c->dChainSum); fr(c->dChainQ); fr(c->dChainMin); fr(c->dChainMax); fr(c->dChainEf); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
@@ -370,6 +370,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dStage, (c->hist_stride + (c->hist_stride + 1) / 2 + 2) * sizeof(long long)));
     RLB_CUDA(c, alloc(c->dScore, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dLambda, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dWeight, N * sizeof(double)));

@@ -150,6 +150,7 @@ struct rlb_ctx {
     size_t hist_stride = 0;         // elements per node: F*RLB_T
     long long* dHistSum = nullptr;  // [max_nodes][F][RLB_T]
     int32_t* dHistCnt = nullptr;    // [max_nodes][F][RLB_T]
+    long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum
     int32_t* dSamples[2] = {nullptr, nullptr};
     int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
     int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
@@ -182,6 +183,7 @@ struct rlb_ctx {
     int graph_events[2] = {0, 0};
     bool capturing = false;
     bool use_graph = true;
+    bool graph_multi = false;       // capture NCCL collectives into the iteration graph (multi-GPU)
     int64_t launches_per_iter = 0;
     // development trace: one event after every kernel launch (RLB_TRACE=1, disables the graph)
     bool trace = false;

@@ -266,3 +266,10 @@ def test_full_size_properties(built):
         assert leaves["count"].sum() == N and len(leaves) == 10
         metrics.append(m)
     assert metrics[-1] > metrics[0]
+
+
+def test_yahoo_shaped_wide_features_lockstep(built):
+    """BASELINE.json configs[3] shape (700 features, 44 feature groups in the histogram kernel) at parity-test size."""
+    X, label, qoff = synth.c4(0.01)
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 4)
+    assert n_equiv == 4
