@@ -28,57 +28,78 @@ __device__ __forceinline__ float canon_value(float v) {
     return v;
 }
 
+// Row-tiled and coalesced: thread = feature, CTA = a slice of rows; every feature owns a hash set of HASH_CAP
+// slots in GLOBAL memory (F x 8 KB).  A value already present costs one plain load; inserts are atomicCAS.
+// Once a feature has more than `limit` distinct values its set is abandoned (only min / max matter then).
 __global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ X, int64_t N, int F, int limit,
-                                                   float* __restrict__ outMin, float* __restrict__ outMax,
-                                                   int* __restrict__ outNDistinct, float* __restrict__ outDistinct) {
-    __shared__ unsigned int table[HASH_CAP];
-    __shared__ int nDistinct;
-    __shared__ float sMin[256], sMax[256];
-    const int f = blockIdx.x;
-    for (int i = threadIdx.x; i < HASH_CAP; i += blockDim.x) table[i] = EMPTY_KEY;
-    if (threadIdx.x == 0) nDistinct = 0;
-    __syncthreads();
-    float mn = FLT_MAX, mx = -INFINITY;  // LambdaMART.java:112-113
-    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
-        float v = canon_value(X[k * F + f]);
-        if (mx < v) mx = v;
-        if (mn > v) mn = v;
-        if (nDistinct <= limit) {  // benign race: only an optimisation once the set has overflowed
-            unsigned int key = __float_as_uint(v);
-            unsigned int h = (key * 2654435761u) >> 21;  // 11 bits
-            for (int probe = 0; probe < HASH_CAP; probe++) {
-                unsigned int slot = (h + probe) & (HASH_CAP - 1);
-                unsigned int old = atomicCAS(&table[slot], EMPTY_KEY, key);
-                if (old == EMPTY_KEY) {
-                    atomicAdd(&nDistinct, 1);
-                    break;
+                                                   unsigned int* __restrict__ table, int* __restrict__ nDistinct,
+                                                   unsigned int* __restrict__ minBits, unsigned int* __restrict__ maxBits) {
+    const int64_t rowsPer = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = blockIdx.x * rowsPer, r1 = min(N, r0 + rowsPer);
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float mn = FLT_MAX, mx = -INFINITY;  // LambdaMART.java:112-113
+        unsigned int* tab = table + (size_t)f * HASH_CAP;
+        bool open_set = ((volatile int*)nDistinct)[f] <= limit;
+        for (int64_t k = r0; k < r1; k++) {
+            const float v = canon_value(X[k * F + f]);
+            if (mx < v) mx = v;
+            if (mn > v) mn = v;
+            if (open_set) {
+                const unsigned int key = __float_as_uint(v);
+                const unsigned int h = (key * 2654435761u) >> 21;  // 11 bits
+                for (int probe = 0; probe < HASH_CAP; probe++) {
+                    const unsigned int slot = (h + probe) & (HASH_CAP - 1);
+                    unsigned int cur = ((volatile unsigned int*)tab)[slot];
+                    if (cur == key) break;
+                    if (cur == EMPTY_KEY) {
+                        cur = atomicCAS(&tab[slot], EMPTY_KEY, key);
+                        if (cur == EMPTY_KEY) {
+                            if (atomicAdd(&nDistinct[f], 1) + 1 > limit) open_set = false;
+                            break;
+                        }
+                        if (cur == key) break;
+                    }
+                    if ((probe & 15) == 15 && ((volatile int*)nDistinct)[f] > limit) {
+                        open_set = false;
+                        break;
+                    }
                 }
-                if (old == key) break;
-                if (nDistinct > limit) break;
             }
         }
-    }
-    sMin[threadIdx.x] = mn;
-    sMax[threadIdx.x] = mx;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            sMin[threadIdx.x] = fminf(sMin[threadIdx.x], sMin[threadIdx.x + s]);
-            sMax[threadIdx.x] = fmaxf(sMax[threadIdx.x], sMax[threadIdx.x + s]);
+        // order-preserving float -> uint map so that atomicMin / atomicMax on integers order like floats
+        auto enc = [](float x) -> unsigned int {
+            const unsigned int b = __float_as_uint(x);
+            return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        };
+        if (r1 > r0) {
+            atomicMin(&minBits[f], enc(mn));
+            atomicMax(&maxBits[f], enc(mx));
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        outMin[f] = sMin[0];
-        outMax[f] = sMax[0];
+}
+
+// compacts every feature's set into outDistinct (unsorted), decodes min / max
+__global__ void k_colstats_finish(const unsigned int* __restrict__ table, const int* __restrict__ nDistinct, int F, int limit,
+                                  const unsigned int* __restrict__ minBits, const unsigned int* __restrict__ maxBits,
+                                  float* __restrict__ outMin, float* __restrict__ outMax, int* __restrict__ outND,
+                                  float* __restrict__ outDistinct) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    auto dec = [](unsigned int e) -> float {
+        const unsigned int b = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+        return __uint_as_float(b);
+    };
+    outMin[f] = dec(minBits[f]);
+    outMax[f] = dec(maxBits[f]);
+    if (nDistinct[f] <= limit) {
         int n = 0;
-        if (nDistinct <= limit) {
-            for (int i = 0; i < HASH_CAP; i++)
-                if (table[i] != EMPTY_KEY) outDistinct[(size_t)f * RLB_T + n++] = __uint_as_float(table[i]);
-            outNDistinct[f] = n;
-        } else {
-            outNDistinct[f] = limit + 1;
+        for (int i = 0; i < HASH_CAP; i++) {
+            const unsigned int k = table[(size_t)f * HASH_CAP + i];
+            if (k != EMPTY_KEY && n < RLB_T) outDistinct[(size_t)f * RLB_T + n++] = __uint_as_float(k);
         }
+        outND[f] = n;
+    } else {
+        outND[f] = limit + 1;
     }
 }
 
@@ -142,6 +163,13 @@ __global__ void k_ideal_dcg(const float* __restrict__ label, const int* __restri
         for (int c = cnt[r]; c > 0 && pos < size; c--, pos++) dcg += g * disc[pos];
     }
     ideal[q] = dcg;
+}
+
+__global__ void k_fill_u32(unsigned int* a, size_t n, unsigned int v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = v;
+}
+void rlb_fill_u32(unsigned int* a, size_t n, unsigned int v, cudaStream_t s) {
+    k_fill_u32<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, s>>>(a, n, v);
 }
 
 __global__ void k_iota(int32_t* a, int64_t n) {
@@ -293,8 +321,27 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         RLB_CUDA(c, cudaMalloc(&dMax, F * sizeof(float)));
         RLB_CUDA(c, cudaMalloc(&dND, F * sizeof(int)));
         RLB_CUDA(c, cudaMalloc(&dDist, (size_t)F * RLB_T * sizeof(float)));
-        k_colstats<<<F, 256, 0, c->stream>>>(c->dX, N, F, p->n_threshold, dMin, dMax, dND, dDist);
-        RLB_CHECK_LAUNCH(c);
+        {
+            unsigned int *dTab = nullptr, *dMinB = nullptr, *dMaxB = nullptr;
+            int* dCnt = nullptr;
+            RLB_CUDA(c, cudaMalloc(&dTab, (size_t)F * HASH_CAP * 4));
+            RLB_CUDA(c, cudaMalloc(&dMinB, F * 4));
+            RLB_CUDA(c, cudaMalloc(&dMaxB, F * 4));
+            RLB_CUDA(c, cudaMalloc(&dCnt, F * 4));
+            // EMPTY_KEY = 0x7fc00001 is not a byte pattern: fill with a kernel-free trick (memset32 via driver API
+            // is not in the runtime) -> cudaMemset2D on 4-byte rows is overkill; use a tiny fill kernel instead
+            extern void rlb_fill_u32(unsigned int*, size_t, unsigned int, cudaStream_t);
+            rlb_fill_u32(dTab, (size_t)F * HASH_CAP, EMPTY_KEY, c->stream);
+            rlb_fill_u32(dMinB, F, 0xffffffffu, c->stream);
+            RLB_CUDA(c, cudaMemsetAsync(dMaxB, 0, F * 4, c->stream));
+            RLB_CUDA(c, cudaMemsetAsync(dCnt, 0, F * 4, c->stream));
+            k_colstats<<<c->sm_count * 4, 256, 0, c->stream>>>(c->dX, N, F, p->n_threshold, dTab, dCnt, dMinB, dMaxB);
+            RLB_CHECK_LAUNCH(c);
+            k_colstats_finish<<<(F + 127) / 128, 128, 0, c->stream>>>(dTab, dCnt, F, p->n_threshold, dMinB, dMaxB, dMin, dMax, dND, dDist);
+            RLB_CHECK_LAUNCH(c);
+            RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(dTab); cudaFree(dMinB); cudaFree(dMaxB); cudaFree(dCnt);
+        }
         const int W = c->world;
         std::vector<float> hMin((size_t)F * W), hMax((size_t)F * W), hDist((size_t)F * RLB_T * W);
         std::vector<int> hND((size_t)F * W);
