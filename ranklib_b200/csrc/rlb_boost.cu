@@ -984,6 +984,7 @@ __device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp,
                 st->other_id = st->small_is_left ? ri : li;
                 st->small_sq_fix = 0;
                 st->n_splits++;
+                st->part_epoch++;
                 const double sq = fix2d(sp.sq_fix, st->scale2_exp);
                 sp.deviance = sq - sumResponse * sumResponse / total;  // Split.set(..., var) (FeatureHistogram.java:348,352)
                 sp.feature_idx = bestF;
@@ -1175,6 +1176,130 @@ __global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreePar
     st->cur = -1;
 }
 
+// K6 (single GPU): the stable partition of FeatureHistogram.java:328-341 in ONE pass.  With one GPU the number
+// of rows going left is known before the partition (it is count[bestF][bestT] of the node's histogram), so the
+// right rows' base is known too and a chained scan suffices: tiles are handed out by an atomic ticket (a tile
+// is always started after its predecessors, which makes the look-back deadlock free); tile t publishes its left
+// count (flag 1), looks back until it meets an inclusive prefix (flag 2), publishes its own inclusive prefix and
+// scatters.  Tile states carry the split ordinal as an epoch, so nothing has to be cleared between steps.
+// Also: clears the staging histogram slot, accumulates the squared responses of the rows on the scanned side,
+// creates the two child records.
+__global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, const uint16_t* __restrict__ bins, int Fp,
+                                                     int32_t* __restrict__ samples0, int32_t* __restrict__ samples1,
+                                                     unsigned long long* __restrict__ tileState, long long* __restrict__ stageSum,
+                                                     int32_t* __restrict__ stageCnt, size_t hist_stride,
+                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq) {
+    if (!st->split_active) return;
+    __shared__ int sw[8];
+    __shared__ int sTile, sExcl;
+    const NodeRec& rec = st->nodes[st->split_node];
+    const int lo = rec.lo, n = rec.hi - rec.lo;
+    const int32_t* src = rec.buf ? samples1 : samples0;
+    int32_t* dst = rec.buf ? samples0 : samples1;
+    const int bf = st->best_f, btv = st->best_t;
+    const int nl = st->n_left_g;
+    const bool smallLeft = st->small_is_left != 0;
+    const unsigned long long epoch = (unsigned long long)(st->part_epoch & 0x3fffffffu);
+    const int tiles = (n + RLB_PART_TILE - 1) / RLB_PART_TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hist_stride; i += (size_t)gridDim.x * blockDim.x) {
+        stageSum[i] = 0;
+        stageCnt[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // child records (FeatureHistogram.java:353-354)
+        NodeRec& l = st->nodes[rec.left];
+        NodeRec& r = st->nodes[rec.right];
+        l.feature_idx = r.feature_idx = -1;
+        l.thr_idx = r.thr_idx = -1;
+        l.left = l.right = r.left = r.right = -1;
+        l.buf = r.buf = 1 - rec.buf;
+        l.lo = lo;
+        l.hi = lo + nl;
+        r.lo = lo + nl;
+        r.hi = rec.hi;
+        l.count = st->n_left_g;
+        r.count = st->n_right_g;
+        l.output = r.output = 0.f;
+        l.leaf_ord = r.leaf_ord = -1;
+        l.deviance = r.deviance = 0.0;
+        st->n_left_l = nl;
+        st->n_right_l = n - nl;
+    }
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTile = (int)atomicAdd(&st->ticket_part, 1u);
+        __syncthreads();
+        const int tile = sTile;
+        if (tile >= tiles) break;
+        const int tbase = tile * RLB_PART_TILE;
+        const int base = tbase + threadIdx.x * 8;
+        int doc[8];
+        unsigned int mask = 0;
+        int c = 0;
+        long long sq = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = base + k;
+            doc[k] = (i < n) ? src[lo + i] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (doc[k] >= 0) {
+                const bool left = bins[(size_t)doc[k] * Fp + bf] <= btv;
+                if (left) {
+                    mask |= 1u << k;
+                    c++;
+                }
+                if (left == smallLeft) sq += sqfix[doc[k]];  // squared responses of the scanned (smaller) child
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+        if (lane == 0 && sq != 0) atomicAdd((unsigned long long*)stageSq, (unsigned long long)sq);
+        const int inc = warp_incl_scan_i(c, lane);
+        if (lane == 31) sw[w] = inc;
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int k = 0; k < 8; k++) {
+            if (k < w) off += sw[k];
+            tot += sw[k];
+        }
+        if (threadIdx.x == 0) {
+            // publish the aggregate, look back for the exclusive prefix, publish the inclusive prefix
+            volatile unsigned long long* ts = tileState;
+            int excl = 0;
+            if (tile > 0) {
+                ts[tile] = (epoch << 34) | (1ull << 32) | (unsigned long long)(unsigned int)tot;
+                __threadfence();
+                for (int p = tile - 1; p >= 0; p--) {
+                    unsigned long long v;
+                    do {
+                        v = ts[p];
+                    } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0ull);
+                    excl += (int)(unsigned int)(v & 0xffffffffull);
+                    if (((v >> 32) & 3ull) == 2ull) break;
+                }
+            }
+            ts[tile] = (epoch << 34) | (2ull << 32) | (unsigned long long)(unsigned int)(excl + tot);
+            __threadfence();
+            sExcl = excl;
+        }
+        __syncthreads();
+        const int toff = sExcl;                                 // lefts before this tile
+        const int leftBefore = off + inc - c;                   // lefts of this tile before this thread
+        int lpos = lo + toff + leftBefore;
+        int rpos = lo + nl + (tbase - toff) + (threadIdx.x * 8 - leftBefore);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (doc[k] >= 0) {
+                if (mask & (1u << k))
+                    dst[lpos++] = doc[k];
+                else
+                    dst[rpos++] = doc[k];
+            }
+        }
+    }
+}
+
 // K6a: count the rows of every tile that go left (FeatureHistogram.java:334-341); zero the
 // histogram slot of the child that will be scanned; the last CTA turns tile counts into offsets and
 // creates the two child records.
@@ -1339,7 +1464,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
                                                  const long long* __restrict__ stageSum,
                                                  const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool,
                                                  const int32_t* __restrict__ nthr, double* __restrict__ nodeFeatS,
-                                                 int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq) {
+                                                 int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq, int sqIsSmall) {
     if (!st->split_active) return;
     __shared__ long long wtS[9];
     __shared__ int wtC[9];
@@ -1409,9 +1534,11 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         volatile NodeRec* ns = &st->nodes[small];
         volatile NodeRec* no = &st->nodes[other];
         const long long sqP = st->nodes[parent].sq_fix;
-        const long long sqLeft = *(volatile long long*)stageSq;  // accumulated by the partition: squared sum of the LEFT rows
-        *stageSq = 0;                                           // ready for the next split step
-        const long long sqS = st->small_is_left ? sqLeft : sqP - sqLeft;
+        const long long sqAcc = *(volatile long long*)stageSq;  // accumulated by the partition pass
+        *stageSq = 0;                                          // ready for the next split step
+        st->ticket_part = 0;
+        // one-pass partition (single GPU): squares of the scanned child; two-pass (multi GPU): squares of the LEFT rows
+        const long long sqS = sqIsSmall ? sqAcc : (st->small_is_left ? sqAcc : sqP - sqAcc);
         ns->sq_fix = sqS;
         no->sq_fix = sqP - sqS;
         const int se = st->scale_exp, s2 = st->scale2_exp;
@@ -2117,11 +2244,17 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         long long* stageSum = c->dStage;
         int32_t* stageCnt = reinterpret_cast<int32_t*>(c->dStage + c->hist_stride);
         long long* stageSq = c->dStage + c->hist_stride + (c->hist_stride + 1) / 2;
-        k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
-                                                          stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
-        RLB_CHECK_LAUNCH(c);
-        k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
-        RLB_CHECK_LAUNCH(c);
+        if (c->world == 1) {
+            k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileState,
+                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
+            RLB_CHECK_LAUNCH(c);
+        } else {  // local left counts are not known in advance: count pass + scatter pass
+            k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
+                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
+            RLB_CHECK_LAUNCH(c);
+            k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
+            RLB_CHECK_LAUNCH(c);
+        }
         rlb_prof_begin(c, 1);
         k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
             c->dBins, c->Fp, c->F, c->dVfixC, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
@@ -2134,7 +2267,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
         k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq);
+                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, c->world == 1 ? 1 : 0);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;

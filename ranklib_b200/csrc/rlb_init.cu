@@ -188,7 +188,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
-    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage);
+    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
     fr(c->dChainSum); fr(c->dChainQ); fr(c->dChainMin); fr(c->dChainMax); fr(c->dChainEf); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
@@ -433,6 +433,8 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dNodeOf, N * sizeof(int32_t)));
     c->n_tiles = (int)((N + RLB_PART_TILE - 1) / RLB_PART_TILE) + 1;
     RLB_CUDA(c, alloc(c->dTileCnt, (size_t)c->n_tiles * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dTileState, (size_t)c->n_tiles * sizeof(unsigned long long)));
+    RLB_CUDA(c, cudaMemsetAsync(c->dTileState, 0xff, (size_t)c->n_tiles * sizeof(unsigned long long), c->stream));
     RLB_CUDA(c, alloc(c->dNodeFeatS, (size_t)c->max_nodes * F * sizeof(double)));
     RLB_CUDA(c, alloc(c->dNodeFeatT, (size_t)c->max_nodes * F * sizeof(int32_t)));
     RLB_CUDA(c, alloc(c->dFeatS, F * sizeof(double)));

@@ -85,6 +85,7 @@ struct DevState {
     double best_S;
     // last-block tickets
     uint32_t ticket_scan, ticket_part, ticket_finish;
+    uint32_t part_epoch;    // split counter that is never reset: epoch of the one-pass partition's tile states
     // feature sampling (FeatureHistogram.java:271-294)
     long long rng_seed;     // java.util.Random state
     int32_t n_used;
@@ -154,6 +155,7 @@ struct rlb_ctx {
     int32_t* dSamples[2] = {nullptr, nullptr};
     int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
     int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
+    unsigned long long* dTileState = nullptr;  // chained-scan tile states of the one-pass partition
     int32_t n_tiles = 0;
     double* dNodeFeatS = nullptr;   // [max_nodes][F] best S of every (node, feature), computed with the node's histogram
     int32_t* dNodeFeatT = nullptr;  // [max_nodes][F] its threshold index
