@@ -85,42 +85,63 @@ __device__ void draw_features(DevState* st, const TreeParams& tp, int32_t* used,
 __device__ void queue_insert(DevState* st, int node) {
     int i = 0;
     const double d = st->nodes[node].deviance;
-    while (i < st->qlen) {
-        if (st->nodes[st->queue[i]].deviance > d)
+    const int cnt = st->nodes[node].count;
+    const int ql = st->qlen;
+    while (i < ql) {
+        if (st->qdev[i] > d)
             i++;
         else
             break;
     }
-    for (int j = st->qlen; j > i; j--) st->queue[j] = st->queue[j - 1];
+    for (int j = ql; j > i; j--) {
+        st->queue[j] = st->queue[j - 1];
+        st->qdev[j] = st->qdev[j - 1];
+        st->qcnt[j] = st->qcnt[j - 1];
+    }
     st->queue[i] = node;
-    st->qlen++;
+    st->qdev[i] = d;
+    st->qcnt[i] = cnt;
+    st->qlen = ql + 1;
 }
 
 // the head of RegressionTree.fit's while loop (RegressionTree.java:69-77) up to the point where a
 // histogram scan is needed; the cheap rejections are consumed here.
 __device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, int32_t* pool) {
+    int head = 0, ql = st->qlen, taken = st->taken;
+    int chosen = -1;
     while (true) {
-        if (!(st->taken + st->qlen < tp.n_leaves) || st->qlen == 0) {
-            st->cur = -1;
-            st->done = 1;
-            return;
-        }
-        const int leaf = st->queue[0];
-        for (int j = 0; j + 1 < st->qlen; j++) st->queue[j] = st->queue[j + 1];
-        st->qlen--;
-        if (st->nodes[leaf].count < 2 * tp.mls) {
-            st->taken++;
+        if (!(taken + (ql - head) < tp.n_leaves) || ql - head == 0) break;
+        const int leaf = st->queue[head];
+        const int cnt = st->qcnt[head];
+        const double dev = st->qdev[head];
+        head++;
+        if (cnt < 2 * tp.mls) {
+            taken++;
             continue;
         }
-        const double dev = st->nodes[leaf].deviance;
         if (dev >= 0.0 && dev <= 0.0) {  // FeatureHistogram.java:267-269
-            st->taken++;
+            taken++;
             continue;
         }
-        draw_features(st, tp, used, pool);
-        st->cur = leaf;
+        chosen = leaf;
+        break;
+    }
+    if (head > 0) {  // drop the popped entries
+        for (int j = head; j < ql; j++) {
+            st->queue[j - head] = st->queue[j];
+            st->qdev[j - head] = st->qdev[j];
+            st->qcnt[j - head] = st->qcnt[j];
+        }
+    }
+    st->qlen = ql - head;
+    st->taken = taken;
+    if (chosen < 0) {
+        st->cur = -1;
+        st->done = 1;
         return;
     }
+    draw_features(st, tp, used, pool);
+    st->cur = chosen;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,6 +100,8 @@ struct DevState {
     float train_metric;
     float chain_out[4];
     int32_t queue[RLB_MAX_NODES];
+    int32_t qcnt[RLB_MAX_NODES];             // sample count of every queued node (kept next to the queue: the controller
+    double qdev[RLB_MAX_NODES];              // is one thread chasing global memory, so its data sits in few cache lines)
     int32_t leaf_nodes[RLB_MAX_LEAVES + 1];   // node ids of the leaves in leaves() order
     int32_t leaf_lo[RLB_MAX_LEAVES + 1];      // their segment starts (ascending) + N sentinel
     float leaf_s1[RLB_MAX_LEAVES + 1], leaf_s2[RLB_MAX_LEAVES + 1];
