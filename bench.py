@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--sample", type=float, default=0.05, help="fraction of the workload the CPU arms run on")
+    ap.add_argument("--sample", type=float, default=0.25, help="fraction of the workload the CPU arms run on")
     ap.add_argument("--scale", type=float, default=1.0, help="(development) shrink the GPU workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -274,7 +274,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_hist_rows<root> (FeatureHistogram.update)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_hist_priv<root> (FeatureHistogram.update)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": root_ms,
                 "share_of_step": (prof[0] / ms) if ms > 0 else None,
@@ -289,7 +289,7 @@ def main():
         Xc, lc, qc = synth.c2(args.sample)
         o = orc.Oracle(Xc, lc, qc, orc.make_params(), nthreads=cores)
         o.boost_iters_timed(1)
-        n_it = 10
+        n_it = 20
         t0 = time.perf_counter()
         o.boost_iters_timed(n_it)
         dt = time.perf_counter() - t0

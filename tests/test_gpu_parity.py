@@ -273,3 +273,39 @@ def test_yahoo_shaped_wide_features_lockstep(built):
     X, label, qoff = synth.c4(0.01)
     n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 4)
     assert n_equiv == 4
+
+
+@pytest.mark.parametrize("kw", [dict(metric=1), dict(n_threshold=16), dict(n_leaves=2), dict(k=3), dict(k=100), dict(lr=0.05, n_leaves=31)],
+                         ids=["dcg", "tc16", "stumps", "ndcg3", "ndcg100", "lr-leaves31"])
+def test_parameter_variants_lockstep(built, kw):
+    """-metric2t DCG@10, -tc 16, -leaf 2, NDCG@3 / NDCG@100 (cutoff above every query size), -shrinkage / -leaf."""
+    X, label, qoff = synth.c1()
+    n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 4, **kw)
+    assert n_equiv == 4
+
+
+def test_degenerate_targets(built):
+    """All labels equal: every lambda is 0, the root still splits on the first admissible candidate (S = 0 > -1,
+    FeatureHistogram.java:255) and both children have deviance 0 and are never split (:267-269)."""
+    X, label, qoff = synth.c1()
+    label = np.full_like(label, 2.0)
+    o, g = _pair(X, label, qoff)
+    for _ in range(2):
+        on, mo = o.boost_iter()
+        gn, mg = g.boost_iter()
+        assert len(on) == len(gn) == 3
+        np.testing.assert_array_equal(on["feature_idx"], gn["feature_idx"])
+        np.testing.assert_array_equal(on["threshold_idx"], gn["threshold_idx"])
+        np.testing.assert_array_equal(on["output"], gn["output"])
+        assert mo == mg
+    np.testing.assert_array_equal(o.read("SCORE"), g.read("SCORE"))
+
+
+def test_single_query_and_tiny_sets(built):
+    rng = np.random.default_rng(5)
+    for N, Q in [(2, 1), (3, 3), (17, 1), (64, 2)]:
+        X = rng.standard_normal((N, 3)).astype(np.float32)
+        label = rng.integers(0, 3, N).astype(np.float32)
+        qoff = np.linspace(0, N, Q + 1).astype(np.int32)
+        n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 3, n_leaves=4)
+        assert n_equiv == 3
