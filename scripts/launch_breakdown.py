@@ -8,7 +8,7 @@ which = [int(a) for a in sys.argv[2:]] or [3]
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = [(x["Kernel Name"].split("(")[0].replace("void ", ""), float(x["Metric Value"])) for x in csv.DictReader(lines)]
-starts = [i for i, (k, v) in enumerate(rows) if k == "k_scale"]
+starts = [i for i, (k, v) in enumerate(rows) if k == "k_quantise"]
 print("launches", len(rows), "iterations seen", len(starts))
 for it in which:
     seg = rows[starts[it]:starts[it + 1]] if it + 1 < len(starts) else rows[starts[it]:]
