@@ -557,6 +557,17 @@ int rlb_stats(rlb_ctx* c, int64_t out[4]) {
         if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
             cudaMemcpy(&fb, &c->dState->chain_fallback, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
             out[2] = s + (fb << 32);
+#ifdef RLB_CHAIN_DEBUG
+        long long dbg[3];
+        cudaMemcpy(dbg, c->dState->chain_dbg, 24, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "chain fallbacks: no-summary %lld, exponent/sign mismatch %lld, range %lld\n", dbg[0], dbg[1], dbg[2]);
+        cudaMemset(c->dState->chain_dbg, 0, 24);
+        static long long prof[64][4];
+        cudaMemcpy(prof, c->dState->chain_prof, sizeof(prof), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 20; i++)
+            fprintf(stderr, "  chain leaf %d %s: chunks %lld walk %lld cyc, fallback %lld cyc in %lld fallbacks\n", i / 2, (i & 1) ? "w" : "lambda",
+                    prof[i][3], prof[i][0], prof[i][1], prof[i][2]);
+#endif
     }
     return RLB_OK;
 }

@@ -1284,25 +1284,43 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
             if (k < w) off += sw[k];
             tot += sw[k];
         }
-        if (threadIdx.x == 0) {
-            // publish the aggregate, look back for the exclusive prefix, publish the inclusive prefix
+        if (w == 0) {
+            // warp 0: publish the aggregate, look back 32 predecessors at a time for the exclusive prefix,
+            // publish the inclusive prefix (decoupled look-back)
             volatile unsigned long long* ts = tileState;
             int excl = 0;
             if (tile > 0) {
-                ts[tile] = (epoch << 34) | (1ull << 32) | (unsigned long long)(unsigned int)tot;
-                __threadfence();
-                for (int p = tile - 1; p >= 0; p--) {
-                    unsigned long long v;
-                    do {
-                        v = ts[p];
-                    } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0ull);
-                    excl += (int)(unsigned int)(v & 0xffffffffull);
-                    if (((v >> 32) & 3ull) == 2ull) break;
+                if (lane == 0) {
+                    ts[tile] = (epoch << 34) | (1ull << 32) | (unsigned long long)(unsigned int)tot;
+                    __threadfence();
+                }
+                int p = tile - 1;  // lane l inspects tile p - l
+                while (true) {
+                    const int q = p - lane;
+                    unsigned long long v = 0;
+                    bool ready = true;
+                    if (q >= 0) {
+                        do {
+                            v = ts[q];
+                        } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0ull);
+                    }
+                    (void)ready;
+                    const bool isPrefix = (q >= 0) && (((v >> 32) & 3ull) == 2ull);
+                    const unsigned int pm = __ballot_sync(0xffffffffu, isPrefix);
+                    // tiles p .. p-k where k is the first lane holding an inclusive prefix (or all 32 / down to tile 0)
+                    const int k = pm ? (__ffs(pm) - 1) : 31;
+                    int val = (q >= 0 && lane <= k) ? (int)(unsigned int)(v & 0xffffffffull) : 0;
+                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                    excl += val;
+                    if (pm || p - 31 <= 0) break;
+                    p -= 32;
                 }
             }
-            ts[tile] = (epoch << 34) | (2ull << 32) | (unsigned long long)(unsigned int)(excl + tot);
-            __threadfence();
-            sExcl = excl;
+            if (lane == 0) {
+                ts[tile] = (epoch << 34) | (2ull << 32) | (unsigned long long)(unsigned int)(excl + tot);
+                __threadfence();
+                sExcl = excl;
+            }
         }
         __syncthreads();
         const int toff = sExcl;                                 // lefts before this tile
@@ -1968,60 +1986,100 @@ __global__ void __launch_bounds__(256) k_chain_summ(int mode, const DevState* __
     }
 }
 
-// Walk the chunk summaries of one chain (all threads of a 1024-thread CTA call this).  Summaries are
-// staged through shared memory 1024 chunks at a time so that the walking thread never waits on HBM.
+// Walk the chunk summaries of one chain (all threads of the CTA call this).  Warp 0 takes 32 consecutive
+// chunks at a time: lane l assumes the running float keeps the exponent and sign it has at the first of
+// them, computes the mantissa at the start of ITS chunk from an exclusive warp scan of the quanta totals, and
+// checks its chunk's summary (valid for that exponent / sign, prefix minimum and maximum keep the mantissa
+// inside (2^23, 2^24)).  Everything before the first failing lane is committed in one step; the failing
+// chunk is redone exactly by the whole CTA (chain_block) and the walk resumes behind it.
 __device__ float chain_two_level(const ChainView v, int c0, int c1, int which, float carry, const ChainBufs& cb,
                                  long long* serialCount) {
     __shared__ float sCur;
     __shared__ int sStop;
-    __shared__ long long bQ[RLB_CHAIN_THREADS], bMin[RLB_CHAIN_THREADS], bMax[RLB_CHAIN_THREADS];
-    __shared__ int bEf[RLB_CHAIN_THREADS];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t o = (size_t)which * cb.maxChunks;
     if (tid == 0) sCur = carry;
-    for (int cbase = c0; cbase < c1; cbase += RLB_CHAIN_THREADS) {
-        const int cend = min(c1, cbase + RLB_CHAIN_THREADS);
-        __syncthreads();
-        if (cbase + tid < cend) {
-            bQ[tid] = cb.Qtot[o + cbase + tid];
-            bMin[tid] = cb.Pmin[o + cbase + tid];
-            bMax[tid] = cb.Pmax[o + cbase + tid];
-            bEf[tid] = cb.ef[o + cbase + tid];
+#ifdef RLB_CHAIN_DEBUG
+    long long cycWalk = 0, cycFb = 0, nFb = 0;
+    long long tmark = clock64();
+#endif
+    int c = c0;
+    __syncthreads();
+    while (c < c1) {
+        if (tid < 32) {
+            float s = sCur;
+            int i = c;
+            bool failed = false;
+            while (i < c1 && !failed) {
+                const int me = i + lane;
+                const bool in = me < c1;
+                int ef = 2;  // out-of-range lanes behave like all-zero chunks
+                long long q = 0, pmn = 0, pmx = 0;
+                if (in) {
+                    ef = cb.ef[o + me];
+                    q = cb.Qtot[o + me];
+                    pmn = cb.Pmin[o + me];
+                    pmx = cb.Pmax[o + me];
+                }
+                const bool zero = (ef & 2) != 0;
+                if (zero) q = 0;
+                const unsigned int bits = __float_as_uint(s);
+                const long long M0 = (long long)((bits & 0x7fffffu) | 0x800000u);
+                const long long incl = warp_incl_scan_ll(q, lane);
+                const long long Mi = M0 + incl - q;  // mantissa at the start of my chunk if all earlier lanes are valid
+                bool ok = zero;
+                if (!zero)
+                    ok = (ef & 1) && (int)((bits >> 23) & 0xff) == (ef >> 8) && (int)(bits >> 31) == ((ef >> 2) & 1) &&
+                         (Mi + pmn > 8388608LL) && (Mi + pmx < 16777216LL);
+                const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+                const int f = bad ? (__ffs(bad) - 1) : 32;  // first failing lane
+                // the non-zero chunks before f moved the mantissa by their quanta; exponent and sign unchanged
+                const long long upto = __shfl_sync(0xffffffffu, incl, f > 0 ? f - 1 : 0);
+                if (f > 0) {
+                    const long long Mn = M0 + upto;
+                    if (Mn != M0) s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mn & 0x7fffffu));
+                }
+                i += f;
+                if (f < 32) failed = true;  // chunk i needs the exact path (or lies beyond c1: handled below)
+            }
+            if (lane == 0) {
+                sCur = s;
+                sStop = min(i, c1);
+            }
         }
         __syncthreads();
-        int c = cbase;
-        while (c < cend) {
-            if (tid == 0) {
-                float s = sCur;
-                int i = c;
-                for (; i < cend; i++) {
-                    const int ef = bEf[i - cbase];
-                    if (ef & 2) continue;  // nothing but zeros: s + 0 = s
-                    const unsigned int bits = __float_as_uint(s);
-                    if (!(ef & 1) || (int)((bits >> 23) & 0xff) != (ef >> 8) || (int)(bits >> 31) != ((ef >> 2) & 1)) break;
-                    const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
-                    if (!(M + bMin[i - cbase] > 8388608LL && M + bMax[i - cbase] < 16777216LL)) break;
-                    s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)(M + bQ[i - cbase]) & 0x7fffffu));
-                }
-                sCur = s;
-                sStop = i;
-            }
-            __syncthreads();
-            const int stop = sStop;
-            const float s = sCur;
-            if (stop >= cend) break;
-            const int64_t off = (int64_t)(stop - c0) * CK;
-            const int64_t len = min((int64_t)CK, v.n - off);
-            const float s2 = chain_block(v.val, v.idx ? v.idx + off : nullptr, len, s, serialCount, v.idx ? 0 : off);
-            __syncthreads();
-            if (tid == 0) {
-                sCur = s2;
-                atomicAdd((unsigned long long*)(serialCount + 1), 1ull);  // chain_fallback follows chain_serial
-            }
-            c = stop + 1;
-            __syncthreads();
+        const int stop = sStop;
+        const float s = sCur;
+#ifdef RLB_CHAIN_DEBUG
+        { const long long now = clock64(); cycWalk += now - tmark; tmark = now; }
+#endif
+        if (stop >= c1) break;
+        const int64_t off = (int64_t)(stop - c0) * CK;
+        const int64_t len = min((int64_t)CK, v.n - off);
+        const float s2 = chain_block(v.val, v.idx ? v.idx + off : nullptr, len, s, serialCount, v.idx ? 0 : off);
+        __syncthreads();
+        if (tid == 0) {
+            sCur = s2;
+            atomicAdd((unsigned long long*)(serialCount + 1), 1ull);  // chain_fallback follows chain_serial
+        }
+        c = stop + 1;
+        __syncthreads();
+#ifdef RLB_CHAIN_DEBUG
+        { const long long now = clock64(); cycFb += now - tmark; tmark = now; nFb++; }
+#endif
+    }
+#ifdef RLB_CHAIN_DEBUG
+    if (tid == 0 && gridDim.x > 1) {
+        DevState* dst = (DevState*)((char*)serialCount - offsetof(DevState, chain_serial));
+        const int slot = blockIdx.x * 2 + blockIdx.y;
+        if (slot < 64) {
+            dst->chain_prof[slot][0] = cycWalk;
+            dst->chain_prof[slot][1] = cycFb;
+            dst->chain_prof[slot][2] = nFb;
+            dst->chain_prof[slot][3] = c1 - c0;
         }
     }
+#endif
     __syncthreads();
     const float r = sCur;
     __syncthreads();

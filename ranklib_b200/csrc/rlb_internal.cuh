@@ -96,6 +96,8 @@ struct DevState {
     long long n_splits;
     long long chain_serial; // float-chain elements that took the exact serial path
     long long chain_fallback; // float-chain chunks redone exactly (speculation miss or binade crossing)
+    long long chain_dbg[3];   // RLB_CHAIN_DEBUG: fallbacks by reason (no summary / exponent-sign mismatch / range)
+    long long chain_prof[64][4]; // RLB_CHAIN_DEBUG: per chain (leaf*2+which): walk cycles, fallback cycles, fallbacks, chunks
     long long small_sq_fix; // scratch: squared-sum of the rows going LEFT (local, then all-reduced)
     float train_metric;
     float chain_out[4];
