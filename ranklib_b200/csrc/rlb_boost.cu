@@ -1205,7 +1205,7 @@ __global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreePar
 // scatters.  Tile states carry the split ordinal as an epoch, so nothing has to be cleared between steps.
 // Also: clears the staging histogram slot, accumulates the squared responses of the rows on the scanned side,
 // creates the two child records.
-__global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, const uint16_t* __restrict__ bins, int Fp,
+__global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, const uint16_t* __restrict__ binsT, int64_t Nrows,
                                                      int32_t* __restrict__ samples0, int32_t* __restrict__ samples1,
                                                      unsigned long long* __restrict__ tileState, long long* __restrict__ stageSum,
                                                      int32_t* __restrict__ stageCnt, size_t hist_stride,
@@ -1221,6 +1221,7 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
     const int nl = st->n_left_g;
     const bool smallLeft = st->small_is_left != 0;
     const unsigned long long epoch = (unsigned long long)(st->part_epoch & 0x3fffffffu);
+    const uint16_t* __restrict__ bcol = binsT + (size_t)bf * Nrows;  // the split feature's column
     const int tiles = (n + RLB_PART_TILE - 1) / RLB_PART_TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hist_stride; i += (size_t)gridDim.x * blockDim.x) {
@@ -1266,7 +1267,7 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (doc[k] >= 0) {
-                const bool left = bins[(size_t)doc[k] * Fp + bf] <= btv;
+                const bool left = bcol[doc[k]] <= btv;
                 if (left) {
                     mask |= 1u << k;
                     c++;
@@ -2324,7 +2325,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         int32_t* stageCnt = reinterpret_cast<int32_t*>(c->dStage + c->hist_stride);
         long long* stageSq = c->dStage + c->hist_stride + (c->hist_stride + 1) / 2;
         if (c->world == 1) {
-            k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileState,
+            k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1], c->dTileState,
                                                               stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
             RLB_CHECK_LAUNCH(c);
         } else {  // local left counts are not known in advance: count pass + scatter pass

@@ -109,7 +109,8 @@ __global__ void k_colstats_finish(const unsigned int* __restrict__ table, const 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, int64_t N, int F, int Fp,
                                                   const float* __restrict__ thr, const int* __restrict__ nthr,
-                                                  uint16_t* __restrict__ bins, int* __restrict__ rootCnt) {
+                                                  uint16_t* __restrict__ bins, uint16_t* __restrict__ binsT,
+                                                  int* __restrict__ rootCnt) {
     const int64_t total = N * (int64_t)Fp;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = i / Fp;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, in
                 lo = mid + 1;
         }
         bins[i] = (uint16_t)lo;
+        binsT[(size_t)f * N + k] = (uint16_t)lo;
         atomicAdd(&rootCnt[(size_t)f * RLB_T + lo], 1);
     }
 }
@@ -185,7 +187,7 @@ void rlb_impl_free(rlb_ctx* c) {
         if (p) cudaFree(p);
         p = nullptr;
     };
-    fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
+    fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
@@ -415,6 +417,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         return cudaMalloc(&ptr, bytes);
     };
     RLB_CUDA(c, alloc(c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
+    RLB_CUDA(c, alloc(c->dBinsT, (size_t)N * F * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
     RLB_CUDA(c, alloc(c->dStage, (c->hist_stride + (c->hist_stride + 1) / 2 + 2) * sizeof(long long)));
@@ -470,7 +473,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     }
 
     // ---- binning + root counts ----
-    k_binning<<<c->grid_rows, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dHistCnt);
+    k_binning<<<c->grid_rows, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, c->dHistCnt);
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i32(c, c->dHistCnt, c->hist_stride)) return rc;
     k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCnt, F);

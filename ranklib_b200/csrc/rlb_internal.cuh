@@ -133,6 +133,7 @@ struct rlb_ctx {
     int32_t* dQoff = nullptr;
     int32_t* dQidOfDoc = nullptr;
     uint16_t* dBins = nullptr;      // [N][Fp]
+    uint16_t* dBinsT = nullptr;     // [F][N] feature-major copy: the partition reads ONE feature of many (ascending) rows
     float* dThr = nullptr;          // [F][RLB_T]
     int32_t* dNThr = nullptr;       // [F]
     double* dDisc = nullptr;        // discount table [max_query + 1]
