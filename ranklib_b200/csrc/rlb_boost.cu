@@ -670,6 +670,24 @@ __device__ __forceinline__ void hist_batch4(long long* Hme, int b0, int b1, int 
     Hme[b3 * T] = h3;
 }
 
+// Default batch (RLB_HIST_VARIANT=1 selects the accumulator-forwarding form above for comparison): merge the
+// ADDENDS of equal bins instead of forwarding accumulators.  The later row
+// of a pair of equal bins carries the running total (its store lands last: a thread's shared-memory stores are
+// ordered), so the four read-modify-writes are independent and the merging, which needs only the bins and the
+// addends, overlaps the accumulator loads.  Branch-free selects.
+template <int T>
+__device__ __forceinline__ void hist_batch4_merge(long long* Hme, int b0, int b1, int b2, int b3, long long v0, long long v1,
+                                                  long long v2, long long v3) {
+    const long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
+    v1 += (b1 == b0) ? v0 : 0LL;
+    v2 += (b2 == b1) ? v1 : ((b2 == b0) ? v0 : 0LL);
+    v3 += (b3 == b2) ? v2 : ((b3 == b1) ? v1 : ((b3 == b0) ? v0 : 0LL));
+    Hme[b0 * T] = h0 + v0;
+    Hme[b1 * T] = h1 + v1;
+    Hme[b2 * T] = h2 + v2;
+    Hme[b3 * T] = h3 + v3;
+}
+
 // Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
 // per non-empty entry and clear the private copies.  Consumer threads only (named barrier 1).
 template <bool CHILD, int PH>
@@ -709,7 +727,7 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 //             stages in flight hide the HBM latency that 3 resident warps could not.
 //   consumer: thread (fi, ph) owns histogram column tid of H[bin][tid] and the rows ph, ph+PH, ... of
 //             each stage.
-template <bool CHILD, int PH>
+template <bool CHILD, int PH, int VAR = 0>
 __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     k_hist_priv(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfix,
                 const long long* __restrict__ sqfix, int64_t N, const int32_t* __restrict__ samples0,
@@ -796,14 +814,33 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
                         cpasync8(vt + j, vfix + row);
                     }
                 }
-            } else {
-                for (int c2 = lane; c2 < 2 * nr; c2 += 32) {
-                    const int j = c2 >> 1, half = c2 & 1;
-                    cpasync16(bt + j * 32 + half * 16, bins + (base + j) * Fp + g * HG + half * 8);
+            } else if (VAR != 3) {
+                if (nr == R) {
+                    // full stage: per-lane source / destination offsets are stage invariant (rows are contiguous),
+                    // so the copy is 2*R/32 + 2 address adds and LDGSTS, nothing else
+                    const uint16_t* gsrc = bins + base * Fp + g * HG;
+#pragma unroll
+                    for (int u = 0; u < (2 * R) / 32; u++) {
+                        const int c2 = lane + 32 * u;
+                        cpasync16(bt + (c2 >> 1) * 32 + (c2 & 1) * 16, gsrc + (size_t)(c2 >> 1) * Fp + (c2 & 1) * 8);
+                    }
+#pragma unroll
+                    for (int u = 0; u < (R / 2 + 31) / 32; u++) {
+                        const int c2 = lane + 32 * u;
+                        if (c2 < R / 2) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
+                    }
+                } else {
+                    for (int c2 = lane; c2 < 2 * nr; c2 += 32) {
+                        const int j = c2 >> 1, half = c2 & 1;
+                        cpasync16(bt + j * 32 + half * 16, bins + (base + j) * Fp + g * HG + half * 8);
+                    }
+                    for (int c2 = lane; c2 < (nr + 1) / 2; c2 += 32) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
                 }
-                for (int c2 = lane; c2 < (nr + 1) / 2; c2 += 32) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
             }
-            cpasync_arrive(&full[s2]);
+            if (VAR == 3)
+                mbar_arrive(&full[s2]);  // experiment: consumers only (stale tile contents)
+            else
+                cpasync_arrive(&full[s2]);
         }
     } else {
         // ===== consumer warps =====
@@ -828,11 +865,29 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
 #pragma unroll
                     for (int kk = 0; kk < 16; kk++) {
                         bb[kk] = btile[(kk * PH + ph) * HG + fi];
+                        if (VAR == 3) bb[kk] &= 255;  // experiment with stale tiles: keep the index in range
                         vv[kk] = vt[kk * PH + ph];
                     }
 #pragma unroll
-                    for (int kk = 0; kk < 16; kk += 4)
-                        hist_batch4<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2], vv[kk + 3]);
+                    for (int kk = 0; kk < 16; kk += 4) {
+                        if (VAR == 4) {  // experiment: pairs instead of quads (one compare per pair)
+#pragma unroll
+                            for (int pp = 0; pp < 4; pp += 2) {
+                                const int ba = bb[kk + pp], bc = bb[kk + pp + 1];
+                                long long va = vv[kk + pp], vc = vv[kk + pp + 1];
+                                const long long ha = Hme[ba * T], hc = Hme[bc * T];
+                                vc += (bc == ba) ? va : 0LL;
+                                Hme[ba * T] = ha + va;
+                                Hme[bc * T] = hc + vc;
+                            }
+                        } else if (VAR == 2) {  // experiment: memory pipeline only
+                            if (bb[kk] == 0x7fff) Hme[0] += vv[kk] + vv[kk + 1] + vv[kk + 2] + vv[kk + 3];
+                        } else if (VAR == 1)
+                            hist_batch4<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2], vv[kk + 3]);
+                        else
+                            hist_batch4_merge<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2],
+                                                 vv[kk + 3]);
+                    }
                 } else {
                     for (int rr = ph; rr < nr; rr += PH) {
                         const int b = btile[rr * HG + fi];
@@ -2299,8 +2354,21 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     RLB_CHECK_LAUNCH(c);
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
-        k_hist_priv<false, PH_ROOT><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-            c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        if (c->hist_variant == 4)
+            k_hist_priv<false, PH_ROOT, 4><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        else if (c->hist_variant == 2)
+            k_hist_priv<false, PH_ROOT, 2><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        else if (c->hist_variant == 3)
+            k_hist_priv<false, PH_ROOT, 3><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        else if (c->hist_variant == 1)
+            k_hist_priv<false, PH_ROOT, 1><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        else
+            k_hist_priv<false, PH_ROOT><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
+                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
     } else {
         k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr,
                                                                 c->dHistSum, c->dHistCnt, c->dState, 0);
@@ -2409,6 +2477,14 @@ int rlb_impl_prepare(rlb_ctx* c) {
                                      (int)hist_smem(false, PH_ROOT)));
     RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<true, PH_CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)hist_smem(true, PH_CHILD)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(false, PH_ROOT)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(false, PH_ROOT)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(false, PH_ROOT)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hist_smem(false, PH_ROOT)));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 24 + 2560 * 16));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 24 + 10240 * 16));

@@ -429,6 +429,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dVfixC, (N + 2) * sizeof(long long)));
     RLB_CUDA(c, alloc(c->dSqfix, N * sizeof(long long)));
     if (const char* e = getenv("RLB_HIST_MIN_ROWS")) c->hist_min_rows = atoi(e);
+    if (const char* e = getenv("RLB_HIST_VARIANT")) c->hist_variant = atoi(e);
     RLB_CUDA(c, alloc(c->dIdeal, (size_t)Q * sizeof(double)));
     RLB_CUDA(c, alloc(c->dRankDoc, N * sizeof(int32_t)));
     RLB_CUDA(c, alloc(c->dSamples[0], N * sizeof(int32_t)));

@@ -145,6 +145,8 @@ struct rlb_ctx {
     long long* dVfix = nullptr;     // fixed-point pseudo responses of the iteration
     long long* dVfixC = nullptr;    // the same + (1 << 52): response and row count in one accumulator
     long long* dSqfix = nullptr;    // fixed-point squared pseudo responses
+    int32_t hist_variant = 0;       // RLB_HIST_VARIANT (root kernel experiments): 0 addend merging (default), 1 accumulator
+                                    // forwarding, 2 no read-modify-writes (memory pipeline only), 3 no loads (consumers only)
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
