@@ -551,8 +551,16 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lam
         sqfix[i] = q;
         sq += q;
     }
+    // one global reduction per CTA (one per warp serialises ~N/32 same-address atomics in L2: ~100 us at C2)
+    __shared__ long long wsq[8];
     for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-    if ((threadIdx.x & 31) == 0 && sq != 0) atomicAdd((unsigned long long*)&st->root_sq_fix, (unsigned long long)sq);
+    if ((threadIdx.x & 31) == 0) wsq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wsq[w];
+        if (t != 0) atomicAdd((unsigned long long*)&st->root_sq_fix, (unsigned long long)t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,9 +617,12 @@ __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ 
 }
 
 #define HG 16        // features per CTA group = one 32-byte sector of a bins row
-#define HSTAGES 8    // depth of the bulk-copy ring
+#define HSTAGES 8    // depth of the cp.async ring of the child kernel
+#define HPH 6        // row phases: HG * HPH = 96 private histograms x 257 bins x 8 B = 197 KB of shared memory
+#define HROOT_CPS 4  // root: 8-row chunks per thread per stage -> RLB_ROOT_R = HPH * 8 * HROOT_CPS = 192 rows per tile
+#define HROOT_STAGES 4
 
-// ---- mbarrier / bulk-copy (TMA engine, SASS UBLKCP) primitives -------------------------------
+// ---- mbarrier / bulk-copy (TMA engine, SASS UBLKCP) / cp.async primitives ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -651,41 +662,58 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// One 4-row batch of private read-modify-writes with forwarding between equal bins.  For child
-// builds v already carries the count increment (v + CNT_ONE).
-template <int T>
-__device__ __forceinline__ void hist_batch4(long long* Hme, int b0, int b1, int b2, int b3, long long v0, long long v1,
-                                            long long v2, long long v3) {
-    long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
-    h0 += v0;
-    Hme[b0 * T] = h0;
-    if (b1 == b0) h1 = h0;
-    h1 += v1;
-    Hme[b1 * T] = h1;
-    if (b2 == b1) h2 = h1; else if (b2 == b0) h2 = h0;
-    h2 += v2;
-    Hme[b2 * T] = h2;
-    if (b3 == b2) h3 = h2; else if (b3 == b1) h3 = h1; else if (b3 == b0) h3 = h0;
-    h3 += v3;
-    Hme[b3 * T] = h3;
+// ---- shared-memory accesses of the consumers: explicit PTX (volatile, so they stay in source order) on 32-bit
+// shared addresses.  The compiler cannot prove that tile reads and private-histogram writes do not alias and would
+// otherwise keep every tile read behind the previous chunk's stores; written this way the next chunk's tile reads
+// are issued BEFORE the current chunk's read-modify-writes and their latency, the address arithmetic and the
+// addend merging all overlap the RMW chains. ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
 }
+__device__ __forceinline__ void lds128ll(uint32_t a, long long& x, long long& y) {
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+}
+__device__ __forceinline__ long long lds64(uint32_t a) {
+    long long r;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t r;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts64(uint32_t a, long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v)); }
 
-// Default batch (RLB_HIST_VARIANT=1 selects the accumulator-forwarding form above for comparison): merge the
-// ADDENDS of equal bins instead of forwarding accumulators.  The later row
-// of a pair of equal bins carries the running total (its store lands last: a thread's shared-memory stores are
-// ordered), so the four read-modify-writes are independent and the merging, which needs only the bins and the
-// addends, overlaps the accumulator loads.  Branch-free selects.
-template <int T>
-__device__ __forceinline__ void hist_batch4_merge(long long* Hme, int b0, int b1, int b2, int b3, long long v0, long long v1,
-                                                  long long v2, long long v3) {
-    const long long h0 = Hme[b0 * T], h1 = Hme[b1 * T], h2 = Hme[b2 * T], h3 = Hme[b3 * T];
-    v1 += (b1 == b0) ? v0 : 0LL;
-    v2 += (b2 == b1) ? v1 : ((b2 == b0) ? v0 : 0LL);
-    v3 += (b3 == b2) ? v2 : ((b3 == b1) ? v1 : ((b3 == b0) ? v0 : 0LL));
-    Hme[b0 * T] = h0 + v0;
-    Hme[b1 * T] = h1 + v1;
-    Hme[b2 * T] = h2 + v2;
-    Hme[b3 * T] = h3 + v3;
+// eight rows of one feature: private-histogram byte addresses and addends
+struct HChunk {
+    uint32_t a[8];
+    long long v[8];
+};
+
+// Eight read-modify-writes on this thread's private histogram as two quads.  Inside a quad the four loads are
+// issued before the four stores, so equal bins are resolved on the ADDENDS first (the later row of a pair of equal
+// bins carries the running total and its store lands last: a thread's shared-memory stores are ordered).  The
+// merging needs only addresses and addends — it is done while the loads are in flight.  Branch-free.
+__device__ __forceinline__ void hist_rmw8(HChunk& c) {
+#pragma unroll
+    for (int p = 0; p < 8; p += 4) {
+        const bool e10 = c.a[p + 1] == c.a[p], e21 = c.a[p + 2] == c.a[p + 1], e20 = c.a[p + 2] == c.a[p];
+        const bool e32 = c.a[p + 3] == c.a[p + 2], e31 = c.a[p + 3] == c.a[p + 1], e30 = c.a[p + 3] == c.a[p];
+        c.v[p + 1] += e10 ? c.v[p] : 0LL;
+        c.v[p + 2] += e21 ? c.v[p + 1] : (e20 ? c.v[p] : 0LL);
+        c.v[p + 3] += e32 ? c.v[p + 2] : (e31 ? c.v[p + 1] : (e30 ? c.v[p] : 0LL));
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p += 4) {
+        const long long h0 = lds64(c.a[p]), h1 = lds64(c.a[p + 1]), h2 = lds64(c.a[p + 2]), h3 = lds64(c.a[p + 3]);
+        sts64(c.a[p], h0 + c.v[p]);
+        sts64(c.a[p + 1], h1 + c.v[p + 1]);
+        sts64(c.a[p + 2], h2 + c.v[p + 2]);
+        sts64(c.a[p + 3], h3 + c.v[p + 3]);
+    }
 }
 
 // Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
@@ -721,21 +749,133 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
     asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
 }
 
-// k_hist_priv<CHILD, PH>: CTA = ceil(16*PH/32) consumer warps + 1 producer warp.
-//   producer: per stage, one 32-byte bulk copy per row (the 16 bins of this CTA's feature group) and
-//             the rows' fixed-point responses, completion tracked by an mbarrier ("full"); HSTAGES
-//             stages in flight hide the HBM latency that 3 resident warps could not.
-//   consumer: thread (fi, ph) owns histogram column tid of H[bin][tid] and the rows ph, ph+PH, ... of
-//             each stage.
-template <bool CHILD, int PH, int VAR = 0>
-__global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
-    k_hist_priv(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfix,
-                const long long* __restrict__ sqfix, int64_t N, const int32_t* __restrict__ samples0,
-                const int32_t* __restrict__ samples1, long long* __restrict__ sum, int32_t* __restrict__ cnt,
-                DevState* __restrict__ st, int nGroups, int minRows) {
+// ------------------------------------------------------------------------------------------------
+// k_hist_root — FeatureHistogram.update (FeatureHistogram.java:126-140) over ALL local rows.
+//
+// The bins of the training set never change, so the root pass reads them from a layout made for it at init
+// (k_tile_bins, rlb_init.cu): tile (g, B) = the 16 features of group g x 192 consecutive rows, feature-major, a
+// thread's 8 consecutive rows of one feature = one 16-byte chunk, chunks XOR-swizzled by (feature & 7) so that the
+// 8 lanes of a quarter warp hit 8 different bank groups.  Tiles of a group are contiguous: one stage is ONE bulk
+// copy (TMA engine, UBLKCP) of 6 KB of bins + one of the 192 fixed-point responses, issued by a single thread and
+// completed on an mbarrier; the three consumer warps never touch global memory.
+//   CTA = (group g, a contiguous range of tiles).  Thread (fi, ph) owns private histogram column tid.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
+    k_hist_root(const uint16_t* __restrict__ tiles, const long long* __restrict__ vfix, int64_t NB, int F, int nGroups,
+                long long* __restrict__ sum) {
+    constexpr int PH = HPH, CPS = HROOT_CPS, STAGES = HROOT_STAGES;
+    constexpr int T = HG * PH;
+    constexpr int R = PH * 8 * CPS;
+    constexpr int CW = (T + 31) / 32;
+    constexpr int TILE_BYTES = R * HG * 2;
+    constexpr int STAGE_BYTES = TILE_BYTES + R * 8;
+    static_assert(R == RLB_ROOT_R, "tile rows");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    long long* H = reinterpret_cast<long long*>(smem_raw);
+    size_t off = (size_t)RLB_T * T * 8;
+    off = (off + 127) & ~(size_t)127;
+    unsigned char* stage0 = smem_raw + off;
+    off += (size_t)STAGES * STAGE_BYTES;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    unsigned long long* empty = full + STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x % nGroups;
+    const int idx = blockIdx.x / nGroups;
+    const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
+    const int64_t B0 = NB * idx / nCta, B1 = NB * (idx + 1) / nCta;
+    const int nst = (int)(B1 - B0);
+    if (nst == 0) return;
+    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < STAGES; s2++) {
+            mbar_init(&full[s2], 1u);
+            mbar_init(&empty[s2], (uint32_t)CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CW) {
+        if (lane == 0) {
+            const unsigned char* gt = reinterpret_cast<const unsigned char*>(tiles) + ((size_t)g * NB + B0) * TILE_BYTES;
+            const long long* gv = vfix + B0 * R;
+            for (int k = 0; k < nst; k++) {
+                const int s2 = k % STAGES;
+                if (k >= STAGES) mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
+                unsigned char* st = stage0 + (size_t)s2 * STAGE_BYTES;
+                mbar_expect_tx(&full[s2], STAGE_BYTES);
+                bulk_g2s(st, gt + (size_t)k * TILE_BYTES, TILE_BYTES, &full[s2]);
+                bulk_g2s(st + TILE_BYTES, gv + (size_t)k * R, R * 8, &full[s2]);
+            }
+        }
+    } else {
+        // threads of an absent feature (last group) walk all-zero bins into their own column; the flush skips them
+        const int fi = tid & (HG - 1), ph = tid / HG;
+        const uint32_t hme = smem_u32(H) + tid * 8;
+        const uint32_t st0 = smem_u32(stage0);
+        const uint32_t boff = fi * (R * 2);
+        const uint32_t swz = fi & 7;
+        auto load = [&](HChunk& c, uint32_t sb, int chunk) {
+            const uint4 bq = lds128(sb + boff + ((chunk ^ swz) << 4));
+            const uint32_t va = sb + TILE_BYTES + chunk * 64;
+            lds128ll(va, c.v[0], c.v[1]);
+            lds128ll(va + 16, c.v[2], c.v[3]);
+            lds128ll(va + 32, c.v[4], c.v[5]);
+            lds128ll(va + 48, c.v[6], c.v[7]);
+            c.a[0] = hme + (bq.x & 0xffff) * (T * 8); c.a[1] = hme + (bq.x >> 16) * (T * 8);
+            c.a[2] = hme + (bq.y & 0xffff) * (T * 8); c.a[3] = hme + (bq.y >> 16) * (T * 8);
+            c.a[4] = hme + (bq.z & 0xffff) * (T * 8); c.a[5] = hme + (bq.z >> 16) * (T * 8);
+            c.a[6] = hme + (bq.w & 0xffff) * (T * 8); c.a[7] = hme + (bq.w >> 16) * (T * 8);
+        };
+        HChunk cur, nxt;
+        mbar_wait(&full[0], 0);
+        load(cur, st0, ph);
+        for (int k = 0; k < nst; k++) {
+            const int s2 = k % STAGES;
+            const uint32_t sb = st0 + s2 * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < CPS; j++) {
+                if (j + 1 < CPS) {
+                    load(nxt, sb, ph + PH * (j + 1));
+                } else {
+                    if (k + 1 < nst) {
+                        const int s1 = (k + 1) % STAGES;
+                        mbar_wait(&full[s1], ((k + 1) / STAGES) & 1);
+                        load(nxt, st0 + s1 * STAGE_BYTES, ph);
+                    }
+                    __syncwarp();  // every read of stage s2 has been issued by this warp
+                    if (lane == 0) mbar_arrive(&empty[s2]);
+                }
+                hist_rmw8(cur);
+                cur = nxt;
+            }
+        }
+        hist_flush<false, PH>(H, tid, g, F, sum, nullptr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_hist_child — FeatureHistogram.construct(parent, soi, labels) (FeatureHistogram.java:176-187) for the rows of
+// one node, gathered through its sample list from the row-major bins [N][Fp].
+//   producer warp: per stage, 96 rows: two 16-byte cp.async (LDGSTS) per row (the 16 bins of this CTA's feature
+//                  group) + its response, straight into shared memory; completion on an mbarrier; 8 stages in flight.
+//   consumers:     thread (fi, ph) owns private histogram column tid; the two phases of a warp interleave the rows of
+//                  a 16-row block (conflict-free 64-byte reads), 8 rows per thread per block, pipelined like the root.
+// The row count rides in the top 12 bits of the same accumulator (v + 2^52, decoded at flush; a private bin holds at
+// most 2032 rows between flushes).  CTAs whose row range is empty return before touching shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
+    k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
+                 const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1, long long* __restrict__ sum,
+                 int32_t* __restrict__ cnt, DevState* __restrict__ st, int nGroups) {
+    constexpr int PH = HPH;
     constexpr int T = HG * PH;           // consumer threads = private histograms
-    constexpr int R = HG * PH;           // rows per stage (16 per consumer thread)
+    constexpr int R = HG * PH;           // rows per stage (16 per consumer thread = 2 blocks of 16 rows per phase pair)
     constexpr int CW = (T + 31) / 32;    // consumer warps
+    constexpr int NBLK = R / 16;         // 16-row blocks per stage
+    constexpr int BPP = NBLK / (PH / 2); // blocks per phase pair per stage
+    static_assert(PH % 2 == 0 && NBLK % (PH / 2) == 0, "phase pairs");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     long long* H = reinterpret_cast<long long*>(smem_raw);                         // [RLB_T][T]
     size_t off = (size_t)RLB_T * T * 8;
@@ -746,27 +886,21 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
     unsigned long long* empty = full + HSTAGES;
 
-    int64_t lo = 0, hi = N;
-    const int32_t* samples = nullptr;
-    if (CHILD) {
-        if (!st->split_active) return;
-        const NodeRec& r = st->nodes[st->small_id];
-        lo = r.lo;
-        hi = r.hi;
-        samples = r.buf ? samples1 : samples0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
-    }
+    if (!st->split_active) return;
+    const NodeRec& r = st->nodes[st->small_id];
+    const int64_t lo = r.lo, hi = r.hi;
+    const int32_t* samples = r.buf ? samples1 : samples0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x % nGroups;
     const int idx = blockIdx.x / nGroups;
     const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
     const int64_t n = hi - lo;
-    // even split points keep the 16-byte alignment the bulk copy of the response tile needs
-    int64_t r0 = lo + ((n * idx / nCta) & ~(int64_t)1), r1 = lo + ((n * (idx + 1) / nCta) & ~(int64_t)1);
-    if (idx == nCta - 1) r1 = hi;
-    if (idx == 0) r0 = lo;
+    const int64_t r0 = lo + n * idx / nCta, r1 = lo + n * (idx + 1) / nCta;
     const int nst = (int)((r1 - r0 + R - 1) / R);
     if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
+    const int nfull = (int)((r1 - r0) / R);
 
     for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
     if (tid == 0) {
@@ -780,13 +914,11 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
 
     if (warp == CW) {
         // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
-        int32_t nxt[(R + 31) / 32];   // CHILD: sample indices of the next stage, fetched one stage ahead
-        if (CHILD) {
+        int32_t nxt[(R + 31) / 32];   // sample indices of the next stage, fetched one stage ahead
 #pragma unroll
-            for (int u = 0; u < (R + 31) / 32; u++) {
-                const int64_t pos = r0 + lane + 32 * u;
-                nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
-            }
+        for (int u = 0; u < (R + 31) / 32; u++) {
+            const int64_t pos = r0 + lane + 32 * u;
+            nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
         }
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
@@ -795,110 +927,90 @@ __global__ void __launch_bounds__(32 * ((HG * PH + 31) / 32 + 1), 1)
             const int nr = (int)min((int64_t)R, r1 - base);
             unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             long long* vt = reinterpret_cast<long long*>(bt + R * 32);
-            if (CHILD) {
-                int32_t cur[(R + 31) / 32];
+            int32_t cur[(R + 31) / 32];
 #pragma unroll
-                for (int u = 0; u < (R + 31) / 32; u++) {
-                    cur[u] = nxt[u];
-                    const int64_t pos = base + R + lane + 32 * u;
-                    nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
-                }
+            for (int u = 0; u < (R + 31) / 32; u++) {
+                cur[u] = nxt[u];
+                const int64_t pos = base + R + lane + 32 * u;
+                nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+            }
 #pragma unroll
-                for (int u = 0; u < (R + 31) / 32; u++) {
-                    const int j = lane + 32 * u;
-                    if (j < nr) {
-                        const int64_t row = cur[u];
-                        const uint16_t* src = bins + row * Fp + g * HG;
-                        cpasync16(bt + j * 32, src);
-                        cpasync16(bt + j * 32 + 16, src + 8);
-                        cpasync8(vt + j, vfix + row);
-                    }
-                }
-            } else if (VAR != 3) {
-                if (nr == R) {
-                    // full stage: per-lane source / destination offsets are stage invariant (rows are contiguous),
-                    // so the copy is 2*R/32 + 2 address adds and LDGSTS, nothing else
-                    const uint16_t* gsrc = bins + base * Fp + g * HG;
-#pragma unroll
-                    for (int u = 0; u < (2 * R) / 32; u++) {
-                        const int c2 = lane + 32 * u;
-                        cpasync16(bt + (c2 >> 1) * 32 + (c2 & 1) * 16, gsrc + (size_t)(c2 >> 1) * Fp + (c2 & 1) * 8);
-                    }
-#pragma unroll
-                    for (int u = 0; u < (R / 2 + 31) / 32; u++) {
-                        const int c2 = lane + 32 * u;
-                        if (c2 < R / 2) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
-                    }
-                } else {
-                    for (int c2 = lane; c2 < 2 * nr; c2 += 32) {
-                        const int j = c2 >> 1, half = c2 & 1;
-                        cpasync16(bt + j * 32 + half * 16, bins + (base + j) * Fp + g * HG + half * 8);
-                    }
-                    for (int c2 = lane; c2 < (nr + 1) / 2; c2 += 32) cpasync16(vt + 2 * c2, vfix + base + 2 * c2);
+            for (int u = 0; u < (R + 31) / 32; u++) {
+                const int j = lane + 32 * u;
+                if (j < nr) {
+                    const int64_t row = cur[u];
+                    const uint16_t* src = bins + row * Fp + g * HG;
+                    cpasync16(bt + j * 32, src);
+                    cpasync16(bt + j * 32 + 16, src + 8);
+                    cpasync8(vt + j, vfixc + row);
                 }
             }
-            if (VAR == 3)
-                mbar_arrive(&full[s2]);  // experiment: consumers only (stale tile contents)
-            else
-                cpasync_arrive(&full[s2]);
+            cpasync_arrive(&full[s2]);
         }
     } else {
         // ===== consumer warps =====
         const int fi = tid & (HG - 1), ph = tid / HG;
         const bool active = (tid < T) && (g * HG + fi < F);
-        long long* Hme = H + tid;
-        for (int k = 0; k < nst; k++) {
+        const uint32_t hme = smem_u32(H) + tid * 8;
+        const uint32_t st0 = smem_u32(tiles);
+        const int pp = ph >> 1, odd = ph & 1;
+        // rows of block b owned by this thread: 16 b + 2 w + odd, w = 0..7
+        auto load = [&](HChunk& c, uint32_t sb, int blk) {
+            const uint32_t ba = sb + (blk * 16 + odd) * 32 + fi * 2;
+            const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+                c.v[w] = lds64(va + w * 16);
+            }
+        };
+        // threads of an absent feature (last group: its bins are stored as 0) run along into their own column, which
+        // keeps every warp-level step of the loop convergent; the flush skips them
+        if (nfull > 0) {
+            HChunk cur, nxt;
+            mbar_wait(&full[0], 0);
+            load(cur, st0, pp);
+            for (int k = 0; k < nfull; k++) {
+                const int s2 = k % HSTAGES;
+                const uint32_t sb = st0 + s2 * STAGE_BYTES;
+                // the packed (count, sum) accumulators hold at most 2^11 rows
+                if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+#pragma unroll
+                for (int j = 0; j < BPP; j++) {
+                    if (j + 1 < BPP) {
+                        load(nxt, sb, pp + (PH / 2) * (j + 1));
+                    } else {
+                        if (k + 1 < nfull) {
+                            const int s1 = (k + 1) % HSTAGES;
+                            mbar_wait(&full[s1], ((k + 1) / HSTAGES) & 1);
+                            load(nxt, st0 + s1 * STAGE_BYTES, pp);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[s2]);
+                    }
+                    hist_rmw8(cur);
+                    cur = nxt;
+                }
+            }
+        }
+        if (nst > nfull) {  // the partial last stage, row by row
+            const int k = nfull;
             const int s2 = k % HSTAGES;
-            // the packed (count, sum) accumulators of a child build hold at most 2^11 rows
-            if (CHILD && k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<CHILD, PH>(H, tid, g, F, sum, cnt);
+            if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
             mbar_wait(&full[s2], (k / HSTAGES) & 1);
             const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
             const long long* vt = reinterpret_cast<const long long*>(bt + R * 32);
-            const int nr = (int)min((int64_t)R, r1 - (r0 + (int64_t)k * R));
+            const int nr = (int)(r1 - (r0 + (int64_t)k * R));
             if (active) {
-                if (nr == R) {
-                    // all 16 (bin, response) pairs of the stage first: the tile reads then overlap the
-                    // read-modify-write chains instead of sitting in front of each of them
-                    int bb[16];
-                    long long vv[16];
-#pragma unroll
-                    for (int kk = 0; kk < 16; kk++) {
-                        bb[kk] = btile[(kk * PH + ph) * HG + fi];
-                        if (VAR == 3) bb[kk] &= 255;  // experiment with stale tiles: keep the index in range
-                        vv[kk] = vt[kk * PH + ph];
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 16; kk += 4) {
-                        if (VAR == 4) {  // experiment: pairs instead of quads (one compare per pair)
-#pragma unroll
-                            for (int pp = 0; pp < 4; pp += 2) {
-                                const int ba = bb[kk + pp], bc = bb[kk + pp + 1];
-                                long long va = vv[kk + pp], vc = vv[kk + pp + 1];
-                                const long long ha = Hme[ba * T], hc = Hme[bc * T];
-                                vc += (bc == ba) ? va : 0LL;
-                                Hme[ba * T] = ha + va;
-                                Hme[bc * T] = hc + vc;
-                            }
-                        } else if (VAR == 2) {  // experiment: memory pipeline only
-                            if (bb[kk] == 0x7fff) Hme[0] += vv[kk] + vv[kk + 1] + vv[kk + 2] + vv[kk + 3];
-                        } else if (VAR == 1)
-                            hist_batch4<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2], vv[kk + 3]);
-                        else
-                            hist_batch4_merge<T>(Hme, bb[kk], bb[kk + 1], bb[kk + 2], bb[kk + 3], vv[kk], vv[kk + 1], vv[kk + 2],
-                                                 vv[kk + 3]);
-                    }
-                } else {
-                    for (int rr = ph; rr < nr; rr += PH) {
-                        const int b = btile[rr * HG + fi];
-                        Hme[b * T] += vt[rr];
-                    }
+                long long* Hme = H + tid;
+                for (int rr = ph; rr < nr; rr += PH) {
+                    const int b = btile[rr * HG + fi];
+                    Hme[b * T] += vt[rr];
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s2]);
         }
-        hist_flush<CHILD, PH>(H, tid, g, F, sum, cnt);
+        hist_flush<true, PH>(H, tid, g, F, sum, cnt);
     }
 }
 
@@ -2333,16 +2445,17 @@ int rlb_impl_pseudo(rlb_ctx* c) {
     return RLB_OK;
 }
 
-#define PH_ROOT 6    // 96 private histograms x 257 bins x 8 B = 197 KB + 8 stages x 3840 B
-#define PH_CHILD 6   // same shape: child builds pack the row count into the top 12 bits of each accumulator
-
-static constexpr size_t hist_smem(bool child, int ph) {
-    size_t t = (size_t)HG * ph;
-    (void)child;
-    size_t off = (size_t)RLB_T * t * 8;
+static constexpr size_t hist_smem_root() {
+    size_t off = (size_t)RLB_T * HG * HPH * 8;
     off = (off + 127) & ~(size_t)127;
-    return off + (size_t)HSTAGES * (t * 40) + 2 * HSTAGES * 8 + HSTAGES * 4;
+    return off + (size_t)HROOT_STAGES * (RLB_ROOT_R * HG * 2 + RLB_ROOT_R * 8) + 2 * HROOT_STAGES * 8;
 }
+static constexpr size_t hist_smem_child() {
+    size_t off = (size_t)RLB_T * HG * HPH * 8;
+    off = (off + 127) & ~(size_t)127;
+    return off + (size_t)HSTAGES * (HG * HPH * 40) + 2 * HSTAGES * 8;
+}
+static constexpr int hist_threads() { return 32 * ((HG * HPH + 31) / 32 + 1); }
 
 static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
 static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
@@ -2354,21 +2467,8 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     RLB_CHECK_LAUNCH(c);
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
-        if (c->hist_variant == 4)
-            k_hist_priv<false, PH_ROOT, 4><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
-        else if (c->hist_variant == 2)
-            k_hist_priv<false, PH_ROOT, 2><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
-        else if (c->hist_variant == 3)
-            k_hist_priv<false, PH_ROOT, 3><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
-        else if (c->hist_variant == 1)
-            k_hist_priv<false, PH_ROOT, 1><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
-        else
-            k_hist_priv<false, PH_ROOT><<<hist_grid(c), 32 * ((HG * PH_ROOT + 31) / 32 + 1), hist_smem(false, PH_ROOT), c->stream>>>(
-                c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr, c->dHistSum, c->dHistCnt, c->dState, hist_groups(c), 0);
+        k_hist_root<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
+                                                                                    hist_groups(c), c->dHistSum);
     } else {
         k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr,
                                                                 c->dHistSum, c->dHistCnt, c->dState, 0);
@@ -2404,9 +2504,9 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             RLB_CHECK_LAUNCH(c);
         }
         rlb_prof_begin(c, 1);
-        k_hist_priv<true, PH_CHILD><<<hist_grid(c), 32 * ((HG * PH_CHILD + 31) / 32 + 1), hist_smem(true, PH_CHILD), c->stream>>>(
-            c->dBins, c->Fp, c->F, c->dVfixC, c->dSqfix, c->N, c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState,
-            hist_groups(c), c->hist_min_rows);
+        k_hist_child<<<hist_grid(c), hist_threads(), hist_smem_child(), c->stream>>>(c->dBins, c->Fp, c->F, c->dVfixC, c->dSamples[0],
+                                                                                      c->dSamples[1], stageSum, stageCnt, c->dState,
+                                                                                      hist_groups(c));
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
         if (c->world > 1) {
@@ -2473,18 +2573,8 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
 
 // one-time kernel attributes (must not happen inside a stream capture)
 int rlb_impl_prepare(rlb_ctx* c) {
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(false, PH_ROOT)));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<true, PH_CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(true, PH_CHILD)));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(false, PH_ROOT)));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(false, PH_ROOT)));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(false, PH_ROOT)));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_priv<false, PH_ROOT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hist_smem(false, PH_ROOT)));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_child, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 24 + 2560 * 16));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 24 + 10240 * 16));

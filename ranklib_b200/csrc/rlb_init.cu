@@ -135,6 +135,28 @@ __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, in
     }
 }
 
+// Root-histogram layout (k_hist_root, rlb_boost.cu): tile (g, B) = [16 features of group g][RLB_ROOT_R rows], the 8 rows
+// c*8 .. c*8+7 of a feature form one 16-byte chunk stored at chunk position c ^ (feature & 7); rows past N and features
+// past F are bin 0.  Tiles of one group are contiguous over B.
+__global__ void __launch_bounds__(256) k_tile_bins(const uint16_t* __restrict__ bins, int Fp, int F, int64_t N, int64_t NB,
+                                                    uint16_t* __restrict__ tiles) {
+    constexpr int R = RLB_ROOT_R;
+    const int64_t total = (int64_t)(Fp / 16) * NB * R * 16;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i & 7);
+        int64_t t = i >> 3;
+        const int cpos = (int)(t % (R / 8));
+        t /= (R / 8);
+        const int fi = (int)(t & 15);
+        t >>= 4;
+        const int64_t B = t % NB;
+        const int g = (int)(t / NB);
+        const int64_t row = B * R + (cpos ^ (fi & 7)) * 8 + w;
+        const int f = g * 16 + fi;
+        tiles[i] = (row < N && f < F) ? bins[row * Fp + f] : (uint16_t)0;
+    }
+}
+
 __global__ void k_cumsum_counts(int* __restrict__ cnt, int F) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -187,7 +209,7 @@ void rlb_impl_free(rlb_ctx* c) {
         if (p) cudaFree(p);
         p = nullptr;
     };
-    fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
+    fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dBinsTile); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
@@ -418,6 +440,8 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     };
     RLB_CUDA(c, alloc(c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dBinsT, (size_t)N * F * sizeof(uint16_t)));
+    c->root_nb = (N + RLB_ROOT_R - 1) / RLB_ROOT_R;
+    RLB_CUDA(c, alloc(c->dBinsTile, (size_t)(Fp / 16) * c->root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
     RLB_CUDA(c, alloc(c->dStage, (c->hist_stride + (c->hist_stride + 1) / 2 + 2) * sizeof(long long)));
@@ -425,11 +449,12 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dLambda, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dWeight, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dQMetric, (size_t)Q * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dVfix, (N + 2) * sizeof(long long)));  // +2: the bulk copy of a tile rounds up to 16 bytes
+    // the root histogram reads responses in whole tiles of RLB_ROOT_R rows: pad with zeros (added to bin 0, harmless)
+    RLB_CUDA(c, alloc(c->dVfix, ((size_t)c->root_nb * RLB_ROOT_R + 2) * sizeof(long long)));
+    RLB_CUDA(c, cudaMemsetAsync(c->dVfix, 0, ((size_t)c->root_nb * RLB_ROOT_R + 2) * sizeof(long long), c->stream));
     RLB_CUDA(c, alloc(c->dVfixC, (N + 2) * sizeof(long long)));
     RLB_CUDA(c, alloc(c->dSqfix, N * sizeof(long long)));
     if (const char* e = getenv("RLB_HIST_MIN_ROWS")) c->hist_min_rows = atoi(e);
-    if (const char* e = getenv("RLB_HIST_VARIANT")) c->hist_variant = atoi(e);
     RLB_CUDA(c, alloc(c->dIdeal, (size_t)Q * sizeof(double)));
     RLB_CUDA(c, alloc(c->dRankDoc, N * sizeof(int32_t)));
     RLB_CUDA(c, alloc(c->dSamples[0], N * sizeof(int32_t)));
@@ -475,6 +500,8 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
 
     // ---- binning + root counts ----
     k_binning<<<c->grid_rows, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, c->dHistCnt);
+    RLB_CHECK_LAUNCH(c);
+    k_tile_bins<<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, Fp, F, N, c->root_nb, c->dBinsTile);
     RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i32(c, c->dHistCnt, c->hist_stride)) return rc;
     k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCnt, F);

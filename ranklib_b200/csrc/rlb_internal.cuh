@@ -47,6 +47,7 @@ bool rlb_nccl_load(std::string* why);
 #define RLB_MAX_NODES (2 * RLB_MAX_LEAVES)
 #define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
 #define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
+#define RLB_ROOT_R 192               // rows per tile of the root-histogram layout (dBinsTile)
 #define RLB_CHAIN_THREADS 256
 #define RLB_CHAIN_PER_THREAD 4
 
@@ -134,6 +135,9 @@ struct rlb_ctx {
     int32_t* dQidOfDoc = nullptr;
     uint16_t* dBins = nullptr;      // [N][Fp]
     uint16_t* dBinsT = nullptr;     // [F][N] feature-major copy: the partition reads ONE feature of many (ascending) rows
+    uint16_t* dBinsTile = nullptr;  // [F/16 groups][root_nb tiles][16 features][192 rows], 16-byte chunks swizzled: the root
+                                    // histogram's layout — one tile = one contiguous bulk copy (rlb_init.cu k_tile_bins)
+    int64_t root_nb = 0;            // tiles per feature group = ceil(N / RLB_ROOT_R)
     float* dThr = nullptr;          // [F][RLB_T]
     int32_t* dNThr = nullptr;       // [F]
     double* dDisc = nullptr;        // discount table [max_query + 1]
@@ -145,8 +149,6 @@ struct rlb_ctx {
     long long* dVfix = nullptr;     // fixed-point pseudo responses of the iteration
     long long* dVfixC = nullptr;    // the same + (1 << 52): response and row count in one accumulator
     long long* dSqfix = nullptr;    // fixed-point squared pseudo responses
-    int32_t hist_variant = 0;       // RLB_HIST_VARIANT (root kernel experiments): 0 addend merging (default), 1 accumulator
-                                    // forwarding, 2 no read-modify-writes (memory pipeline only), 3 no loads (consumers only)
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
