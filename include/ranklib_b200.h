@@ -194,6 +194,12 @@ int rlb_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* tree_o
 int rlb_score_metric(rlb_ctx* ctx, const double* scores, const float* label, const int32_t* qoff,
                      int32_t Q, int32_t metric, int32_t k, double* out);
 
+/* Test hook: the reference's float32 accumulation  float s = carry; for i: s += x[i]  (compound assignment on a
+ * float with a double right-hand side = (float)((double)s + x[i]); LambdaMART.java:401-408,475-481, MART.java:57-63)
+ * over n host doubles, through the kernels the leaf outputs and NDCG-T use.  passes = simulations per chunk (1 or
+ * 2).  info[0] = elements applied one by one, info[1] = chunks redone by the exact block routine. */
+int rlb_float_chain(rlb_ctx* ctx, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t info[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,15 @@ def score_metric(scores, label, qoff, metric=0, k=10):
     return out.value
 
 
+def float_chain(x, carry=0.0):
+    """float s = carry; for v in x: s += v  (Java compound assignment with a double right-hand side)."""
+    lib = load()
+    x = np.ascontiguousarray(x, np.float64)
+    lib.orc_float_chain.restype = C.c_float
+    lib.orc_float_chain.argtypes = [C.c_void_p, C.c_int64, C.c_float]
+    return np.float32(lib.orc_float_chain(_p(x), x.shape[0], C.c_float(carry)))
+
+
 def java_random_ints(seed, bound, n):
     lib = load()
     out = np.zeros(n, np.int32)

@@ -888,4 +888,12 @@ int orc_java_random_ints(int64_t seed, int32_t bound, int32_t n, int32_t* out) {
     return RLB_OK;
 }
 
+// The reference's float accumulation idiom, literally: `float s = carry; for (...) s += x[i];` with a double right-hand side
+// (LambdaMART.java:401-408 leaf sums, :475-481 NDCG-T, MART.java:57-63): each += is (float)((double)s + x[i]).
+float orc_float_chain(const double* x, int64_t n, float carry) {
+    float s = carry;
+    for (int64_t i = 0; i < n; i++) s = (float)((double)s + x[i]);
+    return s;
+}
+
 }  // extern "C"

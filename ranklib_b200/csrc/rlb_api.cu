@@ -459,6 +459,16 @@ __global__ void k_node_to_leaf(const DevState* __restrict__ st, const int32_t* _
         out[i] = st->nodes[nodeOf[i]].leaf_ord;
 }
 
+int rlb_float_chain(rlb_ctx* c, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t info[2]) {
+    if (!c || !out || (n > 0 && !x) || n < 0) return RLB_E_INVALID;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) {
+        rlb_set_error(c, RLB_E_CUDA, "rlb_float_chain", cudaGetErrorString(e));
+        return RLB_E_CUDA;
+    }
+    return rlb_impl_float_chain(c, x, n, carry, passes, out, info);
+}
+
 int rlb_read(rlb_ctx* c, int32_t what, void* dst, int64_t bytes) {
     if (int rc = check_ready(c, "rlb_read")) return rc;
     if (!dst) return RLB_E_INVALID;
@@ -560,13 +570,13 @@ int rlb_stats(rlb_ctx* c, int64_t out[4]) {
 #ifdef RLB_CHAIN_DEBUG
         long long dbg[3];
         cudaMemcpy(dbg, c->dState->chain_dbg, 24, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "chain fallbacks: no-summary %lld, exponent/sign mismatch %lld, range %lld\n", dbg[0], dbg[1], dbg[2]);
+        fprintf(stderr, "chunk start prediction: exact %lld, within 15 ulps %lld, worse %lld\n", dbg[0], dbg[1], dbg[2]);
         cudaMemset(c->dState->chain_dbg, 0, 24);
         static long long prof[64][4];
         cudaMemcpy(prof, c->dState->chain_prof, sizeof(prof), cudaMemcpyDeviceToHost);
         for (int i = 0; i < 20; i++)
-            fprintf(stderr, "  chain leaf %d %s: chunks %lld walk %lld cyc, fallback %lld cyc in %lld fallbacks\n", i / 2, (i & 1) ? "w" : "lambda",
-                    prof[i][3], prof[i][0], prof[i][1], prof[i][2]);
+            fprintf(stderr, "  chain leaf %d %s: chunks %lld walk %lld cyc, fallback %lld cyc in %lld fallbacks, %lld items\n", i / 2, (i & 1) ? "w" : "lambda",
+                    prof[i][3], prof[i][0], prof[i][1], prof[i][2] % 1000, prof[i][2] / 1000);
 #endif
     }
     return RLB_OK;

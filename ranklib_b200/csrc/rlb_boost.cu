@@ -1943,27 +1943,53 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// Two-level float chains.  chain_block alone walks a leaf of 900 k samples chunk after chunk.  The
-// chunks are made independent by SPECULATING the binade the running float is in when a chunk starts:
-//   k_chain_sum   exact double sum of every 1024-element chunk (parallel)
-//   k_chain_pred  prefix of those sums per chain = predicted float at every chunk start (the float
-//                 chain stays within ~1e-3 relative of the exact sum, so the predicted exponent is
-//                 right except next to a power of two)
-//   k_chain_summ  per chunk, under the predicted exponent/sign: total quanta, min/max prefix quanta,
-//                 tie/overflow flag (parallel)
-//   k_*_chain     one CTA per chain walks the chunk summaries: a chunk whose summary is valid for
-//                 the ACTUAL running float (same sign and exponent, mantissa stays inside
-//                 (2^23, 2^24), no tie) costs O(1); any other chunk is redone exactly by chain_block.
-// The result is bit-identical to the sequential chain in every case; speculation only buys time.
+// Float chains as ITEM PROGRAMS.  chain_block alone walks a leaf of 900 k samples chunk after chunk, and a
+// chunk-level summary fails on every chunk in which the running float changes binade — which a signed sum that
+// hovers near zero does thousands of times per chain.  So the element sequence of every 1024-element chunk is
+// compiled, in parallel and ahead of the one sequential walk, into a short program of items:
+//     RUN   a stretch of elements that only moves the mantissa inside one binade: (sign|exponent key, total quanta,
+//           min / max prefix quanta).  Valid for ANY start mantissa M of that key with M + min > 2^23 and
+//           M + max < 2^24; then M += total.  The quanta depend on the key and the elements only, never on M.
+//     X     one element applied with real arithmetic, s = (float)((double)s + x)  (binade crossings, ties)
+//     ZRUN  a stretch of exact zeros met while the running float is +0
+// The item boundaries come from SIMULATING the chunk exactly from a predicted start value (k_chain_sim, one CTA
+// per chunk): pass 1 starts every chunk at the exact double prefix sum, pass 2 at the prefix of the ROUNDED
+// increments pass 1 measured (k_chain_refine), which removes the drift between the float chain and the exact
+// sum, so the simulated trajectory crosses binades at the same elements as the real one.  The walk
+// (k_*_chain, one CTA per chain, one thread stepping) then costs O(1) per item; an item whose guard fails for the
+// actual running float (prediction off by more than the clearance of a crossing) makes the CTA redo that chunk
+// exactly with chain_block.  Whatever the predictions, the result is bit-identical to the sequential chain:
+// every RUN is guarded and every X is the real operation.
+//   k_chain_sum   exact double sum of every chunk (parallel); also stores the gathered values contiguously
+//   k_chain_pred  prefix of those sums per chain = predicted start of every chunk
 // ------------------------------------------------------------------------------------------------
-#define CK 1024   // elements per chunk (256 threads x 4)
+#define CK 1024          // elements per chunk (256 threads x 4)
+#define CH_ITEMS 1100    // item capacity of a chunk's program (worst case: every element its own item)
+#define CH_STREAM (CH_ITEMS + 1)   // stream slots per chunk: its items + the chunk marker
+#define CH_BATCH 1024    // items per batch of the walk (4 per thread)
+
+// 16 bytes.  w0 = kind | key << 2.  RUN: a = total quanta, b / c = min / max prefix quanta (all inside +-2^24 for a
+// run that can pass its guard).  X: (b, c) = the element's double bits.  MARK: a = chunk index (opens a chunk).
+struct __align__(16) ChainItem {
+    uint32_t w0;
+    int32_t a, b, c;
+};
+#define CI_RUN 0u
+#define CI_X 1u
+#define CI_ZRUN 2u
+#define CI_MARK 3u
 
 struct ChainBufs {
-    double* sumD;       // [2][maxChunks] exact chunk sums, then (in place) predicted start values
-    long long* Qtot;    // [2][maxChunks]
-    long long* Pmin;
-    long long* Pmax;
-    int32_t* ef;        // [2][maxChunks] bit0 valid, bit1 all-zero chunk, bit2 sign, bits 8.. biased exponent
+    double* sumD;        // [2][maxChunks] exact chunk sums, then (in place) predicted start values
+    double* xs;          // [2][maxChunks * CK] chain elements in chain order (gathered once by k_chain_sum)
+    ChainItem* items;    // [2][maxChunks][CH_ITEMS] per-chunk programs
+    int32_t* nitems;     // [2][maxChunks]
+    int32_t* ipos;       // [2][maxChunks] stream position of every chunk's marker, relative to its chain's stream
+    int32_t* itot;       // [2][RLB_MAX_LEAVES + 2] stream length of every chain
+    ChainItem* stream;   // [2][maxChunks * CH_STREAM] per-chain item streams (chain l starts at chunk0[l] * CH_STREAM)
+    double* rsum;        // [2][maxChunks] rounded increment of every chunk (k_chain_round)
+    float* simS;         // [2][maxChunks] start value the chunk was simulated from
+    float* simE;         // [2][maxChunks] value at the end of the simulated chunk
     int32_t maxChunks;
 };
 
@@ -2014,13 +2040,18 @@ __global__ void __launch_bounds__(256) k_chain_sum(int mode, const DevState* __r
     const int l = chain_of_chunk(chunk0, nCh, b);
     const ChainView v = chain_view(mode, st, l, which, a0, a1, s0, s1, nMetric);
     const int64_t off = (int64_t)(b - chunk0[l]) * CK;
+    double* xs = cb.xs + ((size_t)which * cb.maxChunks + b) * CK;
     __shared__ double ws[8];
     double acc = 0.0;
+    double x[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int64_t j = off + threadIdx.x * 4 + k;
-        if (j < v.n) acc += v.val[v.idx ? (int64_t)v.idx[j] : j];
+        if (j < v.n) x[k] = v.val[v.idx ? (int64_t)v.idx[j] : j];
+        acc += x[k];
     }
+    reinterpret_cast<double2*>(xs)[threadIdx.x * 2] = make_double2(x[0], x[1]);
+    reinterpret_cast<double2*>(xs)[threadIdx.x * 2 + 1] = make_double2(x[2], x[3]);
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -2054,6 +2085,30 @@ __global__ void __launch_bounds__(32) k_chain_pred(int mode, const DevState* __r
     }
 }
 
+// second prediction: start of chunk i = carry + sum over the earlier chunks of (end - start) of their pass-1
+// simulations, i.e. the prefix of the increments as the float chain ROUNDS them
+__global__ void __launch_bounds__(32) k_chain_refine(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                      const float* __restrict__ carryIn, ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int l = blockIdx.x, which = blockIdx.y;
+    if (l >= nCh) return;
+    const int c0 = chunk0[l], c1 = chunk0[l + 1];
+    double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
+    const size_t o = (size_t)which * cb.maxChunks;
+    const int lane = threadIdx.x;
+    for (int base = c0; base < c1; base += 32) {
+        const int i = base + lane;
+        const double v = (i < c1) ? (double)cb.simE[o + i] - (double)cb.simS[o + i] : 0.0;
+        double inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o2 = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o2;
+        }
+        if (i < c1) cb.sumD[o + i] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
 // quanta of x when added to a float with sign sg (+-1) and exponent e: Q = rn(rn_v(x) / u); bad on ties / overflow
 __device__ __forceinline__ long long chain_quantum(double x, double sg, double scale_v, bool& bad) {
     const double a = sg * x * scale_v;
@@ -2068,186 +2123,478 @@ __device__ __forceinline__ long long chain_quantum(double x, double sg, double s
     return (long long)Qd;
 }
 
-__global__ void __launch_bounds__(256) k_chain_summ(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
-                                                     const double* __restrict__ a0, const double* __restrict__ a1,
-                                                     const int32_t* __restrict__ s0, const int32_t* __restrict__ s1,
-                                                     int64_t nMetric, ChainBufs cb) {
+__device__ __forceinline__ bool chain_is_normal(float s) {
+    const int eb = (__float_as_uint(s) >> 23) & 0xff;
+    return eb != 0 && eb != 0xff;
+}
+
+__device__ __forceinline__ ChainItem ci_x(double x) {
+    ChainItem it;
+    const long long xb = __double_as_longlong(x);
+    it.w0 = CI_X; it.a = 0; it.b = (int32_t)(xb & 0xffffffffLL); it.c = (int32_t)(xb >> 32);
+    return it;
+}
+__device__ __forceinline__ double ci_x_value(const ChainItem& it) {
+    return __longlong_as_double(((long long)it.c << 32) | (long long)(uint32_t)it.b);
+}
+
+// Rounded increment of every chunk — what the float chain adds over the chunk once its per-step rounding is
+// taken into account — without simulating it: element j is quantised under the binade of the EXACT prefix in
+// front of it (scan of the predicted chunk start + the elements), and the quanta are summed as doubles.  The
+// result ignores what happens at the (rare) steps that change binade, which is all the second prediction needs:
+// it removes the drift between the float chain and the exact sum (k_chain_pred2).
+__global__ void __launch_bounds__(256) k_chain_round(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                      ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int b = blockIdx.x, which = blockIdx.y;
+    if (b >= chunk0[nCh]) return;
+    const size_t o = (size_t)which * cb.maxChunks + b;
+    const double* xg = cb.xs + o * CK;
+    __shared__ double wT[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const double2 p0 = reinterpret_cast<const double2*>(xg)[tid * 2], p1 = reinterpret_cast<const double2*>(xg)[tid * 2 + 1];
+    const double x[4] = {p0.x, p0.y, p1.x, p1.y};
+    // exclusive prefix (double) of the elements in front of each of mine
+    double loc[4];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        loc[k] = run;
+        run += x[k];
+    }
+    double inc = run;
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o2 = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o2;
+    }
+    if (lane == 31) wT[w] = inc;
+    __syncthreads();
+    double offp = cb.sumD[o] + (inc - run);
+    for (int i = 0; i < w; i++) offp += wT[i];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float sp = (float)(offp + loc[k]);
+        double r = x[k];
+        if (chain_is_normal(sp) && x[k] != 0.0) {
+            const unsigned int bits = __float_as_uint(sp);
+            const int e = (int)((bits >> 23) & 0xff) - 127;
+            bool bad = false;
+            const double sg = (bits >> 31) ? -1.0 : 1.0;
+            const long long q = chain_quantum(x[k], sg, scalbn(1.0, 52 - e), bad);
+            if (!bad) r = sg * scalbn((double)q, e - 23);
+        }
+        acc += r;
+    }
+    __syncthreads();
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) wT[w] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += wT[i];
+        cb.rsum[o] = t;
+    }
+}
+
+// second prediction: start of chunk i = carry + sum of the rounded increments of the earlier chunks
+__global__ void __launch_bounds__(32) k_chain_pred2(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                     const float* __restrict__ carryIn, ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int l = blockIdx.x, which = blockIdx.y;
+    if (l >= nCh) return;
+    const int c0 = chunk0[l], c1 = chunk0[l + 1];
+    double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
+    const size_t o = (size_t)which * cb.maxChunks;
+    const int lane = threadIdx.x;
+    for (int base = c0; base < c1; base += 32) {
+        const int i = base + lane;
+        const double v = (i < c1) ? cb.rsum[o + i] : 0.0;
+        double inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o2 = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o2;
+        }
+        if (i < c1) cb.sumD[o + i] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// Compile one chunk into its item program by simulating it exactly from the predicted start value: ONE WARP per
+// chunk, no block barriers.  A round quantises the next 256 elements under the running float's binade, scans, and
+// commits the stretch up to the first element that leaves the binade (or ties) into the pending RUN (consecutive
+// stretches of one binade merge); that element becomes an X, applied by lane 0, which goes on one element at a time
+// until SIM_STABLE consecutive steps stayed inside their binade — where the sum is small against the elements
+// nearly every step changes binade, and a round per element would cost several times more.
+#define SIM_EPL 8        // elements per lane and round
+#ifndef SIM_STABLE
+#define SIM_STABLE 0   // 0: hand back to the rounds at the first element that stays inside its binade; k > 0: after k such steps
+#endif
+#define SIM_WARPS 4
+
+__global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const DevState* __restrict__ st,
+                                                               const int32_t* __restrict__ chunk0, int64_t nMetric,
+                                                               const float* __restrict__ carryIn, ChainBufs cb) {
+    __shared__ double xsAll[SIM_WARPS][CK];
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * SIM_WARPS + wid, which = blockIdx.y;
+    if (b >= chunk0[nCh]) return;   // whole warp; nothing below synchronises across warps
+    const int l = chain_of_chunk(chunk0, nCh, b);
+    int64_t n;
+    if (mode == 1) {
+        n = nMetric;
+    } else {
+        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
+        n = r.hi - r.lo;
+    }
+    const int64_t off = (int64_t)(b - chunk0[l]) * CK;
+    const int m = (int)min((int64_t)CK, n - off);
+    const size_t o = (size_t)which * cb.maxChunks + b;
+    const double* xg = cb.xs + o * CK;
+    double* xs = xsAll[wid];
+    ChainItem* items = cb.items + o * CH_ITEMS;
+    for (int i = lane; i < CK / 2; i += 32) reinterpret_cast<double2*>(xs)[i] = reinterpret_cast<const double2*>(xg)[i];
+    __syncwarp();
+    // the first chunk of a chain starts from the carry itself, not from a rounded copy of it
+    float s = (b == chunk0[l]) ? (carryIn ? carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.f) : (float)cb.sumD[o];
+    if (lane == 0) cb.simS[o] = s;
+    int pos = 0, nit = 0;                         // uniform across the warp
+    int pendKey = -1, pendQ = 0, pendMn = 0, pendMx = 0;   // lane 0: the RUN being assembled
+    while (pos < m) {
+        const unsigned int bits = __float_as_uint(s);
+        int fb;   // first element that is not absorbed by the leading RUN / ZRUN
+        if (!chain_is_normal(s)) {
+            fb = pos;
+            if (bits == 0u) {   // +0: the exact zeros that follow change nothing
+                while (fb < m) {
+                    const int j = fb + lane;
+                    const unsigned int nz = __ballot_sync(0xffffffffu, j < m && xs[j] != 0.0);
+                    if (nz) {
+                        fb += __ffs(nz) - 1;
+                        break;
+                    }
+                    fb = min(fb + 32, m);
+                }
+                if (fb > pos) {
+                    if (lane == 0) {
+                        ChainItem it;
+                        it.w0 = CI_ZRUN; it.a = 0; it.b = 0; it.c = 0;
+                        items[nit] = it;
+                    }
+                    nit++;
+                }
+            }
+        } else {
+            const int e = (int)((bits >> 23) & 0xff) - 127;
+            const double sg = (bits >> 31) ? -1.0 : 1.0;
+            const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
+            const double scale_v = scalbn(1.0, 52 - e);
+            const int wend = min(pos + 32 * SIM_EPL, m);
+            const int j0 = pos + lane * SIM_EPL;
+            long long P[SIM_EPL];
+            unsigned int badMask = 0;
+            long long run = 0;
+#pragma unroll
+            for (int k = 0; k < SIM_EPL; k++) {
+                const int j = j0 + k;
+                long long q = 0;
+                if (j < wend) {
+                    const double x = xs[j];
+                    bool bad = false;
+                    if (x != 0.0) q = chain_quantum(x, sg, scale_v, bad);
+                    if (bad) badMask |= 1u << k;
+                }
+                run += q;
+                P[k] = run;
+            }
+            const long long inc = warp_incl_scan_ll(run, lane);
+            const long long offp = inc - run;
+            int myBad = 0x7fffffff;
+#pragma unroll
+            for (int k = SIM_EPL - 1; k >= 0; k--) {
+                const int j = j0 + k;
+                if (j < wend) {
+                    bool bb = (badMask >> k) & 1u;
+                    if (!bb) {
+                        const long long Mi = M + offp + P[k];
+                        bb = !(Mi > 8388608LL && Mi < 16777216LL);
+                    }
+                    if (bb) myBad = j;
+                }
+            }
+            fb = min(__reduce_min_sync(0xffffffffu, myBad), wend);
+            if (fb > pos) {
+                // stretch [pos, fb): total, min and max of the inclusive prefixes (inside +-2^24: every prefix mantissa is
+                // inside the binade)
+                int mn = 0x7fffffff, mx = -0x7fffffff - 1, tot = 0;
+                bool haveTot = false;
+#pragma unroll
+                for (int k = 0; k < SIM_EPL; k++) {
+                    const int j = j0 + k;
+                    if (j < fb) {
+                        const int pv = (int)(offp + P[k]);
+                        mn = min(mn, pv);
+                        mx = max(mx, pv);
+                        if (j == fb - 1) {
+                            tot = pv;
+                            haveTot = true;
+                        }
+                    }
+                }
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                const unsigned int owner = __ballot_sync(0xffffffffu, haveTot);
+                tot = __shfl_sync(0xffffffffu, tot, __ffs(owner) - 1);
+                if (lane == 0) {
+                    const int key = (int)(bits >> 23);
+                    if (pendKey == key) {
+                        pendMn = min(pendMn, pendQ + mn);
+                        pendMx = max(pendMx, pendQ + mx);
+                        pendQ += tot;
+                    } else {
+                        pendKey = key; pendQ = tot; pendMn = mn; pendMx = mx;   // any earlier RUN was flushed by its X
+                    }
+                }
+                const long long Mn = M + tot;  // in (2^23, 2^24): same sign and exponent
+                s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mn & 0x7fffffu));
+                if (fb == wend) {   // nothing left the binade in this window
+                    pos = fb;
+                    continue;
+                }
+            }
+        }
+        // element by element from fb (lane 0): the first one always, then until SIM_STABLE consecutive steps stayed put
+        int npos = fb, nnit = nit;
+        float ns = s;
+        if (lane == 0) {
+            if (pendKey >= 0) {
+                ChainItem it;
+                it.w0 = CI_RUN | ((unsigned int)pendKey << 2); it.a = pendQ; it.b = pendMn; it.c = pendMx;
+                items[nnit++] = it;
+                pendKey = -1;
+            }
+            int stable = 0;
+            while (npos < m) {
+                const double x = xs[npos];
+                const float nxt = (float)((double)ns + x);
+                const unsigned int b0 = __float_as_uint(ns), b1 = __float_as_uint(nxt);
+                if (npos > fb && b0 == 0u && x == 0.0) break;   // a ZRUN takes over
+                const bool st1 = chain_is_normal(ns) && ((b0 ^ b1) & 0xff800000u) == 0;
+                if (SIM_STABLE == 0 && npos > fb && st1) break;  // this element stays inside the binade: a round takes over
+                items[nnit++] = ci_x(x);
+                stable = st1 ? stable + 1 : 0;
+                ns = nxt;
+                npos++;
+                if (SIM_STABLE > 0 && stable >= SIM_STABLE) break;
+            }
+        }
+        pos = __shfl_sync(0xffffffffu, npos, 0);
+        nit = __shfl_sync(0xffffffffu, nnit, 0);
+        s = __shfl_sync(0xffffffffu, ns, 0);
+    }
+    if (lane == 0) {
+        if (pendKey >= 0) {
+            ChainItem it;
+            it.w0 = CI_RUN | ((unsigned int)pendKey << 2); it.a = pendQ; it.b = pendMn; it.c = pendMx;
+            items[nit++] = it;
+        }
+        cb.nitems[o] = nit;
+        cb.simE[o] = s;
+    }
+}
+
+// stream position of every chunk of a chain: exclusive prefix of (items + 1 marker); one warp per (chain, which)
+__global__ void __launch_bounds__(32) k_chain_offsets(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                       ChainBufs cb) {
+    const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
+    const int l = blockIdx.x, which = blockIdx.y;
+    if (l >= nCh) return;
+    const int c0 = chunk0[l], c1 = chunk0[l + 1];
+    const size_t o = (size_t)which * cb.maxChunks;
+    const size_t on = o;
+    const int lane = threadIdx.x;
+    int run = 0;
+    for (int base = c0; base < c1; base += 32) {
+        const int i = base + lane;
+        const int v = (i < c1) ? cb.nitems[on + i] + 1 : 0;
+        const int inc = warp_incl_scan_i(v, lane);
+        if (i < c1) cb.ipos[o + i] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) cb.itot[which * (RLB_MAX_LEAVES + 2) + l] = run;
+}
+
+// copy every chunk's program behind its marker into its chain's stream
+__global__ void __launch_bounds__(128) k_chain_compact(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+                                                        ChainBufs cb) {
     const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
     const int b = blockIdx.x, which = blockIdx.y;
     if (b >= chunk0[nCh]) return;
     const int l = chain_of_chunk(chunk0, nCh, b);
-    const ChainView v = chain_view(mode, st, l, which, a0, a1, s0, s1, nMetric);
-    const int64_t off = (int64_t)(b - chunk0[l]) * CK;
-    const size_t o = (size_t)which * cb.maxChunks + b;
-    const float pred = (float)cb.sumD[o];
-    const unsigned int bits = __float_as_uint(pred);
-    const int ebits = (bits >> 23) & 0xff;
-    const bool normal = (ebits != 0 && ebits != 0xff);
-    const double sg = (bits >> 31) ? -1.0 : 1.0;
-    const double scale_v = scalbn(1.0, 52 - (ebits - 127));
-    __shared__ long long wT[8], wMin[8], wMax[8];
-    __shared__ int sBad, sNonZero;
+    const size_t on = (size_t)which * cb.maxChunks + b;
+    const int ni = cb.nitems[on];
+    ChainItem* dst = cb.stream + ((size_t)which * cb.maxChunks + chunk0[l]) * CH_STREAM + cb.ipos[(size_t)which * cb.maxChunks + b];
     if (threadIdx.x == 0) {
-        sBad = 0;
-        sNonZero = 0;
+        ChainItem mk;
+        mk.w0 = CI_MARK; mk.a = b; mk.b = 0; mk.c = 0;
+        dst[0] = mk;
     }
-    __syncthreads();
-    long long Q[4];
-    bool bad = false, nz = false;
-    long long run = 0, mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int64_t j = off + threadIdx.x * 4 + k;
-        Q[k] = 0;
-        if (j < v.n) {
-            const double x = v.val[v.idx ? (int64_t)v.idx[j] : j];
-            if (x != 0.0) {
-                nz = true;
-                if (normal) Q[k] = chain_quantum(x, sg, scale_v, bad);
-            }
-        }
-        run += Q[k];
-        Q[k] = run;  // thread-local inclusive prefix
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long inc = warp_incl_scan_ll(run, lane);
-    if (lane == 31) wT[w] = inc;
-    __syncthreads();
-    long long offp = inc - run;
-    for (int i = 0; i < w; i++) offp += wT[i];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int64_t j = off + threadIdx.x * 4 + k;
-        if (j < v.n) {
-            const long long P = offp + Q[k];
-            mn = min(mn, P);
-            mx = max(mx, P);
-        }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    }
-    if (lane == 0) {
-        wMin[w] = mn;
-        wMax[w] = mx;
-    }
-    if (bad) atomicOr(&sBad, 1);
-    if (nz) atomicOr(&sNonZero, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long tot = 0;
-        for (int i = 0; i < 8; i++) {
-            tot += wT[i];
-            mn = min(mn, wMin[i]);
-            mx = max(mx, wMax[i]);
-        }
-        cb.Qtot[o] = tot;
-        cb.Pmin[o] = mn;
-        cb.Pmax[o] = mx;
-        int ef = 0;
-        if (!sNonZero) ef |= 2;
-        if (normal && !sBad) ef |= 1;
-        if (bits >> 31) ef |= 4;
-        ef |= ebits << 8;
-        cb.ef[o] = ef;
-    }
+    const ChainItem* src = cb.items + on * CH_ITEMS;
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) dst[1 + i] = src[i];
 }
 
-// Walk the chunk summaries of one chain (all threads of the CTA call this).  Warp 0 takes 32 consecutive
-// chunks at a time: lane l assumes the running float keeps the exponent and sign it has at the first of
-// them, computes the mantissa at the start of ITS chunk from an exclusive warp scan of the quanta totals, and
-// checks its chunk's summary (valid for that exponent / sign, prefix minimum and maximum keep the mantissa
-// inside (2^23, 2^24)).  Everything before the first failing lane is committed in one step; the failing
-// chunk is redone exactly by the whole CTA (chain_block) and the walk resumes behind it.
-__device__ float chain_two_level(const ChainView v, int c0, int c1, int which, float carry, const ChainBufs& cb,
-                                 long long* serialCount) {
-    __shared__ float sCur;
-    __shared__ int sStop;
-    const int tid = threadIdx.x, lane = tid & 31;
+// Walk one chain's item stream, CH_BATCH items per batch.  All threads fetch the next batch (into registers while
+// the walk runs, into shared memory afterwards); thread 0 steps through the items.  An item whose guard fails for
+// the actual running float makes the whole CTA redo that chunk exactly (chain_block) from the value the chunk
+// started with; the walk resumes at the next chunk marker.
+__device__ float chain_walk(const double* __restrict__ xsAll, int64_t n, int chain, int c0, int c1, int which, float carry,
+                            const ChainBufs& cb, long long* serialCount) {
+    __shared__ ChainItem sItems[2][CH_BATCH];
+    __shared__ float sCur, sChunkStart;
+    __shared__ int sFailChunk, sPos, sSkip, sCurChunk;
+    const int tid = threadIdx.x;
+    constexpr int PT = CH_BATCH / RLB_CHAIN_THREADS;  // items per thread and batch
     const size_t o = (size_t)which * cb.maxChunks;
-    if (tid == 0) sCur = carry;
-#ifdef RLB_CHAIN_DEBUG
-    long long cycWalk = 0, cycFb = 0, nFb = 0;
-    long long tmark = clock64();
-#endif
-    int c = c0;
+    const ChainItem* stream = cb.stream + (o + c0) * CH_STREAM;
+    if (tid == 0) {
+        sCur = carry;
+        sChunkStart = carry;
+        sSkip = 0;
+        sCurChunk = c0;
+    }
+    if (c0 >= c1) {
+        __syncthreads();
+        return carry;
+    }
+    const int total = cb.itot[which * (RLB_MAX_LEAVES + 2) + chain];
+    // batch 0
+#pragma unroll
+    for (int k = 0; k < PT; k++) {
+        const int i = tid + k * RLB_CHAIN_THREADS;
+        if (i < total) sItems[0][i] = stream[i];
+    }
     __syncthreads();
-    while (c < c1) {
-        if (tid < 32) {
-            float s = sCur;
-            int i = c;
-            bool failed = false;
-            while (i < c1 && !failed) {
-                const int me = i + lane;
-                const bool in = me < c1;
-                int ef = 2;  // out-of-range lanes behave like all-zero chunks
-                long long q = 0, pmn = 0, pmx = 0;
-                if (in) {
-                    ef = cb.ef[o + me];
-                    q = cb.Qtot[o + me];
-                    pmn = cb.Pmin[o + me];
-                    pmx = cb.Pmax[o + me];
+    long long nX = 0, nFb = 0;
+    int buf = 0;
+#ifdef RLB_CHAIN_DEBUG
+    long long cycWalk = 0, cycFb = 0;
+#endif
+    for (int i0 = 0; i0 < total; i0 += CH_BATCH, buf ^= 1) {
+        ChainItem pre[PT];
+#pragma unroll
+        for (int k = 0; k < PT; k++) {
+            const int i = i0 + CH_BATCH + tid + k * RLB_CHAIN_THREADS;
+            if (i < total) pre[k] = stream[i];
+        }
+        const int nb = min(CH_BATCH, total - i0);
+        int pos = 0;
+        while (pos < nb) {
+#ifdef RLB_CHAIN_DEBUG
+            const long long t0 = clock64();
+#endif
+            if (tid == 0) {
+                float s = sCur;
+                float sChunk = sChunkStart;
+                int skip = sSkip;      // 1: inside a chunk that was redone exactly — ignore items up to the next marker
+                int failChunk = -1;
+                int curChunk = sCurChunk;
+                int i = pos;
+                const ChainItem* its = sItems[buf];
+                ChainItem it = its[i];
+                for (; i < nb;) {
+                    const ChainItem nx = its[min(i + 1, nb - 1)];   // next item's load overlaps this item's arithmetic
+                    const unsigned int kind = it.w0 & 3u;
+                    if (kind == CI_MARK) {
+                        skip = 0;
+                        sChunk = s;
+                        curChunk = it.a;
+#ifdef RLB_CHAIN_DEBUG
+                        if (serialCount) {
+                            DevState* dst = (DevState*)((char*)serialCount - offsetof(DevState, chain_serial));
+                            const unsigned int ba = __float_as_uint(s), bp = __float_as_uint(cb.simS[o + curChunk]);
+                            const long long d = (long long)ba - (long long)bp;
+                            const int slot = (ba >> 23) != (bp >> 23) ? 2 : (d == 0 ? 0 : ((d < 16 && d > -16) ? 1 : 2));
+                            atomicAdd((unsigned long long*)&dst->chain_dbg[slot], 1ull);
+                        }
+#endif
+                    } else if (!skip) {
+                        const unsigned int bits = __float_as_uint(s);
+                        if (kind == CI_RUN) {
+                            const int M = (int)((bits & 0x7fffffu) | 0x800000u);
+                            if ((bits >> 23) != (it.w0 >> 2) || !(M + it.b > 8388608) || !(M + it.c < 16777216)) {
+                                failChunk = curChunk;
+                            } else {
+                                s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)(M + it.a) & 0x7fffffu));
+                            }
+                        } else if (kind == CI_X) {
+                            s = (float)((double)s + ci_x_value(it));
+                            nX++;
+                        } else {
+                            if (bits != 0u) failChunk = curChunk;
+                        }
+                        if (failChunk != -1) break;
+                    }
+                    it = nx;
+                    i++;
                 }
-                const bool zero = (ef & 2) != 0;
-                if (zero) q = 0;
-                const unsigned int bits = __float_as_uint(s);
-                const long long M0 = (long long)((bits & 0x7fffffu) | 0x800000u);
-                const long long incl = warp_incl_scan_ll(q, lane);
-                const long long Mi = M0 + incl - q;  // mantissa at the start of my chunk if all earlier lanes are valid
-                bool ok = zero;
-                if (!zero)
-                    ok = (ef & 1) && (int)((bits >> 23) & 0xff) == (ef >> 8) && (int)(bits >> 31) == ((ef >> 2) & 1) &&
-                         (Mi + pmn > 8388608LL) && (Mi + pmx < 16777216LL);
-                const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
-                const int f = bad ? (__ffs(bad) - 1) : 32;  // first failing lane
-                // the non-zero chunks before f moved the mantissa by their quanta; exponent and sign unchanged
-                const long long upto = __shfl_sync(0xffffffffu, incl, f > 0 ? f - 1 : 0);
-                if (f > 0) {
-                    const long long Mn = M0 + upto;
-                    if (Mn != M0) s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mn & 0x7fffffu));
+                if (failChunk != -1) {
+                    s = sChunk;
+                    skip = 1;
                 }
-                i += f;
-                if (f < 32) failed = true;  // chunk i needs the exact path (or lies beyond c1: handled below)
-            }
-            if (lane == 0) {
                 sCur = s;
-                sStop = min(i, c1);
+                sChunkStart = sChunk;
+                sSkip = skip;
+                sCurChunk = curChunk;
+                sFailChunk = failChunk;
+                sPos = i;
+            }
+            __syncthreads();
+            const int fail = sFailChunk;
+            pos = sPos;
+#ifdef RLB_CHAIN_DEBUG
+            const long long t1 = clock64();
+            cycWalk += t1 - t0;
+#endif
+            if (fail != -1) {
+                const int64_t off = (int64_t)(fail - c0) * CK;
+                const int64_t len = min((int64_t)CK, n - off);
+                const float s2 = chain_block(xsAll + (o + fail) * CK, nullptr, len, sCur, nullptr, 0);
+                __syncthreads();
+                if (tid == 0) {
+                    sCur = s2;
+                    nFb++;
+                }
+                pos = pos + 1;
+                __syncthreads();
+#ifdef RLB_CHAIN_DEBUG
+                cycFb += clock64() - t1;
+#endif
             }
         }
-        __syncthreads();
-        const int stop = sStop;
-        const float s = sCur;
-#ifdef RLB_CHAIN_DEBUG
-        { const long long now = clock64(); cycWalk += now - tmark; tmark = now; }
-#endif
-        if (stop >= c1) break;
-        const int64_t off = (int64_t)(stop - c0) * CK;
-        const int64_t len = min((int64_t)CK, v.n - off);
-        const float s2 = chain_block(v.val, v.idx ? v.idx + off : nullptr, len, s, serialCount, v.idx ? 0 : off);
-        __syncthreads();
-        if (tid == 0) {
-            sCur = s2;
-            atomicAdd((unsigned long long*)(serialCount + 1), 1ull);  // chain_fallback follows chain_serial
+#pragma unroll
+        for (int k = 0; k < PT; k++) {
+            const int i = i0 + CH_BATCH + tid + k * RLB_CHAIN_THREADS;
+            if (i < total) sItems[buf ^ 1][tid + k * RLB_CHAIN_THREADS] = pre[k];
         }
-        c = stop + 1;
         __syncthreads();
-#ifdef RLB_CHAIN_DEBUG
-        { const long long now = clock64(); cycFb += now - tmark; tmark = now; nFb++; }
-#endif
     }
 #ifdef RLB_CHAIN_DEBUG
-    if (tid == 0 && gridDim.x > 1) {
+    if (tid == 0 && serialCount && gridDim.x > 1) {
         DevState* dst = (DevState*)((char*)serialCount - offsetof(DevState, chain_serial));
         const int slot = blockIdx.x * 2 + blockIdx.y;
         if (slot < 64) {
             dst->chain_prof[slot][0] = cycWalk;
             dst->chain_prof[slot][1] = cycFb;
-            dst->chain_prof[slot][2] = nFb;
+            dst->chain_prof[slot][2] = (long long)total * 1000 + nFb;
             dst->chain_prof[slot][3] = c1 - c0;
         }
     }
 #endif
+    if (tid == 0 && serialCount) {
+        if (nX) atomicAdd((unsigned long long*)serialCount, (unsigned long long)nX);
+        if (nFb) atomicAdd((unsigned long long*)(serialCount + 1), (unsigned long long)nFb);  // chain_fallback follows chain_serial
+    }
     __syncthreads();
     const float r = sCur;
     __syncthreads();
@@ -2257,17 +2604,13 @@ __device__ float chain_two_level(const ChainView v, int c0, int c1, int which, f
 // K7: LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.updateTreeOutput (MART.java:54-65):
 // blockIdx.x = leaf ordinal, blockIdx.y = 0 -> sum of pseudo responses, 1 -> sum of weights.
 __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
-                                                                    const double* __restrict__ lambda,
-                                                                    const double* __restrict__ weight,
-                                                                    const int32_t* __restrict__ samples0,
-                                                                    const int32_t* __restrict__ samples1,
                                                                     const float* __restrict__ carryIn, ChainBufs cb) {
     const int l = blockIdx.x;
     if (l >= st->n_leaves_out) return;
     const int which = blockIdx.y;
-    const ChainView v = chain_view(0, st, l, which, lambda, weight, samples0, samples1, 0);
+    const NodeRec& r = st->nodes[st->leaf_nodes[l]];
     const float c0 = carryIn ? carryIn[which * (RLB_MAX_LEAVES + 1) + l] : 0.f;
-    const float s = chain_two_level(v, chunk0[l], chunk0[l + 1], which, c0, cb, &st->chain_serial);
+    const float s = chain_walk(cb.xs, r.hi - r.lo, l, chunk0[l], chunk0[l + 1], which, c0, cb, &st->chain_serial);
     if (threadIdx.x == 0) (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
 }
 
@@ -2314,13 +2657,8 @@ __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st,
 
 // K9 tail: float chain over the per-query metric values (LambdaMART.java:474-483)
 __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
-                                                                      const double* __restrict__ qmetric, int Q,
-                                                                      const float* __restrict__ carryIn, ChainBufs cb) {
-    ChainView v;
-    v.val = qmetric;
-    v.idx = nullptr;
-    v.n = Q;
-    const float s = chain_two_level(v, chunk0[0], chunk0[1], 0, carryIn ? carryIn[0] : 0.f, cb, &st->chain_serial);
+                                                                      int Q, const float* __restrict__ carryIn, ChainBufs cb) {
+    const float s = chain_walk(cb.xs, Q, 0, chunk0[0], chunk0[1], 0, carryIn ? carryIn[0] : 0.f, cb, &st->chain_serial);
     if (threadIdx.x == 0) st->chain_out[0] = s;
 }
 
@@ -2624,7 +2962,7 @@ int rlb_impl_tree_output(rlb_ctx* c) {
         carry = c->dCarry;
     }
     const int nw = c->prm.kind == RLB_KIND_MART ? 1 : 2;
-    ChainBufs cb{c->dChainSum, c->dChainQ, c->dChainMin, c->dChainMax, c->dChainEf, c->chain_max_chunks};
+    ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
     k_leaf_chunks<<<1, 1, 0, c->stream>>>(c->dState, c->dChunk0);
     RLB_CHECK_LAUNCH(c);
     const int gchunks = (int)(c->N / CK) + nl + 1;
@@ -2633,11 +2971,26 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     RLB_CHECK_LAUNCH(c);
     k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
     RLB_CHECK_LAUNCH(c);
-    k_chain_summ<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, c->dLambda, c->dWeight, c->dSamples[0],
-                                                           c->dSamples[1], 0, cb);
+    const int gsim = (gchunks + SIM_WARPS - 1) / SIM_WARPS;
+    if (c->chain_passes >= 2) {   // second prediction from the rounded increments (default)
+        k_chain_round<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_pred2<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
+        RLB_CHECK_LAUNCH(c);
+    }
+    for (int pass = 2; pass < c->chain_passes; pass++) {   // RLB_CHAIN_PASSES > 2: further refinement from full simulations
+        k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, carry, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_refine<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
+        RLB_CHECK_LAUNCH(c);
+    }
+    k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, carry, cb);
     RLB_CHECK_LAUNCH(c);
-    k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, c->dLambda, c->dWeight, c->dSamples[0],
-                                                                    c->dSamples[1], carry, cb);
+    k_chain_offsets<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_compact<<<dim3(gchunks, nw), 128, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, carry, cb);
     RLB_CHECK_LAUNCH(c);
     if (c->world > 1) {
         // leaf_s1 and leaf_s2 are adjacent in DevState: one carry message
@@ -2701,16 +3054,20 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
         carry = c->dCarry;
     }
     {
-        ChainBufs cb{c->dChainSum, c->dChainQ, c->dChainMin, c->dChainMax, c->dChainEf, c->chain_max_chunks};
+        ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
         int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2;  // static table of the metric chain: {0, ceil(Q / CK)}
         const int gchunks = (c->Q + CK - 1) / CK;
         k_chain_sum<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
         RLB_CHECK_LAUNCH(c);
         k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, carry, cb);
         RLB_CHECK_LAUNCH(c);
-        k_chain_summ<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, c->dState, ch0, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
+        k_chain_sim<<<dim3((gchunks + SIM_WARPS - 1) / SIM_WARPS, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, c->dState, ch0, c->Q, carry, cb);
         RLB_CHECK_LAUNCH(c);
-        k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, c->dQMetric, c->Q, carry, cb);
+        k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, c->dState, ch0, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, c->Q, carry, cb);
         RLB_CHECK_LAUNCH(c);
     }
     if (c->world > 1) {
@@ -2718,6 +3075,77 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
     }
     k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, rlb_q_total(c));
     RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+// Test hook (rlb_float_chain): the float32 accumulation chain  s = carry; s = (float)((double)s + x[i])  over n host
+// doubles, through the same kernels the leaf outputs and NDCG-T use.  info[0] = X items walked, info[1] = chunks
+// redone exactly.
+int rlb_impl_float_chain(rlb_ctx* c, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t* info) {
+    const int gchunks = (int)((n + CK - 1) / CK);
+    const int maxc = gchunks + 1;
+    double *dX = nullptr, *dSum = nullptr, *dXs = nullptr, *dRSum = nullptr;
+    ChainItem *dItems = nullptr, *dStream = nullptr;
+    int32_t *dNI = nullptr, *dCh0 = nullptr, *dIPos = nullptr, *dITot = nullptr;
+    float *dS = nullptr, *dE = nullptr, *dCarry = nullptr;
+    DevState* dSt = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dX); cudaFree(dSum); cudaFree(dXs); cudaFree(dRSum); cudaFree(dItems); cudaFree(dStream); cudaFree(dNI); cudaFree(dIPos); cudaFree(dITot); cudaFree(dCh0); cudaFree(dS); cudaFree(dE);
+        cudaFree(dCarry); cudaFree(dSt);
+    };
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b ? b : 8); };
+    A((void**)&dX, (size_t)n * 8); A((void**)&dSum, (size_t)2 * maxc * 8); A((void**)&dRSum, (size_t)2 * maxc * 8); A((void**)&dXs, (size_t)2 * maxc * CK * 8);
+    A((void**)&dItems, (size_t)2 * maxc * CH_ITEMS * sizeof(ChainItem)); A((void**)&dNI, (size_t)2 * maxc * 4);
+    A((void**)&dStream, (size_t)2 * maxc * CH_STREAM * sizeof(ChainItem)); A((void**)&dIPos, (size_t)2 * maxc * 4);
+    A((void**)&dITot, (size_t)2 * (RLB_MAX_LEAVES + 2) * 4);
+    A((void**)&dCh0, 2 * 4); A((void**)&dS, (size_t)2 * maxc * 4); A((void**)&dE, (size_t)2 * maxc * 4); A((void**)&dCarry, 4);
+    A((void**)&dSt, sizeof(DevState));
+    if (e != cudaSuccess) {
+        cleanup();
+        rlb_set_error(c, RLB_E_CUDA, "rlb_float_chain", cudaGetErrorString(e));
+        return RLB_E_CUDA;
+    }
+    const int32_t ch0[2] = {0, gchunks};
+    cudaMemcpyAsync(dX, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dCh0, ch0, 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dCarry, &carry, 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(dSt, 0, sizeof(DevState), c->stream);
+    ChainBufs cb{dSum, dXs, dItems, dNI, dIPos, dITot, dStream, dRSum, dS, dE, maxc};
+    if (gchunks > 0) {
+        k_chain_sum<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, dSt, dCh0, 1, dX, nullptr, nullptr, nullptr, n, cb);
+        k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, dCarry, cb);
+        const int gsim = (gchunks + SIM_WARPS - 1) / SIM_WARPS;
+        if (passes >= 2) {
+            k_chain_round<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, dSt, dCh0, cb);
+            k_chain_pred2<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, dCarry, cb);
+        }
+        for (int pass = 2; pass < passes; pass++) {
+            k_chain_sim<<<dim3(gsim, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, dSt, dCh0, n, dCarry, cb);
+            k_chain_refine<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, dCarry, cb);
+        }
+        k_chain_sim<<<dim3(gsim, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, dSt, dCh0, n, dCarry, cb);
+        k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, cb);
+        k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, dSt, dCh0, cb);
+    }
+    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(dSt, dCh0, (int)n, dCarry, cb);
+    DevState* h = (DevState*)malloc(sizeof(DevState));
+    cudaMemcpyAsync(h, dSt, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        *out = h->chain_out[0];
+        if (info) {
+            info[0] = h->chain_serial;
+            info[1] = h->chain_fallback;
+        }
+    }
+    free(h);
+    cleanup();
+    if (e != cudaSuccess) {
+        rlb_set_error(c, RLB_E_CUDA, "rlb_float_chain", cudaGetErrorString(e));
+        return RLB_E_CUDA;
+    }
     return RLB_OK;
 }
 

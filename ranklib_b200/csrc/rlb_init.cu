@@ -213,7 +213,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
-    fr(c->dChainSum); fr(c->dChainQ); fr(c->dChainMin); fr(c->dChainMax); fr(c->dChainEf); fr(c->dChunk0);
+    fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
     c->loaded = c->inited = false;
@@ -473,10 +473,22 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dCarry, 4 * (RLB_MAX_LEAVES + 1) * sizeof(float)));
     c->chain_max_chunks = (int)(std::max<int64_t>(N, Q) / 1024) + RLB_MAX_LEAVES + 2;
     RLB_CUDA(c, alloc(c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainQ, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
-    RLB_CUDA(c, alloc(c->dChainMin, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
-    RLB_CUDA(c, alloc(c->dChainMax, (size_t)2 * c->chain_max_chunks * sizeof(long long)));
-    RLB_CUDA(c, alloc(c->dChainEf, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dChainXs, (size_t)2 * c->chain_max_chunks * 1024 * sizeof(double)));
+    RLB_CUDA(c, alloc(c->dChainRSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
+    {
+        void* p = c->dChainItems;   // 1100 items of 16 bytes per chunk (ChainItem, CH_ITEMS: rlb_boost.cu)
+        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * 1100 * 16));
+        c->dChainItems = (struct ChainItem*)p;
+        p = c->dChainStream;        // the same + one marker per chunk (CH_STREAM)
+        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * 1101 * 16));
+        c->dChainStream = (struct ChainItem*)p;
+    }
+    RLB_CUDA(c, alloc(c->dChainIPos, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dChainITot, (size_t)2 * (RLB_MAX_LEAVES + 2) * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dChainNItems, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, alloc(c->dChainSimS, (size_t)2 * c->chain_max_chunks * sizeof(float)));
+    RLB_CUDA(c, alloc(c->dChainSimE, (size_t)2 * c->chain_max_chunks * sizeof(float)));
+    if (const char* e = getenv("RLB_CHAIN_PASSES")) c->chain_passes = std::max(1, atoi(e));
     RLB_CUDA(c, alloc(c->dChunk0, (size_t)(RLB_MAX_LEAVES + 4) * sizeof(int32_t)));
     {
         const int32_t mc[2] = {0, (Q + 1023) / 1024};

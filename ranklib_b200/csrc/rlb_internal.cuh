@@ -175,10 +175,16 @@ struct rlb_ctx {
     DevState* hState = nullptr;     // pinned mirror (partial copies)
     float* dCarry = nullptr;        // cross-rank float-chain carries
     // two-level float chains (rlb_boost.cu)
-    double* dChainSum = nullptr;
-    long long *dChainQ = nullptr, *dChainMin = nullptr, *dChainMax = nullptr;
-    int32_t *dChainEf = nullptr, *dChunk0 = nullptr;
+    double* dChainSum = nullptr;    // per-chunk exact sums / predicted start values
+    double* dChainXs = nullptr;     // chain elements in chain order
+    double* dChainRSum = nullptr;   // rounded increment of every chunk
+    struct ChainItem* dChainItems = nullptr;   // per-chunk item programs
+    struct ChainItem* dChainStream = nullptr;  // per-chain item streams
+    int32_t *dChainNItems = nullptr, *dChainIPos = nullptr, *dChainITot = nullptr;
+    float *dChainSimS = nullptr, *dChainSimE = nullptr;
+    int32_t* dChunk0 = nullptr;
     int32_t chain_max_chunks = 0;
+    int32_t chain_passes = 2;       // RLB_CHAIN_PASSES: simulations per chain (2 = with the rounded-increment refinement)
     int32_t grid_rows = 0;          // CTAs of the row-oriented kernels (multiple of the SM count)
     int32_t sm_count = 0;
     int64_t stats[4] = {0, 0, 0, 0};
@@ -258,6 +264,7 @@ int rlb_impl_update_scores(rlb_ctx* ctx);
 int rlb_impl_train_metric(rlb_ctx* ctx, bool with_pseudo);
 int rlb_impl_assign_nodes(rlb_ctx* ctx);
 int rlb_impl_export_tree(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
+int rlb_impl_float_chain(rlb_ctx* ctx, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t* info);
 int rlb_impl_launch_rank_metric(rlb_ctx* ctx, const double* dScores, const float* dLabel, const int32_t* dQoff,
                                 int32_t Q, int64_t N, int32_t metric, int32_t k, const double* dDisc, double* dOut);
 

@@ -24,7 +24,7 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_comm_init", "rlb_load_dense", "rlb_set_thresholds", "rlb_lambdamart_init", "rlb_get_thresholds",
            "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
-           "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read"]
+           "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain"]
 
 
 class RankLibError(RuntimeError):
@@ -210,6 +210,15 @@ class Context:
         out = np.zeros(8, np.float64)
         self._ck(self.lib.rlb_profile_read(self.h, _p(out)))
         return out
+
+    def float_chain(self, x, carry=0.0, passes=2):
+        """Test hook: float s = carry; for v in x: s += v  (Java compound assignment), on the device."""
+        x = np.ascontiguousarray(x, np.float64)
+        out = C.c_float(0.0)
+        info = np.zeros(2, np.int64)
+        self.lib.rlb_float_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+        self._ck(self.lib.rlb_float_chain(self.h, _p(x), x.shape[0], C.c_float(carry), passes, C.byref(out), _p(info)))
+        return np.float32(out.value), info
 
     # ---- scoring ----
     def ensemble_eval(self, nodes, tree_off, weights, X):

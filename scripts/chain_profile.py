@@ -30,4 +30,4 @@ for it in range(n_it):
         agg[n] = agg.get(n, 0.0) + float(us); tot += float(us)
     st = g.stats()
     if it % 5 == 4 or it < 3:
-        print(f"it {it:3d} total {tot:7.0f} us  leaf_chain {agg.get('k_leaf_chain', 0):6.0f}  hist_child {agg.get('k_hist_child', 0):5.0f}  part {agg.get('k_part_fused', 0):4.0f}  finish {agg.get('k_finish', 0):4.0f}  serial {st[2] & 0xffffffff} fallbacks {st[2] >> 32}")
+        print(f"it {it:3d} total {tot:7.0f} us  leaf_chain {agg.get('k_leaf_chain', 0):6.0f} sim {agg.get('k_chain_sim', 0):5.0f} sum {agg.get('k_chain_sum', 0):4.0f} pred+ref {agg.get('k_chain_pred', 0) + agg.get('k_chain_refine', 0):4.0f} metric_chain {agg.get('k_metric_chain', 0):4.0f} hist_child {agg.get('k_hist_child', 0):5.0f}  part {agg.get('k_part_fused', 0):4.0f}  finish {agg.get('k_finish', 0):4.0f}  serial {st[2] & 0xffffffff} fallbacks {st[2] >> 32}")

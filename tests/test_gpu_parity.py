@@ -309,3 +309,41 @@ def test_single_query_and_tiny_sets(built):
         qoff = np.linspace(0, N, Q + 1).astype(np.int32)
         n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 3, n_leaves=4)
         assert n_equiv == 3
+
+
+def _chain_cases():
+    rng = np.random.default_rng(7)
+    n = 300_000
+    yield "signed, sum hovering at zero", rng.standard_normal(n) * np.exp(rng.standard_normal(n)), 0.0
+    yield "positive (weights)", np.abs(rng.standard_normal(n)) * 1e-3, 0.0
+    w = rng.standard_normal(n)
+    w[::3] = 0.0
+    w[1000:5000] = 0.0
+    yield "zero stretches, carry", w, 3.25
+    yield "leading zeros from +0", np.concatenate([np.zeros(5000), rng.standard_normal(3000)]), 0.0
+    yield "huge dynamic range", rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n), -1.0
+    t = rng.integers(-4, 5, n).astype(np.float64) * 2.0 ** -24     # exact half-ulp ties against s ~ 1
+    yield "half-ulp ties", t, 1.0
+    yield "cancellation to exact zero", np.tile(np.array([1.5, -1.5, 2.0 ** -30, -(2.0 ** -30)]), 20000), 0.0
+    yield "alternating large / small", np.where(np.arange(n) % 2 == 0, 1e6, -1e6 + 1e-3) * (1 + 1e-9 * rng.standard_normal(n)), 0.0
+    yield "drifting sum with many binade crossings", np.sin(np.arange(n) * 1e-3) * 5 + rng.standard_normal(n) * 0.01, 0.0
+    yield "tiny", np.array([0.1, 0.2, 0.3]), 0.0
+    yield "exactly one chunk", rng.standard_normal(1024), 0.0
+    yield "one past a chunk", rng.standard_normal(1025), 0.5
+    yield "subnormal results", rng.standard_normal(5000) * 1e-42, 0.0
+    yield "overflow to inf", np.full(3000, 3e38), 0.0
+
+
+def test_float_chain_bit_exact(built):
+    """The reference's `float s += double` accumulation (LambdaMART.java:401-408,475-481) against the device chain
+    kernels on adversarial inputs: every result must be the identical float."""
+    g = native.Context(0)
+    for name, x, carry in _chain_cases():
+        want = orc.float_chain(x, carry)
+        for passes in (1, 2, 3):
+            got, info = g.float_chain(x, carry, passes)
+            assert got.tobytes() == np.float32(want).tobytes(), (name, passes, got, want, info)
+    # an empty chain returns the carry
+    got, _ = g.float_chain(np.zeros(0), 1.5)
+    assert got == np.float32(1.5)
+    g.close()
