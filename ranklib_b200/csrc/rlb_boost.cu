@@ -534,7 +534,8 @@ __global__ void k_scale(DevState* st, long long n_total) {
 // root's squared sum (FeatureHistogram.update's sqSumResponse, FeatureHistogram.java:134-137)
 #define CNT_SHIFT 52                      // packed private accumulator of child builds: count << 52 | 52-bit signed sum
 #define CNT_ONE (1LL << CNT_SHIFT)
-#define FLUSH_STAGES 127                  // 127 stages x 16 rows per thread = 2032 rows < 2^11 per private bin
+#define HCHILD_RPT 32                     // child kernel: rows per consumer thread and stage
+#define FLUSH_STAGES (2040 / HCHILD_RPT)  // rows per private bin between flushes stay below 2^11
 
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lambda, int64_t N, long long* __restrict__ vfix,
                                                    long long* __restrict__ vfixc, long long* __restrict__ sqfix,
@@ -617,7 +618,8 @@ __global__ void __launch_bounds__(256) k_hist_rows(const uint16_t* __restrict__ 
 }
 
 #define HG 16        // features per CTA group = one 32-byte sector of a bins row
-#define HSTAGES 8    // depth of the cp.async ring of the child kernel
+#define HSTAGES 4    // depth of the cp.async ring of the child kernel (stages of HG * HPH * HCHILD_RPT / 16 rows)
+#define HIDX 4       // ... and of its sample-index ring
 #define HPH 6        // row phases: HG * HPH = 96 private histograms x 257 bins x 8 B = 197 KB of shared memory
 #define HROOT_CPS 4  // root: 8-row chunks per thread per stage -> RLB_ROOT_R = HPH * 8 * HROOT_CPS = 192 rows per tile
 #define HROOT_STAGES 4
@@ -648,6 +650,9 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void cpasync16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpasync4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cpasync8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -871,7 +876,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                  int32_t* __restrict__ cnt, DevState* __restrict__ st, int nGroups) {
     constexpr int PH = HPH;
     constexpr int T = HG * PH;           // consumer threads = private histograms
-    constexpr int R = HG * PH;           // rows per stage (16 per consumer thread = 2 blocks of 16 rows per phase pair)
+    constexpr int R = PH * HCHILD_RPT;   // rows per stage (HCHILD_RPT per consumer thread, in blocks of 16 rows per phase pair)
     constexpr int CW = (T + 31) / 32;    // consumer warps
     constexpr int NBLK = R / 16;         // 16-row blocks per stage
     constexpr int BPP = NBLK / (PH / 2); // blocks per phase pair per stage
@@ -885,6 +890,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     off += (size_t)HSTAGES * STAGE_BYTES;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
     unsigned long long* empty = full + HSTAGES;
+    int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
     if (!st->split_active) return;
     const NodeRec& r = st->nodes[st->small_id];
@@ -914,12 +920,21 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 
     if (warp == CW) {
         // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
-        int32_t nxt[(R + 31) / 32];   // sample indices of the next stage, fetched one stage ahead
+        // The sample indices of a stage travel through shared memory too: 4-byte cp.async into a private ring, HIDX stages
+        // ahead, completion by cp.async groups.  (Fetched into registers they put a dependent global load on the
+        // critical path of every stage, and the kernel ran at one stage per memory latency.)  Every lane reads back
+        // exactly the ring entries it copied itself.
+        constexpr int U = (R + 31) / 32;
+        auto fetch_idx = [&](int k) {
+            const int64_t base = r0 + (int64_t)k * R;
 #pragma unroll
-        for (int u = 0; u < (R + 31) / 32; u++) {
-            const int64_t pos = r0 + lane + 32 * u;
-            nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
-        }
+            for (int u = 0; u < U; u++) {
+                const int j = lane + 32 * u;
+                if (j < R && base + j < r1) cpasync4(&iring[(k % HIDX) * R + j], samples + base + j);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int d = 0; d < HIDX; d++) fetch_idx(d);   // stages past the end commit empty groups: the count stays uniform
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
             if (k >= HSTAGES) mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
@@ -927,15 +942,15 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             const int nr = (int)min((int64_t)R, r1 - base);
             unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             long long* vt = reinterpret_cast<long long*>(bt + R * 32);
-            int32_t cur[(R + 31) / 32];
+            asm volatile("cp.async.wait_group %0;" ::"n"(HIDX - 1) : "memory");   // the indices of stage k have landed
+            int32_t cur[U];
 #pragma unroll
-            for (int u = 0; u < (R + 31) / 32; u++) {
-                cur[u] = nxt[u];
-                const int64_t pos = base + R + lane + 32 * u;
-                nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+            for (int u = 0; u < U; u++) {
+                const int j = lane + 32 * u;
+                cur[u] = (j < nr) ? iring[(k % HIDX) * R + j] : 0;
             }
 #pragma unroll
-            for (int u = 0; u < (R + 31) / 32; u++) {
+            for (int u = 0; u < U; u++) {
                 const int j = lane + 32 * u;
                 if (j < nr) {
                     const int64_t row = cur[u];
@@ -946,6 +961,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 }
             }
             cpasync_arrive(&full[s2]);
+            fetch_idx(k + HIDX);   // reuses the ring slot just read (the row copies above depend on those reads)
         }
     } else {
         // ===== consumer warps =====
@@ -2791,7 +2807,7 @@ static constexpr size_t hist_smem_root() {
 static constexpr size_t hist_smem_child() {
     size_t off = (size_t)RLB_T * HG * HPH * 8;
     off = (off + 127) & ~(size_t)127;
-    return off + (size_t)HSTAGES * (HG * HPH * 40) + 2 * HSTAGES * 8;
+    return off + (size_t)HSTAGES * (HPH * HCHILD_RPT * 40) + 2 * HSTAGES * 8 + (size_t)HIDX * HPH * HCHILD_RPT * 4;
 }
 static constexpr int hist_threads() { return 32 * ((HG * HPH + 31) / 32 + 1); }
 

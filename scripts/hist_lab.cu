@@ -22,7 +22,7 @@
 #define NB_BINS 257
 #define HG 16
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
@@ -452,6 +452,225 @@ template <int PH, int CPS, int STAGES, int MODE>
 static void run_pipe(const char* name, const uint16_t* tiles, const long long* v, int64_t NB, int F, int grid,
                      unsigned long long* sum, const std::vector<unsigned long long>& ref, int64_t N, bool expect_exact);
 
+__device__ __forceinline__ void cpasync16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpasync8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier gets one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cpasync_arrive(void* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t r;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(r) : "r"(a));
+    return r;
+}
+// eight rows of one feature: private-histogram byte addresses and addends
+struct HChunk {
+    uint32_t a[8];
+    long long v[8];
+};
+
+// Eight read-modify-writes on this thread's private histogram as two quads.  Inside a quad the four loads are
+// issued before the four stores, so equal bins are resolved on the ADDENDS first (the later row of a pair of equal
+// bins carries the running total and its store lands last: a thread's shared-memory stores are ordered).  The
+// merging needs only addresses and addends — it is done while the loads are in flight.  Branch-free.
+__device__ __forceinline__ void hist_rmw8(HChunk& c) {
+#pragma unroll
+    for (int p = 0; p < 8; p += 4) {
+        const bool e10 = c.a[p + 1] == c.a[p], e21 = c.a[p + 2] == c.a[p + 1], e20 = c.a[p + 2] == c.a[p];
+        const bool e32 = c.a[p + 3] == c.a[p + 2], e31 = c.a[p + 3] == c.a[p + 1], e30 = c.a[p + 3] == c.a[p];
+        c.v[p + 1] += e10 ? c.v[p] : 0LL;
+        c.v[p + 2] += e21 ? c.v[p + 1] : (e20 ? c.v[p] : 0LL);
+        c.v[p + 3] += e32 ? c.v[p + 2] : (e31 ? c.v[p + 1] : (e30 ? c.v[p] : 0LL));
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p += 4) {
+        const long long h0 = lds64(c.a[p]), h1 = lds64(c.a[p + 1]), h2 = lds64(c.a[p + 2]), h3 = lds64(c.a[p + 3]);
+        sts64(c.a[p], h0 + c.v[p]);
+        sts64(c.a[p + 1], h1 + c.v[p + 1]);
+        sts64(c.a[p + 2], h2 + c.v[p + 2]);
+        sts64(c.a[p + 3], h3 + c.v[p + 3]);
+    }
+}
+
+
+#define CNT_SHIFT 52
+#define CNT_ONE (1LL << CNT_SHIFT)
+template <bool CHILD, int PH>
+__device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, long long* __restrict__ sum,
+                                           int32_t* __restrict__ cnt) {
+    constexpr int T = HG * PH;
+    constexpr int NC = 32 * ((T + 31) / 32);
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    for (int p = tid; p < NB_BINS * HG; p += NC) {
+        const int bin = p / HG, ff = p % HG;
+        const int fo = g * HG + ff;
+        long long sacc = 0;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < PH; q++) {
+            const long long pk = H[bin * T + q * HG + ff];
+            H[bin * T + q * HG + ff] = 0;
+            const long long sv = ((pk + (1LL << (CNT_SHIFT - 1))) & (CNT_ONE - 1)) - (1LL << (CNT_SHIFT - 1));
+            sacc += sv;
+            c += (int)((pk - sv) >> CNT_SHIFT);
+        }
+        if (fo < F) {
+            if (sacc != 0) atomicAdd((unsigned long long*)&sum[(size_t)fo * NB_BINS + bin], (unsigned long long)sacc);
+            if (c != 0) atomicAdd(&cnt[(size_t)fo * NB_BINS + bin], c);
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+}
+__global__ void __launch_bounds__(32 * ((HG * 6 + 31) / 32 + 1), 1)
+    k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
+                 const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1, long long* __restrict__ sum,
+                 int32_t* __restrict__ cnt, int64_t lo, int64_t hi, int nGroups) {
+    constexpr int PH = 6;
+    constexpr int T = HG * PH;           // consumer threads = private histograms
+    constexpr int R = HG * PH;           // rows per stage (16 per consumer thread = 2 blocks of 16 rows per phase pair)
+    constexpr int CW = (T + 31) / 32;    // consumer warps
+    constexpr int NBLK = R / 16;         // 16-row blocks per stage
+    constexpr int BPP = NBLK / (PH / 2); // blocks per phase pair per stage
+    static_assert(PH % 2 == 0 && NBLK % (PH / 2) == 0, "phase pairs");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    long long* H = reinterpret_cast<long long*>(smem_raw);                         // [NB_BINS][T]
+    size_t off = (size_t)NB_BINS * T * 8;
+    off = (off + 127) & ~(size_t)127;
+    unsigned char* tiles = smem_raw + off;                                         // 8 x (R*32 + R*8)
+    constexpr int STAGE_BYTES = R * 32 + R * 8;
+    off += (size_t)8 * STAGE_BYTES;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    unsigned long long* empty = full + 8;
+
+    const int32_t* samples = samples0;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x % nGroups;
+    const int idx = blockIdx.x / nGroups;
+    const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
+    const int64_t n = hi - lo;
+    const int64_t r0 = lo + n * idx / nCta, r1 = lo + n * (idx + 1) / nCta;
+    const int nst = (int)((r1 - r0 + R - 1) / R);
+    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
+    const int nfull = (int)((r1 - r0) / R);
+
+    for (int i = tid; i < NB_BINS * T; i += blockDim.x) H[i] = 0;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < 8; s2++) {
+            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
+            mbar_init(&empty[s2], (uint32_t)CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CW) {
+        // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
+        int32_t nxt[(R + 31) / 32];   // sample indices of the next stage, fetched one stage ahead
+#pragma unroll
+        for (int u = 0; u < (R + 31) / 32; u++) {
+            const int64_t pos = r0 + lane + 32 * u;
+            nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+        }
+        for (int k = 0; k < nst; k++) {
+            const int s2 = k % 8;
+            if (k >= 8) mbar_wait(&empty[s2], ((k / 8) + 1) & 1);
+            const int64_t base = r0 + (int64_t)k * R;
+            const int nr = (int)min((int64_t)R, r1 - base);
+            unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
+            long long* vt = reinterpret_cast<long long*>(bt + R * 32);
+            int32_t cur[(R + 31) / 32];
+#pragma unroll
+            for (int u = 0; u < (R + 31) / 32; u++) {
+                cur[u] = nxt[u];
+                const int64_t pos = base + R + lane + 32 * u;
+                nxt[u] = (lane + 32 * u < R && pos < r1) ? samples[pos] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < (R + 31) / 32; u++) {
+                const int j = lane + 32 * u;
+                if (j < nr) {
+                    const int64_t row = cur[u];
+                    const uint16_t* src = bins + row * Fp + g * HG;
+                    cpasync16(bt + j * 32, src);
+                    cpasync16(bt + j * 32 + 16, src + 8);
+                    cpasync8(vt + j, vfixc + row);
+                }
+            }
+            cpasync_arrive(&full[s2]);
+        }
+    } else {
+        // ===== consumer warps =====
+        const int fi = tid & (HG - 1), ph = tid / HG;
+        const bool active = (tid < T) && (g * HG + fi < F);
+        const uint32_t hme = smem_u32(H) + tid * 8;
+        const uint32_t st0 = smem_u32(tiles);
+        const int pp = ph >> 1, odd = ph & 1;
+        // rows of block b owned by this thread: 16 b + 2 w + odd, w = 0..7
+        auto load = [&](HChunk& c, uint32_t sb, int blk) {
+            const uint32_t ba = sb + (blk * 16 + odd) * 32 + fi * 2;
+            const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+                c.v[w] = lds64(va + w * 16);
+            }
+        };
+        // threads of an absent feature (last group: its bins are stored as 0) run along into their own column, which
+        // keeps every warp-level step of the loop convergent; the flush skips them
+        if (nfull > 0) {
+            HChunk cur, nxt;
+            mbar_wait(&full[0], 0);
+            load(cur, st0, pp);
+            for (int k = 0; k < nfull; k++) {
+                const int s2 = k % 8;
+                const uint32_t sb = st0 + s2 * STAGE_BYTES;
+                // the packed (count, sum) accumulators hold at most 2^11 rows
+                if (k > 0 && (k % 127) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+#pragma unroll
+                for (int j = 0; j < BPP; j++) {
+                    if (j + 1 < BPP) {
+                        load(nxt, sb, pp + (PH / 2) * (j + 1));
+                    } else {
+                        if (k + 1 < nfull) {
+                            const int s1 = (k + 1) % 8;
+                            mbar_wait(&full[s1], ((k + 1) / 8) & 1);
+                            load(nxt, st0 + s1 * STAGE_BYTES, pp);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[s2]);
+                    }
+                    hist_rmw8(cur);
+                    cur = nxt;
+                }
+            }
+        }
+        if (nst > nfull) {  // the partial last stage, row by row
+            const int k = nfull;
+            const int s2 = k % 8;
+            if (k > 0 && (k % 127) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+            mbar_wait(&full[s2], (k / 8) & 1);
+            const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
+            const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
+            const long long* vt = reinterpret_cast<const long long*>(bt + R * 32);
+            const int nr = (int)(r1 - (r0 + (int64_t)k * R));
+            if (active) {
+                long long* Hme = H + tid;
+                for (int rr = ph; rr < nr; rr += PH) {
+                    const int b = btile[rr * HG + fi];
+                    Hme[b * T] += vt[rr];
+                }
+            }
+        }
+        hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+    }
+}
+
+
 __global__ void k_read(const uint4* __restrict__ p, size_t n, unsigned long long* out) {
     uint4 acc = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -610,6 +829,48 @@ int main(int argc, char** argv) {
         run_variant<3, 8, 8, 6>("staging+xor        PH3 CPS8 ST8", tiles, v, NB, F, sms, sum, ref, N, false);
         run_variant<3, 8, 8, 2>("oct no-merge       PH3 CPS8 ST8", tiles, v, NB, F, sms, sum, ref, N, false);
         cudaFree(tiles);
+    }
+
+    {   // child kernel on sample lists of different densities
+        long long* vc;
+        CK(cudaMalloc(&vc, (size_t)(N + 2) * 8));
+        std::vector<long long> hv(N);
+        CK(cudaMemcpy(hv.data(), v, (size_t)N * 8, cudaMemcpyDeviceToHost));
+        for (auto& t : hv) t += (1LL << 52);
+        CK(cudaMemcpy(vc, hv.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+        int32_t* dcnt;
+        CK(cudaMalloc(&dcnt, (size_t)F * NB_BINS * 4));
+        size_t sm = (size_t)NB_BINS * 96 * 8;
+        sm = (sm + 127) & ~(size_t)127;
+        sm += 8 * (96 * 40) + 2 * 8 * 8;
+        CK(cudaFuncSetAttribute(k_hist_child, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int dens[5] = {100, 40, 10, 2, 1};
+        for (int di = 0; di < 5; di++) {
+            std::vector<int32_t> hs;
+            for (int64_t i = 0; i < N; i++)
+                if ((int)(hash32((uint32_t)i * 2654435761u + 12345u) % 100) < dens[di]) hs.push_back((int32_t)i);
+            int32_t* ds;
+            CK(cudaMalloc(&ds, hs.size() * 4 + 16));
+            CK(cudaMemcpy(ds, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            float best = 1e9f;
+            for (int r = 0; r < 6; r++) {
+                CK(cudaMemsetAsync(sum, 0, (size_t)F * NB_BINS * 8));
+                CK(cudaMemsetAsync(dcnt, 0, (size_t)F * NB_BINS * 4));
+                cudaEventRecord(e0);
+                k_hist_child<<<sms, 128, sm>>>(bins, Fp, F, vc, ds, ds, (long long*)sum, dcnt, 0, (int64_t)hs.size(), nGroups);
+                cudaEventRecord(e1);
+                CK(cudaEventSynchronize(e1));
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (r >= 1 && ms < best) best = ms;
+            }
+            printf("child kernel density %3d%%: rows %8zu  %7.1f us  (%.3f us per 1000 rows)\n", dens[di], hs.size(), best * 1e3,
+                   best * 1e3 / (hs.size() / 1000.0));
+            cudaFree(ds);
+        }
     }
     return 0;
 }
