@@ -46,6 +46,12 @@ extern "C" {
 /* rlb_params.metric — the MetricScorer used for swapChange()/score() */
 #define RLB_METRIC_NDCG 0 /* R/metric/NDCGScorer.java:103-160 */
 #define RLB_METRIC_DCG  1 /* R/metric/DCGScorer.java:59-90 */
+#define RLB_METRIC_ERR  2 /* R/metric/ERRScorer.java:45-115 (MAX = 16; the CLI's default -metric2t is ERR@10) */
+#define RLB_METRIC_MAP  3 /* R/metric/APScorer.java:75-162 (k is ignored: getK() = 0, whole list) */
+#define RLB_METRIC_PRECISION 4 /* R/metric/PrecisionScorer.java:29-84 */
+#define RLB_METRIC_RR   5 /* R/metric/ReciprocalRankScorer.java:25-107 */
+#define RLB_METRIC_BEST 6 /* R/metric/BestAtKScorer.java:28-120 */
+#define RLB_METRIC_COUNT 7
 
 /* Maximum number of histogram bins per feature: nThreshold(256) candidates + the Float.MAX_VALUE
  * sentinel (R/learning/tree/LambdaMART.java:39,135-149). */

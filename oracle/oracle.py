@@ -160,6 +160,26 @@ def score_metric(scores, label, qoff, metric=0, k=10):
     return out.value
 
 
+METRICS = dict(NDCG=0, DCG=1, ERR=2, MAP=3, P=4, RR=5, BEST=6)
+
+
+def swap_change(lab, metric, k):
+    """MetricScorer.swapChange on a ranked label list: the full n x n table."""
+    lib = load()
+    lab = np.ascontiguousarray(lab, np.float32)
+    n = lab.shape[0]
+    out = np.zeros((n, n), np.float64)
+    assert lib.orc_swap_change(_p(lab), n, metric, k, _p(out)) == 0
+    return out
+
+
+def metric_score(lab, metric, k):
+    lib = load()
+    lab = np.ascontiguousarray(lab, np.float32)
+    lib.orc_metric_score.restype = C.c_double
+    return float(lib.orc_metric_score(_p(lab), lab.shape[0], metric, k))
+
+
 def float_chain(x, carry=0.0):
     """float s = carry; for v in x: s += v  (Java compound assignment with a double right-hand side)."""
     lib = load()

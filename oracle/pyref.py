@@ -130,6 +130,201 @@ def swap_change(rel, k):
     return ch
 
 
+# ---- the other MetricScorers, transliterated line by line (labels are the ranked list's float labels) ----
+ERR_MAX = 16.0
+
+
+def _err_R(rel):
+    return ((1 << rel) - 1) / ERR_MAX
+
+
+def err_swap_change(lab, k):
+    """ERRScorer.swapChange (R/metric/ERRScorer.java:76-115)."""
+    n = len(lab)
+    size = k if n > k else n
+    labels, R, np_ = [0] * n, [0.0] * n, [0.0] * n
+    p = 1.0
+    for i in range(size):
+        labels[i] = int(lab[i])
+        R[i] = _err_R(labels[i])
+        np_[i] = p * (1.0 - R[i])
+        p *= np_[i]
+    ch = [[0.0] * n for _ in range(n)]
+    for i in range(size):
+        v1 = 1.0 / (i + 1) * (1 if i == 0 else np_[i - 1])
+        for j in range(i + 1, n):
+            if labels[i] == labels[j]:
+                change = 0.0
+            else:
+                change = v1 * (R[j] - R[i])
+                p = (1 if i == 0 else np_[i - 1]) * (R[i] - R[j])
+                for kk in range(i + 1, j):
+                    change += p * R[kk] / (1 + kk)
+                    p *= 1.0 - R[kk]
+                change += (np_[j - 1] * (1.0 - R[j]) * R[i] / (1.0 - R[i]) - np_[j - 1] * R[j]) / (j + 1)
+            ch[j][i] = ch[i][j] = change
+    return ch
+
+
+def err_score(lab, k):
+    """ERRScorer.score (R/metric/ERRScorer.java:45-66)."""
+    n = len(lab)
+    size = n if (k > n or k <= 0) else k
+    s, p = 0.0, 1.0
+    for i in range(1, size + 1):
+        R = _err_R(int(lab[i - 1]))
+        s += p * R / i
+        p *= (1.0 - R)
+    return s
+
+
+def map_swap_change(lab):
+    """APScorer.swapChange without external judgments (R/metric/APScorer.java:108-162)."""
+    n = len(lab)
+    relCount, labels = [0] * n, [0] * n
+    count = 0
+    for i in range(n):
+        if lab[i] > 0:
+            labels[i] = 1
+            count += 1
+        relCount[i] = count
+    ch = [[0.0] * n for _ in range(n)]
+    if count == 0:
+        return ch
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            change = 0.0
+            if labels[i] != labels[j]:
+                diff = labels[j] - labels[i]
+                change += float((relCount[i] + diff) * labels[j] - relCount[i] * labels[i]) / (i + 1)
+                for kk in range(i + 1, j):
+                    if labels[kk] > 0:
+                        change += float(diff) / (kk + 1)
+                change += float(-relCount[j] * diff) / (j + 1)
+            ch[j][i] = ch[i][j] = change / count
+    return ch
+
+
+def map_score(lab):
+    ap, count = 0.0, 0
+    for i in range(len(lab)):
+        if lab[i] > 0.0:
+            count += 1
+            ap += float(count) / (i + 1)
+    return 0.0 if count == 0 else ap / count
+
+
+def precision_swap_change(lab, k):
+    """PrecisionScorer.swapChange (R/metric/PrecisionScorer.java:58-76): ((float) c) / size."""
+    n = len(lab)
+    size = k if n > k else n
+    ch = [[0.0] * n for _ in range(n)]
+    for i in range(size):
+        for j in range(size, n):
+            c = (1 if lab[j] > 0.0 else 0) - (1 if lab[i] > 0.0 else 0)
+            ch[i][j] = ch[j][i] = float(F32(F32(c) / F32(size)))
+    return ch
+
+
+def precision_score(lab, k):
+    n = len(lab)
+    size = n if (k > n or k <= 0) else k
+    return float(sum(1 for i in range(size) if lab[i] > 0.0)) / size
+
+
+def rr_swap_change(lab, k):
+    """ReciprocalRankScorer.swapChange (R/metric/ReciprocalRankScorer.java:47-106)."""
+    n = len(lab)
+    size = k if n > k else n
+    first = second = -1
+    for i in range(size):
+        if lab[i] > 0.0:
+            if first == -1:
+                first = i
+            elif second == -1:
+                second = i
+    ch = [[0.0] * n for _ in range(n)]
+    rr = 0.0
+    if first != -1:
+        rr = 1.0 / (first + 1)
+        for j in range(first + 1, size):
+            if int(lab[j]) == 0:
+                if second == -1 or j < second:
+                    ch[first][j] = ch[j][first] = 1.0 / (j + 1) - rr
+                else:
+                    ch[first][j] = ch[j][first] = 1.0 / (second + 1) - rr
+        for j in range(size, n):
+            if int(lab[j]) == 0:
+                if second == -1:
+                    ch[first][j] = ch[j][first] = -rr
+                else:
+                    ch[first][j] = ch[j][first] = 1.0 / (second + 1) - rr
+    else:
+        first = size
+    for i in range(first):
+        for j in range(first, n):
+            if lab[j] > 0:
+                ch[i][j] = ch[j][i] = 1.0 / (i + 1) - rr
+    return ch
+
+
+def rr_score(lab, k):
+    n = len(lab)
+    size = k if n > k else n
+    for i in range(size):
+        if lab[i] > 0.0:
+            return float(F32(1.0) / F32(i + 1))
+    return 0.0
+
+
+def best_swap_change(lab, k):
+    """BestAtKScorer.swapChange (R/metric/BestAtKScorer.java:64-119)."""
+    n = len(lab)
+    labels, best = [0] * n, [0] * n
+    mx, maxVal, secondMaxVal, maxCount = -1, -1, -1, 0
+    for i in range(n):
+        v = int(lab[i])
+        labels[i] = v
+        if maxVal < v:
+            if i < k:
+                secondMaxVal = maxVal
+                maxCount = 0
+            maxVal = v
+            mx = i
+        elif maxVal == v and i < k:
+            maxCount += 1
+        best[i] = mx
+    if secondMaxVal == -1:
+        secondMaxVal = 0
+    ch = [[0.0] * n for _ in range(n)]
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            if j < k or i >= k:
+                change = 0
+            elif labels[i] == labels[j] or labels[j] == labels[best[k - 1]]:
+                change = 0
+            elif labels[j] > labels[best[k - 1]]:
+                change = labels[j] - labels[best[i]]
+            elif labels[i] < labels[best[k - 1]] or maxCount > 1:
+                change = 0
+            else:
+                change = maxVal - max(secondMaxVal, labels[j])
+            ch[i][j] = ch[j][i] = float(change)
+    return ch
+
+
+def best_score(lab, k):
+    n = len(lab)
+    size = k - 1
+    if size < 0 or size > n - 1:
+        size = n - 1
+    mx, mi = -1.0, 0
+    for i in range(size + 1):
+        if mx < lab[i]:
+            mx, mi = lab[i], i
+    return float(lab[mi])
+
+
 class Hist:
     pass
 

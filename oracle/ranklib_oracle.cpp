@@ -124,18 +124,213 @@ static double get_dcg(const std::vector<int>& rel, int topK) {
     return dcg;
 }
 
-// NDCGScorer.score / DCGScorer.score on an already ranked label list
-// (R/metric/NDCGScorer.java:103-129, R/metric/DCGScorer.java:59-72).  The idealGains cache is keyed
-// by query id; with unique ids it is a pure memo, which is what this restatement assumes (Q3).
-static double metric_score(const std::vector<int>& rel, int metric, int k) {
-    int n = (int)rel.size();
-    if (n == 0) return 0;
+// MetricScorer.score(RankList) on an already ranked label list: NDCGScorer / DCGScorer
+// (R/metric/NDCGScorer.java:103-129, R/metric/DCGScorer.java:59-72; the idealGains cache is keyed by query id — with
+// unique ids it is a pure memo, which is what this restatement assumes, Q3), ERRScorer (R/metric/ERRScorer.java:45-66),
+// APScorer without external judgments (R/metric/APScorer.java:75-103), PrecisionScorer (R/metric/PrecisionScorer.java:29-43),
+// ReciprocalRankScorer (R/metric/ReciprocalRankScorer.java:25-35), BestAtKScorer (R/metric/BestAtKScorer.java:28-57).
+static const double ERR_MAX = 16;  // ERRScorer.MAX
+static inline double err_R(int rel) { return ((1 << rel) - 1) / ERR_MAX; }
+
+static double metric_score(const std::vector<float>& lab, int metric, int k) {
+    const int n = (int)lab.size();
+    if (metric == RLB_METRIC_MAP) {
+        double ap = 0.0;
+        int count = 0;
+        for (int i = 0; i < n; i++)
+            if (lab[i] > 0.0) {
+                count++;
+                ap += ((double)count) / (i + 1);
+            }
+        if (count == 0) return 0.0;
+        return ap / count;
+    }
+    if (metric == RLB_METRIC_RR) {
+        const int size = (n > k) ? k : n;
+        int firstRank = -1;
+        for (int i = 0; i < size && firstRank == -1; i++)
+            if (lab[i] > 0.0) firstRank = i + 1;
+        return (firstRank == -1) ? 0 : (double)(1.0f / firstRank);
+    }
+    if (n == 0) return 0;   // NDCG / DCG return 0; the others are not reached with empty lists in training
     int size = k;
     if (k > n || k <= 0) size = n;
+    if (metric == RLB_METRIC_PRECISION) {
+        int count = 0;
+        for (int i = 0; i < size; i++)
+            if (lab[i] > 0.0) count++;
+        return ((double)count) / size;
+    }
+    if (metric == RLB_METRIC_BEST) {   // rl.get(maxToK(rl, k - 1)).getLabel()
+        int sz = k - 1;
+        if (sz < 0 || sz > n - 1) sz = n - 1;
+        double mx = -1.0;
+        int mi = 0;
+        for (int i = 0; i <= sz; i++)
+            if (mx < lab[i]) {
+                mx = lab[i];
+                mi = i;
+            }
+        return lab[mi];
+    }
+    std::vector<int> rel(n);
+    for (int i = 0; i < n; i++) rel[i] = (int)lab[i];
+    if (metric == RLB_METRIC_ERR) {
+        double s = 0.0, p = 1.0;
+        for (int i = 1; i <= size; i++) {
+            const double R = err_R(rel[i - 1]);
+            s += p * R / i;
+            p *= (1.0 - R);
+        }
+        return s;
+    }
     if (metric == RLB_METRIC_DCG) return get_dcg(rel, size);
     double ideal = ideal_dcg(rel, size);
     if (ideal <= 0.0) return 0.0;
     return get_dcg(rel, size) / ideal;
+}
+
+// MetricScorer.getK() as LambdaMART reads it (LambdaMART.java:362): APScorer forces k = 0 (APScorer.java:36)
+static inline int metric_cutoff(int metric, int k) { return metric == RLB_METRIC_MAP ? 0 : k; }
+
+// MetricScorer.swapChange(RankList) as the full n x n table, literally (ERRScorer.java:76-115, APScorer.java:108-162,
+// PrecisionScorer.java:58-76, ReciprocalRankScorer.java:47-106, BestAtKScorer.java:64-119).  NDCG / DCG are evaluated pair by
+// pair in pseudo_responses_range.
+static void swap_change_table(const std::vector<float>& lab, int metric, int k, std::vector<double>& ch) {
+    const int n = (int)lab.size();
+    ch.assign((size_t)n * n, 0.0);
+    auto C = [&](int i, int j) -> double& { return ch[(size_t)i * n + j]; };
+    if (metric == RLB_METRIC_ERR) {
+        const int size = (n > k) ? k : n;
+        std::vector<int> labels(n, 0);
+        std::vector<double> R(n, 0.0), np(n, 0.0);
+        double p = 1.0;
+        for (int i = 0; i < size; i++) {
+            labels[i] = (int)lab[i];
+            R[i] = err_R(labels[i]);
+            np[i] = p * (1.0 - R[i]);
+            p *= np[i];
+        }
+        for (int i = 0; i < size; i++) {
+            const double v1 = 1.0 / (i + 1) * (i == 0 ? 1 : np[i - 1]);
+            double change = 0;
+            for (int j = i + 1; j < n; j++) {
+                if (labels[i] == labels[j]) {
+                    change = 0;
+                } else {
+                    change = v1 * (R[j] - R[i]);
+                    p = (i == 0 ? 1 : np[i - 1]) * (R[i] - R[j]);
+                    for (int kk = i + 1; kk < j; kk++) {
+                        change += p * R[kk] / (1 + kk);
+                        p *= 1.0 - R[kk];
+                    }
+                    change += (np[j - 1] * (1.0 - R[j]) * R[i] / (1.0 - R[i]) - np[j - 1] * R[j]) / (j + 1);
+                }
+                C(j, i) = C(i, j) = change;
+            }
+        }
+    } else if (metric == RLB_METRIC_MAP) {
+        std::vector<int> relCount(n), labels(n);
+        int count = 0;
+        for (int i = 0; i < n; i++) {
+            if (lab[i] > 0) {
+                labels[i] = 1;
+                count++;
+            } else {
+                labels[i] = 0;
+            }
+            relCount[i] = count;
+        }
+        const int rdCount = count;
+        if (rdCount == 0 || count == 0) return;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) {
+                double change = 0;
+                if (labels[i] != labels[j]) {
+                    const int diff = labels[j] - labels[i];
+                    change += ((double)((relCount[i] + diff) * labels[j] - relCount[i] * labels[i])) / (i + 1);
+                    for (int kk = i + 1; kk <= j - 1; kk++)
+                        if (labels[kk] > 0) change += ((double)diff) / (kk + 1);
+                    change += ((double)(-relCount[j] * diff)) / (j + 1);
+                }
+                C(j, i) = C(i, j) = change / rdCount;
+            }
+    } else if (metric == RLB_METRIC_PRECISION) {
+        const int size = (n > k) ? k : n;
+        for (int i = 0; i < size; i++)
+            for (int j = size; j < n; j++) {
+                const int c = (lab[j] > 0.0 ? 1 : 0) - (lab[i] > 0.0 ? 1 : 0);
+                C(i, j) = C(j, i) = (double)(((float)c) / size);
+            }
+    } else if (metric == RLB_METRIC_RR) {
+        int firstRank = -1, secondRank = -1;
+        const int size = (n > k) ? k : n;
+        for (int i = 0; i < size; i++)
+            if (lab[i] > 0.0) {
+                if (firstRank == -1)
+                    firstRank = i;
+                else if (secondRank == -1)
+                    secondRank = i;
+            }
+        double rr = 0.0;
+        if (firstRank != -1) {
+            rr = 1.0 / (firstRank + 1);
+            for (int j = firstRank + 1; j < size; j++)
+                if (((int)lab[j]) == 0) {
+                    if (secondRank == -1 || j < secondRank)
+                        C(firstRank, j) = C(j, firstRank) = 1.0 / (j + 1) - rr;
+                    else
+                        C(firstRank, j) = C(j, firstRank) = 1.0 / (secondRank + 1) - rr;
+                }
+            for (int j = size; j < n; j++)
+                if (((int)lab[j]) == 0) {
+                    if (secondRank == -1)
+                        C(firstRank, j) = C(j, firstRank) = -rr;
+                    else
+                        C(firstRank, j) = C(j, firstRank) = 1.0 / (secondRank + 1) - rr;
+                }
+        } else {
+            firstRank = size;
+        }
+        for (int i = 0; i < firstRank; i++)
+            for (int j = firstRank; j < n; j++)
+                if (lab[j] > 0) C(i, j) = C(j, i) = 1.0 / (i + 1) - rr;
+    } else if (metric == RLB_METRIC_BEST) {
+        std::vector<int> labels(n), best(n);
+        int max = -1, maxVal = -1, secondMaxVal = -1, maxCount = 0;
+        for (int i = 0; i < n; i++) {
+            const int v = (int)lab[i];
+            labels[i] = v;
+            if (maxVal < v) {
+                if (i < k) {
+                    secondMaxVal = maxVal;
+                    maxCount = 0;
+                }
+                maxVal = v;
+                max = i;
+            } else if (maxVal == v && i < k) {
+                maxCount++;
+            }
+            best[i] = max;
+        }
+        if (secondMaxVal == -1) secondMaxVal = 0;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) {
+                double change = 0;
+                if (j < k || i >= k) {
+                    change = 0;
+                } else if (labels[i] == labels[j] || labels[j] == labels[best[k - 1]]) {
+                    change = 0;
+                } else if (labels[j] > labels[best[k - 1]]) {
+                    change = labels[j] - labels[best[i]];
+                } else if (labels[i] < labels[best[k - 1]] || maxCount > 1) {
+                    change = 0;
+                } else {
+                    change = maxVal - std::max(secondMaxVal, labels[j]);
+                }
+                C(i, j) = C(j, i) = change;
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -283,8 +478,11 @@ static void lambdamart_init(orc_ctx* c) {
 // with NDCGScorer.swapChange / DCGScorer.swapChange (R/metric/NDCGScorer.java:132-160,
 // R/metric/DCGScorer.java:74-90) evaluated pair by pair instead of through an n x n table.
 static void pseudo_responses_range(orc_ctx* c, int start, int end) {
-    const int cutoff = c->prm.metric_k;
+    const int cutoff = metric_cutoff(c->prm.metric, c->prm.metric_k);
+    const bool tabled = c->prm.metric != RLB_METRIC_NDCG && c->prm.metric != RLB_METRIC_DCG;
     std::vector<int> idx, rel;
+    std::vector<float> lab;
+    std::vector<double> table;
     for (int q = start; q <= end; q++) {
         const int cur = c->qoff[q];
         const int n = c->qoff[q + 1] - cur;
@@ -296,7 +494,13 @@ static void pseudo_responses_range(orc_ctx* c, int start, int end) {
         double ideal = 0;
         const bool ndcg = (c->prm.metric == RLB_METRIC_NDCG);
         if (ndcg) ideal = ideal_dcg(rel, size);
+        if (tabled) {
+            lab.resize(n);
+            for (int i = 0; i < n; i++) lab[i] = c->label[idx[i]];
+            swap_change_table(lab, c->prm.metric, c->prm.metric_k, table);
+        }
         auto change = [&](int a, int b) -> double {  // changes[a][b], symmetric
+            if (tabled) return table[(size_t)a * n + b];
             int i = std::min(a, b), j = std::max(a, b);
             if (i == j || i >= size) return 0.0;
             if (ndcg) {
@@ -644,13 +848,14 @@ static void update_scores(orc_ctx* c) {
 // LambdaMART.computeModelScoreOnTraining (LambdaMART.java:442-483)
 static float train_metric(orc_ctx* c) {
     float s = 0;
-    std::vector<int> idx, rel;
+    std::vector<int> idx;
+    std::vector<float> rel;
     for (int q = 0; q < c->Q; q++) {
         const int cur = c->qoff[q];
         const int n = c->qoff[q + 1] - cur;
         stable_argsort(c->modelScores.data(), cur, n, false, idx);
         rel.resize(n);
-        for (int i = 0; i < n; i++) rel[i] = (int)c->label[idx[i]];
+        for (int i = 0; i < n; i++) rel[i] = c->label[idx[i]];
         s = (float)((double)s + metric_score(rel, c->prm.metric, c->prm.metric_k));
     }
     s = s / c->Q;
@@ -867,13 +1072,14 @@ int orc_ensemble_eval(const rlb_node* nodes, const int32_t* tree_off, int32_t n_
 int orc_score_metric(const double* scores, const float* label, const int32_t* qoff, int32_t Q, int32_t metric, int32_t k,
                      double* out) {
     double score = 0.0;
-    std::vector<int> idx, rel;
+    std::vector<int> idx;
+    std::vector<float> rel;
     for (int q = 0; q < Q; q++) {
         const int cur = qoff[q];
         const int n = qoff[q + 1] - cur;
         stable_argsort(scores, cur, n, false, idx);
         rel.resize(n);
-        for (int i = 0; i < n; i++) rel[i] = (int)label[idx[i]];
+        for (int i = 0; i < n; i++) rel[i] = label[idx[i]];
         score += metric_score(rel, metric, k);
     }
     *out = score / Q;
@@ -894,6 +1100,35 @@ float orc_float_chain(const double* x, int64_t n, float carry) {
     float s = carry;
     for (int64_t i = 0; i < n; i++) s = (float)((double)s + x[i]);
     return s;
+}
+
+// test access to the metric restatements: MetricScorer.swapChange as the full n x n table (NDCG / DCG included) and
+// MetricScorer.score, on an already ranked label list
+int orc_swap_change(const float* lab, int32_t n, int32_t metric, int32_t k, double* out) {
+    std::vector<float> l(lab, lab + n);
+    if (metric == RLB_METRIC_NDCG || metric == RLB_METRIC_DCG) {
+        std::vector<int> rel(n);
+        for (int i = 0; i < n; i++) rel[i] = (int)l[i];
+        const int size = (n > k) ? k : n;
+        const double ideal = (metric == RLB_METRIC_NDCG) ? ideal_dcg(rel, size) : 0.0;
+        for (int i = 0; i < n * n; i++) out[i] = 0.0;
+        for (int i = 0; i < size; i++)
+            for (int j = i + 1; j < n; j++) {
+                double v = (discount(i) - discount(j)) * (gain(rel[i]) - gain(rel[j]));
+                if (metric == RLB_METRIC_NDCG) v = (ideal > 0) ? v / ideal : 0.0;
+                out[(size_t)i * n + j] = out[(size_t)j * n + i] = v;
+            }
+        return RLB_OK;
+    }
+    std::vector<double> t;
+    swap_change_table(l, metric, k, t);
+    for (size_t i = 0; i < t.size(); i++) out[i] = t[i];
+    return RLB_OK;
+}
+
+double orc_metric_score(const float* lab, int32_t n, int32_t metric, int32_t k) {
+    std::vector<float> l(lab, lab + n);
+    return metric_score(l, metric, k);
 }
 
 }  // extern "C"

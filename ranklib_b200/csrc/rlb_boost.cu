@@ -145,6 +145,217 @@ __device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// The other MetricScorers (ERR, MAP, P@k, RR@k, Best@k) as LambdaMART uses them: MetricScorer.score(RankList) for
+// the training metric and MetricScorer.swapChange(RankList) for the pair weights (LambdaMART.java:369,382).  The
+// reference fills an n x n table per query and iteration; here a per-query prologue (one thread, O(n)) leaves what a
+// single entry needs in shared memory and metric_change(a, b) returns changes[a][b] for a < b, a < rows — the only
+// entries LambdaMART's loop guard (`j > cutoff && k > cutoff`, :375) lets through with a non-zero value.  Every
+// expression keeps the operand order of the Java source (no FMA contraction: --fmad=false), so the values are the
+// reference's doubles bit for bit.
+// ------------------------------------------------------------------------------------------------
+struct QAux {
+    int rows;        // table rows: min(k, n); MAP: min(1, n) (APScorer.k = 0 -> only pairs touching rank 0 are visited)
+    int size;        // min(k, n)
+    int first, second;            // RR: ranks of the first two relevant documents among the top `size` (-1: none)
+    double rr;                    // RR: 1 / (first + 1)
+    int maxVal, secondMaxVal, maxCount, lbk;   // Best@k (lbk = labels[best[k - 1]])
+    int count;                    // MAP: number of relevant documents
+};
+static_assert(sizeof(QAux) <= 64, "QAux slot in the query kernels' shared memory");
+
+__device__ __forceinline__ double err_R(int rel) { return ((1 << rel) - 1) / 16.0; }  // ERRScorer.R, MAX = 16
+
+// LambdaMART's cutoff = scorer.getK() (LambdaMART.java:362); APScorer pins k to 0 (APScorer.java:36)
+__device__ __forceinline__ int metric_cutoff(int metric, int k) { return metric == RLB_METRIC_MAP ? 0 : k; }
+
+// per-query prologue, ONE thread.  lab = ranked labels; auxD (2 n doubles) / auxI (n ints) receive:
+//   ERR: R[i] | np[i] (i < size, 0 beyond, like the reference's zero-initialised arrays)    (ERRScorer.java:77-89)
+//   MAP: changes[0][j] for every j                                                          (APScorer.java:108-160)
+//   BEST: best[i] in auxI                                                                    (BestAtKScorer.java:66-88)
+template <typename LabFn>
+__device__ void metric_prologue(int metric, int k, int n, LabFn lab, double* auxD, int* auxI, int capN, QAux& ax) {
+    ax.size = (n > k) ? k : n;
+    ax.rows = (metric == RLB_METRIC_MAP) ? min(1, n) : ax.size;
+    ax.first = ax.second = -1;
+    ax.rr = 0.0;
+    ax.maxVal = ax.secondMaxVal = -1;
+    ax.maxCount = 0;
+    ax.lbk = 0;
+    ax.count = 0;
+    if (metric == RLB_METRIC_ERR) {
+        double* R = auxD;
+        double* np = auxD + capN;
+        double p = 1.0;
+        for (int i = 0; i < n; i++) {
+            if (i < ax.size) {
+                R[i] = err_R((int)lab(i));
+                np[i] = p * (1.0 - R[i]);
+                p *= np[i];
+            } else {
+                R[i] = 0.0;
+                np[i] = 0.0;
+            }
+        }
+    } else if (metric == RLB_METRIC_MAP) {
+        int count = 0;
+        for (int i = 0; i < n; i++) count += (lab(i) > 0) ? 1 : 0;
+        ax.count = count;
+        double* ch0 = auxD;
+        for (int j = 0; j < n; j++) ch0[j] = 0.0;
+        if (count > 0 && n > 1) {
+            const int l0 = (lab(0) > 0) ? 1 : 0;
+            const int diff = (1 - l0) - l0;           // labels[j] - labels[0] for every j whose label differs
+            const int lj = 1 - l0;
+            const int rc0 = l0;                        // relCount[0]
+            double run = 0.0;
+            run += ((double)((rc0 + diff) * lj - rc0 * l0)) / (0 + 1);
+            int rc = rc0;
+            for (int j = 1; j < n; j++) {
+                const int bj = (lab(j) > 0) ? 1 : 0;
+                rc += bj;                              // relCount[j]
+                if (bj != l0) {
+                    double change = run;
+                    change += ((double)(-rc * diff)) / (j + 1);
+                    ch0[j] = change / count;
+                }
+                if (bj > 0) run += ((double)diff) / (j + 1);
+            }
+        }
+    } else if (metric == RLB_METRIC_RR) {
+        for (int i = 0; i < ax.size; i++)
+            if (lab(i) > 0.0f) {
+                if (ax.first == -1)
+                    ax.first = i;
+                else if (ax.second == -1)
+                    ax.second = i;
+            }
+        if (ax.first != -1) ax.rr = 1.0 / (ax.first + 1);
+    } else if (metric == RLB_METRIC_BEST) {
+        int mx = -1;
+        for (int i = 0; i < n; i++) {
+            const int v = (int)lab(i);
+            if (ax.maxVal < v) {
+                if (i < k) {
+                    ax.secondMaxVal = ax.maxVal;
+                    ax.maxCount = 0;
+                }
+                ax.maxVal = v;
+                mx = i;
+            } else if (ax.maxVal == v && i < k) {
+                ax.maxCount++;
+            }
+            auxI[i] = mx;
+        }
+        if (ax.secondMaxVal == -1) ax.secondMaxVal = 0;
+        if (k - 1 >= 0 && k - 1 < n) ax.lbk = (int)lab(auxI[k - 1]);
+    }
+}
+
+// changes[a][b], a < b, a < ax.rows
+template <typename LabFn>
+__device__ double metric_change(int metric, int k, int n, int a, int b, LabFn lab, const double* auxD, const int* auxI, int capN,
+                                const QAux& ax) {
+    if (metric == RLB_METRIC_ERR) {
+        const double* R = auxD;
+        const double* np = auxD + capN;
+        const int size = ax.size;
+        const int li = (int)lab(a), lj = (b < size) ? (int)lab(b) : 0;   // labels[] is filled for the top `size` only
+        if (li == lj) return 0.0;
+        const double Ri = R[a], Rj = R[b];
+        const double npi = (a == 0) ? 1 : np[a - 1];
+        const double v1 = 1.0 / (a + 1) * npi;
+        double change = v1 * (Rj - Ri);
+        double p = npi * (Ri - Rj);
+        const int kend = min(b, size);   // R[kk] = 0 beyond: the remaining terms add 0.0 and leave p unchanged
+        for (int kk = a + 1; kk < kend; kk++) {
+            change += p * R[kk] / (1 + kk);
+            p *= 1.0 - R[kk];
+        }
+        change += (np[b - 1] * (1.0 - Rj) * Ri / (1.0 - Ri) - np[b - 1] * Rj) / (b + 1);
+        return change;
+    }
+    if (metric == RLB_METRIC_MAP) return auxD[b];   // a == 0
+    if (metric == RLB_METRIC_PRECISION) {
+        if (b < ax.size) return 0.0;
+        const int c = ((lab(b) > 0.0f) ? 1 : 0) - ((lab(a) > 0.0f) ? 1 : 0);
+        return (double)(((float)c) / ax.size);
+    }
+    if (metric == RLB_METRIC_RR) {
+        const int size = ax.size;
+        int first = ax.first;
+        if (first != -1) {
+            if (a == first) {
+                if (((int)lab(b)) != 0) return 0.0;
+                if (b < size) return (ax.second == -1 || b < ax.second) ? 1.0 / (b + 1) - ax.rr : 1.0 / (ax.second + 1) - ax.rr;
+                return (ax.second == -1) ? -ax.rr : 1.0 / (ax.second + 1) - ax.rr;
+            }
+        } else {
+            first = size;
+        }
+        if (a < first && b >= first && lab(b) > 0) return 1.0 / (a + 1) - ax.rr;
+        return 0.0;
+    }
+    if (metric == RLB_METRIC_BEST) {
+        if (b < k || a >= k) return 0.0;
+        const int la = (int)lab(a), lb = (int)lab(b);
+        if (la == lb || lb == ax.lbk) return 0.0;
+        if (lb > ax.lbk) return (double)(lb - (int)lab(auxI[a]));
+        if (la < ax.lbk || ax.maxCount > 1) return 0.0;
+        return (double)(ax.maxVal - max(ax.secondMaxVal, lb));
+    }
+    return 0.0;
+}
+
+// MetricScorer.score(RankList) for the metrics above (ERRScorer.java:45-66, APScorer.java:75-103,
+// PrecisionScorer.java:29-43, ReciprocalRankScorer.java:25-35, BestAtKScorer.java:28-57); one thread
+template <typename LabFn>
+__device__ double metric_value(int metric, int k, int n, LabFn lab) {
+    if (metric == RLB_METRIC_MAP) {
+        double ap = 0.0;
+        int count = 0;
+        for (int i = 0; i < n; i++)
+            if (lab(i) > 0.0f) {
+                count++;
+                ap += ((double)count) / (i + 1);
+            }
+        return count == 0 ? 0.0 : ap / count;
+    }
+    if (metric == RLB_METRIC_RR) {
+        const int size = (n > k) ? k : n;
+        for (int i = 0; i < size; i++)
+            if (lab(i) > 0.0f) return (double)(1.0f / (float)(i + 1));
+        return 0.0;
+    }
+    int size = k;
+    if (k > n || k <= 0) size = n;
+    if (metric == RLB_METRIC_PRECISION) {
+        int count = 0;
+        for (int i = 0; i < size; i++) count += (lab(i) > 0.0f) ? 1 : 0;
+        return ((double)count) / size;
+    }
+    if (metric == RLB_METRIC_BEST) {
+        int sz = k - 1;
+        if (sz < 0 || sz > n - 1) sz = n - 1;
+        double mx = -1.0;
+        int mi = 0;
+        for (int i = 0; i <= sz; i++)
+            if (mx < lab(i)) {
+                mx = lab(i);
+                mi = i;
+            }
+        return (double)lab(mi);
+    }
+    // ERR
+    double s = 0.0, p = 1.0;
+    for (int i = 1; i <= size; i++) {
+        const double R = err_R((int)lab(i - 1));
+        s += p * R / i;
+        p *= (1.0 - R);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 / K9: per-query ranking, NDCG@k and pairwise lambdas
 //   LambdaMART.computePseudoResponses (LambdaMART.java:361-396), NDCGScorer.swapChange
 //   (NDCGScorer.java:132-160), NDCGScorer.score (:103-129), MergeSorter.sort (stable, descending).
@@ -165,7 +376,13 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
     __shared__ float sLabel[QCAP];
     __shared__ double sIdeal;
     __shared__ unsigned long long sMax;
+    __shared__ double sAuxD[2 * QCAP];   // metric_prologue arrays of the generic metrics (queries of up to QCAP documents)
+    __shared__ int sAuxI[QCAP];
+    __shared__ QAux sAx;
     const int tid = threadIdx.x;
+    const bool generic = metric > RLB_METRIC_DCG;
+    const int kparam = cutoff;                       // MetricScorer.k as the scorer itself uses it
+    const int cut = metric_cutoff(metric, cutoff);   // LambdaMART's loop guard (LambdaMART.java:362,375)
     double thrMax = 0.0;
     for (int qi = blockIdx.x; qi < Q; qi += gridDim.x) {
         const int q = qlist ? qlist[qi] : qi;
@@ -227,19 +444,30 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
             }
             sIdeal = ideal;
             if (qmetric) {
-                double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
-                for (int i = 0; i < size; i++) dcg += (double)((1 << (int)L(i)) - 1) * disc[i];
-                double m = dcg;
-                if (metric == RLB_METRIC_NDCG) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
-                qmetric[q] = m;
+                if (generic) {
+                    qmetric[q] = metric_value(metric, cutoff, n, L);
+                } else {
+                    double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
+                    for (int i = 0; i < size; i++) dcg += (double)((1 << (int)L(i)) - 1) * disc[i];
+                    double m = dcg;
+                    if (metric == RLB_METRIC_NDCG) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
+                    qmetric[q] = m;
+                }
+            }
+            if (LAMBDA && generic && small) {
+                QAux ax;
+                metric_prologue(metric, cutoff, n, L, sAuxD, sAuxI, QCAP, ax);
+                sAx = ax;
             }
         }
         if (LAMBDA) {
             __syncthreads();
             const double ideal = sIdeal;
             const bool ndcg = (metric == RLB_METRIC_NDCG);
-            const bool have = !ndcg || ideal > 0.0;
-            const int size = (n > cutoff) ? cutoff : n;  // swapChange (NDCGScorer.java:133)
+            // generic metrics keep their per-query arrays in shared memory: queries above QCAP documents are refused at init
+            const bool have = generic ? small : (!ndcg || ideal > 0.0);
+            const int cutoff = cut;                        // shadows the parameter: the loop guard's value from here on
+            const int size = generic ? sAx.rows : ((n > cutoff) ? cutoff : n);  // swapChange (NDCGScorer.java:133)
             for (int p = tid; p < n; p += blockDim.x) {
                 double lam = 0.0, w = 0.0;
                 if (have) {
@@ -249,6 +477,7 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
                     const double dp = disc[p];
                     // |changes[a][b]| for a < b, a < size
                     auto delta = [&](int a, int b, double ga, double gb) -> double {
+                        if (generic) return fabs(metric_change(metric, kparam, n, a, b, L, sAuxD, sAuxI, QCAP, sAx));
                         double ch = (disc[a] - disc[b]) * (ga - gb);
                         if (ndcg) ch = ch / ideal;
                         return fabs(ch);
@@ -342,7 +571,8 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
                                            const double* __restrict__ disc, const double* __restrict__ idealIn,
                                            double* __restrict__ lambda, double* __restrict__ weight,
                                            double* __restrict__ qmetric, double* sRaw, double* sScore, float* sLabel,
-                                           int* sDoc, double* tL, double* tW, double& thrMax) {
+                                           int* sDoc, double* tL, double* tW, double* auxD, int* auxI, QAux* sAux, int capN,
+                                           double& thrMax) {
     const int lo = qoff[q];
     const int n = qoff[q + 1] - lo;
     if (n <= 0) {
@@ -364,18 +594,35 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
     }
     group_sync<G>();
     const bool ndcg = (metric == RLB_METRIC_NDCG);
+    const bool generic = metric > RLB_METRIC_DCG;   // ERR, MAP, P@k, RR@k, Best@k: see metric_change
     const double ideal = ndcg ? idealIn[q] : 0.0;
+    auto labf = [&](int i) -> float { return sLabel[i]; };
+    if (generic && lambda) {
+        if (gt == 0) {
+            QAux ax;
+            metric_prologue(metric, cutoff, n, labf, auxD, auxI, capN, ax);
+            *sAux = ax;
+        }
+        group_sync<G>();
+    }
     if (qmetric && gt == 0) {
-        int sz = cutoff;
-        if (cutoff > n || cutoff <= 0) sz = n;
-        double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
-        for (int i = 0; i < sz; i++) dcg += (double)((1 << (int)sLabel[i]) - 1) * disc[i];
-        double m = dcg;
-        if (ndcg) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
-        qmetric[q] = m;
+        if (generic) {
+            qmetric[q] = metric_value(metric, cutoff, n, labf);
+        } else {
+            int sz = cutoff;
+            if (cutoff > n || cutoff <= 0) sz = n;
+            double dcg = 0.0;  // DCGScorer.getDCG (DCGScorer.java:97-103)
+            for (int i = 0; i < sz; i++) dcg += (double)((1 << (int)sLabel[i]) - 1) * disc[i];
+            double m = dcg;
+            if (ndcg) m = (ideal <= 0.0) ? 0.0 : dcg / ideal;
+            qmetric[q] = m;
+        }
     }
     if (lambda) {
-        const int size = (n > cutoff) ? cutoff : n;  // swapChange (NDCGScorer.java:133)
+        QAux ax;
+        if (generic) ax = *sAux;
+        // rows of the pair table: swapChange fills changes[i][j] for i < size = min(k, n) (NDCGScorer.java:133,151)
+        const int size = generic ? ax.rows : ((n > cutoff) ? cutoff : n);
         const bool have = !ndcg || ideal > 0.0;
         const int np = size > 0 ? size * n : 0;
         for (int e = gt; e < np; e += G) {
@@ -384,8 +631,13 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
             if (b > a && have) {
                 const float la = sLabel[a], lb = sLabel[b];
                 if (la != lb) {
-                    double ch = (disc[a] - disc[b]) * ((double)((1 << (int)la) - 1) - (double)((1 << (int)lb) - 1));
-                    if (ndcg) ch = ch / ideal;
+                    double ch;
+                    if (generic) {
+                        ch = metric_change(metric, cutoff, n, a, b, labf, auxD, auxI, capN, ax);
+                    } else {
+                        ch = (disc[a] - disc[b]) * ((double)((1 << (int)la) - 1) - (double)((1 << (int)lb) - 1));
+                        if (ndcg) ch = ch / ideal;
+                    }
                     const double d = fabs(ch);
                     if (d > 0) {
                         const double diff = (la > lb) ? (sScore[a] - sScore[b]) : (sScore[b] - sScore[a]);
@@ -440,7 +692,7 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
 
 #define QA_N 64      // warp path: documents per query
 #define QA_T 640     // warp path: table entries (min(k, n) * n)
-#define QA_WARP_BYTES (QA_N * (8 + 8 + 4 + 4) + QA_T * 16)
+#define QA_WARP_BYTES (QA_N * (8 + 8 + 4 + 4) + QA_T * 16 + QA_N * (16 + 4) + 64)   // + metric_prologue arrays + QAux
 
 __device__ __forceinline__ void publish_max(double thrMax, DevState* st) {
     unsigned long long b = (unsigned long long)__double_as_longlong(thrMax);
@@ -464,13 +716,16 @@ __global__ void __launch_bounds__(256) k_query_warp(const double* __restrict__ s
     double* sScore = sRaw + QA_N;
     double* tL = sScore + QA_N;
     double* tW = tL + QA_T;
-    float* sLabel = reinterpret_cast<float*>(tW + QA_T);
+    double* auxD = tW + QA_T;
+    QAux* sAux = reinterpret_cast<QAux*>(auxD + 2 * QA_N);
+    float* sLabel = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sAux) + 64);
     int* sDoc = reinterpret_cast<int*>(sLabel + QA_N);
+    int* auxI = sDoc + QA_N;
     double thrMax = 0.0;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
     for (int i = gw; i < nq; i += nw)
         query_fast<32>(qlist[i], lane, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw, sScore,
-                       sLabel, sDoc, tL, tW, thrMax);
+                       sLabel, sDoc, tL, tW, auxD, auxI, sAux, QA_N, thrMax);
     if (lambda) publish_max(thrMax, st);
 }
 
@@ -486,12 +741,15 @@ __global__ void __launch_bounds__(G) k_query_block(const double* __restrict__ sc
     double* sScore = sRaw + capN;
     double* tL = sScore + capN;
     double* tW = tL + capT;
-    float* sLabel = reinterpret_cast<float*>(tW + capT);
+    double* auxD = tW + capT;
+    QAux* sAux = reinterpret_cast<QAux*>(auxD + 2 * capN);
+    float* sLabel = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sAux) + 64);
     int* sDoc = reinterpret_cast<int*>(sLabel + capN);
+    int* auxI = sDoc + capN;
     double thrMax = 0.0;
     for (int i = blockIdx.x; i < nq; i += gridDim.x)
         query_fast<G>(qlist[i], threadIdx.x, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw,
-                      sScore, sLabel, sDoc, tL, tW, thrMax);
+                      sScore, sLabel, sDoc, tL, tW, auxD, auxI, sAux, capN, thrMax);
     if (lambda) publish_max(thrMax, st);
 }
 
@@ -2723,7 +2981,7 @@ int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* 
 // (want_lambda).  Queries are routed by size class (lists built at init).
 static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
     const int B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
-    const size_t smA = (size_t)8 * QA_WARP_BYTES, smB1 = (size_t)B1N * 24 + (size_t)B1T * 16, smB2 = (size_t)B2N * 24 + (size_t)B2T * 16;
+    const size_t smA = (size_t)8 * QA_WARP_BYTES, smB1 = (size_t)B1N * 44 + (size_t)B1T * 16 + 64, smB2 = (size_t)B2N * 44 + (size_t)B2T * 16 + 64;
     double* lam = want_lambda ? c->dLambda : nullptr;
     double* wgt = want_lambda ? c->dWeight : nullptr;
     const int k = c->prm.metric_k, m = c->prm.metric;
@@ -2930,8 +3188,8 @@ int rlb_impl_prepare(rlb_ctx* c) {
     RLB_CUDA(c, cudaFuncSetAttribute(k_hist_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_hist_child, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 24 + 2560 * 16));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 24 + 10240 * 16));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 44 + 10240 * 16 + 64));
     return RLB_OK;
 }
 

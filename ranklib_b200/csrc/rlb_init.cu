@@ -304,9 +304,15 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     }
     if (p->n_threshold < 1 || p->n_leaves < 2 || p->n_leaves > RLB_MAX_LEAVES || p->min_leaf_support < 0 ||
         (p->kind != RLB_KIND_LAMBDAMART && p->kind != RLB_KIND_MART) ||
-        (p->metric != RLB_METRIC_NDCG && p->metric != RLB_METRIC_DCG)) {
+        p->metric < 0 || p->metric >= RLB_METRIC_COUNT) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_lambdamart_init", "parameter out of range");
         return RLB_E_INVALID;
+    }
+    if (p->metric > RLB_METRIC_DCG && p->kind == RLB_KIND_LAMBDAMART && c->max_query > 1024) {
+        // ERR / MAP / P / RR / Best keep per-query arrays in shared memory (metric_prologue, rlb_boost.cu)
+        rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_lambdamart_init",
+                      "metrics other than NDCG / DCG support queries of up to 1024 documents");
+        return RLB_E_UNSUPPORTED;
     }
     RLB_CUDA(c, cudaSetDevice(c->device));
     c->prm = *p;
@@ -536,7 +542,9 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         std::vector<int32_t> la, lb1, lb2, lc;
         for (int q = 0; q < Q; q++) {
             const int64_t n = qoffh[q + 1] - qoffh[q];
-            const int64_t sz = (p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0;
+            // rows of the pair table (query_fast): min(k, n); MAP visits only the pairs touching rank 0 (APScorer.k = 0)
+            const int64_t sz = (p->metric == RLB_METRIC_MAP) ? std::min<int64_t>(1, n)
+                                                              : ((p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0);
             const int64_t terms = sz * n;
             if (n <= 64 && terms <= 640) la.push_back(q);
             else if (n <= 256 && terms <= 2560) lb1.push_back(q);

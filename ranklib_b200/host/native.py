@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(CSRC, "libranklib_b200.so")
 
 RLB_OK = 0
 KIND_LAMBDAMART, KIND_MART = 0, 1
-METRIC_NDCG, METRIC_DCG = 0, 1
+METRIC_NDCG, METRIC_DCG, METRIC_ERR, METRIC_MAP, METRIC_PRECISION, METRIC_RR, METRIC_BEST = range(7)
 MAX_BINS = 257
 
 READ = dict(LAMBDA=1, WEIGHT=2, SCORE=3, LEAF_ID=4, BINS=5, ROOT_SUM=6, ROOT_COUNT=7, ROOT_STATS=8, NODE_ID=9)

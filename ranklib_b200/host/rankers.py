@@ -143,6 +143,65 @@ class DCGScorer(NDCGScorer):
         return f"DCG@{self.k}"
 
 
+class ERRScorer(NDCGScorer):
+    """R/metric/ERRScorer.java (MAX = 16); the CLI's default training metric is ERR@10 (Evaluator.java:84)."""
+    metric = native.METRIC_ERR
+
+    def name(self):
+        return f"ERR@{self.k}"
+
+
+class APScorer(NDCGScorer):
+    """R/metric/APScorer.java: the whole list, k pinned to 0 (:36) — LambdaMART's pair loop then only visits pairs
+    that touch rank 0 (LambdaMART.java:362,375)."""
+    metric = native.METRIC_MAP
+
+    def __init__(self, k=0):
+        self.k = 0
+
+    def name(self):
+        return "MAP"
+
+
+class PrecisionScorer(NDCGScorer):
+    metric = native.METRIC_PRECISION
+
+    def name(self):
+        return f"P@{self.k}"
+
+
+class ReciprocalRankScorer(NDCGScorer):
+    metric = native.METRIC_RR
+
+    def name(self):
+        return f"RR@{self.k}"
+
+
+class BestAtKScorer(NDCGScorer):
+    metric = native.METRIC_BEST
+
+    def name(self):
+        return f"Best@{self.k}"
+
+
+class MetricScorerFactory:
+    """R/metric/MetricScorerFactory.java:43-57: "NDCG@10", "ERR@10", "MAP", "P@5", "RR@10", "BEST@3", "DCG@10"."""
+    _map = {"MAP": APScorer, "NDCG": NDCGScorer, "DCG": DCGScorer, "P": PrecisionScorer, "RR": ReciprocalRankScorer,
+            "BEST": BestAtKScorer, "ERR": ERRScorer}
+
+    def createScorer(self, metric):
+        if "@" in metric:
+            m, k = metric.split("@", 1)
+            cls = self._map.get(m.upper())
+            if cls is None:
+                raise RankLibError(f"unknown metric {metric}")
+            return cls(int(k))
+        cls = self._map.get(metric.upper())
+        if cls is None:
+            raise RankLibError(f"unknown metric {metric}")
+        return cls()
+
+
 # ---------------------------------------------------------------------------------------------------
 # Java number formatting for the model text (Float.toString / Double.toString)
 # ---------------------------------------------------------------------------------------------------

@@ -16,6 +16,11 @@ want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__lsu_writeback_active_mem_lg.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__pcsamp_warps_issue_stalled_mio_throttle",
+        "smsp__pcsamp_warps_issue_stalled_lg_throttle", "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
+        "smsp__pcsamp_warps_issue_stalled_not_selected", "smsp__pcsamp_warps_issue_stalled_dispatch_stall",
         "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_selected",
         "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
         "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_branch_resolving"]
@@ -28,7 +33,7 @@ for r in rows[2:]:
     for i in idx:
         lines.append(f"{hdr[i]:70s} {r[i]} {units[i]}")
         d[hdr[i]] = r[i]
-    if first_root is None and "k_hist_priv<0" in d["Kernel Name"].replace("(bool)", "").replace(" ", ""):
+    if first_root is None and "k_hist_root" in d["Kernel Name"]:
         first_root = d
 open(out_txt, "w").write("\n".join(lines) + "\n")
 if out_json and first_root:

@@ -347,3 +347,31 @@ def test_float_chain_bit_exact(built):
     got, _ = g.float_chain(np.zeros(0), 1.5)
     assert got == np.float32(1.5)
     g.close()
+
+
+@pytest.mark.parametrize("metric,k", [("ERR", 10), ("ERR", 3), ("ERR", 60), ("MAP", 0), ("P", 5), ("P", 60), ("RR", 10), ("BEST", 3), ("DCG", 7)])
+def test_other_swap_change_metrics_lockstep(built, metric, k):
+    """LambdaMART driven by the other MetricScorers (ERR@10 is the CLI default): lambdas / weights,
+    trees and the training metric against the oracle, which fills the reference's n x n swapChange tables literally.
+    k = 60 pushes the larger queries off the pair-table kernels onto the table-free one (k_query)."""
+    X, label, qoff = synth.c2(0.01)
+    m = orc.METRICS[metric]
+    o, g = _pair(X, label, qoff, metric=m, k=k)
+    for it in range(4):
+        o.compute_pseudo_responses()
+        g.compute_pseudo_responses()
+        np.testing.assert_allclose(g.read("LAMBDA"), o.read("LAMBDA"), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(g.read("WEIGHT"), o.read("WEIGHT"), rtol=1e-12, atol=1e-15)
+        on, mo = o.boost_iter()
+        gn, mg = g.boost_iter()
+        ng, no = g.read("NODE_ID"), o.read("NODE_ID")
+        identical, equivalent = compare_tree(gn, on, ng, no)
+        assert equivalent, f"{metric}@{k} tree {it}: partitions differ"
+        assert np.max(rel_err(gn["output"][ng], on["output"][no])) <= 1e-5, f"tree {it}"
+        assert round(float(mo), 4) == round(float(mg), 4), (metric, it, mo, mg)
+    # the metric itself, on caller-provided scores (rlb_score_metric) against the oracle
+    rng = np.random.default_rng(5)
+    sc = rng.standard_normal(X.shape[0])
+    assert g.score_metric(sc, label, qoff, m, k) == orc.score_metric(sc, label, qoff, m, k)
+
+

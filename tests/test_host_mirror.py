@@ -107,3 +107,13 @@ def test_random_forest_bags_match_oracle(built):
         assert np.all(np.isfinite(s)) and s.shape == (1000,)
     finally:
         R.RFRanker.nBag, R.RFRanker.nTreeLeaves, R.RFRanker.seed = 300, 100, 0
+
+
+def test_metric_scorer_factory():
+    """MetricScorerFactory.createScorer(String) (R/metric/MetricScorerFactory.java:43-57)."""
+    from ranklib_b200.host import native, rankers as R
+    f = R.MetricScorerFactory()
+    assert f.createScorer("ERR@10").name() == "ERR@10" and f.createScorer("map").getK() == 0
+    assert f.createScorer("P@5").metric == native.METRIC_PRECISION and f.createScorer("NDCG@3").getK() == 3
+    with pytest.raises(R.RankLibError):
+        f.createScorer("XYZ@3")

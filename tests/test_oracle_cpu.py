@@ -189,3 +189,22 @@ def test_no_cpu_fallback_without_a_gpu(built):
         pytest.skip("a CUDA device is visible")
     with pytest.raises(native.RankLibError):
         native.Context(0)
+
+
+def test_other_metric_scorers_oracle_vs_transliteration():
+    """ERR / MAP / P / RR / Best: the C++ restatement of MetricScorer.swapChange + score against the independent
+    line-by-line Python transliteration (oracle/pyref.py) — identical doubles on random ranked label lists."""
+    from oracle import oracle as orc, pyref
+    rng = np.random.default_rng(3)
+    for trial in range(120):
+        n = int(rng.integers(1, 40))
+        k = int(rng.integers(1, 14))
+        lab = rng.choice([0, 0, 0, 1, 1, 2, 3, 4], size=n).astype(np.float32)
+        fl = [float(v) for v in lab]
+        cases = [("ERR", pyref.err_swap_change(fl, k), pyref.err_score(fl, k)), ("MAP", pyref.map_swap_change(fl), pyref.map_score(fl)),
+                 ("P", pyref.precision_swap_change(fl, k), pyref.precision_score(fl, k)),
+                 ("RR", pyref.rr_swap_change(fl, k), pyref.rr_score(fl, k)), ("BEST", pyref.best_swap_change(fl, k), pyref.best_score(fl, k))]
+        for name, table, score in cases:
+            m = orc.METRICS[name]
+            assert orc.swap_change(lab, m, k).tobytes() == np.array(table, np.float64).reshape(n, n).tobytes(), (name, n, k)
+            assert orc.metric_score(lab, m, k) == score, (name, n, k)
