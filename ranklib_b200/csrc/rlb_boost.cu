@@ -1688,6 +1688,9 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
         st->n_left_l = nl;
         st->n_right_l = n - nl;
     }
+    // at most `tiles` CTAs can get work: the others leave before touching the ticket (1184 CTAs serialising two
+    // same-address atomics each cost more than partitioning a small node)
+    if ((int)blockIdx.x >= tiles) return;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) sTile = (int)atomicAdd(&st->ticket_part, 1u);
@@ -2336,6 +2339,40 @@ __global__ void __launch_bounds__(256) k_chain_sum(int mode, const DevState* __r
     }
 }
 
+// Exclusive prefix over the chunks [c0, c1) of one chain by ONE warp, 8 chunks per lane and step: the loads of a step are
+// independent (one memory round trip per 256 chunks instead of one per 32).  out(i, prefix) receives the running value
+// in front of chunk i; returns the total.
+template <typename T, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ T warp_chunk_scan(int c0, int c1, T init, LoadFn load, StoreFn out) {
+    const int lane = threadIdx.x & 31;
+    T run = init;
+    for (int base = c0; base < c1; base += 256) {
+        T v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = base + lane * 8 + k;
+            v[k] = (i < c1) ? load(i) : T(0);
+        }
+        T tot = T(0);
+#pragma unroll
+        for (int k = 0; k < 8; k++) tot += v[k];
+        T inc = tot;
+        for (int d = 1; d < 32; d <<= 1) {
+            const T o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        T pre = run + (inc - tot);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = base + lane * 8 + k;
+            if (i < c1) out(i, pre);
+            pre += v[k];
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    return run;
+}
+
 // one warp per (chain, which): exclusive prefix of the chunk sums, starting from the carry
 __global__ void __launch_bounds__(32) k_chain_pred(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                     const float* __restrict__ carryIn, ChainBufs cb) {
@@ -2345,18 +2382,8 @@ __global__ void __launch_bounds__(32) k_chain_pred(int mode, const DevState* __r
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
     double* sd = cb.sumD + (size_t)which * cb.maxChunks;
-    const int lane = threadIdx.x;
-    for (int base = c0; base < c1; base += 32) {
-        const int i = base + lane;
-        const double v = (i < c1) ? sd[i] : 0.0;
-        double inc = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (i < c1) sd[i] = run + inc - v;  // predicted running value at the start of chunk i
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
+    warp_chunk_scan<double>(c0, c1, run, [&](int i) { return sd[i]; },
+                            [&](int i, double pre) { sd[i] = pre; });  // predicted running value at the start of chunk i
 }
 
 // second prediction: start of chunk i = carry + sum over the earlier chunks of (end - start) of their pass-1
@@ -2369,18 +2396,8 @@ __global__ void __launch_bounds__(32) k_chain_refine(int mode, const DevState* _
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
     const size_t o = (size_t)which * cb.maxChunks;
-    const int lane = threadIdx.x;
-    for (int base = c0; base < c1; base += 32) {
-        const int i = base + lane;
-        const double v = (i < c1) ? (double)cb.simE[o + i] - (double)cb.simS[o + i] : 0.0;
-        double inc = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            const double o2 = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o2;
-        }
-        if (i < c1) cb.sumD[o + i] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
+    warp_chunk_scan<double>(c0, c1, run, [&](int i) { return (double)cb.simE[o + i] - (double)cb.simS[o + i]; },
+                            [&](int i, double pre) { cb.sumD[o + i] = pre; });
 }
 
 // quanta of x when added to a float with sign sg (+-1) and exponent e: Q = rn(rn_v(x) / u); bad on ties / overflow
@@ -2480,18 +2497,7 @@ __global__ void __launch_bounds__(32) k_chain_pred2(int mode, const DevState* __
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
     const size_t o = (size_t)which * cb.maxChunks;
-    const int lane = threadIdx.x;
-    for (int base = c0; base < c1; base += 32) {
-        const int i = base + lane;
-        const double v = (i < c1) ? cb.rsum[o + i] : 0.0;
-        double inc = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            const double o2 = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o2;
-        }
-        if (i < c1) cb.sumD[o + i] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
+    warp_chunk_scan<double>(c0, c1, run, [&](int i) { return cb.rsum[o + i]; }, [&](int i, double pre) { cb.sumD[o + i] = pre; });
 }
 
 // Compile one chunk into its item program by simulating it exactly from the predicted start value: ONE WARP per
@@ -2686,17 +2692,9 @@ __global__ void __launch_bounds__(32) k_chain_offsets(int mode, const DevState* 
     if (l >= nCh) return;
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     const size_t o = (size_t)which * cb.maxChunks;
-    const size_t on = o;
-    const int lane = threadIdx.x;
-    int run = 0;
-    for (int base = c0; base < c1; base += 32) {
-        const int i = base + lane;
-        const int v = (i < c1) ? cb.nitems[on + i] + 1 : 0;
-        const int inc = warp_incl_scan_i(v, lane);
-        if (i < c1) cb.ipos[o + i] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) cb.itot[which * (RLB_MAX_LEAVES + 2) + l] = run;
+    const int total = warp_chunk_scan<int>(c0, c1, 0, [&](int i) { return cb.nitems[o + i] + 1; },
+                                           [&](int i, int pre) { cb.ipos[o + i] = pre; });
+    if ((threadIdx.x & 31) == 0) cb.itot[which * (RLB_MAX_LEAVES + 2) + l] = total;
 }
 
 // copy every chunk's program behind its marker into its chain's stream
