@@ -2240,13 +2240,14 @@ __device__ float chain_block(const double* __restrict__ val, const int32_t* __re
 //   k_chain_sum   exact double sum of every chunk (parallel); also stores the gathered values contiguously
 //   k_chain_pred  prefix of those sums per chain = predicted start of every chunk
 // ------------------------------------------------------------------------------------------------
-#define CK 1024          // elements per chunk (256 threads x 4)
-#define CH_ITEMS 1100    // item capacity of a chunk's program (worst case: every element its own item)
-#define CH_STREAM (CH_ITEMS + 1)   // stream slots per chunk: its items + the chunk marker
+#define CK RLB_CHAIN_CK         // elements per chunk (CK / 4 threads x 4 in the block-per-chunk kernels)
+#define CH_ITEMS RLB_CHAIN_ITEMS // item capacity of a chunk's program (worst case: every element its own item)
+#define CH_STREAM CH_ITEMS          // stream slots per chunk
 #define CH_BATCH 1024    // items per batch of the walk (4 per thread)
 
-// 16 bytes.  w0 = kind | key << 2.  RUN: a = total quanta, b / c = min / max prefix quanta (all inside +-2^24 for a
-// run that can pass its guard).  X: (b, c) = the element's double bits.  MARK: a = chunk index (opens a chunk).
+// 16 bytes.  w0 = kind | key << 2 | CI_FIRST on the first item of a chunk (in the chain's stream).  RUN: a = total
+// quanta, b / c = min / max prefix quanta (all inside +-2^24 for a run that can pass its guard).  X: (b, c) = the
+// element's double bits.
 struct __align__(16) ChainItem {
     uint32_t w0;
     int32_t a, b, c;
@@ -2254,7 +2255,7 @@ struct __align__(16) ChainItem {
 #define CI_RUN 0u
 #define CI_X 1u
 #define CI_ZRUN 2u
-#define CI_MARK 3u
+#define CI_FIRST 0x80000000u
 
 struct ChainBufs {
     double* sumD;        // [2][maxChunks] exact chunk sums, then (in place) predicted start values
@@ -2306,7 +2307,7 @@ __device__ __forceinline__ int chain_of_chunk(const int32_t* chunk0, int nCh, in
     return lo;
 }
 
-__global__ void __launch_bounds__(256) k_chain_sum(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+__global__ void __launch_bounds__(CK / 4) k_chain_sum(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                     int nChIn, const double* __restrict__ a0, const double* __restrict__ a1,
                                                     const int32_t* __restrict__ s0, const int32_t* __restrict__ s1,
                                                     int64_t nMetric, ChainBufs cb) {
@@ -2334,7 +2335,7 @@ __global__ void __launch_bounds__(256) k_chain_sum(int mode, const DevState* __r
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int i = 0; i < 8; i++) t += ws[i];
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += ws[i];
         cb.sumD[(size_t)which * cb.maxChunks + b] = t;
     }
 }
@@ -2434,7 +2435,7 @@ __device__ __forceinline__ double ci_x_value(const ChainItem& it) {
 // front of it (scan of the predicted chunk start + the elements), and the quanta are summed as doubles.  The
 // result ignores what happens at the (rare) steps that change binade, which is all the second prediction needs:
 // it removes the drift between the float chain and the exact sum (k_chain_pred2).
-__global__ void __launch_bounds__(256) k_chain_round(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
+__global__ void __launch_bounds__(CK / 4) k_chain_round(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                       ChainBufs cb) {
     const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
     const int b = blockIdx.x, which = blockIdx.y;
@@ -2483,7 +2484,7 @@ __global__ void __launch_bounds__(256) k_chain_round(int mode, const DevState* _
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int i = 0; i < 8; i++) t += wT[i];
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += wT[i];
         cb.rsum[o] = t;
     }
 }
@@ -2534,7 +2535,14 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     const double* xg = cb.xs + o * CK;
     double* xs = xsAll[wid];
     ChainItem* items = cb.items + o * CH_ITEMS;
-    for (int i = lane; i < CK / 2; i += 32) reinterpret_cast<double2*>(xs)[i] = reinterpret_cast<const double2*>(xg)[i];
+    {   // the whole chunk in one memory round trip: all loads first, then the stores
+        constexpr int PL = CK / 64;
+        double2 t[PL];
+#pragma unroll
+        for (int k = 0; k < PL; k++) t[k] = reinterpret_cast<const double2*>(xg)[lane + 32 * k];
+#pragma unroll
+        for (int k = 0; k < PL; k++) reinterpret_cast<double2*>(xs)[lane + 32 * k] = t[k];
+    }
     __syncwarp();
     // the first chunk of a chain starts from the carry itself, not from a rounded copy of it
     float s = (b == chunk0[l]) ? (carryIn ? carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.f) : (float)cb.sumD[o];
@@ -2684,7 +2692,7 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     }
 }
 
-// stream position of every chunk of a chain: exclusive prefix of (items + 1 marker); one warp per (chain, which)
+// stream position of every chunk of a chain: exclusive prefix of its item counts; one warp per (chain, which)
 __global__ void __launch_bounds__(32) k_chain_offsets(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                        ChainBufs cb) {
     const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
@@ -2692,12 +2700,12 @@ __global__ void __launch_bounds__(32) k_chain_offsets(int mode, const DevState* 
     if (l >= nCh) return;
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     const size_t o = (size_t)which * cb.maxChunks;
-    const int total = warp_chunk_scan<int>(c0, c1, 0, [&](int i) { return cb.nitems[o + i] + 1; },
+    const int total = warp_chunk_scan<int>(c0, c1, 0, [&](int i) { return cb.nitems[o + i]; },
                                            [&](int i, int pre) { cb.ipos[o + i] = pre; });
     if ((threadIdx.x & 31) == 0) cb.itot[which * (RLB_MAX_LEAVES + 2) + l] = total;
 }
 
-// copy every chunk's program behind its marker into its chain's stream
+// copy every chunk's program into its chain's stream
 __global__ void __launch_bounds__(128) k_chain_compact(int mode, const DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                         ChainBufs cb) {
     const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
@@ -2707,13 +2715,12 @@ __global__ void __launch_bounds__(128) k_chain_compact(int mode, const DevState*
     const size_t on = (size_t)which * cb.maxChunks + b;
     const int ni = cb.nitems[on];
     ChainItem* dst = cb.stream + ((size_t)which * cb.maxChunks + chunk0[l]) * CH_STREAM + cb.ipos[(size_t)which * cb.maxChunks + b];
-    if (threadIdx.x == 0) {
-        ChainItem mk;
-        mk.w0 = CI_MARK; mk.a = b; mk.b = 0; mk.c = 0;
-        dst[0] = mk;
-    }
     const ChainItem* src = cb.items + on * CH_ITEMS;
-    for (int i = threadIdx.x; i < ni; i += blockDim.x) dst[1 + i] = src[i];
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) {
+        ChainItem it = src[i];
+        if (i == 0) it.w0 |= CI_FIRST;   // opens chunk b: the walk remembers the running value for an exact redo
+        dst[i] = it;
+    }
 }
 
 // Walk one chain's item stream, CH_BATCH items per batch.  All threads fetch the next batch (into registers while
@@ -2733,7 +2740,7 @@ __device__ float chain_walk(const double* __restrict__ xsAll, int64_t n, int cha
         sCur = carry;
         sChunkStart = carry;
         sSkip = 0;
-        sCurChunk = c0;
+        sCurChunk = c0 - 1;
     }
     if (c0 >= c1) {
         __syncthreads();
@@ -2777,24 +2784,16 @@ __device__ float chain_walk(const double* __restrict__ xsAll, int64_t n, int cha
                 for (; i < nb;) {
                     const ChainItem nx = its[min(i + 1, nb - 1)];   // next item's load overlaps this item's arithmetic
                     const unsigned int kind = it.w0 & 3u;
-                    if (kind == CI_MARK) {
+                    if (it.w0 & CI_FIRST) {   // a new chunk (every chunk has at least one item)
                         skip = 0;
                         sChunk = s;
-                        curChunk = it.a;
-#ifdef RLB_CHAIN_DEBUG
-                        if (serialCount) {
-                            DevState* dst = (DevState*)((char*)serialCount - offsetof(DevState, chain_serial));
-                            const unsigned int ba = __float_as_uint(s), bp = __float_as_uint(cb.simS[o + curChunk]);
-                            const long long d = (long long)ba - (long long)bp;
-                            const int slot = (ba >> 23) != (bp >> 23) ? 2 : (d == 0 ? 0 : ((d < 16 && d > -16) ? 1 : 2));
-                            atomicAdd((unsigned long long*)&dst->chain_dbg[slot], 1ull);
-                        }
-#endif
-                    } else if (!skip) {
+                        curChunk++;
+                    }
+                    if (!skip) {
                         const unsigned int bits = __float_as_uint(s);
                         if (kind == CI_RUN) {
                             const int M = (int)((bits & 0x7fffffu) | 0x800000u);
-                            if ((bits >> 23) != (it.w0 >> 2) || !(M + it.b > 8388608) || !(M + it.c < 16777216)) {
+                            if ((bits >> 23) != ((it.w0 >> 2) & 0x1ffu) || !(M + it.b > 8388608) || !(M + it.c < 16777216)) {
                                 failChunk = curChunk;
                             } else {
                                 s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)(M + it.a) & 0x7fffffu));
@@ -3238,14 +3237,14 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     k_leaf_chunks<<<1, 1, 0, c->stream>>>(c->dState, c->dChunk0);
     RLB_CHECK_LAUNCH(c);
     const int gchunks = (int)(c->N / CK) + nl + 1;
-    k_chain_sum<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
+    k_chain_sum<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
                                                           c->dSamples[1], 0, cb);
     RLB_CHECK_LAUNCH(c);
     k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
     RLB_CHECK_LAUNCH(c);
     const int gsim = (gchunks + SIM_WARPS - 1) / SIM_WARPS;
     if (c->chain_passes >= 2) {   // second prediction from the rounded increments (default)
-        k_chain_round<<<dim3(gchunks, nw), 256, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
+        k_chain_round<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
         RLB_CHECK_LAUNCH(c);
         k_chain_pred2<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
         RLB_CHECK_LAUNCH(c);
@@ -3329,7 +3328,7 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
         ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
         int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2;  // static table of the metric chain: {0, ceil(Q / CK)}
         const int gchunks = (c->Q + CK - 1) / CK;
-        k_chain_sum<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
+        k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
         RLB_CHECK_LAUNCH(c);
         k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, carry, cb);
         RLB_CHECK_LAUNCH(c);
@@ -3385,11 +3384,11 @@ int rlb_impl_float_chain(rlb_ctx* c, const double* x, int64_t n, float carry, in
     cudaMemsetAsync(dSt, 0, sizeof(DevState), c->stream);
     ChainBufs cb{dSum, dXs, dItems, dNI, dIPos, dITot, dStream, dRSum, dS, dE, maxc};
     if (gchunks > 0) {
-        k_chain_sum<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, dSt, dCh0, 1, dX, nullptr, nullptr, nullptr, n, cb);
+        k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, dSt, dCh0, 1, dX, nullptr, nullptr, nullptr, n, cb);
         k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, dCarry, cb);
         const int gsim = (gchunks + SIM_WARPS - 1) / SIM_WARPS;
         if (passes >= 2) {
-            k_chain_round<<<dim3(gchunks, 1), 256, 0, c->stream>>>(1, dSt, dCh0, cb);
+            k_chain_round<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, dSt, dCh0, cb);
             k_chain_pred2<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, dCarry, cb);
         }
         for (int pass = 2; pass < passes; pass++) {

@@ -477,16 +477,16 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dUsed, 2 * F * sizeof(int32_t)));  // usedFeatures + sampling pool
     RLB_CUDA(c, alloc(c->dState, sizeof(DevState)));
     RLB_CUDA(c, alloc(c->dCarry, 4 * (RLB_MAX_LEAVES + 1) * sizeof(float)));
-    c->chain_max_chunks = (int)(std::max<int64_t>(N, Q) / 1024) + RLB_MAX_LEAVES + 2;
+    c->chain_max_chunks = (int)(std::max<int64_t>(N, Q) / RLB_CHAIN_CK) + RLB_MAX_LEAVES + 2;
     RLB_CUDA(c, alloc(c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainXs, (size_t)2 * c->chain_max_chunks * 1024 * sizeof(double)));
+    RLB_CUDA(c, alloc(c->dChainXs, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_CK * sizeof(double)));
     RLB_CUDA(c, alloc(c->dChainRSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
     {
-        void* p = c->dChainItems;   // 1100 items of 16 bytes per chunk (ChainItem, CH_ITEMS: rlb_boost.cu)
-        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * 1100 * 16));
+        void* p = c->dChainItems;   // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu)
+        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));
         c->dChainItems = (struct ChainItem*)p;
         p = c->dChainStream;        // the same + one marker per chunk (CH_STREAM)
-        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * 1101 * 16));
+        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * (RLB_CHAIN_ITEMS + 1) * 16));
         c->dChainStream = (struct ChainItem*)p;
     }
     RLB_CUDA(c, alloc(c->dChainIPos, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
@@ -497,7 +497,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     if (const char* e = getenv("RLB_CHAIN_PASSES")) c->chain_passes = std::max(1, atoi(e));
     RLB_CUDA(c, alloc(c->dChunk0, (size_t)(RLB_MAX_LEAVES + 4) * sizeof(int32_t)));
     {
-        const int32_t mc[2] = {0, (Q + 1023) / 1024};
+        const int32_t mc[2] = {0, (Q + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK};
         RLB_CUDA(c, cudaMemcpyAsync(c->dChunk0 + RLB_MAX_LEAVES + 2, mc, sizeof(mc), cudaMemcpyHostToDevice, c->stream));
         RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     }

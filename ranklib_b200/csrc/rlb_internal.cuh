@@ -48,6 +48,8 @@ bool rlb_nccl_load(std::string* why);
 #define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
 #define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
 #define RLB_ROOT_R 192               // rows per tile of the root-histogram layout (dBinsTile)
+#define RLB_CHAIN_CK 512             // float-chain elements per chunk (rlb_boost.cu: one warp compiles a chunk's item program)
+#define RLB_CHAIN_ITEMS (RLB_CHAIN_CK + 88)   // item capacity of a chunk's program
 #define RLB_CHAIN_THREADS 256
 #define RLB_CHAIN_PER_THREAD 4
 
