@@ -2401,9 +2401,24 @@ __global__ void __launch_bounds__(32) k_chain_refine(int mode, const DevState* _
                             [&](int i, double pre) { cb.sumD[o + i] = pre; });
 }
 
-// quanta of x when added to a float with sign sg (+-1) and exponent e: Q = rn(rn_v(x) / u); bad on ties / overflow
+// 2^n as a double, |n| <= 1022 (exponent field built directly; scalbn is a subroutine)
+__device__ __forceinline__ double pow2d(int n) { return __hiloint2double((1023 + n) << 20, 0); }
+
+// quanta of x when added to a float with sign sg (+-1) and exponent e: Q = rn(rn_v(x) / u); bad on ties / overflow.
+// The two roundings to integer go through the full-rate FP64 adder ((a + 1.5 * 2^52) - 1.5 * 2^52 is rint(a) in round-to-
+// nearest-even for |a| < 2^51, and the low word of the biased sum is the integer itself) instead of the conversion unit
+// (FRND / F2I run at a quarter of the rate and were most of a simulation round); larger |a| take the conversions.
 __device__ __forceinline__ long long chain_quantum(double x, double sg, double scale_v, bool& bad) {
     const double a = sg * x * scale_v;
+    if (fabs(a) < 2251799813685248.0) {  // 2^51
+        const double C = 6755399441055744.0;  // 1.5 * 2^52 (low word 0)
+        const double ya = (a + C) - C;
+        const double qd = ya * (1.0 / 536870912.0);  // / 2^29: |qd| < 2^22
+        const double t = qd + C;
+        const double Qd = t - C;
+        if (fabs(qd - Qd) == 0.5) bad = true;
+        return (long long)__double2loint(t);
+    }
     const double ya = rint(a);
     if (!(fabs(ya) < 2305843009213693952.0)) {  // 2^61; also NaN / inf
         bad = true;
@@ -2473,8 +2488,8 @@ __global__ void __launch_bounds__(CK / 4) k_chain_round(int mode, const DevState
             const int e = (int)((bits >> 23) & 0xff) - 127;
             bool bad = false;
             const double sg = (bits >> 31) ? -1.0 : 1.0;
-            const long long q = chain_quantum(x[k], sg, scalbn(1.0, 52 - e), bad);
-            if (!bad) r = sg * scalbn((double)q, e - 23);
+            const long long q = chain_quantum(x[k], sg, pow2d(52 - e), bad);
+            if (!bad) r = sg * ((double)q * pow2d(e - 23));
         }
         acc += r;
     }
@@ -2577,7 +2592,7 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
             const int e = (int)((bits >> 23) & 0xff) - 127;
             const double sg = (bits >> 31) ? -1.0 : 1.0;
             const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
-            const double scale_v = scalbn(1.0, 52 - e);
+            const double scale_v = pow2d(52 - e);
             const int wend = min(pos + 32 * SIM_EPL, m);
             const int j0 = pos + lane * SIM_EPL;
             long long P[SIM_EPL];
