@@ -274,7 +274,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_hist_priv<root> (FeatureHistogram.update)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_hist_root (FeatureHistogram.update)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": root_ms,
                 "share_of_step": (prof[0] / ms) if ms > 0 else None,

@@ -3093,12 +3093,14 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     if (c->N >= c->hist_min_rows) {
         k_hist_root<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
                                                                                     hist_groups(c), c->dHistSum);
+        rlb_prof_end(c);
+        RLB_CHECK_LAUNCH(c);
     } else {
         k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr,
                                                                 c->dHistSum, c->dHistCnt, c->dState, 0);
+        rlb_prof_end(c);
+        RLB_CHECK_LAUNCH(c);
     }
-    rlb_prof_end(c);
-    RLB_CHECK_LAUNCH(c);
     if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
     if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
     k_root_cumsum<<<c->F, 288, 0, c->stream>>>(c->dHistSum, c->dHistCnt, c->dNThr, c->dState, c->prm.min_leaf_support,
