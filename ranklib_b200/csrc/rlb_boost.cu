@@ -2269,7 +2269,22 @@ struct ChainBufs {
     float* simS;         // [2][maxChunks] start value the chunk was simulated from
     float* simE;         // [2][maxChunks] value at the end of the simulated chunk
     int32_t maxChunks;
+    // N GPUs: the chains continue across ranks.  Only the walk needs the previous rank's ACTUAL running value; the
+    // predictions take the all-gathered per-rank totals (exact sums, then rounded increments), so every rank compiles
+    // its chunks at the same time.
+    double* tot = nullptr;           // [2][RLB_MAX_LEAVES + 1] this rank's total per chain (written by k_chain_pred / pred2)
+    const double* gtot = nullptr;    // [world][2][RLB_MAX_LEAVES + 1] the totals of every rank (null on one GPU)
+    int32_t rank = 0;
 };
+
+// predicted value in front of this rank's part of chain (l, which): the totals of the ranks before it
+__device__ __forceinline__ double chain_rank_prefix(const ChainBufs& cb, int mode, int which, int l) {
+    if (!cb.gtot) return 0.0;
+    const int ch = (mode == 1) ? 0 : which * (RLB_MAX_LEAVES + 1) + l;
+    double s = 0.0;
+    for (int r = 0; r < cb.rank; r++) s += cb.gtot[(size_t)r * 2 * (RLB_MAX_LEAVES + 1) + ch];
+    return s;
+}
 
 struct ChainView {
     const double* val;
@@ -2383,8 +2398,9 @@ __global__ void __launch_bounds__(32) k_chain_pred(int mode, const DevState* __r
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
     double* sd = cb.sumD + (size_t)which * cb.maxChunks;
-    warp_chunk_scan<double>(c0, c1, run, [&](int i) { return sd[i]; },
-                            [&](int i, double pre) { sd[i] = pre; });  // predicted running value at the start of chunk i
+    const double end = warp_chunk_scan<double>(c0, c1, run, [&](int i) { return sd[i]; },
+                                               [&](int i, double pre) { sd[i] = pre; });  // predicted value at the start of chunk i
+    if (cb.tot && threadIdx.x == 0) cb.tot[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] = end - run;
 }
 
 // second prediction: start of chunk i = carry + sum over the earlier chunks of (end - start) of their pass-1
@@ -2477,6 +2493,7 @@ __global__ void __launch_bounds__(CK / 4) k_chain_round(int mode, const DevState
     if (lane == 31) wT[w] = inc;
     __syncthreads();
     double offp = cb.sumD[o] + (inc - run);
+    if (cb.gtot) offp += chain_rank_prefix(cb, mode, which, chain_of_chunk(chunk0, nCh, b));
     for (int i = 0; i < w; i++) offp += wT[i];
     double acc = 0.0;
 #pragma unroll
@@ -2513,7 +2530,9 @@ __global__ void __launch_bounds__(32) k_chain_pred2(int mode, const DevState* __
     const int c0 = chunk0[l], c1 = chunk0[l + 1];
     double run = carryIn ? (double)carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.0;
     const size_t o = (size_t)which * cb.maxChunks;
-    warp_chunk_scan<double>(c0, c1, run, [&](int i) { return cb.rsum[o + i]; }, [&](int i, double pre) { cb.sumD[o + i] = pre; });
+    const double end = warp_chunk_scan<double>(c0, c1, run, [&](int i) { return cb.rsum[o + i]; },
+                                               [&](int i, double pre) { cb.sumD[o + i] = pre; });
+    if (cb.tot && threadIdx.x == 0) cb.tot[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] = end - run;
 }
 
 // Compile one chunk into its item program by simulating it exactly from the predicted start value: ONE WARP per
@@ -2560,7 +2579,13 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     }
     __syncwarp();
     // the first chunk of a chain starts from the carry itself, not from a rounded copy of it
-    float s = (b == chunk0[l]) ? (carryIn ? carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.f) : (float)cb.sumD[o];
+    float s;
+    if (cb.gtot) {   // N GPUs: predicted from the all-gathered totals (rank 0 starts its chains from exactly 0)
+        const double pc = chain_rank_prefix(cb, mode, which, l);
+        s = (b == chunk0[l]) ? (float)pc : (float)(pc + cb.sumD[o]);
+    } else {
+        s = (b == chunk0[l]) ? (carryIn ? carryIn[mode == 1 ? 0 : which * (RLB_MAX_LEAVES + 1) + l] : 0.f) : (float)cb.sumD[o];
+    }
     if (lane == 0) cb.simS[o] = s;
     int pos = 0, nit = 0;                         // uniform across the warp
     int pendKey = -1, pendQ = 0, pendMn = 0, pendMx = 0;   // lane 0: the RUN being assembled
@@ -3244,40 +3269,59 @@ int rlb_impl_tree_output(rlb_ctx* c) {
         return RLB_E_INVALID;
     }
     const int nl = c->prm.n_leaves;
-    const float* carry = nullptr;
-    if (c->world > 1) {
-        if (int rc = rlb_chain_carry_begin(c, 2 * (RLB_MAX_LEAVES + 1))) return rc;
-        carry = c->dCarry;
+    const bool multi = c->world > 1;
+    if (multi && c->chain_gtot_world != c->world) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_update_tree_output", "rlb_comm_init must precede rlb_lambdamart_init");
+        return RLB_E_INVALID;
     }
+    const int NT = 2 * (RLB_MAX_LEAVES + 1);   // chain totals per rank
     const int nw = c->prm.kind == RLB_KIND_MART ? 1 : 2;
     ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
+    if (multi) cb.tot = c->dChainTot;
     k_leaf_chunks<<<1, 1, 0, c->stream>>>(c->dState, c->dChunk0);
     RLB_CHECK_LAUNCH(c);
     const int gchunks = (int)(c->N / CK) + nl + 1;
     k_chain_sum<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
                                                           c->dSamples[1], 0, cb);
     RLB_CHECK_LAUNCH(c);
-    k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
+    // N GPUs: every rank compiles its part of the chains from PREDICTED starts (all-gathered totals of the ranks before it);
+    // only the walk below waits for the previous rank's actual values
+    k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, nullptr, cb);
     RLB_CHECK_LAUNCH(c);
+    ChainBufs cbp = cb;   // the view with the other ranks' totals
+    if (multi) {
+        RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
+        cbp.gtot = c->dChainGTot;
+        cbp.rank = c->rank;
+    }
     const int gsim = (gchunks + SIM_WARPS - 1) / SIM_WARPS;
     if (c->chain_passes >= 2) {   // second prediction from the rounded increments (default)
-        k_chain_round<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
+        k_chain_round<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, cbp);
         RLB_CHECK_LAUNCH(c);
-        k_chain_pred2<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
+        k_chain_pred2<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, nullptr, cb);
+        RLB_CHECK_LAUNCH(c);
+        if (multi) {
+            RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot + (size_t)c->world * NT, NT, ncclDouble, c->comm, c->stream));
+            cbp.gtot = c->dChainGTot + (size_t)c->world * NT;
+        }
+    }
+    for (int pass = 2; pass < c->chain_passes && !multi; pass++) {   // RLB_CHAIN_PASSES > 2 (one GPU): refinement from full simulations
+        k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, nullptr, cb);
+        RLB_CHECK_LAUNCH(c);
+        k_chain_refine<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, nullptr, cb);
         RLB_CHECK_LAUNCH(c);
     }
-    for (int pass = 2; pass < c->chain_passes; pass++) {   // RLB_CHAIN_PASSES > 2: further refinement from full simulations
-        k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, carry, cb);
-        RLB_CHECK_LAUNCH(c);
-        k_chain_refine<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, carry, cb);
-        RLB_CHECK_LAUNCH(c);
-    }
-    k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, carry, cb);
+    k_chain_sim<<<dim3(gsim, nw), 32 * SIM_WARPS, 0, c->stream>>>(0, c->dState, c->dChunk0, 0, nullptr, cbp);
     RLB_CHECK_LAUNCH(c);
     k_chain_offsets<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
     RLB_CHECK_LAUNCH(c);
     k_chain_compact<<<dim3(gchunks, nw), 128, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
     RLB_CHECK_LAUNCH(c);
+    const float* carry = nullptr;
+    if (multi) {
+        if (int rc = rlb_chain_carry_begin(c, 2 * (RLB_MAX_LEAVES + 1))) return rc;
+        carry = c->dCarry;
+    }
     k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, carry, cb);
     RLB_CHECK_LAUNCH(c);
     if (c->world > 1) {
@@ -3336,25 +3380,34 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
     } else {
         if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
     }
-    const float* carry = nullptr;
-    if (c->world > 1) {
-        if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
-        carry = c->dCarry;
-    }
     {
+        const bool multi = c->world > 1;
+        const int NT = 2 * (RLB_MAX_LEAVES + 1);
         ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
+        if (multi) cb.tot = c->dChainTot;
         int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2;  // static table of the metric chain: {0, ceil(Q / CK)}
         const int gchunks = (c->Q + CK - 1) / CK;
         k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
         RLB_CHECK_LAUNCH(c);
-        k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, carry, cb);
+        k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, nullptr, cb);
         RLB_CHECK_LAUNCH(c);
-        k_chain_sim<<<dim3((gchunks + SIM_WARPS - 1) / SIM_WARPS, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, c->dState, ch0, c->Q, carry, cb);
+        ChainBufs cbp = cb;
+        if (multi) {   // per-query values are >= 0 and the sum grows: the exact totals of the earlier ranks predict well enough
+            RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
+            cbp.gtot = c->dChainGTot;
+            cbp.rank = c->rank;
+        }
+        k_chain_sim<<<dim3((gchunks + SIM_WARPS - 1) / SIM_WARPS, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, c->dState, ch0, c->Q, nullptr, cbp);
         RLB_CHECK_LAUNCH(c);
         k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, cb);
         RLB_CHECK_LAUNCH(c);
         k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, c->dState, ch0, cb);
         RLB_CHECK_LAUNCH(c);
+        const float* carry = nullptr;
+        if (multi) {
+            if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
+            carry = c->dCarry;
+        }
         k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, c->Q, carry, cb);
         RLB_CHECK_LAUNCH(c);
     }

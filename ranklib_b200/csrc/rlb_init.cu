@@ -213,7 +213,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
-    fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
+    fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainTot); fr(c->dChainGTot); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
     c->loaded = c->inited = false;
@@ -481,6 +481,10 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
     RLB_CUDA(c, alloc(c->dChainXs, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_CK * sizeof(double)));
     RLB_CUDA(c, alloc(c->dChainRSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
+    RLB_CUDA(c, alloc(c->dChainTot, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
+    RLB_CUDA(c, alloc(c->dChainGTot, (size_t)2 * std::max(c->world, 1) * 2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
+    RLB_CUDA(c, cudaMemsetAsync(c->dChainTot, 0, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double), c->stream));
+    c->chain_gtot_world = std::max(c->world, 1);
     {
         void* p = c->dChainItems;   // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu)
         RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));

@@ -180,6 +180,9 @@ struct rlb_ctx {
     double* dChainSum = nullptr;    // per-chunk exact sums / predicted start values
     double* dChainXs = nullptr;     // chain elements in chain order
     double* dChainRSum = nullptr;   // rounded increment of every chunk
+    double* dChainTot = nullptr;    // this rank's total per chain (N GPUs)
+    double* dChainGTot = nullptr;   // [2][world] the totals of every rank (exact sums | rounded increments)
+    int32_t chain_gtot_world = 0;   // world size dChainGTot was allocated for
     struct ChainItem* dChainItems = nullptr;   // per-chunk item programs
     struct ChainItem* dChainStream = nullptr;  // per-chain item streams
     int32_t *dChainNItems = nullptr, *dChainIPos = nullptr, *dChainITot = nullptr;
