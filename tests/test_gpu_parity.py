@@ -150,6 +150,55 @@ def test_ragged_and_degenerate_queries(built):
     assert n_equiv == 5
 
 
+@pytest.mark.parametrize("metric,k", [("ERR", 10), ("MAP", 0), ("P", 3), ("RR", 4), ("BEST", 2)])
+def test_degenerate_queries_other_metrics(built, metric, k):
+    """Singleton queries, queries shorter than k, all-equal and all-zero labels, one query near the 1024-document limit of
+    the generic metrics, under every non-DCG scorer."""
+    rng = np.random.default_rng(11)
+    sizes = np.array([1, 2, 1, 37, 3, 1000, 5, 1, 64, 11, 300])
+    qoff = np.zeros(len(sizes) + 1, np.int32)
+    qoff[1:] = np.cumsum(sizes)
+    N = int(qoff[-1])
+    X = rng.standard_normal((N, 6)).astype(np.float32)
+    label = rng.integers(0, 5, N).astype(np.float32)
+    label[qoff[4]:qoff[5]] = 2.0      # all equal
+    label[qoff[8]:qoff[9]] = 0.0      # no relevant document at all
+    label[qoff[9]] = 3.0              # a single relevant document, first in list order
+    label[qoff[9] + 1:qoff[10]] = 0.0
+    m = orc.METRICS[metric]
+    # all scores 0: every pair has rho = 1/2, the lambdas are the swap changes themselves
+    o, g = _pair(X, label, qoff, metric=m, k=k)
+    o.compute_pseudo_responses()
+    g.compute_pseudo_responses()
+    np.testing.assert_allclose(g.read("LAMBDA"), o.read("LAMBDA"), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(g.read("WEIGHT"), o.read("WEIGHT"), rtol=1e-12, atol=1e-15)
+    assert round(float(o.train_metric()), 4) == round(float(g.train_metric()), 4)
+    if metric in ("ERR", "MAP"):
+        # graded / rank-weighted changes: no exact ties between different partitions, the trees can be followed in lockstep
+        # (with P / RR / Best the lambdas of the first trees take a handful of values, several different splits have
+        # exactly the same S and the reference itself picks among them by rounding noise, SURVEY.md F10)
+        n_ident, n_equiv, o, g = _run_lockstep(X, label, qoff, 4, metric=m, k=k)
+        assert n_equiv == 4
+        o.compute_pseudo_responses()      # for the scores after the fourth tree, on both sides
+        g.compute_pseudo_responses()
+        np.testing.assert_allclose(g.read("LAMBDA"), o.read("LAMBDA"), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(g.read("WEIGHT"), o.read("WEIGHT"), rtol=1e-12, atol=1e-15)
+
+
+def test_generic_metric_query_limit(built):
+    """ERR / MAP / P / RR / Best keep per-query arrays in shared memory: queries above 1024 documents are refused."""
+    rng = np.random.default_rng(3)
+    qoff = np.array([0, 1100, 1150], np.int32)
+    X = rng.standard_normal((1150, 4)).astype(np.float32)
+    label = rng.integers(0, 3, 1150).astype(np.float32)
+    g = native.Context(0)
+    g.load_dense(X, label, qoff)
+    with pytest.raises(native.RankLibError):
+        g.init(native.make_params(metric=native.METRIC_ERR))
+    g.init(native.make_params(metric=native.METRIC_NDCG))    # NDCG has no such limit
+    g.close()
+
+
 def test_ensemble_eval_and_score_metric(built):
     X, label, qoff = synth.c1()
     o, g = _pair(X, label, qoff)
