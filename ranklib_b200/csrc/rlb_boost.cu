@@ -81,6 +81,12 @@ __device__ void draw_features(DevState* st, const TreeParams& tp, int32_t* used,
     }
 }
 
+// element offset of the staging block the CURRENT split accumulates in: on N GPUs two blocks alternate with the split
+// ordinal (a peer may still be reading the previous one), on one GPU stageStride is 0
+__device__ __forceinline__ size_t stage_offset(const DevState* st, size_t stageStride) {
+    return (size_t)(st->part_epoch & 1u) * stageStride;
+}
+
 // RegressionTree.insert (RegressionTree.java:147-157)
 __device__ void queue_insert(DevState* st, int node) {
     int i = 0;
@@ -1131,7 +1137,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
                  const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1, long long* __restrict__ sum,
-                 int32_t* __restrict__ cnt, DevState* __restrict__ st, int nGroups) {
+                 int32_t* __restrict__ cnt, DevState* __restrict__ st, int nGroups, size_t stageStride) {
     constexpr int PH = HPH;
     constexpr int T = HG * PH;           // consumer threads = private histograms
     constexpr int R = PH * HCHILD_RPT;   // rows per stage (HCHILD_RPT per consumer thread, in blocks of 16 rows per phase pair)
@@ -1151,6 +1157,11 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
     if (!st->split_active) return;
+    {
+        const size_t so = stage_offset(st, stageStride);
+        sum += so;
+        cnt += 2 * so;
+    }
     const NodeRec& r = st->nodes[st->small_id];
     const int64_t lo = r.lo, hi = r.hi;
     const int32_t* samples = r.buf ? samples1 : samples0;
@@ -1791,8 +1802,15 @@ __global__ void __launch_bounds__(256) k_part_count(DevState* __restrict__ st, c
                                                      const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1,
                                                      int32_t* __restrict__ tileCnt, long long* __restrict__ histSum,
                                                      int32_t* __restrict__ histCnt, size_t hist_stride,
-                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq) {
+                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq,
+                                                     size_t stageStride) {
     if (!st->split_active) return;
+    {
+        const size_t so = stage_offset(st, stageStride);
+        histSum += so;
+        histCnt += 2 * so;
+        stageSq += so;
+    }
     __shared__ int sw[8];
     __shared__ bool amLast;
     const NodeRec& rec = st->nodes[st->split_node];
@@ -1948,8 +1966,40 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
                                                  const long long* __restrict__ stageSum,
                                                  const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool,
                                                  const int32_t* __restrict__ nthr, double* __restrict__ nodeFeatS,
-                                                 int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq, int sqIsSmall) {
+                                                 int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq, int sqIsSmall,
+                                                 size_t stageStride, const PeerTab* __restrict__ peers) {
     if (!st->split_active) return;
+    const size_t so = stage_offset(st, stageStride);
+    stageSum += so;
+    stageCnt += 2 * so;
+    stageSq += so;
+    if (peers) {
+        // ---- the all-reduce of this split, fused: every rank reads every rank's staging block over NVLink ----
+        // hand-shake: "my block of split `epoch` is complete" -> one flag per peer, written into the PEER's memory
+        // (release, system scope: the child-histogram kernel before this one has finished, its global reductions are
+        // performed); then wait until every peer has said the same.  All CTAs of this kernel are co-resident (F <= a few
+        // hundred CTAs of 288 threads), so spinning is safe; the spin is bounded and reports through st->p2p_timeout.
+        const unsigned int epoch = st->part_epoch;
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                for (int r = 0; r < peers->world; r++)
+                    if (r != peers->rank)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers->flags[r] + peers->rank), "r"(epoch) : "memory");
+            }
+            for (int r = 0; r < peers->world; r++) {
+                if (r == peers->rank) continue;
+                const unsigned int* fl = peers->flags[peers->rank] + r;
+                unsigned int v;
+                long long spins = 0;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                } while ((int)(v - epoch) < 0 && ++spins < (1LL << 22));
+                if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
+            }
+        }
+        __syncthreads();
+    }
     __shared__ long long wtS[9];
     __shared__ int wtC[9];
     __shared__ bool amLast;
@@ -1962,8 +2012,18 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     long long vS = 0, oS = 0;
     int vC = 0, oC = 0;
     if (t < RLB_T) {
-        vS = stageSum[o];
-        vC = stageCnt[o];
+        if (peers) {
+            // rank order: the same integer additions on every rank (fixed point: any order gives the same bits anyway)
+            for (int r = 0; r < peers->world; r++) {
+                const long long* ps = peers->stage[r] + so;
+                const int32_t* pc = reinterpret_cast<const int32_t*>(peers->stage[r] + so + hist_stride);
+                vS += __ldcv(ps + o);   // peer memory: never through L1
+                vC += __ldcv(pc + o);
+            }
+        } else {
+            vS = stageSum[o];
+            vC = stageCnt[o];
+        }
     }
     vS = warp_incl_scan_ll(vS, lane);
     vC = warp_incl_scan_i(vC, lane);
@@ -2018,8 +2078,18 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         volatile NodeRec* ns = &st->nodes[small];
         volatile NodeRec* no = &st->nodes[other];
         const long long sqP = st->nodes[parent].sq_fix;
-        const long long sqAcc = *(volatile long long*)stageSq;  // accumulated by the partition pass
-        *stageSq = 0;                                          // ready for the next split step
+        long long sqAcc;
+        if (peers) {
+            sqAcc = 0;
+            const size_t sqo = hist_stride + (hist_stride + 1) / 2;
+            for (int r = 0; r < peers->world; r++) sqAcc += __ldcv(peers->stage[r] + so + sqo);
+            // the OTHER block is free again (every peer has finished the previous split, or it could not have sent this
+            // split's flag): clear its scalar for the next split; its histogram part is cleared by the partition
+            *(stageSq - so + (stageStride - so)) = 0;
+        } else {
+            sqAcc = *(volatile long long*)stageSq;  // accumulated by the partition pass
+            *stageSq = 0;                            // ready for the next split step
+        }
         st->ticket_part = 0;
         // one-pass partition (single GPU): squares of the scanned child; two-pass (multi GPU): squares of the LEFT rows
         const long long sqS = sqIsSmall ? sqAcc : (st->small_is_left ? sqAcc : sqP - sqAcc);
@@ -3143,13 +3213,16 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         long long* stageSum = c->dStage;
         int32_t* stageCnt = reinterpret_cast<int32_t*>(c->dStage + c->hist_stride);
         long long* stageSq = c->dStage + c->hist_stride + (c->hist_stride + 1) / 2;
+        // N GPUs with peer access: two staging blocks alternate (the kernels pick by split parity) and k_finish reduces
+        // over peer memory itself; otherwise one block and an NCCL all-reduce
+        const size_t stageStride = c->p2p ? c->stage_elems : 0;
         if (c->world == 1) {
             k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1], c->dTileState,
                                                               stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
             RLB_CHECK_LAUNCH(c);
         } else {  // local left counts are not known in advance: count pass + scatter pass
             k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
-                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
+                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride);
             RLB_CHECK_LAUNCH(c);
             k_part_scatter<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt);
             RLB_CHECK_LAUNCH(c);
@@ -3157,16 +3230,17 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         rlb_prof_begin(c, 1);
         k_hist_child<<<hist_grid(c), hist_threads(), hist_smem_child(), c->stream>>>(c->dBins, c->Fp, c->F, c->dVfixC, c->dSamples[0],
                                                                                       c->dSamples[1], stageSum, stageCnt, c->dState,
-                                                                                      hist_groups(c));
+                                                                                      hist_groups(c), stageStride);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
-        if (c->world > 1) {
+        if (c->world > 1 && !c->p2p) {
             // one all-reduce per node split: raw sums + counts of the scanned child
             // and its squared-sum scalar, at fixed addresses
             if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
         k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, c->world == 1 ? 1 : 0);
+                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, c->world == 1 ? 1 : 0,
+                                              stageStride, c->p2p ? c->dPeers : nullptr);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;
@@ -3184,6 +3258,9 @@ static int sync_state_header(rlb_ctx* c) {
 int rlb_impl_tree_enqueue(rlb_ctx* c) {
     const TreeParams tp = tree_params(c);
     RLB_CUDA(c, cudaMemsetAsync(c->dStage + c->hist_stride + (c->hist_stride + 1) / 2, 0, sizeof(long long), c->stream));
+    if (c->p2p)
+        RLB_CUDA(c, cudaMemsetAsync(c->dStage + c->stage_elems + c->hist_stride + (c->hist_stride + 1) / 2, 0, sizeof(long long),
+                                    c->stream));
     k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
     RLB_CHECK_LAUNCH(c);
     k_tree_begin<<<1, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F,
@@ -3248,6 +3325,10 @@ int rlb_impl_enqueue_iter(rlb_ctx* c) {
 
 // after the stream has been synchronised: finish trees that needed more split steps
 int rlb_impl_finish_iter(rlb_ctx* c) {
+    if (c->hState->p2p_timeout) {
+        rlb_set_error(c, RLB_E_NCCL, "rlb_boost_iter", "a peer GPU did not reach the split hand-shake (fused all-reduce timed out)");
+        return RLB_E_NCCL;
+    }
     int recovered = 0;
     if (int rc = rlb_impl_tree_check(c, &recovered)) return rc;
     if (recovered) {  // the leaf / score / metric kernels of the sequence were no-ops on the unfinished tree

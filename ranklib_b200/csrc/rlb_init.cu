@@ -7,6 +7,7 @@
 // (b) fmin/fmax, (c) the bin of every value.  (a)+(b) come from one pass with a shared-memory hash
 // set per feature, (c) from a lower_bound per value — no sort, no int[F][N] index arrays.
 #include <algorithm>
+#include <cstdio>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -203,12 +204,104 @@ __global__ void k_iota(int32_t* a, int64_t n) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// N GPUs, one process each: map every rank's staging block and hand-shake flags into this process (CUDA IPC) so that
+// k_finish can reduce the scanned child's histogram over NVLink itself (rlb_boost.cu).  Collective: every rank calls it
+// from rlb_lambdamart_init; if any rank cannot map its peers all of them keep the NCCL all-reduce.
+// ------------------------------------------------------------------------------------------------
+void rlb_p2p_close(rlb_ctx* c) {
+    for (void*& m : c->peer_maps) {
+        if (m) cudaIpcCloseMemHandle(m);
+        m = nullptr;
+    }
+    c->p2p = false;
+}
+
+int rlb_p2p_setup(rlb_ctx* c) {
+    c->p2p = false;
+    if (c->world <= 1 || c->world > RLB_MAX_RANKS || !c->comm) return RLB_OK;
+    int want = 1;
+    if (const char* e = getenv("RLB_P2P")) want = atoi(e) != 0;
+    struct Rec {
+        cudaIpcMemHandle_t stage, flags;
+        int ok;
+        int pad[15];
+    };
+    static_assert(sizeof(Rec) % 8 == 0, "record size");
+    if (!c->dXFlags) RLB_CUDA(c, cudaMalloc(&c->dXFlags, RLB_MAX_RANKS * sizeof(unsigned int)));
+    RLB_CUDA(c, cudaMemsetAsync(c->dXFlags, 0, RLB_MAX_RANKS * sizeof(unsigned int), c->stream));
+    Rec mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = want && cudaIpcGetMemHandle(&mine.stage, c->dStage) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.flags, c->dXFlags) == cudaSuccess;
+    cudaGetLastError();
+    Rec *dSend = nullptr, *dRecv = nullptr;
+    RLB_CUDA(c, cudaMalloc(&dSend, sizeof(Rec)));
+    RLB_CUDA(c, cudaMalloc(&dRecv, sizeof(Rec) * c->world));
+    std::vector<Rec> all(c->world);
+    auto gather = [&]() -> int {
+        RLB_CUDA(c, cudaMemcpyAsync(dSend, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+        RLB_NCCL(c, ncclAllGather(dSend, dRecv, sizeof(Rec), ncclChar, c->comm, c->stream));
+        RLB_CUDA(c, cudaMemcpyAsync(all.data(), dRecv, sizeof(Rec) * c->world, cudaMemcpyDeviceToHost, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        return RLB_OK;
+    };
+    int rc = gather();
+    bool ok = rc == RLB_OK;
+    for (int r = 0; ok && r < c->world; r++) ok = all[r].ok != 0;
+    PeerTab tab;
+    memset(&tab, 0, sizeof(tab));
+    tab.world = c->world;
+    tab.rank = c->rank;
+    if (ok) {
+        for (int r = 0; r < c->world; r++) {
+            if (r == c->rank) {
+                tab.stage[r] = c->dStage;
+                tab.flags[r] = c->dXFlags;
+                continue;
+            }
+            void *ps = nullptr, *pf = nullptr;
+            if (cudaIpcOpenMemHandle(&ps, all[r].stage, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                if (ps) cudaIpcCloseMemHandle(ps);
+                ok = false;
+                break;
+            }
+            c->peer_maps[2 * r] = ps;
+            c->peer_maps[2 * r + 1] = pf;
+            tab.stage[r] = (long long*)ps;
+            tab.flags[r] = (unsigned int*)pf;
+        }
+    }
+    // second round: everybody must have mapped everybody, or nobody uses the mappings
+    mine.ok = ok ? 1 : 0;
+    if (rc == RLB_OK) rc = gather();
+    for (int r = 0; rc == RLB_OK && ok && r < c->world; r++) ok = all[r].ok != 0;
+    cudaFree(dSend);
+    cudaFree(dRecv);
+    if (rc != RLB_OK) return rc;
+    if (getenv("RLB_P2P_VERBOSE"))
+        fprintf(stderr, "ranklib_b200 rank %d: per-split all-reduce %s\n", c->rank,
+                ok ? "fused into k_finish over peer memory" : "through NCCL (peer mapping unavailable or RLB_P2P=0)");
+    if (!ok) {
+        rlb_p2p_close(c);
+        return RLB_OK;
+    }
+    if (!c->dPeers) RLB_CUDA(c, cudaMalloc(&c->dPeers, sizeof(PeerTab)));
+    RLB_CUDA(c, cudaMemcpy(c->dPeers, &tab, sizeof(PeerTab), cudaMemcpyHostToDevice));
+    c->p2p = true;
+    return RLB_OK;
+}
+
 void rlb_impl_free(rlb_ctx* c) {
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) {
         if (p) cudaFree(p);
         p = nullptr;
     };
+    rlb_p2p_close(c);
+    fr(c->dPeers); fr(c->dXFlags);
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dBinsTile); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
@@ -450,7 +543,10 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dBinsTile, (size_t)(Fp / 16) * c->root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dStage, (c->hist_stride + (c->hist_stride + 1) / 2 + 2) * sizeof(long long)));
+    c->stage_elems = c->hist_stride + (c->hist_stride + 1) / 2 + 2;
+    rlb_p2p_close(c);   // mappings of an earlier init point at buffers that are about to be freed
+    RLB_CUDA(c, alloc(c->dStage, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long)));
+    RLB_CUDA(c, cudaMemsetAsync(c->dStage, 0, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long), c->stream));
     RLB_CUDA(c, alloc(c->dScore, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dLambda, N * sizeof(double)));
     RLB_CUDA(c, alloc(c->dWeight, N * sizeof(double)));
@@ -485,6 +581,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dChainGTot, (size_t)2 * std::max(c->world, 1) * 2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
     RLB_CUDA(c, cudaMemsetAsync(c->dChainTot, 0, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double), c->stream));
     c->chain_gtot_world = std::max(c->world, 1);
+    if (int rc = rlb_p2p_setup(c)) return rc;
     {
         void* p = c->dChainItems;   // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu)
         RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));

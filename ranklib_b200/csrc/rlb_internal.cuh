@@ -45,6 +45,7 @@ bool rlb_nccl_load(std::string* why);
 #define RLB_T RLB_MAX_BINS          // bins per feature in every padded table (257)
 #define RLB_MAX_LEAVES 1024          // n_leaves limit of the device tree controller
 #define RLB_MAX_NODES (2 * RLB_MAX_LEAVES)
+#define RLB_MAX_RANKS 16
 #define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
 #define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
 #define RLB_ROOT_R 192               // rows per tile of the root-histogram layout (dBinsTile)
@@ -69,6 +70,13 @@ struct NodeRec {
     int32_t leaf_ord;      // ordinal in leaves() order once the tree is finished, else -1
 };
 
+// peer-memory view of the staging blocks and hand-shake flags of every rank (own entries = local pointers)
+struct PeerTab {
+    long long* stage[RLB_MAX_RANKS];
+    unsigned int* flags[RLB_MAX_RANKS];
+    int32_t world, rank;
+};
+
 struct DevState {
     // fixed-point scales of this iteration: v = rint(lambda * 2^scale_exp), q = rint(lambda^2 * 2^scale2_exp)
     unsigned long long max_abs_bits;  // max |pseudo response| as a double bit pattern (atomicMax)
@@ -80,6 +88,7 @@ struct DevState {
     int32_t cur;            // node to scan at the next split step, -1 = none
     int32_t done;           // growth finished
     int32_t incomplete;     // ran out of split steps before the loop of RegressionTree.fit ended
+    int32_t p2p_timeout;    // a peer's hand-shake flag did not arrive (k_finish gave up waiting)
     int32_t split_active;   // the current step performs a split (set by the scan, read by partition/hist/finish)
     int32_t split_node, best_f, best_t;
     int32_t small_is_left, small_id, other_id;
@@ -162,7 +171,14 @@ struct rlb_ctx {
     size_t hist_stride = 0;         // elements per node: F*RLB_T
     long long* dHistSum = nullptr;  // [max_nodes][F][RLB_T]
     int32_t* dHistCnt = nullptr;    // [max_nodes][F][RLB_T]
-    long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum
+    long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum (two of them on N GPUs)
+    size_t stage_elems = 0;         // i64 elements of one staging block
+    // N GPUs: the per-split all-reduce is done by k_finish itself over peer memory (NVLink loads of every rank's staging
+    // block, flags for the hand-shake); NCCL stays as the fallback when the IPC mapping is not available (RLB_P2P=0)
+    struct PeerTab* dPeers = nullptr;
+    unsigned int* dXFlags = nullptr;      // [RLB_MAX_RANKS] written by the peers: their split epoch
+    void* peer_maps[2 * 16] = {nullptr};  // cudaIpcOpenMemHandle results (to close)
+    bool p2p = false;
     int32_t* dSamples[2] = {nullptr, nullptr};
     int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
     int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
@@ -256,6 +272,8 @@ int rlb_impl_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* t
 int rlb_impl_score_metric(rlb_ctx* ctx, const double* scores, const float* label, const int32_t* qoff, int32_t Q,
                           int32_t metric, int32_t k, double* out);
 void rlb_impl_free(rlb_ctx* ctx);
+int rlb_p2p_setup(rlb_ctx* ctx);
+void rlb_p2p_close(rlb_ctx* ctx);
 
 // ---- rlb_boost.cu ----
 int rlb_impl_pseudo(rlb_ctx* ctx);
