@@ -1387,7 +1387,8 @@ __global__ void __launch_bounds__(256) k_identity(int32_t* __restrict__ a, int64
 // (S == -1 -> RegressionTree.java:79-80 takes the leaf), so a failed scan does not use up a split step.
 __device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp, const int32_t* __restrict__ histCnt,
                                 size_t hist_stride, const double* __restrict__ nodeFeatS,
-                                const int32_t* __restrict__ nodeFeatT, int32_t* used, int32_t* pool) {
+                                const int32_t* __restrict__ nodeFeatT, int32_t* used, int32_t* pool,
+                                const int32_t* __restrict__ histCntL = nullptr) {
     __shared__ double zS[9];
     __shared__ int zP[9];
     __shared__ int zCur;
@@ -1452,6 +1453,11 @@ __device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp,
                 st->best_S = bestS;
                 st->n_left_g = nl;
                 st->n_right_g = nr;
+                if (histCntL) {   // N GPUs: this rank's rows going left, from its own cumulative counts (one-pass partition)
+                    const int nlL = __ldcg(&histCntL[(size_t)node * hist_stride + (size_t)bestF * RLB_T + bestT]);
+                    st->n_left_l = nlL;
+                    st->n_right_l = (sp.hi - sp.lo) - nlL;
+                }
                 st->small_is_left = (nl <= nr) ? 1 : 0;
                 st->small_id = st->small_is_left ? li : ri;
                 st->other_id = st->small_is_left ? ri : li;
@@ -1474,7 +1480,8 @@ __device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp,
 
 __global__ void __launch_bounds__(288) k_tree_begin(DevState* st, TreeParams tp, const long long* __restrict__ histSum, int64_t N_local,
                              long long N_total, int32_t* used, int32_t* pool, const int32_t* __restrict__ histCnt,
-                             size_t hist_stride, const double* __restrict__ nodeFeatS, const int32_t* __restrict__ nodeFeatT) {
+                             size_t hist_stride, const double* __restrict__ nodeFeatS, const int32_t* __restrict__ nodeFeatT,
+                             const int32_t* __restrict__ histCntL) {
     if (threadIdx.x == 0) {
     st->n_nodes = 1;
     NodeRec& r = st->nodes[0];
@@ -1505,7 +1512,7 @@ __global__ void __launch_bounds__(288) k_tree_begin(DevState* st, TreeParams tp,
     st->cur = 0;
     }
     __syncthreads();
-    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool);  // the root's split
+    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool, histCntL);  // the root's split
 }
 
 // K5 (stand-alone form, kept for reference / debugging; the step sequence uses scan_and_decide):
@@ -1661,8 +1668,15 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
                                                      int32_t* __restrict__ samples0, int32_t* __restrict__ samples1,
                                                      unsigned long long* __restrict__ tileState, long long* __restrict__ stageSum,
                                                      int32_t* __restrict__ stageCnt, size_t hist_stride,
-                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq) {
+                                                     const long long* __restrict__ sqfix, long long* __restrict__ stageSq,
+                                                     size_t stageStride, int localCounts) {
     if (!st->split_active) return;
+    {
+        const size_t so = stage_offset(st, stageStride);
+        stageSum += so;
+        stageCnt += 2 * so;
+        stageSq += so;
+    }
     __shared__ int sw[8];
     __shared__ int sTile, sExcl;
     const NodeRec& rec = st->nodes[st->split_node];
@@ -1670,7 +1684,8 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
     const int32_t* src = rec.buf ? samples1 : samples0;
     int32_t* dst = rec.buf ? samples0 : samples1;
     const int bf = st->best_f, btv = st->best_t;
-    const int nl = st->n_left_g;
+    // rows of THIS rank that go left: the global count on one GPU, on N GPUs the rank's own (scan_and_decide)
+    const int nl = localCounts ? st->n_left_l : st->n_left_g;
     const bool smallLeft = st->small_is_left != 0;
     const unsigned long long epoch = (unsigned long long)(st->part_epoch & 0x3fffffffu);
     const uint16_t* __restrict__ bcol = binsT + (size_t)bf * Nrows;  // the split feature's column
@@ -1696,8 +1711,10 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
         l.output = r.output = 0.f;
         l.leaf_ord = r.leaf_ord = -1;
         l.deviance = r.deviance = 0.0;
-        st->n_left_l = nl;
-        st->n_right_l = n - nl;
+        if (!localCounts) {
+            st->n_left_l = nl;
+            st->n_right_l = n - nl;
+        }
     }
     // at most `tiles` CTAs can get work: the others leave before touching the ticket (1184 CTAs serialising two
     // same-address atomics each cost more than partitioning a small node)
@@ -1967,7 +1984,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
                                                  const int32_t* __restrict__ stageCnt, int32_t* used, int32_t* pool,
                                                  const int32_t* __restrict__ nthr, double* __restrict__ nodeFeatS,
                                                  int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq, int sqIsSmall,
-                                                 size_t stageStride, const PeerTab* __restrict__ peers) {
+                                                 size_t stageStride, const PeerTab* __restrict__ peers,
+                                                 int32_t* __restrict__ histCntL) {
     if (!st->split_active) return;
     const size_t so = stage_offset(st, stageStride);
     stageSum += so;
@@ -2011,8 +2029,10 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     const size_t o = (size_t)f * RLB_T + t;
     long long vS = 0, oS = 0;
     int vC = 0, oC = 0;
+    int lC = 0;   // this rank's own raw count of the scanned child (N GPUs: kept cumulative per node for the one-pass partition)
     if (t < RLB_T) {
         if (peers) {
+            lC = stageCnt[o];
             // rank order: the same integer additions on every rank (fixed point: any order gives the same bits anyway)
             for (int r = 0; r < peers->world; r++) {
                 const long long* ps = peers->stage[r] + so;
@@ -2027,14 +2047,23 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     }
     vS = warp_incl_scan_ll(vS, lane);
     vC = warp_incl_scan_i(vC, lane);
+    __shared__ int wtL[9];
+    if (peers) lC = warp_incl_scan_i(lC, lane);
     if (lane == 31) {
         wtS[w] = vS;
         wtC[w] = vC;
+        wtL[w] = lC;
     }
     __syncthreads();
     for (int i = 0; i < w; i++) {
         vS += wtS[i];
         vC += wtC[i];
+        lC += wtL[i];
+    }
+    if (peers && histCntL && t < RLB_T) {
+        const int pL = histCntL[(size_t)parent * hist_stride + o];
+        histCntL[(size_t)small * hist_stride + o] = lC;
+        histCntL[(size_t)other * hist_stride + o] = pL - lC;
     }
     if (t < RLB_T) {
         const long long pS = histSum[(size_t)parent * hist_stride + o];
@@ -2112,7 +2141,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     }
     __syncthreads();
     // the scan of the node just selected, by this (last) CTA: the next step starts with its partition
-    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool);
+    scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool, peers ? histCntL : nullptr);
 }
 
 // end of RegressionTree.fit: leaves() in left-first DFS order (Split.java:100-113)
@@ -3216,11 +3245,14 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         // N GPUs with peer access: two staging blocks alternate (the kernels pick by split parity) and k_finish reduces
         // over peer memory itself; otherwise one block and an NCCL all-reduce
         const size_t stageStride = c->p2p ? c->stage_elems : 0;
-        if (c->world == 1) {
+        if (c->world == 1 || c->p2p) {
+            // one pass: the number of this rank's rows going left is known beforehand (N GPUs: from the rank's own cumulative
+            // counts, which the peer-memory path keeps per node)
             k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1], c->dTileState,
-                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq);
+                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride,
+                                                              c->p2p ? 1 : 0);
             RLB_CHECK_LAUNCH(c);
-        } else {  // local left counts are not known in advance: count pass + scatter pass
+        } else {  // NCCL path: local left counts are not known in advance: count pass + scatter pass
             k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
                                                               stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride);
             RLB_CHECK_LAUNCH(c);
@@ -3239,8 +3271,9 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
         k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, c->world == 1 ? 1 : 0,
-                                              stageStride, c->p2p ? c->dPeers : nullptr);
+                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq,
+                                              (c->world == 1 || c->p2p) ? 1 : 0, stageStride, c->p2p ? c->dPeers : nullptr,
+                                              c->p2p ? c->dHistCntL : nullptr);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;
@@ -3264,7 +3297,8 @@ int rlb_impl_tree_enqueue(rlb_ctx* c) {
     k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
     RLB_CHECK_LAUNCH(c);
     k_tree_begin<<<1, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F,
-                                           c->dHistCnt, c->hist_stride, c->dNodeFeatS, c->dNodeFeatT);
+                                           c->dHistCnt, c->hist_stride, c->dNodeFeatS, c->dNodeFeatT,
+                                           c->p2p ? c->dHistCntL : nullptr);
     RLB_CHECK_LAUNCH(c);
     if (int rc = enqueue_split_steps(c, c->prm.n_leaves - 1)) return rc;
     k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);

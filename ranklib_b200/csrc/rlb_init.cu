@@ -304,7 +304,7 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dPeers); fr(c->dXFlags);
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dBinsTile); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
-    fr(c->dHistCnt); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
+    fr(c->dHistCnt); fr(c->dHistCntL); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
     fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainTot); fr(c->dChainGTot); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
     if (c->hState) cudaFreeHost(c->hState);
@@ -543,6 +543,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, alloc(c->dBinsTile, (size_t)(Fp / 16) * c->root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
     RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
+    if (c->world > 1) RLB_CUDA(c, alloc(c->dHistCntL, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
     c->stage_elems = c->hist_stride + (c->hist_stride + 1) / 2 + 2;
     rlb_p2p_close(c);   // mappings of an earlier init point at buffers that are about to be freed
     RLB_CUDA(c, alloc(c->dStage, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long)));
@@ -622,6 +623,11 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CHECK_LAUNCH(c);
     k_tile_bins<<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, Fp, F, N, c->root_nb, c->dBinsTile);
     RLB_CHECK_LAUNCH(c);
+    if (c->world > 1) {   // this rank's own root counts, kept next to the global ones
+        RLB_CUDA(c, cudaMemcpyAsync(c->dHistCntL, c->dHistCnt, c->hist_stride * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+        k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCntL, F);
+        RLB_CHECK_LAUNCH(c);
+    }
     if (int rc = rlb_allreduce_i32(c, c->dHistCnt, c->hist_stride)) return rc;
     k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCnt, F);
     RLB_CHECK_LAUNCH(c);

@@ -171,6 +171,7 @@ struct rlb_ctx {
     size_t hist_stride = 0;         // elements per node: F*RLB_T
     long long* dHistSum = nullptr;  // [max_nodes][F][RLB_T]
     int32_t* dHistCnt = nullptr;    // [max_nodes][F][RLB_T]
+    int32_t* dHistCntL = nullptr;   // N GPUs: the same from this rank's rows only (cumulative), for the one-pass partition
     long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum (two of them on N GPUs)
     size_t stage_elems = 0;         // i64 elements of one staging block
     // N GPUs: the per-split all-reduce is done by k_finish itself over peer memory (NVLink loads of every rank's staging
