@@ -2145,10 +2145,11 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
 }
 
 // end of RegressionTree.fit: leaves() in left-first DFS order (Split.java:100-113)
-__global__ void k_tree_end(DevState* st, int64_t N_local) {
+__global__ void k_tree_end(DevState* st, int64_t N_local, int32_t* __restrict__ chunk0) {
     if (!st->done && st->cur >= 0) {
         st->incomplete = 1;
         st->n_leaves_out = 0;  // the leaf / score kernels that follow become no-ops
+        chunk0[0] = 0;
         return;
     }
     st->incomplete = 0;
@@ -2171,6 +2172,14 @@ __global__ void k_tree_end(DevState* st, int64_t N_local) {
     }
     st->leaf_lo[nl] = (int32_t)N_local;
     st->n_leaves_out = nl;
+    // chunk table of the leaf chains: chunk0[l] = first chunk of leaf l
+    int run = 0;
+    for (int l = 0; l < nl; l++) {
+        chunk0[l] = run;
+        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
+        run += (r.hi - r.lo + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK;
+    }
+    chunk0[nl] = run;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3072,18 +3081,6 @@ __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __
     if (threadIdx.x == 0) st->chain_out[0] = s;
 }
 
-// chunk table of the leaf chains (after k_tree_end): chunk0[l] = first chunk of leaf l
-__global__ void k_leaf_chunks(const DevState* __restrict__ st, int32_t* __restrict__ chunk0) {
-    int run = 0;
-    const int nl = st->n_leaves_out;
-    for (int l = 0; l < nl; l++) {
-        chunk0[l] = run;
-        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
-        run += (r.hi - r.lo + CK - 1) / CK;
-    }
-    chunk0[nl] = run;
-}
-
 __global__ void k_metric_final(DevState* st, long long Q_total) {
     st->train_metric = st->chain_out[0] / (float)(int)Q_total;  // LambdaMART.java:470
 }
@@ -3301,7 +3298,7 @@ int rlb_impl_tree_enqueue(rlb_ctx* c) {
                                            c->p2p ? c->dHistCntL : nullptr);
     RLB_CHECK_LAUNCH(c);
     if (int rc = enqueue_split_steps(c, c->prm.n_leaves - 1)) return rc;
-    k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);
+    k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
     RLB_CHECK_LAUNCH(c);
     return RLB_OK;
 }
@@ -3312,7 +3309,7 @@ int rlb_impl_tree_check(rlb_ctx* c, int* recovered) {
     for (int round = 0; c->hState->incomplete && round < 4 * c->prm.n_leaves + 8; round++) {
         if (recovered) *recovered = 1;
         if (int rc = enqueue_split_steps(c, 2)) return rc;
-        k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N);
+        k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
         RLB_CHECK_LAUNCH(c);
         if (int rc = sync_state_header(c)) return rc;
     }
@@ -3393,8 +3390,6 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     const int nw = c->prm.kind == RLB_KIND_MART ? 1 : 2;
     ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
     if (multi) cb.tot = c->dChainTot;
-    k_leaf_chunks<<<1, 1, 0, c->stream>>>(c->dState, c->dChunk0);
-    RLB_CHECK_LAUNCH(c);
     const int gchunks = (int)(c->N / CK) + nl + 1;
     k_chain_sum<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
                                                           c->dSamples[1], 0, cb);
