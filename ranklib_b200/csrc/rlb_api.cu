@@ -199,7 +199,7 @@ int rlb_create(int device, rlb_ctx** out) {
         delete c;
         return RLB_E_CUDA;
     }
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {
         cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
@@ -217,7 +217,7 @@ int rlb_destroy(rlb_ctx* c) {
         if (c->iter_graph[i]) cudaGraphExecDestroy(c->iter_graph[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }

@@ -3113,8 +3113,8 @@ int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* 
 // One pass over all training queries: NDCG@k per query (qmetric != null) and / or lambdas + weights
 // (want_lambda).  Queries are routed by size class (lists built at init).
 static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
-    const int B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
-    const size_t smA = (size_t)8 * QA_WARP_BYTES, smB1 = (size_t)B1N * 44 + (size_t)B1T * 16 + 64, smB2 = (size_t)B2N * 44 + (size_t)B2T * 16 + 64;
+    const int B0N = 128, B0T = 1280, B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
+    const size_t smA = (size_t)8 * QA_WARP_BYTES, smB0 = (size_t)B0N * 44 + (size_t)B0T * 16 + 64, smB1 = (size_t)B1N * 44 + (size_t)B1T * 16 + 64, smB2 = (size_t)B2N * 44 + (size_t)B2T * 16 + 64;
     double* lam = want_lambda ? c->dLambda : nullptr;
     double* wgt = want_lambda ? c->dWeight : nullptr;
     const int k = c->prm.metric_k, m = c->prm.metric;
@@ -3122,30 +3122,37 @@ static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
     // capture this becomes parallel graph branches).  The warp-path kernel stays on the main stream.
     int nside = 0;
     const bool fork = !c->trace;
-    if (fork && (c->nqB1 > 0 || c->nqB2 > 0 || c->nqC > 0)) RLB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    if (fork && (c->nqB0 > 0 || c->nqB1 > 0 || c->nqB2 > 0 || c->nqC > 0)) RLB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
     auto branch = [&](int i) -> cudaStream_t {
         if (!fork) return c->stream;
         cudaStreamWaitEvent(c->side[i], c->ev_fork, 0);
         nside = std::max(nside, i + 1);
         return c->side[i];
     };
+    if (c->nqB0 > 0) {   // 65 .. 128 documents: two warps per query (a 128-thread CTA mostly waits at its barriers here)
+        const int grid = std::min(c->nqB0, c->sm_count * 8);
+        k_query_block<64><<<grid, 64, smB0, branch(3)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB0, k, m, c->dDisc,
+                                                         c->dIdeal, lam, wgt, qmetric, c->dState, B0N, B0T);
+        RLB_CHECK_LAUNCH(c);
+        if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[3], c->side[3]));
+    }
     if (c->nqB1 > 0) {
         const int grid = std::min(c->nqB1, c->sm_count * 4);
-        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB1, k, m, c->dDisc,
+        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB0, c->nqB1, k, m, c->dDisc,
                                                            c->dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
     }
     if (c->nqB2 > 0) {
         const int grid = std::min(c->nqB2, c->sm_count);
-        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB1, c->nqB2, k, m,
+        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB0 + c->nqB1, c->nqB2, k, m,
                                                            c->dDisc, c->dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
     }
     if (c->nqC > 0) {
         const int grid = std::min(c->nqC, c->sm_count * 8);
-        const int32_t* ql = c->dQList + c->nqA + c->nqB1 + c->nqB2;
+        const int32_t* ql = c->dQList + c->nqA + c->nqB0 + c->nqB1 + c->nqB2;
         cudaStream_t sC = branch(2);
         if (want_lambda)
             k_query<true><<<grid, 128, 0, sC>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, lam, wgt,
@@ -3163,6 +3170,7 @@ static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
         RLB_CHECK_LAUNCH(c);
     }
     if (fork) {
+        if (c->nqB0 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[3], 0));
         if (c->nqB1 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
         if (c->nqB2 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
         if (c->nqC > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[2], 0));
@@ -3335,6 +3343,7 @@ int rlb_impl_prepare(rlb_ctx* c) {
     RLB_CUDA(c, cudaFuncSetAttribute(k_hist_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_hist_child, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
+    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 44 + 1280 * 16 + 64));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 44 + 10240 * 16 + 64));
     return RLB_OK;

@@ -646,7 +646,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     {
         std::vector<int32_t> qoffh((size_t)Q + 1);
         RLB_CUDA(c, cudaMemcpy(qoffh.data(), c->dQoff, ((size_t)Q + 1) * 4, cudaMemcpyDeviceToHost));
-        std::vector<int32_t> la, lb1, lb2, lc;
+        std::vector<int32_t> la, lb0, lb1, lb2, lc;
         for (int q = 0; q < Q; q++) {
             const int64_t n = qoffh[q + 1] - qoffh[q];
             // rows of the pair table (query_fast): min(k, n); MAP visits only the pairs touching rank 0 (APScorer.k = 0)
@@ -654,11 +654,13 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
                                                               : ((p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0);
             const int64_t terms = sz * n;
             if (n <= 64 && terms <= 640) la.push_back(q);
+            else if (n <= 128 && terms <= 1280) lb0.push_back(q);
             else if (n <= 256 && terms <= 2560) lb1.push_back(q);
             else if (n <= 1024 && terms <= 10240) lb2.push_back(q);
             else lc.push_back(q);
         }
-        c->nqA = (int)la.size(); c->nqB1 = (int)lb1.size(); c->nqB2 = (int)lb2.size(); c->nqC = (int)lc.size();
+        c->nqA = (int)la.size(); c->nqB0 = (int)lb0.size(); c->nqB1 = (int)lb1.size(); c->nqB2 = (int)lb2.size(); c->nqC = (int)lc.size();
+        la.insert(la.end(), lb0.begin(), lb0.end());
         la.insert(la.end(), lb1.begin(), lb1.end());
         la.insert(la.end(), lb2.begin(), lb2.end());
         la.insert(la.end(), lc.begin(), lc.end());

@@ -125,8 +125,8 @@ struct DevState {
 struct rlb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // fork/join branches for independent kernels (query size classes)
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // fork/join branches for independent kernels (query size classes)
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // comm
     ncclComm_t comm = nullptr;
@@ -163,9 +163,9 @@ struct rlb_ctx {
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
-    // query ids grouped by size class: [A: warp path | B1: 128-thread CTA | B2: 256-thread CTA | C: fallback]
+    // query ids grouped by size class: [A: warp path | B0: 64-thread CTA | B1: 128-thread CTA | B2: 256-thread CTA | C: fallback]
     int32_t* dQList = nullptr;
-    int32_t nqA = 0, nqB1 = 0, nqB2 = 0, nqC = 0;
+    int32_t nqA = 0, nqB0 = 0, nqB1 = 0, nqB2 = 0, nqC = 0;
     // tree state
     int32_t max_nodes = 0;
     size_t hist_stride = 0;         // elements per node: F*RLB_T
