@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "rlb_internal.cuh"
 
@@ -2697,6 +2698,7 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     if (lane == 0) cb.simS[o] = s;
     int pos = 0, nit = 0;                         // uniform across the warp
     int pendKey = -1, pendQ = 0, pendMn = 0, pendMx = 0;   // lane 0: the RUN being assembled
+    bool mini = false;                            // the next round looks at 32 elements only (uniform)
     while (pos < m) {
         const unsigned int bits = __float_as_uint(s);
         int fb;   // first element that is not absorbed by the leading RUN / ZRUN
@@ -2722,84 +2724,100 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
                 }
             }
         } else {
-            const int e = (int)((bits >> 23) & 0xff) - 127;
-            const double sg = (bits >> 31) ? -1.0 : 1.0;
-            const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
-            const double scale_v = pow2d(52 - e);
-            const int wend = min(pos + 32 * SIM_EPL, m);
-            const int j0 = pos + lane * SIM_EPL;
-            long long P[SIM_EPL];
-            unsigned int badMask = 0;
-            long long run = 0;
+            // one round over the next 32 * EPL elements; returns the first element that is not absorbed.  Right behind a
+            // crossing the window is 32 elements (EPL 1): where the sum oscillates around a binade boundary the next
+            // crossing is a few elements away and a 256-element round per crossing was the slowest warp of the kernel.
+            auto round = [&](auto eplc, bool& consumed) -> int {
+                constexpr int EPL = decltype(eplc)::value;
+                const int e = (int)((bits >> 23) & 0xff) - 127;
+                const double sg = (bits >> 31) ? -1.0 : 1.0;
+                const long long M = (long long)((bits & 0x7fffffu) | 0x800000u);
+                const double scale_v = pow2d(52 - e);
+                const int wend = min(pos + 32 * EPL, m);
+                const int j0 = pos + lane * EPL;
+                long long P[EPL];
+                unsigned int badMask = 0;
+                long long run = 0;
 #pragma unroll
-            for (int k = 0; k < SIM_EPL; k++) {
-                const int j = j0 + k;
-                long long q = 0;
-                if (j < wend) {
-                    const double x = xs[j];
-                    bool bad = false;
-                    if (x != 0.0) q = chain_quantum(x, sg, scale_v, bad);
-                    if (bad) badMask |= 1u << k;
-                }
-                run += q;
-                P[k] = run;
-            }
-            const long long inc = warp_incl_scan_ll(run, lane);
-            const long long offp = inc - run;
-            int myBad = 0x7fffffff;
-#pragma unroll
-            for (int k = SIM_EPL - 1; k >= 0; k--) {
-                const int j = j0 + k;
-                if (j < wend) {
-                    bool bb = (badMask >> k) & 1u;
-                    if (!bb) {
-                        const long long Mi = M + offp + P[k];
-                        bb = !(Mi > 8388608LL && Mi < 16777216LL);
-                    }
-                    if (bb) myBad = j;
-                }
-            }
-            fb = min(__reduce_min_sync(0xffffffffu, myBad), wend);
-            if (fb > pos) {
-                // stretch [pos, fb): total, min and max of the inclusive prefixes (inside +-2^24: every prefix mantissa is
-                // inside the binade)
-                int mn = 0x7fffffff, mx = -0x7fffffff - 1, tot = 0;
-                bool haveTot = false;
-#pragma unroll
-                for (int k = 0; k < SIM_EPL; k++) {
+                for (int k = 0; k < EPL; k++) {
                     const int j = j0 + k;
-                    if (j < fb) {
-                        const int pv = (int)(offp + P[k]);
-                        mn = min(mn, pv);
-                        mx = max(mx, pv);
-                        if (j == fb - 1) {
-                            tot = pv;
-                            haveTot = true;
+                    long long q = 0;
+                    if (j < wend) {
+                        const double x = xs[j];
+                        bool bad = false;
+                        if (x != 0.0) q = chain_quantum(x, sg, scale_v, bad);
+                        if (bad) badMask |= 1u << k;
+                    }
+                    run += q;
+                    P[k] = run;
+                }
+                const long long inc = warp_incl_scan_ll(run, lane);
+                const long long offp = inc - run;
+                int myBad = 0x7fffffff;
+#pragma unroll
+                for (int k = EPL - 1; k >= 0; k--) {
+                    const int j = j0 + k;
+                    if (j < wend) {
+                        bool bb = (badMask >> k) & 1u;
+                        if (!bb) {
+                            const long long Mi = M + offp + P[k];
+                            bb = !(Mi > 8388608LL && Mi < 16777216LL);
+                        }
+                        if (bb) myBad = j;
+                    }
+                }
+                const int f = min(__reduce_min_sync(0xffffffffu, myBad), wend);
+                consumed = false;
+                if (f > pos) {
+                    // stretch [pos, f): total, min and max of the inclusive prefixes (inside +-2^24: every prefix mantissa is
+                    // inside the binade)
+                    int mn = 0x7fffffff, mx = -0x7fffffff - 1, tot = 0;
+                    bool haveTot = false;
+#pragma unroll
+                    for (int k = 0; k < EPL; k++) {
+                        const int j = j0 + k;
+                        if (j < f) {
+                            const int pv = (int)(offp + P[k]);
+                            mn = min(mn, pv);
+                            mx = max(mx, pv);
+                            if (j == f - 1) {
+                                tot = pv;
+                                haveTot = true;
+                            }
                         }
                     }
-                }
-                mn = __reduce_min_sync(0xffffffffu, mn);
-                mx = __reduce_max_sync(0xffffffffu, mx);
-                const unsigned int owner = __ballot_sync(0xffffffffu, haveTot);
-                tot = __shfl_sync(0xffffffffu, tot, __ffs(owner) - 1);
-                if (lane == 0) {
-                    const int key = (int)(bits >> 23);
-                    if (pendKey == key) {
-                        pendMn = min(pendMn, pendQ + mn);
-                        pendMx = max(pendMx, pendQ + mx);
-                        pendQ += tot;
-                    } else {
-                        pendKey = key; pendQ = tot; pendMn = mn; pendMx = mx;   // any earlier RUN was flushed by its X
+                    mn = __reduce_min_sync(0xffffffffu, mn);
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    const unsigned int owner = __ballot_sync(0xffffffffu, haveTot);
+                    tot = __shfl_sync(0xffffffffu, tot, __ffs(owner) - 1);
+                    if (lane == 0) {
+                        const int key = (int)(bits >> 23);
+                        if (pendKey == key) {
+                            pendMn = min(pendMn, pendQ + mn);
+                            pendMx = max(pendMx, pendQ + mx);
+                            pendQ += tot;
+                        } else {
+                            pendKey = key; pendQ = tot; pendMn = mn; pendMx = mx;   // any earlier RUN was flushed by its X
+                        }
                     }
+                    const long long Mn = M + tot;  // in (2^23, 2^24): same sign and exponent
+                    s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mn & 0x7fffffu));
+                    consumed = (f == wend);   // nothing left the binade in this window
                 }
-                const long long Mn = M + tot;  // in (2^23, 2^24): same sign and exponent
-                s = __uint_as_float((bits & 0xff800000u) | ((unsigned int)Mn & 0x7fffffu));
-                if (fb == wend) {   // nothing left the binade in this window
-                    pos = fb;
-                    continue;
-                }
+                return f;
+            };
+            bool consumed;
+            if (mini)
+                fb = round(std::integral_constant<int, 1>{}, consumed);
+            else
+                fb = round(std::integral_constant<int, SIM_EPL>{}, consumed);
+            if (consumed) {
+                mini = false;
+                pos = fb;
+                continue;
             }
         }
+        mini = true;
         // element by element from fb (lane 0): the first one always, then until SIM_STABLE consecutive steps stayed put
         int npos = fb, nnit = nit;
         float ns = s;
