@@ -209,6 +209,41 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- process warm-up: a small training set through the same calls loads the CUDA modules, creates the NCCL channels and
+    # takes the first-use cost of the allocator off both timed regions ----
+    Xw, lw, qw = synth.c2(0.01)
+    wq0, wq1 = shard_queries(qw, rank, world)
+    wd0, wd1 = int(qw[wq0]), int(qw[wq1])
+    ctx = new_ctx()
+    ctx.load_dense(Xw[wd0:wd1], lw[wd0:wd1].copy(), (qw[wq0:wq1 + 1] - qw[wq0]).astype(np.int32))
+    ctx.init(params)
+    for _ in range(3):
+        ctx.boost_iter(want_tree=True)
+    ctx.close()
+    barrier()
+
+    # ---- e2e: host buffers -> C ABI -> trees on the host (first, on a clean allocator: it contains the one-time upload and
+    # init of the job, which would otherwise be timed right behind the release of the previous context's 2.5 GB) ----
+    ctx = new_ctx()
+    ext, e0, e1 = events(ctx)
+    barrier()
+    e0.record(ext)
+    t0 = time.perf_counter()
+    ctx.load_dense(Xs.numpy(), ls.numpy(), qs)
+    ctx.init(params)
+    d2h = 0
+    for _ in range(args.steps):
+        nodes, m2 = ctx.boost_iter(want_tree=True)
+        d2h += nodes.nbytes + 4
+    e1.record(ext)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))   # host work between calls counts too
+    h2d = Xs.numel() * 4 + ls.numel() * 4 + qs.nbytes
+    e2e_value = args.steps / (e2e_ms / 1000.0)
+    ctx.close()
+    barrier()
+
     # ---- value: data resident in HBM ----
     ctx = new_ctx()
     ctx.load_dense(Xs.numpy(), ls.numpy(), qs)
@@ -234,26 +269,6 @@ def main():
     launches = int(ctx.stats()[3]) - launches0
     rows_child = prof[5] / max(args.steps, 1)
     value = args.steps / (ms / 1000.0)
-    ctx.close()
-
-    # ---- e2e: host buffers -> C ABI -> trees on the host ----
-    ctx = new_ctx()
-    ext, e0, e1 = events(ctx)
-    barrier()
-    e0.record(ext)
-    t0 = time.perf_counter()
-    ctx.load_dense(Xs.numpy(), ls.numpy(), qs)
-    ctx.init(params)
-    d2h = 0
-    for _ in range(args.steps):
-        nodes, m2 = ctx.boost_iter(want_tree=True)
-        d2h += nodes.nbytes + 4
-    e1.record(ext)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1000.0
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))   # host work between calls counts too
-    h2d = Xs.numel() * 4 + ls.numel() * 4 + qs.nbytes
-    e2e_value = args.steps / (e2e_ms / 1000.0)
     ctx.close()
 
     if rank != 0:
