@@ -146,7 +146,8 @@ int rlb_compute_pseudo_responses(rlb_ctx* ctx);
 /* FeatureHistogram.update (FeatureHistogram.java:114-146) */
 int rlb_hist_update(rlb_ctx* ctx);
 /* RegressionTree.fit (RegressionTree.java:58-87) incl. FeatureHistogram.findBestSplit
- * (FeatureHistogram.java:236-359).  nodes_out has capacity `cap` >= 2*n_leaves-1. */
+ * (FeatureHistogram.java:236-359).  nodes_out has capacity `cap` >= max(3, 2*n_leaves-1)
+ * (the root is split before the leaf budget is consulted, RegressionTree.java:64-67). */
 int rlb_tree_fit(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
 /* LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.java:54-65; fills node.output */
 int rlb_update_tree_output(rlb_ctx* ctx, rlb_node* nodes_inout, int32_t n_nodes);

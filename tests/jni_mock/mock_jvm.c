@@ -1,0 +1,262 @@
+/*
+ * mock_jvm.c — a JNIEnv over plain C arrays + the call sequence of B200LambdaMART.init()/learn()
+ * (jni/java/ciir/umass/edu/learning/tree/B200LambdaMART.java), so that jni/ranklib_b200_jni.c is compiled and
+ * executed by the test suite although this image has no JVM.  Test infrastructure only.
+ *
+ * Element-copy semantics are the strict ones a JVM may choose: Get*ArrayElements / GetPrimitiveArrayCritical hand
+ * out a COPY, and Release* writes it back unless the mode is JNI_ABORT — a shim that forgets a release, releases
+ * with the wrong mode, or touches an array after releasing it fails here (outstanding-pin counter, stale data).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "jni.h"
+
+enum { OBJ_ARRAY = 1, OBJ_STRING, OBJ_CLASS, OBJ_THROWABLE };
+
+struct mock_object {
+    int kind;
+    int elem;      /* bytes per element (arrays) */
+    jsize len;     /* elements (arrays) */
+    void* data;    /* array payload / string bytes */
+    void* pinned;  /* outstanding copy handed to native code */
+};
+struct mock_method {
+    char name[64];
+};
+
+static struct {
+    int pins;            /* Get* without Release* */
+    int pin_errors;      /* double pins, releases of unknown pointers */
+    int thrown;          /* Throw calls */
+    char message[1024];  /* message of the last thrown RankLibError */
+    char klass[128];     /* class the shim looked up */
+    char method[64], sig[160];
+} J;
+
+static struct mock_object the_class = {OBJ_CLASS, 0, 0, NULL, NULL};
+static struct mock_method the_method;
+
+static jclass m_FindClass(JNIEnv* env, const char* name) {
+    (void)env;
+    snprintf(J.klass, sizeof J.klass, "%s", name);
+    return &the_class;
+}
+static jmethodID m_GetStaticMethodID(JNIEnv* env, jclass cls, const char* name, const char* sig) {
+    (void)env; (void)cls;
+    snprintf(J.method, sizeof J.method, "%s", name);
+    snprintf(J.sig, sizeof J.sig, "%s", sig);
+    return &the_method;
+}
+static jstring m_NewStringUTF(JNIEnv* env, const char* utf) {
+    (void)env;
+    struct mock_object* s = calloc(1, sizeof *s);
+    s->kind = OBJ_STRING;
+    s->data = strdup(utf ? utf : "");
+    return s;
+}
+/* RankLibError.create(String) -> a throwable carrying the message */
+static jobject m_CallStaticObjectMethod(JNIEnv* env, jclass cls, jmethodID m, ...) {
+    (void)env; (void)cls; (void)m;
+    va_list ap;
+    va_start(ap, m);
+    jstring msg = va_arg(ap, jstring);
+    va_end(ap);
+    struct mock_object* t = calloc(1, sizeof *t);
+    t->kind = OBJ_THROWABLE;
+    t->data = strdup(msg && msg->kind == OBJ_STRING ? (const char*)msg->data : "<not a string>");
+    return t;
+}
+static jint m_Throw(JNIEnv* env, jthrowable obj) {
+    (void)env;
+    J.thrown++;
+    snprintf(J.message, sizeof J.message, "%s", obj && obj->kind == OBJ_THROWABLE ? (const char*)obj->data : "<not a throwable>");
+    return 0;
+}
+static jsize m_GetArrayLength(JNIEnv* env, jarray a) {
+    (void)env;
+    return a->len;
+}
+static void* pin(jarray a) {
+    if (a->pinned) J.pin_errors++;
+    size_t bytes = (size_t)a->len * (size_t)a->elem;
+    a->pinned = malloc(bytes ? bytes : 1);
+    memcpy(a->pinned, a->data, bytes);
+    J.pins++;
+    return a->pinned;
+}
+static void unpin(jarray a, void* p, jint mode) {
+    if (!a->pinned || a->pinned != p) {
+        J.pin_errors++;
+        return;
+    }
+    if (mode != JNI_ABORT) memcpy(a->data, p, (size_t)a->len * (size_t)a->elem);
+    if (mode != JNI_COMMIT) {
+        memset(p, 0xA5, (size_t)a->len * (size_t)a->elem); /* a use after release reads garbage */
+        free(p);
+        a->pinned = NULL;
+        J.pins--;
+    }
+}
+static void* m_GetPrimitiveArrayCritical(JNIEnv* env, jarray a, jboolean* isCopy) {
+    (void)env;
+    if (isCopy) *isCopy = 1;
+    return pin(a);
+}
+static void m_ReleasePrimitiveArrayCritical(JNIEnv* env, jarray a, void* p, jint mode) {
+    (void)env;
+    unpin(a, p, mode);
+}
+static jint* m_GetIntArrayElements(JNIEnv* env, jintArray a, jboolean* isCopy) { return m_GetPrimitiveArrayCritical(env, a, isCopy); }
+static void m_ReleaseIntArrayElements(JNIEnv* env, jintArray a, jint* p, jint mode) { (void)env; unpin(a, p, mode); }
+static jfloat* m_GetFloatArrayElements(JNIEnv* env, jfloatArray a, jboolean* isCopy) { return m_GetPrimitiveArrayCritical(env, a, isCopy); }
+static void m_ReleaseFloatArrayElements(JNIEnv* env, jfloatArray a, jfloat* p, jint mode) { (void)env; unpin(a, p, mode); }
+static void m_SetIntArrayRegion(JNIEnv* env, jintArray a, jsize start, jsize len, const jint* buf) {
+    (void)env;
+    if (start < 0 || len < 0 || start + len > a->len) {
+        J.pin_errors++;
+        return;
+    }
+    memcpy((jint*)a->data + start, buf, (size_t)len * sizeof(jint));
+}
+
+static const struct JNINativeInterface_ table = {
+    m_FindClass, m_GetStaticMethodID, m_CallStaticObjectMethod, m_NewStringUTF, m_Throw, m_GetArrayLength,
+    m_GetPrimitiveArrayCritical, m_ReleasePrimitiveArrayCritical, m_GetIntArrayElements, m_ReleaseIntArrayElements,
+    m_GetFloatArrayElements, m_ReleaseFloatArrayElements, m_SetIntArrayRegion};
+static JNIEnv the_env = &table;
+
+static jarray new_array(int elem, jsize len, const void* init) {
+    struct mock_object* a = calloc(1, sizeof *a);
+    a->kind = OBJ_ARRAY;
+    a->elem = elem;
+    a->len = len;
+    a->data = calloc((size_t)(len > 0 ? len : 1), (size_t)elem);
+    if (init) memcpy(a->data, init, (size_t)len * (size_t)elem);
+    return a;
+}
+static void free_array(jarray a) {
+    if (!a) return;
+    free(a->pinned);
+    free(a->data);
+    free(a);
+}
+
+/* the natives of the shim (declared by NativeBridge.java) */
+#define BRIDGE(name) Java_ciir_umass_edu_learning_tree_NativeBridge_##name
+jlong BRIDGE(create)(JNIEnv*, jclass, jint);
+jint BRIDGE(destroy)(JNIEnv*, jclass, jlong);
+jint BRIDGE(loadDense)(JNIEnv*, jclass, jlong, jfloatArray, jlong, jint, jintArray, jfloatArray, jintArray);
+jint BRIDGE(init)(JNIEnv*, jclass, jlong, jint, jint, jfloat, jint, jint, jint, jint, jfloat, jlong);
+jfloat BRIDGE(boostIter)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jdoubleArray, jintArray);
+jint BRIDGE(readScores)(JNIEnv*, jclass, jlong, jdoubleArray);
+jint BRIDGE(ensembleEval)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jintArray, jfloatArray, jfloatArray, jlong, jint, jfloatArray);
+
+/* --- what the Python test reads back --- */
+int mock_thrown(void) { return J.thrown; }
+const char* mock_message(void) { return J.message; }
+const char* mock_error_class(void) { return J.klass; }
+const char* mock_error_method(void) { return J.method; }
+const char* mock_error_sig(void) { return J.sig; }
+int mock_outstanding_pins(void) { return J.pins; }
+int mock_pin_errors(void) { return J.pin_errors; }
+void mock_reset(void) { memset(&J, 0, sizeof J); }
+
+/*
+ * B200LambdaMART.init() + learn() for n_trees trees (no validation set), then readScores, then one batched
+ * Ensemble.eval of the training rows with the trees just learnt — every native of NativeBridge once.
+ *   X [N][F] row-major (column j = fid j+1), labels [N], qoff [Q+1]
+ *   out: node_ints [n_trees][cap*7], node_floats [n_trees][cap*2], node_dev [n_trees][cap], n_nodes [n_trees],
+ *        metric [n_trees], scores [N], eval_out [N]
+ * Returns 0, or the ordinal (1..) of the native call after which a Java exception was pending.
+ */
+int mock_train(int device, const float* X, long long N, int F, const float* labels, const int* qoff, int Q, int n_leaves,
+               int min_leaf_support, float lr, int n_threshold, int kind, int metric, int k, int n_trees, int* node_ints,
+               float* node_floats, double* node_dev, int* n_nodes, float* metric_out, double* scores, float* eval_out) {
+    JNIEnv* env = &the_env;
+    int step = 0, rc = 0;
+    int cap = 2 * n_leaves + 1; /* NativeBridge.nodeCapacity */
+    jlong h = 0;
+    jarray jx = NULL, jf = NULL, jl = NULL, jq = NULL, jni_ = NULL, jnf = NULL, jnd = NULL, jnn = NULL, jsc = NULL;
+    jarray ani = NULL, anf = NULL, ato = NULL, aw = NULL, ax = NULL, ao = NULL;
+    int* fids = malloc(sizeof(int) * (size_t)F);
+    for (int j = 0; j < F; j++) fids[j] = j + 1;
+
+    step++;
+    h = BRIDGE(create)(env, NULL, device);
+    if (J.thrown) { rc = step; goto done; }
+
+    jx = new_array(4, (jsize)(N * F), X);
+    jf = new_array(4, F, fids);
+    jl = new_array(4, (jsize)N, labels);
+    jq = new_array(4, Q + 1, qoff);
+    step++;
+    BRIDGE(loadDense)(env, NULL, h, jx, N, F, jf, jl, jq);
+    if (J.thrown) { rc = step; goto done; }
+
+    step++;
+    BRIDGE(init)(env, NULL, h, n_leaves, min_leaf_support, lr, n_threshold, kind, metric, k, 1.0f, 0);
+    if (J.thrown) { rc = step; goto done; }
+
+    jni_ = new_array(4, cap * 7, NULL);
+    jnf = new_array(4, cap * 2, NULL);
+    jnd = new_array(8, cap, NULL);
+    jnn = new_array(4, 1, NULL);
+    for (int t = 0; t < n_trees; t++) {
+        step++;
+        metric_out[t] = BRIDGE(boostIter)(env, NULL, h, jni_, jnf, jnd, jnn);
+        if (J.thrown) { rc = step; goto done; }
+        n_nodes[t] = ((int*)jnn->data)[0];
+        memcpy(node_ints + (size_t)t * cap * 7, jni_->data, sizeof(int) * (size_t)cap * 7);
+        memcpy(node_floats + (size_t)t * cap * 2, jnf->data, sizeof(float) * (size_t)cap * 2);
+        memcpy(node_dev + (size_t)t * cap, jnd->data, sizeof(double) * (size_t)cap);
+    }
+
+    jsc = new_array(8, (jsize)N, NULL);
+    step++;
+    BRIDGE(readScores)(env, NULL, h, jsc);
+    if (J.thrown) { rc = step; goto done; }
+    memcpy(scores, jsc->data, sizeof(double) * (size_t)N);
+
+    /* Ensemble.eval over the learnt trees: concatenate the node arrays, weights = learningRate each; the feature
+     * matrix is indexed by fid directly (column 0 unused) */
+    {
+        int total = 0;
+        for (int t = 0; t < n_trees; t++) total += n_nodes[t];
+        int* ci = calloc((size_t)total * 7 + 1, sizeof(int));
+        float* cf = calloc((size_t)total * 2 + 1, sizeof(float));
+        int* off = calloc((size_t)n_trees + 1, sizeof(int));
+        float* w = calloc((size_t)n_trees + 1, sizeof(float));
+        float* xe = calloc((size_t)N * (size_t)(F + 1), sizeof(float));
+        int at = 0;
+        for (int t = 0; t < n_trees; t++) {
+            off[t] = at;
+            w[t] = lr;
+            memcpy(ci + (size_t)at * 7, node_ints + (size_t)t * cap * 7, sizeof(int) * (size_t)n_nodes[t] * 7);
+            memcpy(cf + (size_t)at * 2, node_floats + (size_t)t * cap * 2, sizeof(float) * (size_t)n_nodes[t] * 2);
+            at += n_nodes[t];
+        }
+        off[n_trees] = at;
+        for (long long i = 0; i < N; i++) memcpy(xe + i * (F + 1) + 1, X + i * F, sizeof(float) * (size_t)F);
+        ani = new_array(4, total * 7, ci);
+        anf = new_array(4, total * 2, cf);
+        ato = new_array(4, n_trees + 1, off);
+        aw = new_array(4, n_trees, w);
+        ax = new_array(4, (jsize)(N * (F + 1)), xe);
+        ao = new_array(4, (jsize)N, NULL);
+        free(ci); free(cf); free(off); free(w); free(xe);
+        step++;
+        BRIDGE(ensembleEval)(env, NULL, h, ani, anf, ato, aw, ax, N, F + 1, ao);
+        if (J.thrown) { rc = step; goto done; }
+        memcpy(eval_out, ao->data, sizeof(float) * (size_t)N);
+    }
+
+done:
+    if (h) BRIDGE(destroy)(env, NULL, h);
+    free(fids);
+    free_array(jx); free_array(jf); free_array(jl); free_array(jq);
+    free_array(jni_); free_array(jnf); free_array(jnd); free_array(jnn); free_array(jsc);
+    free_array(ani); free_array(anf); free_array(ato); free_array(aw); free_array(ax); free_array(ao);
+    return rc;
+}
