@@ -207,6 +207,26 @@ int rlb_score_metric(rlb_ctx* ctx, const double* scores, const float* label, con
  * 2).  info[0] = elements applied one by one, info[1] = chunks redone by the exact block routine. */
 int rlb_float_chain(rlb_ctx* ctx, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t info[2]);
 
+/* --- LETOR / SVMrank text reader (host only, works without a GPU) ---------------------------------------------
+ * FeatureManager.readInput(file, mustHaveRelDoc, sparse=false) (R/features/FeatureManager.java:187-245) with
+ * DataPoint.parse (R/learning/DataPoint.java:58-110) for every line: `<label> qid:<id> <fid>:<value> ... # description`.
+ * Same skipping of blank / '#' lines, same token rules (id and value = text after the LAST ':', fid = text before the
+ * FIRST ':'), Float.parseFloat / Integer.parseInt grammar, label >= 0 and fid >= 1 checks, consecutive equal ids = one
+ * RankList, lists without a relevant document dropped when must_have_rel_doc != 0.  The file is parsed by `nthreads`
+ * threads (<= 0: all cores).  Errors: RLB_E_INVALID with the reference's message + file:line in rlb_last_error(NULL). */
+typedef struct rlb_letor rlb_letor;
+int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads, rlb_letor** out);
+/* documents and rank lists kept, largest feature id seen (DataPoint.featureCount), entries read before the filter */
+int rlb_letor_dims(const rlb_letor* h, int64_t* n_docs, int32_t* n_queries, int32_t* max_fid, int64_t* n_entries);
+/* The layout rlb_load_dense takes: X float[N][F] with column j = feature feature_ids[j] (NaN where the line does not
+ * list the feature: DataPoint.UNKNOWN), label float[N], qoff int32[Q+1].  Any of X / label / qoff may be NULL. */
+int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, float* X, float* label, int32_t* qoff);
+/* RankList.getID() of list q */
+const char* rlb_letor_qid(const rlb_letor* h, int32_t q);
+int rlb_letor_free(rlb_letor* h);
+/* Test hook: Float.parseFloat(text) as the reader implements it (RLB_E_INVALID = NumberFormatException). */
+int rlb_parse_java_float(const char* text, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,8 @@ bool rlb_nccl_load(std::string* why) {
     }
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) {
-        if (why) *why = dlerror() ? dlerror() : "libnccl.so.2 not found";
+        const char* de = dlerror();  // one call: dlerror() clears the message it returns
+        if (why) *why = de ? de : "libnccl.so.2 not found";
         return false;
     }
     struct { const char* name; void** dst; } syms[] = {

@@ -24,7 +24,8 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_comm_init", "rlb_load_dense", "rlb_set_thresholds", "rlb_lambdamart_init", "rlb_get_thresholds",
            "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
-           "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain"]
+           "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain",
+           "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_qid", "rlb_letor_free", "rlb_parse_java_float"]
 
 
 class RankLibError(RuntimeError):
@@ -60,6 +61,39 @@ def lib():
 
 def device_count():
     return lib().rlb_device_count()
+
+
+def parse_java_float(text):
+    """Float.parseFloat(text) as the native LETOR reader implements it; None where Java throws NumberFormatException."""
+    out = C.c_float()
+    rc = lib().rlb_parse_java_float(text.encode(), C.byref(out))
+    return np.float32(out.value) if rc == RLB_OK else None
+
+
+def read_letor(path, must_have_rel_doc=False, features=None, nthreads=0):
+    """FeatureManager.readInput through the native multithreaded reader (rlb_letor_*; host only, no GPU needed).
+    Returns X[N][F] (NaN = unknown), label[N], qoff[Q+1], feature ids[F], qids[Q], entries read before the filter."""
+    L = lib()
+    h = C.c_void_p()
+    rc = L.rlb_letor_read(os.fsencode(path), 1 if must_have_rel_doc else 0, nthreads, C.byref(h))
+    if rc != RLB_OK:
+        raise RankLibError(L.rlb_last_error(None).decode())
+    try:
+        n, q, mf, ne = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int64()
+        L.rlb_letor_dims(h, C.byref(n), C.byref(q), C.byref(mf), C.byref(ne))
+        fids = (np.arange(1, mf.value + 1, dtype=np.int32) if features is None else np.ascontiguousarray(features, np.int32))
+        X = np.empty((n.value, len(fids)), np.float32)
+        label = np.empty(n.value, np.float32)
+        qoff = np.empty(q.value + 1, np.int32)
+        rc = L.rlb_letor_fill(h, _p(fids), len(fids), _p(X), _p(label), _p(qoff))
+        if rc != RLB_OK:
+            raise RankLibError(L.rlb_last_error(None).decode())
+        L.rlb_letor_qid.restype = C.c_char_p
+        L.rlb_letor_qid.argtypes = [C.c_void_p, C.c_int32]
+        qids = [L.rlb_letor_qid(h, i).decode() for i in range(q.value)]
+        return X, label, qoff, fids, qids, ne.value
+    finally:
+        L.rlb_letor_free(h)
 
 
 def _p(a):

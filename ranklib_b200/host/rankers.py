@@ -55,44 +55,13 @@ class RankLists:
         return out
 
 
-def read_letor(path):
-    """FeatureManager.readInput (R/features/FeatureManager.java:187-245) + DataPoint.parse
+def read_letor(path, must_have_rel_doc=False, nthreads=0):
+    """FeatureManager.readInput(file, mustHaveRelDoc, false) (R/features/FeatureManager.java:187-245) + DataPoint.parse
     (R/learning/DataPoint.java:58-110): `<label> qid:<id> <fid>:<val> ... # comment`; consecutive lines with the
-    same qid form one RankList; missing features are NaN (= unknown, read as 0)."""
-    labels, qids, rows, maxf = [], [], [], 0
-    with open(path) as fh:
-        for line in fh:
-            line = line.split("#", 1)[0].strip()
-            if not line:
-                continue
-            parts = line.split()
-            lab = float(parts[0])
-            if lab < 0:
-                raise RankLibError("Relevance label cannot be negative. System will now exit.")
-            qids.append(parts[1].split(":", 1)[1])
-            feats = {}
-            for tok in parts[2:]:
-                k, v = tok.rsplit(":", 1)
-                f = int(k)
-                if f <= 0:
-                    raise RankLibError("Cannot use feature numbering less than or equal to zero. Start your features at 1.")
-                feats[f] = float(v)
-                maxf = max(maxf, f)
-            labels.append(lab)
-            rows.append(feats)
-    X = np.full((len(rows), maxf), np.nan, np.float32)
-    for i, feats in enumerate(rows):
-        for f, v in feats.items():
-            X[i, f - 1] = v
-    qoff, names = [0], []
-    for i, q in enumerate(qids):
-        if i > 0 and q != qids[i - 1]:
-            qoff.append(i)
-            names.append(qids[i - 1])
-    qoff.append(len(qids))
-    if qids:
-        names.append(qids[-1])
-    return RankLists(X, np.array(labels, np.float32), np.array(qoff, np.int32), None, names)
+    same qid form one RankList; missing features are NaN (= unknown, read as 0).  Parsed by the library's
+    multithreaded reader (rlb_letor_*, csrc/rlb_letor.cpp); malformed input raises RankLibError as in the reference."""
+    X, label, qoff, fids, qids, _ = native.read_letor(path, must_have_rel_doc, None, nthreads)
+    return RankLists(X, label, qoff, fids, qids)
 
 
 # ---------------------------------------------------------------------------------------------------
