@@ -13,6 +13,7 @@ All numeric work happens in libranklib_b200.so (CUDA); nothing here computes a h
 tree on the CPU.
 """
 import re
+import warnings
 
 import numpy as np
 
@@ -369,6 +370,12 @@ class LambdaMART(Ranker):
         if self.samples is None or self.samples.size() == 0:
             raise RankLibError("Error in LambdaMART::init(): no training data")
         s = self.samples
+        if self.scorer.metric == native.METRIC_NDCG and len(set(s.qids)) != len(s.qids):
+            # NDCGScorer memoises the ideal DCG by RankList id (R/metric/NDCGScorer.java:116-122,137-143): lists that
+            # share an id share the ideal of whichever was scored first — order dependent under the reference's own
+            # threading.  The library computes every list's own ideal.
+            warnings.warn("training lists with duplicate ids: the reference's NDCG ideal-DCG cache is keyed by id and would "
+                          "share one ideal among them; ranklib_b200 uses each list's own ideal", RuntimeWarning)
         cols = np.arange(s.X.shape[1]) if self.features is None else \
             np.array([int(np.nonzero(s.features == f)[0][0]) for f in self.features])
         self.features = s.features[cols]
