@@ -197,8 +197,13 @@ def java_float_str(x, single=True):
         return "-Infinity" if x < 0 else "Infinity"
     s = np.format_float_scientific(x, unique=True, trim="-")  # shortest round-trip digits
     m, e = s.split("e")
+    if len(m.lstrip("-")) == 1:
+        # Java always prints a fractional digit; when ONE digit already identifies the value it prints the two-digit
+        # decimal closest to it (Float.MIN_VALUE is "1.4E-45", Double.MIN_VALUE "4.9E-324"; only deep subnormals differ)
+        m, e = ("%.1e" % float(x)).split("e")
     neg = m.startswith("-")
     digits = m.lstrip("-").replace(".", "")
+    digits = digits.rstrip("0") or "0"
     out = _java_fmt(digits, int(e) + 1)
     return "-" + out if neg else out
 
@@ -366,11 +371,22 @@ class LambdaMART(Ranker):
     def createNew(self):
         return type(self)()
 
+    @staticmethod
+    def _ids_share_different_ideals(s):
+        """True when two lists with the same id hold different label multisets (copies of one list, as in a bootstrap
+        bag, have the same ideal DCG and are harmless)."""
+        seen = {}
+        for q, qid in enumerate(s.qids):
+            key = tuple(sorted(s.label[s.qoff[q]:s.qoff[q + 1]].tolist()))
+            if seen.setdefault(qid, key) != key:
+                return True
+        return False
+
     def init(self):
         if self.samples is None or self.samples.size() == 0:
             raise RankLibError("Error in LambdaMART::init(): no training data")
         s = self.samples
-        if self.scorer.metric == native.METRIC_NDCG and len(set(s.qids)) != len(s.qids):
+        if self.scorer.metric == native.METRIC_NDCG and len(set(s.qids)) != len(s.qids) and self._ids_share_different_ideals(s):
             # NDCGScorer memoises the ideal DCG by RankList id (R/metric/NDCGScorer.java:116-122,137-143): lists that
             # share an id share the ideal of whichever was scored first — order dependent under the reference's own
             # threading.  The library computes every list's own ideal (SURVEY.md Q3).
@@ -518,9 +534,15 @@ class RFRanker(Ranker):
             s += e.eval(self._ctx, Xf).astype(np.float64)
         return s / len(self.ensembles)
 
-    def model(self):
-        return "".join(f"## {self.name()}\n## No. of bags = {type(self).nBag}\n\n" if i == 0 else "" for i in range(1)) + \
-            "".join(e.toString() for e in self.ensembles)
+    def toString(self):  # RFRanker.toString (RFRanker.java:130-137)
+        return "".join(e.toString() + "\n" for e in self.ensembles)
+
+    def model(self):  # RFRanker.model (RFRanker.java:139-151)
+        cls = type(self)
+        return (f"## {self.name()}\n## No. of bags = {cls.nBag}\n## Sub-sampling = {java_float_str(cls.subSamplingRate)}\n"
+                f"## Feature-sampling = {java_float_str(cls.featureSamplingRate)}\n## No. of trees = {cls.nTrees}\n"
+                f"## No. of leaves = {cls.nTreeLeaves}\n## No. of threshold candidates = {cls.nThreshold}\n"
+                f"## Learning rate = {java_float_str(cls.learningRate)}\n\n" + self.toString())
 
 
 class RankerFactory:
