@@ -208,3 +208,66 @@ def test_other_metric_scorers_oracle_vs_transliteration():
             m = orc.METRICS[name]
             assert orc.swap_change(lab, m, k).tobytes() == np.array(table, np.float64).reshape(n, n).tobytes(), (name, n, k)
             assert orc.metric_score(lab, m, k) == score, (name, n, k)
+
+
+def test_lambda_known_answers_from_the_published_formulas(built):
+    """Known-answer vectors derived BY HAND from the published LambdaMART gradient (Burges, "From RankNet to LambdaRank
+    to LambdaMART", 2010: lambda_ij = -|dNDCG_ij| / (1 + exp(s_i - s_j)), w = rho (1 - rho) |dNDCG|) with RankLib's
+    conventions (gain 2^l - 1, discount 1 / log2(rank + 2), sign: the more relevant document of a pair is pushed up,
+    LambdaMART.java:380-392).  The expected values below are written out from those formulas, not from oracle or
+    pyref code."""
+    from math import exp, log2
+    d = [1.0 / log2(r + 2) for r in range(3)]
+
+    def run(label, score_by_tree=None):
+        n = len(label)
+        X = np.zeros((n, 1), np.float32)
+        o = orc.Oracle(X, np.array(label, np.float32), np.array([0, n], np.int32), orc.make_params(n_leaves=2))
+        o.compute_pseudo_responses()
+        return o.read("LAMBDA"), o.read("WEIGHT")
+
+    # A: two documents, labels (1, 0), tied scores: one pair, rho = 1/2, |dNDCG| = (d0 - d1)(1 - 0) / idealDCG(= 1)
+    lam, w = run([1, 0])
+    delta = (d[0] - d[1]) * 1.0 / 1.0
+    np.testing.assert_allclose(lam, [0.5 * delta, -0.5 * delta], rtol=1e-15)
+    np.testing.assert_allclose(w, [0.25 * delta, 0.25 * delta], rtol=1e-15)
+    assert abs(lam[0] - 0.18453512321427141) < 1e-15
+
+    # B: labels (2, 0, 1), all scores tied: the stable ranking keeps the input order
+    lam, w = run([2, 0, 1])
+    ideal = 3 * d[0] + 1 * d[1] + 0 * d[2]
+    p01 = (d[0] - d[1]) * (3 - 0) / ideal       # doc0 (rank 0, gain 3) over doc1 (rank 1, gain 0)
+    p02 = (d[0] - d[2]) * (3 - 1) / ideal       # doc0 over doc2 (rank 2, gain 1)
+    p21 = (d[1] - d[2]) * (1 - 0) / ideal       # doc2 over doc1
+    np.testing.assert_allclose(lam, [0.5 * (p01 + p02), -0.5 * (p01 + p21), 0.5 * (p21 - p02)], rtol=1e-14)
+    np.testing.assert_allclose(w, [0.25 * (p01 + p02), 0.25 * (p01 + p21), 0.25 * (p02 + p21)], rtol=1e-14)
+    assert abs(lam.sum()) < 1e-16
+
+    # C: the cut-off. With NDCG@1 only pairs touching rank 0 count; RankLib fills changes[i][j] for i < min(k, n) and ALL
+    # j > i with the full discounts of both positions (NDCGScorer.java:151-157)
+    X = np.zeros((3, 1), np.float32)
+    o = orc.Oracle(X, np.array([0, 1, 2], np.float32), np.array([0, 3], np.int32), orc.make_params(n_leaves=2, k=1))
+    o.compute_pseudo_responses()
+    lam = o.read("LAMBDA")
+    ideal1 = 3 * d[0]                           # top-1 of the ideal order (2, 1, 0)
+    q10 = abs((d[1] - d[0]) * (1 - 0)) / ideal1  # doc1 over doc0 (touches rank 0)
+    q20 = abs((d[2] - d[0]) * (3 - 0)) / ideal1  # doc2 over doc0 (touches rank 0)
+    # the pair (doc2, doc1) at ranks (2, 1) does not touch rank 0: no contribution
+    np.testing.assert_allclose(lam, [-0.5 * (q10 + q20), 0.5 * q10, 0.5 * q20], rtol=1e-14)
+
+    # D: one whole boosting iteration.  Labels (1, 0, 1, 0), one feature equal to the label, tied scores.  Every positive
+    # document has lambda = 2 w (each of its pairs adds rho*delta = delta/2 to lambda and rho(1-rho)*delta = delta/4 to w),
+    # every negative one lambda = -2 w; the only useful split is x <= 0, so the Newton leaf values sum(lambda)/sum(w) are
+    # exactly -2 and +2 (scaling by 2 commutes with every float rounding of the chains), the scores become
+    # (double)0.1f * (+-2) and the training NDCG@10 is 1.
+    X = np.array([[1], [0], [1], [0]], np.float32)
+    o = orc.Oracle(X, np.array([1, 0, 1, 0], np.float32), np.array([0, 4], np.int32), orc.make_params(n_leaves=2))
+    nodes, metric = o.boost_iter()
+    assert len(nodes) == 3 and nodes["feature_id"][0] == 1 and nodes["threshold"][0] == 0.0 and nodes["threshold_idx"][0] == 0
+    left, right = nodes[nodes["left"][0]], nodes[nodes["right"][0]]
+    assert left["feature_id"] == -1 and right["feature_id"] == -1
+    assert left["output"] == np.float32(-2.0) and right["output"] == np.float32(2.0)
+    assert left["count"] == 2 and right["count"] == 2
+    lr = float(np.float32(0.1))
+    np.testing.assert_array_equal(o.read("SCORE"), [2 * lr, -2 * lr, 2 * lr, -2 * lr])
+    assert metric == np.float32(1.0)
