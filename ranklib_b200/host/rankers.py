@@ -500,34 +500,57 @@ class RFRanker(Ranker):
         size = int(np.float32(type(self).subSamplingRate) * np.float32(n))
         return [rnd.next_int(n) for _ in range(size)]
 
-    def learn(self, bags=None):
+    def bag_plan(self):
+        """The query picks of every bag, in bag order, from ONE seeded stream — a pure host computation, so every
+        process of a bag-parallel run derives the same bags without communicating."""
+        rnd = JavaRandom(type(self).seed)
+        return [self.bag_queries(rnd) for _ in range(type(self).nBag)]
+
+    def _train_bag(self, i, picks):
+        """One bag: rf.createRanker(rType, bag, features, scorer); r.init(); r.learn() (RFRanker.java:80-85)."""
         cls = type(self)
         base = MART if cls.rType == R_MART else LambdaMART
-        rnd = JavaRandom(cls.seed)
-        self.ensembles = []
-        bag_ids = range(cls.nBag) if bags is None else bags
-        for i in range(cls.nBag):
-            picks = self.bag_queries(rnd)          # every bag consumes its draws, also when another GPU trains it
-            if i not in bag_ids:
-                continue
 
-            class _Bag(base):
-                nTrees, nTreeLeaves, learningRate = cls.nTrees, cls.nTreeLeaves, cls.learningRate
-                nThreshold, minLeafSupport, nRoundToStopEarly = cls.nThreshold, cls.minLeafSupport, -1
-                samplingRate, seed = cls.featureSamplingRate, cls.seed + 1 + i
+        class _Bag(base):
+            nTrees, nTreeLeaves, learningRate = cls.nTrees, cls.nTreeLeaves, cls.learningRate
+            nThreshold, minLeafSupport = cls.nThreshold, cls.minLeafSupport
+            # RFRanker.init sets nRoundToStopEarly = -1 (RFRanker.java:66); with no validation set the loop runs nTrees times
+            nRoundToStopEarly = (1 << 30)
+            samplingRate, seed = cls.featureSamplingRate, cls.seed + 1 + i
 
-            r = _Bag(self.samples.select(picks), self.features, self.scorer)
-            r.device = self.device
-            r.init()
-            r.nRoundToStopEarly = -1
-            # RFRanker.init sets nRoundToStopEarly = -1 (RFRanker.java:66): with no validation set the loop runs nTrees times
-            _Bag.nRoundToStopEarly = (1 << 30)
-            r.learn()
-            self.ensembles.append(r.getEnsemble())
-            self._ctx = r.ctx
+        r = _Bag(self.samples.select(picks), self.features, self.scorer)
+        r.device = self.device
+        r.init()
+        r.learn()
+        self._ctx = r.ctx
+        return r.getEnsemble()
+
+    def learn(self, bags=None):
+        """RFRanker.learn (RFRanker.java:72-114).  `bags` = the bag ordinals this process trains (default: all)."""
+        plan = self.bag_plan()
+        todo = range(type(self).nBag) if bags is None else sorted(bags)
+        self.bag_ids = list(todo)
+        self.ensembles = [self._train_bag(i, plan[i]) for i in todo]
+
+    def learn_bag_parallel(self, rank, world, dist=None):
+        """Config C5: replicas + bag parallelism.  Every process holds the whole training set, trains
+        bags rank, rank + world, ... on its own GPU, and the ensembles are exchanged once at the end as model text
+        (torch.distributed all_gather_object; no collective during training).  Afterwards every rank holds all nBag
+        ensembles in bag order — the same model a single process produces."""
+        self.learn(bags=range(rank, type(self).nBag, world))
+        if world > 1:
+            mine = [(i, e.toString()) for i, e in zip(self.bag_ids, self.ensembles)]
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            merged = sorted((i, text) for part in parts for i, text in part)
+            assert [i for i, _ in merged] == list(range(type(self).nBag)), "every bag exactly once"
+            self.ensembles = [Ensemble(text) for _, text in merged]
+            self.bag_ids = list(range(type(self).nBag))
 
     def eval(self, rl):
         """RFRanker.eval (RFRanker.java:117-123): double mean of the bag ensembles' float scores."""
+        if getattr(self, "_ctx", None) is None:
+            self._ctx = native.Context(self.device)
         Xf = rl.dense_with_fid_columns()
         s = np.zeros(rl.X.shape[0], np.float64)
         for e in self.ensembles:

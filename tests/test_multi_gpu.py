@@ -68,3 +68,72 @@ def test_two_gpus_bit_identical_to_one(built):
            "--master-port", "29611", os.path.join(ROOT, "scripts", "mgpu_check.py"), "0.05", "6"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "MGPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ---- Random Forests, bag-parallel replicas (BASELINE.json configs[4]) -----------------------------
+def _stub_rf(samples):
+    """RFRanker whose per-bag trainer is a host stub (one leaf whose value encodes the bag and its picks): the plan,
+    the assignment of bags to ranks and the final exchange are exactly the production code, only the GPU work is not."""
+    from ranklib_b200.host import rankers as R
+
+    class StubRF(R.RFRanker):
+        nBag, subSamplingRate, seed = 7, 0.5, 21
+
+        def _train_bag(self, i, picks):
+            nodes = np.zeros(1, native.NODE_DTYPE)
+            nodes[0] = (-1, -1, 0, -1, -1, -1, float(i) + (sum((j + 1) * p for j, p in enumerate(picks)) % 997) / 1000.0, len(picks), 0)
+            e = R.Ensemble()
+            e.add(R.RegressionTree(nodes), 0.1)
+            return e
+
+    rf = StubRF(samples, None, R.NDCGScorer(10))
+    rf.init()
+    return rf
+
+
+def _rf_samples():
+    from ranklib_b200.host import rankers as R
+    X, label, qoff = synth.c1()
+    return R.RankLists(X, label, qoff)
+
+
+def _gloo_rf_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rf = _stub_rf(_rf_samples())
+    rf.learn_bag_parallel(rank, world, dist)
+    ret.put((rank, rf.toString(), rf.bag_ids))
+    dist.destroy_process_group()
+
+
+def test_rf_bag_plan_is_one_seeded_stream():
+    from ranklib_b200.host import rankers as R
+    rf = _stub_rf(_rf_samples())
+    plan = rf.bag_plan()
+    rnd = R.JavaRandom(21)
+    n = rf.samples.size()
+    assert len(plan) == 7 and all(len(p) == int(np.float32(0.5) * np.float32(n)) for p in plan)
+    assert [q for p in plan for q in p] == [rnd.next_int(n) for _ in range(7 * len(plan[0]))]
+    rf.learn(bags=[5, 2])
+    assert rf.bag_ids == [2, 5] and len(rf.ensembles) == 2
+
+
+def test_gloo_world2_rf_bag_parallel_equals_single_process():
+    """world_size-2 gloo run of the bag-parallel driver: both ranks end with all bags, in bag order, and the model text
+    equals the single-process one."""
+    import torch.multiprocessing as mp
+    single = _stub_rf(_rf_samples())
+    single.learn()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_rf_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [ret.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, text, ids in got:
+        assert ids == list(range(7)) and text == single.toString(), rank
