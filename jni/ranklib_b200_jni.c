@@ -1,17 +1,17 @@
 /*
  * ranklib_b200_jni.c — the thin JNI shim between RankLib's Java façades and libranklib_b200.so.
  *
- * NOT COMPILED IN THIS IMAGE: there is no JDK here (no jni.h, no javac — SURVEY.md F1), so this
- * file is kept mechanical: every native method is one call into the C ABI of
- * include/ranklib_b200.h plus array pinning, and every behaviour is testable through that ABI
- * (tests/ drive the same entry points through ctypes).  Build, where a JDK exists:
+ * There is no JDK in this image (no jni.h, no javac — SURVEY.md F1), so no JVM has loaded this file yet.  It is kept
+ * mechanical — every native method is one call into the C ABI of include/ranklib_b200.h plus array pinning — and it IS
+ * compiled and executed by the test suite: tests/test_zz_jni_shim.py builds it against a mock <jni.h> (tests/jni_mock/)
+ * and runs the call sequence of jni/java/.../B200LambdaMART.java through a mock JNIEnv.  Build, where a JDK exists:
  *
- *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../include \
+ *   gcc -shared -fPIC -DRLB_HAVE_JNI -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../include \
  *       ranklib_b200_jni.c -L../ranklib_b200/csrc -lranklib_b200 -o libranklib_b200_jni.so
  *
- * Java side: class ciir.umass.edu.learning.tree.NativeBridge declares the
- * `native` methods below; LambdaMART.init()/learn() (R/learning/tree/LambdaMART.java:68-272) keep
- * their signatures and delegate.  A non-zero status becomes RankLibError.create(msg)
+ * Java side (jni/java/): class ciir.umass.edu.learning.tree.NativeBridge declares the
+ * `native` methods below; B200LambdaMART overrides LambdaMART.init()/learn() (R/learning/tree/LambdaMART.java:68-272)
+ * and delegates.  A non-zero status becomes RankLibError.create(msg)
  * (R/utilities/RankLibError.java:25-42), the error convention of the reference.
  */
 #ifdef RLB_HAVE_JNI
@@ -97,11 +97,20 @@ JNIEXPORT jfloat JNICALL BRIDGE(boostIter)(JNIEnv* env, jclass c, jlong h, jintA
                                             jdoubleArray nodeDeviance, jintArray nNodes) {
     rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
     jint cap = (*env)->GetArrayLength(env, nodeDeviance);
-    rlb_node nodes[4096];
+    rlb_node* nodes;
     int32_t n = 0;
     float metric = 0.f;
-    if (cap > 4096) cap = 4096;
-    CHECK(ctx, rlb_boost_iter(ctx, nodes, cap, &n, &metric));
+    /* the three arrays must agree: cap nodes of 7 ints, 2 floats, 1 double */
+    if (cap < 1 || (*env)->GetArrayLength(env, nodeInts) < 7 * cap || (*env)->GetArrayLength(env, nodeFloats) < 2 * cap ||
+        (*env)->GetArrayLength(env, nNodes) < 1)
+        cap = 0;
+    nodes = (rlb_node*)malloc(sizeof(rlb_node) * (size_t)(cap > 0 ? cap : 1));
+    if (!nodes) return 0.f;
+    if (rlb_boost_iter(ctx, nodes, cap, &n, &metric) != RLB_OK) { /* cap == 0 ends here: "node buffer too small" */
+        free(nodes);
+        throw_ranklib_error(env, ctx);
+        return 0.f;
+    }
     jint* ni = (*env)->GetPrimitiveArrayCritical(env, nodeInts, NULL);
     jfloat* nf = (*env)->GetPrimitiveArrayCritical(env, nodeFloats, NULL);
     jdouble* nd = (*env)->GetPrimitiveArrayCritical(env, nodeDeviance, NULL);
@@ -120,6 +129,7 @@ JNIEXPORT jfloat JNICALL BRIDGE(boostIter)(JNIEnv* env, jclass c, jlong h, jintA
     (*env)->ReleasePrimitiveArrayCritical(env, nodeDeviance, nd, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, nodeFloats, nf, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, nodeInts, ni, 0);
+    free(nodes);
     (*env)->SetIntArrayRegion(env, nNodes, 0, 1, (jint*)&n);
     return metric;
 }

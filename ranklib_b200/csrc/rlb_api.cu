@@ -263,15 +263,17 @@ int rlb_comm_init(rlb_ctx* c, int rank, int world, const uint8_t id[128]) {
     RLB_NCCL(c, ncclCommInitRank(&c->comm, world, nid, rank));
     c->rank = rank;
     c->world = world;
-    {   // connect the rings now (first collective) rather than inside the first training call
-        int* d = nullptr;
-        RLB_CUDA(c, cudaMalloc(&d, 4));
+    // connect the rings now (first collective) rather than inside the first training call
+    int* d = nullptr;
+    RLB_CUDA(c, cudaMalloc(&d, 4));
+    const int rc = [&]() -> int {
         RLB_CUDA(c, cudaMemsetAsync(d, 0, 4, c->stream));
         RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt32, ncclSum, c->comm, c->stream));
         RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(d);
-    }
-    return RLB_OK;
+        return RLB_OK;
+    }();
+    cudaFree(d);  // also on the error paths
+    return rc;
 }
 
 int rlb_load_dense(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
@@ -305,11 +307,15 @@ int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
     if (c->world > 1) {
         long long* d = nullptr;
         RLB_CUDA(c, cudaMalloc(&d, 8));
-        RLB_CUDA(c, cudaMemcpyAsync(d, &q, 8, cudaMemcpyHostToDevice, c->stream));
-        RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt64, ncclSum, c->comm, c->stream));
-        RLB_CUDA(c, cudaMemcpyAsync(&q, d, 8, cudaMemcpyDeviceToHost, c->stream));
-        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(d);
+        const int rq = [&]() -> int {
+            RLB_CUDA(c, cudaMemcpyAsync(d, &q, 8, cudaMemcpyHostToDevice, c->stream));
+            RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt64, ncclSum, c->comm, c->stream));
+            RLB_CUDA(c, cudaMemcpyAsync(&q, d, 8, cudaMemcpyDeviceToHost, c->stream));
+            RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+            return RLB_OK;
+        }();
+        cudaFree(d);  // also on the error paths
+        if (rq) return rq;
     }
     c->Q_total = q;
     if (const char* e = getenv("RLB_NO_GRAPH")) c->use_graph = (atoi(e) == 0);
