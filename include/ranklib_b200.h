@@ -212,7 +212,9 @@ int rlb_float_chain(rlb_ctx* ctx, const double* x, int64_t n, float carry, int32
  * DataPoint.parse (R/learning/DataPoint.java:58-110) for every line: `<label> qid:<id> <fid>:<value> ... # description`.
  * Same skipping of blank / '#' lines, same token rules (id and value = text after the LAST ':', fid = text before the
  * FIRST ':'), Float.parseFloat / Integer.parseInt grammar, label >= 0 and fid >= 1 checks, consecutive equal ids = one
- * RankList, lists without a relevant document dropped when must_have_rel_doc != 0.  The file is parsed by `nthreads`
+ * RankList, lists without a relevant document dropped when must_have_rel_doc != 0; a path ending in ".gz" is read
+ * through zlib like FileUtils.smartReader's GZIPInputStream (R/utilities/FileUtils.java:40-46); lines end at \n, \r or
+ * \r\n like BufferedReader.readLine.  The file is parsed by `nthreads`
  * threads (<= 0: all cores).  Errors: RLB_E_INVALID with the reference's message + file:line in rlb_last_error(NULL). */
 typedef struct rlb_letor rlb_letor;
 int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads, rlb_letor** out);

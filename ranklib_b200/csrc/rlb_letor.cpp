@@ -34,6 +34,7 @@
 #include <thread>
 #include <vector>
 
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -257,9 +258,14 @@ void parse_slab(const char* b, const char* e, Slab& S) {
         }
     };
     while (p < e && S.err.empty()) {
+        // BufferedReader.readLine: a line ends at "\n", "\r" or "\r\n"
         const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
         const char* le = nl ? nl : e;
         const char* next = nl ? nl + 1 : e;
+        if (const char* cr = (const char*)memchr(p, '\r', (size_t)(le - p))) {
+            le = cr;
+            next = (cr + 1 < e && cr[1] == '\n') ? cr + 2 : cr + 1;
+        }
         ordinal++;
         const char* s = p;
         p = next;
@@ -343,6 +349,55 @@ void parse_slab(const char* b, const char* e, Slab& S) {
     if (!S.err.empty()) return;
 }
 
+// gzip input through the system's zlib, bound at first use (no link-time dependency: a plain-text run never needs it)
+bool inflate_file(const char* path, std::vector<char>* out, std::string* why) {
+    void* z = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!z) {
+        *why = "cannot read a .gz file: libz.so.1 is not loadable";
+        return false;
+    }
+    typedef void* (*gzopen_t)(const char*, const char*);
+    typedef int (*gzread_t)(void*, void*, unsigned);
+    typedef int (*gzclose_t)(void*);
+    gzopen_t p_open = (gzopen_t)dlsym(z, "gzopen");
+    gzread_t p_read = (gzread_t)dlsym(z, "gzread");
+    gzclose_t p_close = (gzclose_t)dlsym(z, "gzclose");
+    if (!p_open || !p_read || !p_close) {
+        *why = "cannot read a .gz file: gzopen/gzread/gzclose not found in libz.so.1";
+        return false;
+    }
+    {   // GZIPInputStream refuses anything without the gzip magic ("Not in GZIP format"); gzread would pass it through
+        unsigned char magic[2] = {0, 0};
+        FILE* raw = fopen(path, "rb");
+        const size_t got = raw ? fread(magic, 1, 2, raw) : 0;
+        if (raw) fclose(raw);
+        if (got != 2 || magic[0] != 0x1f || magic[1] != 0x8b) {
+            *why = std::string("Not in GZIP format: ") + path;
+            return false;
+        }
+    }
+    void* f = p_open(path, "rb");
+    if (!f) {
+        *why = std::string("cannot open ") + path;
+        return false;
+    }
+    std::vector<char> chunk(1u << 22);
+    int n;
+    while ((n = p_read(f, chunk.data(), (unsigned)chunk.size())) > 0) out->insert(out->end(), chunk.begin(), chunk.begin() + n);
+    // a truncated stream decodes up to the cut and then reports Z_BUF_ERROR through gzerror (GZIPInputStream throws
+    // "Unexpected end of ZLIB input stream")
+    typedef const char* (*gzerror_t)(void*, int*);
+    gzerror_t p_error = (gzerror_t)dlsym(z, "gzerror");
+    int zerr = 0;
+    if (p_error) p_error(f, &zerr);
+    p_close(f);
+    if (n < 0 || (zerr != 0 && zerr != 1)) {
+        *why = std::string("corrupt or truncated gzip stream in ") + path;
+        return false;
+    }
+    return true;
+}
+
 }  // namespace
 
 struct rlb_letor {
@@ -373,19 +428,33 @@ int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads
         close(fd);
         return RLB_E_INVALID;
     }
-    const size_t size = (size_t)sb.st_size;
+    size_t size = (size_t)sb.st_size;
     const char* base = nullptr;
-    if (size > 0) {
-        void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m == MAP_FAILED) {
-            rlb_set_error(nullptr, RLB_E_NOMEM, "Error in FeatureManager::readInput()", strerror(errno));
-            close(fd);
-            return RLB_E_NOMEM;
+    std::vector<char> inflated;  // FileUtils.smartReader: a name ending in ".gz" is read through GZIPInputStream
+    const size_t plen = strlen(path);
+    const bool gz = plen >= 3 && strcmp(path + plen - 3, ".gz") == 0;
+    if (gz) {
+        close(fd);
+        std::string why;
+        if (!inflate_file(path, &inflated, &why)) {
+            rlb_set_error(nullptr, RLB_E_INVALID, "Error in FeatureManager::readInput()", why.c_str());
+            return RLB_E_INVALID;
         }
-        base = (const char*)m;
-        madvise(m, size, MADV_SEQUENTIAL);
+        size = inflated.size();
+        base = inflated.data();
+    } else {
+        if (size > 0) {
+            void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) {
+                rlb_set_error(nullptr, RLB_E_NOMEM, "Error in FeatureManager::readInput()", strerror(errno));
+                close(fd);
+                return RLB_E_NOMEM;
+            }
+            base = (const char*)m;
+            madvise(m, size, MADV_SEQUENTIAL);
+        }
+        close(fd);
     }
-    close(fd);
     if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     int nslab = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, size / (1u << 12)));
     rlb_letor* h = new rlb_letor();
@@ -407,7 +476,8 @@ int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads
         parse_slab(base + cut[0], base + cut[1], h->slabs[0]);
         for (auto& t : th) t.join();
     }
-    if (base) munmap((void*)base, size);
+    if (base && !gz) munmap((void*)base, size);
+    inflated = std::vector<char>();
     // first error in file order
     int64_t line0 = 0;
     for (int i = 0; i < nslab; i++) {

@@ -326,3 +326,32 @@ def test_java_float_near_float_midpoints(frac, e2, delta, digits):
     got = native.parse_java_float(text)
     want = _round_f32(text)
     assert got is not None and got.view(np.uint32) == want.view(np.uint32), (text, got, want)
+
+
+def test_gzip_input_and_lone_carriage_returns(tmp_path):
+    """FileUtils.smartReader (R/utilities/FileUtils.java:40-46) reads *.gz through GZIPInputStream, and
+    BufferedReader.readLine ends a line at \\n, \\r or \\r\\n."""
+    import gzip
+    X, label, qoff = synth.c1()
+    p = tmp_path / "t.txt"
+    synth.write_letor(str(p), X[:300, :12], label[:300], qoff[:8])
+    raw = p.read_bytes()
+    want = native.read_letor(str(p))
+    (tmp_path / "t.txt.gz").write_bytes(gzip.compress(raw))
+    got = native.read_letor(str(tmp_path / "t.txt.gz"))
+    assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32)) and np.array_equal(got[2], want[2]) and got[4] == want[4]
+    (tmp_path / "cr.txt").write_bytes(raw.replace(b"\n", b"\r"))          # classic Mac line ends
+    got = native.read_letor(str(tmp_path / "cr.txt"))
+    assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32)) and np.array_equal(got[2], want[2])
+    (tmp_path / "mixed.txt").write_bytes(raw.replace(b"\n", b"\r\n", 100).replace(b"\n1 ", b"\r1 ", 50))
+    got = native.read_letor(str(tmp_path / "mixed.txt"), False, None, 4)
+    assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32)) and np.array_equal(got[2], want[2])
+    (tmp_path / "bad.gz").write_bytes(b"1 qid:1 1:2\n")                    # GZIPInputStream: "Not in GZIP format"
+    with pytest.raises(native.RankLibError, match="Not in GZIP format"):
+        native.read_letor(str(tmp_path / "bad.gz"))
+    (tmp_path / "cut.gz").write_bytes(gzip.compress(raw)[:-20])            # truncated stream
+    with pytest.raises(native.RankLibError):
+        native.read_letor(str(tmp_path / "cut.gz"))
+    (tmp_path / "err.txt").write_bytes(b"1 qid:1 1:1\r\n\r\n1 qid:1 1:x\r\n")
+    with pytest.raises(native.RankLibError, match="line 3"):
+        native.read_letor(str(tmp_path / "err.txt"))
