@@ -513,7 +513,14 @@ class Ranker {
         }
         return out;
     }
-    // Ranker.save(modelFile) writes model()
+    // Ranker.save(modelFile) (Ranker.java:106-122): the model text as a file
+    void save(const std::string& modelFile) const {
+        std::FILE* f = std::fopen(modelFile.c_str(), "wb");
+        if (!f) throw RankLibError::create("Error in Ranker::save(): cannot write " + modelFile);
+        const std::string m = model();
+        const bool ok = std::fwrite(m.data(), 1, m.size(), f) == m.size();
+        if (std::fclose(f) != 0 || !ok) throw RankLibError::create("Error in Ranker::save(): cannot write " + modelFile);
+    }
 };
 
 class LambdaMART : public Ranker {
