@@ -223,6 +223,10 @@ int rlb_letor_dims(const rlb_letor* h, int64_t* n_docs, int32_t* n_queries, int3
 /* The layout rlb_load_dense takes: X float[N][F] with column j = feature feature_ids[j] (NaN where the line does not
  * list the feature: DataPoint.UNKNOWN), label float[N], qoff int32[Q+1].  Any of X / label / qoff may be NULL. */
 int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, float* X, float* label, int32_t* qoff);
+/* Binary cache of a parsed set (no counterpart in the reference, which re-parses the text on every run): header, labels,
+ * list offsets, list ids and the dense float[N][max_fid] matrix (NaN = unknown).  rlb_letor_read recognises the file by its
+ * magic bytes and maps it instead of parsing; must_have_rel_doc is applied on load like on a text read. */
+int rlb_letor_write_binary(const rlb_letor* h, const char* path);
 /* RankList.getID() of list q */
 const char* rlb_letor_qid(const rlb_letor* h, int32_t q);
 int rlb_letor_free(rlb_letor* h);

@@ -410,7 +410,77 @@ struct rlb_letor {
     int32_t max_fid = 0;
     int64_t entries = 0;  // data points read before the mustHaveRelDoc filter
     int nthreads = 1;
+    // a set loaded from the binary cache (rlb_letor_write_binary) has no slabs: rows live here, [n][max_fid], NaN = unknown
+    bool dense = false;
+    std::vector<float> dense_x, dense_label;
+    int64_t n_docs() const { return dense ? (int64_t)dense_label.size() : (int64_t)dp_slab.size(); }
 };
+
+namespace {
+const char kMagic[16] = "RLB-DENSE-v1\0\0\0";   // 16 bytes
+
+struct BinHeader {
+    char magic[16];
+    int64_t n_docs, entries;
+    int32_t n_lists, max_fid;
+    uint64_t qid_bytes;
+};
+
+// the binary cache: header | label f32[N] | qoff i32[Q+1] | qids (NUL-terminated, qid_bytes in all) | pad to 64 | X f32[N][max_fid]
+int load_binary(const char* path, const char* base, size_t size, bool filter, int nthreads, rlb_letor** out) {
+    auto bad = [&](const char* why) {
+        rlb_set_error(nullptr, RLB_E_INVALID, "Error in FeatureManager::readInput()", (std::string(why) + " (" + path + ")").c_str());
+        return RLB_E_INVALID;
+    };
+    BinHeader H;
+    if (size < sizeof H) return bad("truncated binary cache");
+    memcpy(&H, base, sizeof H);
+    if (H.n_docs < 0 || H.n_lists < 0 || H.max_fid < 0 || H.n_lists > H.n_docs) return bad("corrupt binary cache header");
+    // sizes that cannot fit the file are refused before any product is formed (no overflow in the offsets below)
+    if ((uint64_t)H.n_docs > size / 4 || H.qid_bytes > size || (H.max_fid > 0 && (uint64_t)H.n_docs > size / 4 / (uint64_t)H.max_fid))
+        return bad("truncated binary cache");
+    size_t off = sizeof H;
+    const size_t lab_b = (size_t)H.n_docs * 4, qoff_b = ((size_t)H.n_lists + 1) * 4;
+    if (size < off + lab_b + qoff_b + H.qid_bytes) return bad("truncated binary cache");
+    const float* lab = (const float*)(base + off);
+    off += lab_b;
+    const int32_t* qoff = (const int32_t*)(base + off);
+    off += qoff_b;
+    const char* qids = base + off;
+    off += (size_t)H.qid_bytes;
+    off = (off + 63) & ~(size_t)63;
+    const size_t x_b = (size_t)H.n_docs * (size_t)H.max_fid * 4;
+    if (size < off + x_b) return bad("truncated binary cache");
+    const float* X = (const float*)(base + off);
+    if (qoff[0] != 0 || qoff[H.n_lists] != H.n_docs) return bad("corrupt binary cache offsets");
+    rlb_letor* h = new rlb_letor();
+    h->nthreads = nthreads;
+    h->dense = true;
+    h->max_fid = H.max_fid;
+    h->entries = H.entries;
+    h->qoff.push_back(0);
+    const char* q = qids;
+    const char* qend = qids + H.qid_bytes;
+    for (int32_t l = 0; l < H.n_lists; l++) {
+        const char* z = (const char*)memchr(q, 0, (size_t)(qend - q));
+        if (!z || qoff[l + 1] < qoff[l]) {
+            delete h;
+            return bad("corrupt binary cache lists");
+        }
+        bool has_rel = false;
+        for (int32_t i = qoff[l]; i < qoff[l + 1]; i++) has_rel |= lab[i] > 0;
+        if (!filter || has_rel) {
+            h->qids.emplace_back(q, (size_t)(z - q));
+            h->dense_label.insert(h->dense_label.end(), lab + qoff[l], lab + qoff[l + 1]);
+            h->dense_x.insert(h->dense_x.end(), X + (size_t)qoff[l] * H.max_fid, X + (size_t)qoff[l + 1] * H.max_fid);
+            h->qoff.push_back((int32_t)h->dense_label.size());
+        }
+        q = z + 1;
+    }
+    *out = h;
+    return RLB_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -454,6 +524,12 @@ int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads
             madvise(m, size, MADV_SEQUENTIAL);
         }
         close(fd);
+    }
+    if (size >= sizeof kMagic && memcmp(base, kMagic, sizeof kMagic) == 0) {  // the binary cache of an earlier read
+        if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+        const int rc = load_binary(path, base, size, must_have_rel_doc != 0, nthreads, out);
+        if (!gz) munmap((void*)base, size);
+        return rc;
     }
     if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     int nslab = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, size / (1u << 12)));
@@ -539,7 +615,7 @@ int rlb_letor_read(const char* path, int32_t must_have_rel_doc, int32_t nthreads
 
 int rlb_letor_dims(const rlb_letor* h, int64_t* n_docs, int32_t* n_queries, int32_t* max_fid, int64_t* n_entries) {
     if (!h) return RLB_E_INVALID;
-    if (n_docs) *n_docs = (int64_t)h->dp_slab.size();
+    if (n_docs) *n_docs = h->n_docs();
     if (n_queries) *n_queries = (int32_t)h->qids.size();
     if (max_fid) *max_fid = h->max_fid;
     if (n_entries) *n_entries = h->entries;
@@ -548,7 +624,7 @@ int rlb_letor_dims(const rlb_letor* h, int64_t* n_docs, int32_t* n_queries, int3
 
 int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, float* X, float* label, int32_t* qoff) {
     if (!h || F < 0 || (F > 0 && !feature_ids)) return RLB_E_INVALID;
-    const int64_t N = (int64_t)h->dp_slab.size();
+    const int64_t N = h->n_docs();
     if (qoff) memcpy(qoff, h->qoff.data(), sizeof(int32_t) * h->qoff.size());
     // fid -> column (-1: not selected); a fid listed twice fills both columns
     std::vector<std::vector<int32_t>> dup;
@@ -574,7 +650,14 @@ int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, fl
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(h->nthreads, N / 4096 + 1));
     auto work = [&](int t) {
         const int64_t i0 = N * t / nt, i1 = N * (t + 1) / nt;
-        for (int64_t i = i0; i < i1; i++) {
+        for (int64_t i = i0; i < i1 && h->dense; i++) {  // binary cache: a column gather
+            if (label) label[i] = h->dense_label[(size_t)i];
+            if (!X) continue;
+            const float* src = h->dense_x.data() + (size_t)i * (size_t)h->max_fid;
+            float* row = X + (size_t)i * (size_t)F;
+            for (int32_t j = 0; j < F; j++) row[j] = feature_ids[j] <= h->max_fid ? src[feature_ids[j] - 1] : unknown;
+        }
+        for (int64_t i = i0; i < i1 && !h->dense; i++) {
             const Slab& S = h->slabs[h->dp_slab[(size_t)i]];
             const Line& L = S.lines[h->dp_line[(size_t)i]];
             if (label) label[i] = L.label;
@@ -596,6 +679,56 @@ int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, fl
     for (int t = 1; t < nt; t++) th.emplace_back(work, t);
     work(0);
     for (auto& t : th) t.join();
+    return RLB_OK;
+}
+
+int rlb_letor_write_binary(const rlb_letor* h, const char* path) {
+    if (!h || !path) return RLB_E_INVALID;
+    const int64_t N = h->n_docs();
+    const int32_t F = h->max_fid;
+    std::vector<int32_t> fid((size_t)F);
+    for (int32_t j = 0; j < F; j++) fid[(size_t)j] = j + 1;
+    std::vector<float> X((size_t)N * (size_t)F), lab((size_t)N);
+    if (int rc = rlb_letor_fill(h, fid.data(), F, X.data(), lab.data(), nullptr)) return rc;
+    BinHeader H;
+    memset(&H, 0, sizeof H);
+    memcpy(H.magic, kMagic, sizeof kMagic);
+    H.n_docs = N;
+    H.entries = h->entries;
+    H.n_lists = (int32_t)h->qids.size();
+    H.max_fid = F;
+    std::string qids;
+    for (const auto& q : h->qids) {
+        if (q.find('\0') != std::string::npos) {
+            rlb_set_error(nullptr, RLB_E_INVALID, "rlb_letor_write_binary", "a list id contains a NUL byte");
+            return RLB_E_INVALID;
+        }
+        qids.append(q).push_back('\0');
+    }
+    H.qid_bytes = qids.size();
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        rlb_set_error(nullptr, RLB_E_INVALID, "rlb_letor_write_binary", strerror(errno));
+        return RLB_E_INVALID;
+    }
+    size_t off = 0;
+    bool ok = true;
+    auto put = [&](const void* p, size_t n) {
+        ok = ok && (n == 0 || fwrite(p, 1, n, f) == n);
+        off += n;
+    };
+    put(&H, sizeof H);
+    put(lab.data(), lab.size() * 4);
+    put(h->qoff.data(), h->qoff.size() * 4);
+    put(qids.data(), qids.size());
+    static const char zeros[64] = {0};
+    put(zeros, ((off + 63) & ~(size_t)63) - off);
+    put(X.data(), X.size() * 4);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) {
+        rlb_set_error(nullptr, RLB_E_INVALID, "rlb_letor_write_binary", "short write");
+        return RLB_E_INVALID;
+    }
     return RLB_OK;
 }
 

@@ -25,7 +25,8 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
            "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain",
-           "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_qid", "rlb_letor_free", "rlb_parse_java_float"]
+           "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_write_binary", "rlb_letor_qid", "rlb_letor_free",
+           "rlb_parse_java_float"]
 
 
 class RankLibError(RuntimeError):
@@ -68,6 +69,19 @@ def parse_java_float(text):
     out = C.c_float()
     rc = lib().rlb_parse_java_float(text.encode(), C.byref(out))
     return np.float32(out.value) if rc == RLB_OK else None
+
+
+def letor_to_binary(text_path, binary_path, nthreads=0):
+    """Parse a LETOR text (or .gz) file once and store the binary cache that rlb_letor_read maps on later runs."""
+    L = lib()
+    h = C.c_void_p()
+    if L.rlb_letor_read(os.fsencode(text_path), 0, nthreads, C.byref(h)) != RLB_OK:
+        raise RankLibError(L.rlb_last_error(None).decode())
+    try:
+        if L.rlb_letor_write_binary(h, os.fsencode(binary_path)) != RLB_OK:
+            raise RankLibError(L.rlb_last_error(None).decode())
+    finally:
+        L.rlb_letor_free(h)
 
 
 def read_letor(path, must_have_rel_doc=False, features=None, nthreads=0):

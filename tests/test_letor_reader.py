@@ -355,3 +355,37 @@ def test_gzip_input_and_lone_carriage_returns(tmp_path):
     (tmp_path / "err.txt").write_bytes(b"1 qid:1 1:1\r\n\r\n1 qid:1 1:x\r\n")
     with pytest.raises(native.RankLibError, match="line 3"):
         native.read_letor(str(tmp_path / "err.txt"))
+
+
+def test_binary_cache_round_trip(tmp_path):
+    p = tmp_path / "tricky.txt"
+    p.write_bytes(TRICKY.encode())
+    b = tmp_path / "tricky.rlb"
+    native.letor_to_binary(str(p), str(b))
+    for must in (False, True):
+        t = native.read_letor(str(p), must)
+        c = native.read_letor(str(b), must)
+        assert np.array_equal(np.isnan(t[0]), np.isnan(c[0])) and np.array_equal(np.nan_to_num(t[0]).view(np.uint32), np.nan_to_num(c[0]).view(np.uint32))
+        assert np.array_equal(t[1], c[1]) and np.array_equal(t[2], c[2]) and np.array_equal(t[3], c[3]) and t[4] == c[4] and t[5] == c[5]
+    sel = np.array([3, 99, 1], np.int32)
+    assert np.array_equal(np.nan_to_num(native.read_letor(str(b), False, sel)[0]), np.nan_to_num(native.read_letor(str(p), False, sel)[0]))
+    # a larger set through several fill threads, and a cache of a cache
+    X, label, qoff = synth.c1()
+    big = tmp_path / "big.txt"
+    synth.write_letor(str(big), X, label, qoff)
+    native.letor_to_binary(str(big), str(tmp_path / "big.rlb"))
+    native.letor_to_binary(str(tmp_path / "big.rlb"), str(tmp_path / "big2.rlb"))
+    assert (tmp_path / "big.rlb").read_bytes() == (tmp_path / "big2.rlb").read_bytes()
+    got = native.read_letor(str(tmp_path / "big2.rlb"))
+    assert np.array_equal(got[0].view(np.uint32), X.view(np.uint32)) and np.array_equal(got[1], label) and np.array_equal(got[2], qoff)
+    # damaged caches are refused, not read past their end
+    raw = (tmp_path / "big.rlb").read_bytes()
+    for cut in (20, 60, 5000, len(raw) - 4):
+        (tmp_path / "cut.rlb").write_bytes(raw[:cut])
+        with pytest.raises(native.RankLibError, match="binary cache"):
+            native.read_letor(str(tmp_path / "cut.rlb"))
+    bad = bytearray(raw)
+    bad[16:24] = (2 ** 62).to_bytes(8, "little")
+    (tmp_path / "bad.rlb").write_bytes(bytes(bad))
+    with pytest.raises(native.RankLibError, match="binary cache"):
+        native.read_letor(str(tmp_path / "bad.rlb"))
