@@ -29,6 +29,8 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -50,6 +52,66 @@ static std::vector<int> partition(int listSize, int size) {
     return p;
 }
 
+// A persistent pool, like the reference's: MyThreadPool keeps `size` worker threads alive for the whole run
+// (R/utilities/MyThreadPool.java:27-31) and execute()/await() only hand them ranges.  Creating threads per call would
+// charge the CPU baseline for work the JVM never does.  Workers are started on first use and never joined (they are
+// parked on a condition variable); one parallel region runs at a time.
+class WorkerPool {
+    std::mutex run_mu_;              // serialises parallel regions (several oracle contexts may exist)
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int, int, int)>* fn_ = nullptr;
+    const std::vector<int>* part_ = nullptr;
+    int next_ = 0, chunks_ = 0, pending_ = 0;
+    int workers_ = 0;
+
+    void worker() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_work_.wait(lk, [&] { return next_ < chunks_; });
+            const int i = next_++;
+            const auto* fn = fn_;
+            const auto* part = part_;
+            lk.unlock();
+            (*fn)((*part)[i], (*part)[i + 1] - 1, i);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+
+  public:
+    void run(const std::vector<int>& part, const std::function<void(int, int, int)>& fn) {
+        std::lock_guard<std::mutex> region(run_mu_);
+        const int chunks = (int)part.size() - 1;
+        std::unique_lock<std::mutex> lk(mu_);
+        while (workers_ < chunks - 1) {  // the calling thread takes ranges too: chunks threads work, as in the reference's pool
+            std::thread(&WorkerPool::worker, this).detach();
+            workers_++;
+        }
+        fn_ = &fn;
+        part_ = &part;
+        next_ = 0;
+        chunks_ = chunks;
+        pending_ = chunks;
+        cv_work_.notify_all();
+        while (next_ < chunks_) {
+            const int i = next_++;
+            lk.unlock();
+            fn(part[i], part[i + 1] - 1, i);
+            lk.lock();
+            --pending_;
+        }
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        chunks_ = 0;
+        next_ = 0;
+    }
+};
+
+static WorkerPool& pool() {
+    static WorkerPool* p = new WorkerPool();  // never destroyed: its parked workers outlive main()
+    return *p;
+}
+
 // runs fn(start, end_inclusive, workerIndex) over the partition of nTasks
 static void parallel_ranges(int nTasks, int nthreads, const std::function<void(int, int, int)>& fn) {
     if (nTasks <= 0) return;
@@ -57,10 +119,12 @@ static void parallel_ranges(int nTasks, int nthreads, const std::function<void(i
         fn(0, nTasks - 1, 0);
         return;
     }
-    std::vector<int> p = partition(nTasks, nthreads);
-    std::vector<std::thread> th;
-    for (size_t i = 0; i + 1 < p.size(); i++) th.emplace_back(fn, p[i], p[i + 1] - 1, (int)i);
-    for (auto& t : th) t.join();
+    const std::vector<int> p = partition(nTasks, nthreads);
+    if (p.size() <= 2) {
+        fn(p[0], p[1] - 1, 0);
+        return;
+    }
+    pool().run(p, fn);
 }
 
 // ---------------------------------------------------------------------------------------------
