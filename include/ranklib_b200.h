@@ -227,6 +227,10 @@ int rlb_letor_fill(const rlb_letor* h, const int32_t* feature_ids, int32_t F, fl
  * list offsets, list ids and the dense float[N][max_fid] matrix (NaN = unknown).  rlb_letor_read recognises the file by its
  * magic bytes and maps it instead of parsing; must_have_rel_doc is applied on load like on a text read. */
 int rlb_letor_write_binary(const rlb_letor* h, const char* path);
+/* rlb_load_dense straight from a parsed set: the columns feature_ids[0..F) (NULL: every id 1..max_fid, as
+ * FeatureManager.getFeatureFromSampleVector, R/features/FeatureManager.java:303-322) of all its lists.  A Java caller that
+ * trains from a file never materialises DataPoint objects this way. */
+int rlb_load_letor(rlb_ctx* ctx, const rlb_letor* h, const int32_t* feature_ids, int32_t F);
 /* RankList.getID() of list q */
 const char* rlb_letor_qid(const rlb_letor* h, int32_t q);
 int rlb_letor_free(rlb_letor* h);

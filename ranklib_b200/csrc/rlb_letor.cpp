@@ -732,6 +732,22 @@ int rlb_letor_write_binary(const rlb_letor* h, const char* path) {
     return RLB_OK;
 }
 
+int rlb_load_letor(rlb_ctx* ctx, const rlb_letor* h, const int32_t* feature_ids, int32_t F) {
+    if (!ctx || !h || F < 0) return RLB_E_INVALID;
+    std::vector<int32_t> all;
+    if (!feature_ids) {  // FeatureManager.getFeatureFromSampleVector: every feature id up to the largest seen
+        F = h->max_fid;
+        all.resize((size_t)F);
+        for (int32_t j = 0; j < F; j++) all[(size_t)j] = j + 1;
+        feature_ids = all.data();
+    }
+    const int64_t N = h->n_docs();
+    std::vector<float> X((size_t)N * (size_t)F), label((size_t)N);
+    std::vector<int32_t> qoff(h->qoff.size());
+    if (int rc = rlb_letor_fill(h, feature_ids, F, X.data(), label.data(), qoff.data())) return rc;
+    return rlb_load_dense(ctx, X.data(), N, F, feature_ids, label.data(), qoff.data(), (int32_t)h->qids.size());
+}
+
 const char* rlb_letor_qid(const rlb_letor* h, int32_t q) {
     if (!h || q < 0 || (size_t)q >= h->qids.size()) return "";
     return h->qids[(size_t)q].c_str();

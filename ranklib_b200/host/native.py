@@ -25,7 +25,7 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_compute_pseudo_responses", "rlb_hist_update", "rlb_tree_fit", "rlb_update_tree_output",
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
            "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain",
-           "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_write_binary", "rlb_letor_qid", "rlb_letor_free",
+           "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_write_binary", "rlb_load_letor", "rlb_letor_qid", "rlb_letor_free",
            "rlb_parse_java_float"]
 
 
@@ -170,6 +170,20 @@ class Context:
                 else np.ascontiguousarray(feature_ids, np.int32))
         self._ck(self.lib.rlb_load_dense(self.h, _p(X), C.c_int64(N), F, _p(fids), _p(label), _p(qoff), len(qoff) - 1))
         self.N, self.F, self.Q = N, F, len(qoff) - 1
+
+    def load_letor(self, path, must_have_rel_doc=False, features=None, nthreads=0):
+        """FeatureManager.readInput + the flattening of LambdaMART.init in one native step: file -> device."""
+        h = C.c_void_p()
+        if self.lib.rlb_letor_read(os.fsencode(path), 1 if must_have_rel_doc else 0, nthreads, C.byref(h)) != RLB_OK:
+            raise RankLibError(self.lib.rlb_last_error(None).decode())
+        try:
+            n, q, mf = C.c_int64(), C.c_int32(), C.c_int32()
+            self.lib.rlb_letor_dims(h, C.byref(n), C.byref(q), C.byref(mf), None)
+            fids = None if features is None else np.ascontiguousarray(features, np.int32)
+            self._ck(self.lib.rlb_load_letor(self.h, h, None if fids is None else _p(fids), 0 if fids is None else len(fids)))
+            self.N, self.F, self.Q = n.value, (mf.value if fids is None else len(fids)), q.value
+        finally:
+            self.lib.rlb_letor_free(h)
 
     def set_thresholds(self, thr, n_thr):
         thr = np.ascontiguousarray(thr, np.float32)

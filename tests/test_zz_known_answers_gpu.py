@@ -69,3 +69,30 @@ def test_one_whole_iteration_analytically(built):
     np.testing.assert_array_equal(g.read("SCORE"), [2 * lr, -2 * lr, 2 * lr, -2 * lr])
     assert np.float32(metric) == np.float32(1.0)
     g.close()
+
+
+@pytest.mark.gpu
+def test_load_letor_file_equals_load_dense(built, tmp_path):
+    """rlb_load_letor (file -> device in one native step) against rlb_load_dense of the arrays the reader returns:
+    same thresholds, same first trees, also with a feature subset."""
+    from ranklib_b200.host import synth
+    X, label, qoff = synth.c1()
+    p = tmp_path / "c1.txt"
+    synth.write_letor(str(p), X[:600, :12], label[:600], qoff[:16])
+    for feats in (None, [7, 2, 11]):
+        a = native.Context(0)
+        a.load_letor(str(p), features=feats)
+        a.init(native.make_params(n_leaves=6))
+        Xr, lr, qr, fids, _, _ = native.read_letor(str(p), False, feats)
+        b = native.Context(0)
+        b.load_dense(Xr, lr, qr, fids)
+        b.init(native.make_params(n_leaves=6))
+        assert (a.N, a.F, a.Q) == (b.N, b.F, b.Q)
+        for f in range(a.F):
+            assert np.array_equal(a.thresholds(f), b.thresholds(f))
+        for _ in range(3):
+            na, ma = a.boost_iter()
+            nb, mb = b.boost_iter()
+            assert na.tobytes() == nb.tobytes() and ma == mb
+        a.close()
+        b.close()
