@@ -118,6 +118,34 @@ public class B200LambdaMART extends LambdaMART {
                 scorer.getK(), FeatureHistogram.samplingRate, seed);
     }
 
+    /**
+     * init() for a training set that is still a file: FeatureManager.readInput (FeatureManager.java:187-245) and the
+     * flattening above happen in the library's multithreaded reader, and no DataPoint object is created.  `samples` stays
+     * empty, so the final scorer.score(rank(samples)) of learn() is replaced by the library's own score on the training
+     * data (scoreOnTrainingData keeps the last NDCG@k-T); validation sets still go through setValidationSet.
+     */
+    public void initFromFile(final String trainingFile, final boolean mustHaveRelDoc) {
+        if (validationSamples != null) {
+            modelScoresOnValidation = new double[validationSamples.size()][];
+            for (int i = 0; i < validationSamples.size(); i++) {
+                modelScoresOnValidation[i] = new double[validationSamples.get(i).size()];
+            }
+        }
+        release();
+        handle = NativeBridge.create(device);
+        final int[] dims = new int[3];
+        NativeBridge.loadLetorFile(handle, trainingFile, mustHaveRelDoc, features, dims);
+        if (features == null) {
+            features = new int[dims[2]];
+            for (int f = 0; f < features.length; f++) {
+                features[f] = f + 1;
+            }
+        }
+        modelScores = new double[dims[0]];
+        NativeBridge.init(handle, nTreeLeaves, minLeafSupport, learningRate, nThreshold, kind(), metricCode(scorer),
+                scorer.getK(), FeatureHistogram.samplingRate, seed);
+    }
+
     /** Split objects (Split.java:44-83) from the flat node arrays of NativeBridge.boostIter. */
     protected static Split treeFromFlat(final int[] ni, final float[] nf, final double[] nd, final int node) {
         final int left = ni[7 * node + 3];
@@ -190,7 +218,9 @@ public class B200LambdaMART extends LambdaMART {
             ensemble.remove(ensemble.treeCount() - 1);
         }
 
-        scoreOnTrainingData = scorer.score(rank(samples));
+        if (!samples.isEmpty()) { // initFromFile leaves no Java-side copy of the training set
+            scoreOnTrainingData = scorer.score(rank(samples));
+        }
         if (validationSamples != null) {
             bestScoreOnValidationData = scorer.score(rank(validationSamples));
         }

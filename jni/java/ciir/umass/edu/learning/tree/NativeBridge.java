@@ -50,6 +50,9 @@ final class NativeBridge {
 
     static native int loadDense(long handle, float[] X, long N, int F, int[] features, float[] labels, int[] qoff);
 
+    /** Parses a LETOR text / .gz / binary-cache file natively and uploads it; dims receives {N, Q, maxFid}. */
+    static native int loadLetorFile(long handle, String path, boolean mustHaveRelDoc, int[] features, int[] dims);
+
     static native int init(long handle, int nLeaves, int minLeafSupport, float learningRate, int nThreshold, int kind,
             int metric, int k, float featureSamplingRate, long seed);
 

@@ -71,6 +71,45 @@ JNIEXPORT jint JNICALL BRIDGE(loadDense)(JNIEnv* env, jclass c, jlong h, jfloatA
     return 0;
 }
 
+/* int loadLetorFile(long h, String path, boolean mustHaveRelDoc, int[] features (null = all), int[] dims (out: N, Q, maxFid))
+ * FeatureManager.readInput (R/features/FeatureManager.java:187-245) + the flattening of LambdaMART.init in one native step:
+ * the file is parsed by the library's multithreaded reader and goes to the device without becoming DataPoint objects. */
+JNIEXPORT jint JNICALL BRIDGE(loadLetorFile)(JNIEnv* env, jclass c, jlong h, jstring path, jboolean mustHaveRelDoc, jintArray features,
+                                              jintArray dims) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    rlb_letor* set = NULL;
+    const char* p = (*env)->GetStringUTFChars(env, path, NULL);
+    int rc;
+    if (!p) return 0; /* OutOfMemoryError is already pending */
+    rc = rlb_letor_read(p, mustHaveRelDoc ? 1 : 0, 0, &set);
+    (*env)->ReleaseStringUTFChars(env, path, p);
+    if (rc != RLB_OK) {
+        throw_ranklib_error(env, NULL); /* reader errors are context-free */
+        return 0;
+    }
+    {
+        int64_t n = 0;
+        int32_t q = 0, mf = 0;
+        jint d[3];
+        rlb_letor_dims(set, &n, &q, &mf, NULL);
+        d[0] = (jint)n;
+        d[1] = q;
+        d[2] = mf;
+        if (features) {
+            jsize nf = (*env)->GetArrayLength(env, features);
+            jint* f = (*env)->GetIntArrayElements(env, features, NULL);
+            rc = rlb_load_letor(ctx, set, (const int32_t*)f, nf);
+            (*env)->ReleaseIntArrayElements(env, features, f, JNI_ABORT);
+        } else {
+            rc = rlb_load_letor(ctx, set, NULL, 0);
+        }
+        rlb_letor_free(set);
+        CHECK(ctx, rc);
+        (*env)->SetIntArrayRegion(env, dims, 0, 3, d);
+    }
+    return 0;
+}
+
 /* int init(long h, int nLeaves, int minLeafSupport, float learningRate, int nThreshold, int kind, int metric, int k,
  *          float featureSamplingRate, long seed) — the static fields of LambdaMART.java:37-42 at init() time */
 JNIEXPORT jint JNICALL BRIDGE(init)(JNIEnv* env, jclass c, jlong h, jint nLeaves, jint mls, jfloat lr, jint nThreshold, jint kind,

@@ -54,6 +54,8 @@ struct JNINativeInterface_ {
     jfloat* (*GetFloatArrayElements)(JNIEnv* env, jfloatArray a, jboolean* isCopy);
     void (*ReleaseFloatArrayElements)(JNIEnv* env, jfloatArray a, jfloat* elems, jint mode);
     void (*SetIntArrayRegion)(JNIEnv* env, jintArray a, jsize start, jsize len, const jint* buf);
+    const char* (*GetStringUTFChars)(JNIEnv* env, jstring s, jboolean* isCopy);
+    void (*ReleaseStringUTFChars)(JNIEnv* env, jstring s, const char* utf);
 };
 
 #endif

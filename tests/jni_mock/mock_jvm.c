@@ -121,10 +121,32 @@ static void m_SetIntArrayRegion(JNIEnv* env, jintArray a, jsize start, jsize len
     memcpy((jint*)a->data + start, buf, (size_t)len * sizeof(jint));
 }
 
+static const char* m_GetStringUTFChars(JNIEnv* env, jstring s, jboolean* isCopy) {
+    (void)env;
+    if (isCopy) *isCopy = 1;
+    if (!s || s->kind != OBJ_STRING || s->pinned) {
+        J.pin_errors++;
+        return NULL;
+    }
+    s->pinned = strdup((const char*)s->data);
+    J.pins++;
+    return (const char*)s->pinned;
+}
+static void m_ReleaseStringUTFChars(JNIEnv* env, jstring s, const char* utf) {
+    (void)env;
+    if (!s || s->pinned != (void*)utf) {
+        J.pin_errors++;
+        return;
+    }
+    free(s->pinned);
+    s->pinned = NULL;
+    J.pins--;
+}
+
 static const struct JNINativeInterface_ table = {
     m_FindClass, m_GetStaticMethodID, m_CallStaticObjectMethod, m_NewStringUTF, m_Throw, m_GetArrayLength,
     m_GetPrimitiveArrayCritical, m_ReleasePrimitiveArrayCritical, m_GetIntArrayElements, m_ReleaseIntArrayElements,
-    m_GetFloatArrayElements, m_ReleaseFloatArrayElements, m_SetIntArrayRegion};
+    m_GetFloatArrayElements, m_ReleaseFloatArrayElements, m_SetIntArrayRegion, m_GetStringUTFChars, m_ReleaseStringUTFChars};
 static JNIEnv the_env = &table;
 
 static jarray new_array(int elem, jsize len, const void* init) {
@@ -149,6 +171,7 @@ jlong BRIDGE(create)(JNIEnv*, jclass, jint);
 jint BRIDGE(destroy)(JNIEnv*, jclass, jlong);
 jint BRIDGE(loadDense)(JNIEnv*, jclass, jlong, jfloatArray, jlong, jint, jintArray, jfloatArray, jintArray);
 jint BRIDGE(init)(JNIEnv*, jclass, jlong, jint, jint, jfloat, jint, jint, jint, jint, jfloat, jlong);
+jint BRIDGE(loadLetorFile)(JNIEnv*, jclass, jlong, jstring, jboolean, jintArray, jintArray);
 jfloat BRIDGE(boostIter)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jdoubleArray, jintArray);
 jint BRIDGE(readScores)(JNIEnv*, jclass, jlong, jdoubleArray);
 jint BRIDGE(ensembleEval)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jintArray, jfloatArray, jfloatArray, jlong, jint, jfloatArray);
@@ -258,5 +281,49 @@ done:
     free_array(jx); free_array(jf); free_array(jl); free_array(jq);
     free_array(jni_); free_array(jnf); free_array(jnd); free_array(jnn); free_array(jsc);
     free_array(ani); free_array(anf); free_array(ato); free_array(aw); free_array(ax); free_array(ao);
+    return rc;
+}
+
+/*
+ * B200LambdaMART.initFromFile(path) + n_trees x boostIter: the file goes to the device through NativeBridge.loadLetorFile.
+ *   out: dims[3] = N, Q, maxFid; node_ints / node_floats / n_nodes / metric_out as in mock_train.
+ * Returns 0, or the ordinal (1..) of the native call after which a Java exception was pending.
+ */
+int mock_train_from_file(int device, const char* path, int must_have_rel, const int* features, int n_features, int n_leaves, int n_trees,
+                         int* dims, int* node_ints, float* node_floats, int* n_nodes, float* metric_out) {
+    JNIEnv* env = &the_env;
+    int step = 0, rc = 0;
+    int cap = 2 * n_leaves + 1;
+    jlong h = 0;
+    jarray jf = NULL, jd = NULL, jni_ = NULL, jnf = NULL, jnd = NULL, jnn = NULL;
+    jstring jpath = m_NewStringUTF(env, path);
+    step++;
+    h = BRIDGE(create)(env, NULL, device);
+    if (J.thrown) { rc = step; goto done; }
+    if (features) jf = new_array(4, n_features, features);
+    jd = new_array(4, 3, NULL);
+    step++;
+    BRIDGE(loadLetorFile)(env, NULL, h, jpath, (jboolean)must_have_rel, jf, jd);
+    if (J.thrown) { rc = step; goto done; }
+    memcpy(dims, jd->data, 3 * sizeof(int));
+    step++;
+    BRIDGE(init)(env, NULL, h, n_leaves, 1, 0.1f, 256, 0, 0, 10, 1.0f, 0);
+    if (J.thrown) { rc = step; goto done; }
+    jni_ = new_array(4, cap * 7, NULL);
+    jnf = new_array(4, cap * 2, NULL);
+    jnd = new_array(8, cap, NULL);
+    jnn = new_array(4, 1, NULL);
+    for (int t = 0; t < n_trees; t++) {
+        step++;
+        metric_out[t] = BRIDGE(boostIter)(env, NULL, h, jni_, jnf, jnd, jnn);
+        if (J.thrown) { rc = step; goto done; }
+        n_nodes[t] = ((int*)jnn->data)[0];
+        memcpy(node_ints + (size_t)t * cap * 7, jni_->data, sizeof(int) * (size_t)cap * 7);
+        memcpy(node_floats + (size_t)t * cap * 2, jnf->data, sizeof(float) * (size_t)cap * 2);
+    }
+done:
+    if (h) BRIDGE(destroy)(env, NULL, h);
+    free_array(jf); free_array(jd); free_array(jni_); free_array(jnf); free_array(jnd); free_array(jnn);
+    if (jpath) { free(jpath->pinned); free(jpath->data); free(jpath); }
     return rc;
 }

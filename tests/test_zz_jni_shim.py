@@ -65,7 +65,7 @@ def test_shim_exports_every_native_of_the_bridge_class(shim):
     java = open(os.path.join(ROOT, "jni", "java", "ciir", "umass", "edu", "learning", "tree", "NativeBridge.java")).read()
     import re
     natives = re.findall(r"static native \w+ (\w+)\(", java)
-    assert sorted(natives) == ["boostIter", "create", "destroy", "ensembleEval", "init", "loadDense", "readScores"]
+    assert sorted(natives) == ["boostIter", "create", "destroy", "ensembleEval", "init", "loadDense", "loadLetorFile", "readScores"]
     for n in natives:
         assert hasattr(shim, "Java_ciir_umass_edu_learning_tree_NativeBridge_" + n), n
 
@@ -126,3 +126,51 @@ def test_shim_training_equals_ctypes_binding_and_oracle(shim, kind, metric, k):
     ev = g.ensemble_eval(np.concatenate(all_nodes), off, np.full(T, 0.1, np.float32), Xe)
     assert np.array_equal(out["ev"], ev)
     g.close()
+
+
+def _train_from_file(lib, device, path, features=None, n_leaves=6, n_trees=3, must=False):
+    cap = 2 * n_leaves + 1
+    out = dict(dims=np.zeros(3, np.int32), ni=np.zeros((n_trees, cap, 7), np.int32), nf=np.zeros((n_trees, cap, 2), np.float32),
+               nn=np.zeros(n_trees, np.int32), m=np.zeros(n_trees, np.float32))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    f = None if features is None else np.ascontiguousarray(features, np.int32)
+    lib.mock_reset()
+    rc = lib.mock_train_from_file(C.c_int(device), os.fsencode(str(path)), C.c_int(1 if must else 0), None if f is None else p(f),
+                                  C.c_int(0 if f is None else len(f)), C.c_int(n_leaves), C.c_int(n_trees), p(out["dims"]), p(out["ni"]),
+                                  p(out["nf"]), p(out["nn"]), p(out["m"]))
+    return rc, out
+
+
+def test_shim_load_letor_file_error_paths(shim, tmp_path):
+    """create fails first on a machine without a GPU; with an impossible device ordinal everywhere.  The reader's own
+    errors (missing / malformed file) are checked where a context can exist (gpu test below)."""
+    rc, _ = _train_from_file(shim, 9999, tmp_path / "nope.txt")
+    assert rc == 1 and shim.mock_thrown() == 1 and shim.mock_outstanding_pins() == 0 and shim.mock_pin_errors() == 0
+
+
+@pytest.mark.gpu
+def test_shim_training_from_a_letor_file(shim, tmp_path):
+    from ranklib_b200.host import native, synth
+    X, label, qoff = synth.c1()
+    p = tmp_path / "c1.txt"
+    synth.write_letor(str(p), X[:500, :10], label[:500], qoff[:13])
+    for feats in (None, [3, 9, 1, 4]):
+        rc, out = _train_from_file(shim, 0, p, feats)
+        assert rc == 0, shim.mock_message()
+        assert shim.mock_outstanding_pins() == 0 and shim.mock_pin_errors() == 0
+        assert list(out["dims"]) == [480, 12, 10]          # 12 lists of 40 documents, 10 features
+        g = native.Context(0)
+        g.load_letor(str(p), features=feats)
+        g.init(native.make_params(n_leaves=6))
+        for t in range(3):
+            nodes, m = g.boost_iter()
+            n = int(out["nn"][t])
+            assert n == len(nodes) and np.float32(out["m"][t]) == np.float32(m)
+            assert np.array_equal(out["ni"][t, :n, 0], nodes["feature_id"]) and np.array_equal(out["ni"][t, :n, 2], nodes["threshold_idx"])
+            assert np.array_equal(out["nf"][t, :n, 1], nodes["output"]) and np.array_equal(out["nf"][t, :n, 0], nodes["threshold"])
+        g.close()
+    rc, _ = _train_from_file(shim, 0, tmp_path / "missing.txt")
+    assert rc == 2 and "readInput" in shim.mock_message().decode() and shim.mock_outstanding_pins() == 0
+    (tmp_path / "bad.txt").write_text("1 qid:1 0:1\n")
+    rc, _ = _train_from_file(shim, 0, tmp_path / "bad.txt")
+    assert rc == 2 and "less than or equal to zero" in shim.mock_message().decode()
