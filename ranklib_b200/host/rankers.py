@@ -557,6 +557,24 @@ class RFRanker(Ranker):
             s += e.eval(self._ctx, Xf).astype(np.float64)
         return s / len(self.ensembles)
 
+    def loadFromString(self, fullText):  # RFRanker.loadFromString (RFRanker.java:153-181): one Ensemble per <ensemble> block
+        self.ensembles = []
+        at = 0
+        while True:
+            a = fullText.find("<ensemble>", at)
+            if a < 0:
+                break
+            b = fullText.find("</ensemble>", a)
+            if b < 0:
+                raise RankLibError("Error in RFRanker::loadFromString(): unterminated <ensemble>")
+            self.ensembles.append(Ensemble(fullText[a:b + len("</ensemble>")]))
+            at = b + len("</ensemble>")
+        feats = set()
+        for e in self.ensembles:
+            feats.update(e.getFeatures())
+        self.features = np.array(sorted(feats), np.int32)
+        type(self).nBag = len(self.ensembles)
+
     def toString(self):  # RFRanker.toString (RFRanker.java:130-137)
         return "".join(e.toString() + "\n" for e in self.ensembles)
 
@@ -566,6 +584,28 @@ class RFRanker(Ranker):
                 f"## Feature-sampling = {java_float_str(cls.featureSamplingRate)}\n## No. of trees = {cls.nTrees}\n"
                 f"## No. of leaves = {cls.nTreeLeaves}\n## No. of threshold candidates = {cls.nThreshold}\n"
                 f"## Learning rate = {java_float_str(cls.learningRate)}\n\n" + self.toString())
+
+
+class Combiner:
+    """R/learning/Combiner.java:28-45: assembles one Random-Forests model from a directory of per-bag model files (the first
+    ensemble of each file, files named *.progress skipped).  The natural last step of a bag-parallel run whose processes
+    saved their bags separately.  File order: the reference takes File.list()'s (unspecified); sorted by name here."""
+
+    def combine(self, directory, outputFile):
+        import os
+        try:
+            with open(outputFile, "w", encoding="ascii") as out:
+                out.write("## " + RFRanker().name() + "\n")
+                for fn in sorted(os.listdir(directory)):
+                    if ".progress" in fn:
+                        continue
+                    r = RFRanker()
+                    r.loadFromString(open(os.path.join(directory, fn)).read())
+                    out.write(r.ensembles[0].toString())
+        except RankLibError:
+            raise
+        except Exception as e:
+            raise RankLibError(f"Error in Combiner::combine(): {e}")
 
 
 class RankerFactory:

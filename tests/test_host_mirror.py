@@ -117,3 +117,30 @@ def test_metric_scorer_factory():
     assert f.createScorer("P@5").metric == native.METRIC_PRECISION and f.createScorer("NDCG@3").getK() == 3
     with pytest.raises(R.RankLibError):
         f.createScorer("XYZ@3")
+
+
+def test_combiner_assembles_per_bag_files(tmp_path):
+    """Combiner.combine (R/learning/Combiner.java:28-45): "## Random Forests" + the first ensemble of every model file."""
+    saved = R.RFRanker.nBag
+    try:
+        d = tmp_path / "bags"
+        d.mkdir()
+        texts = []
+        for i in range(3):
+            nodes = np.zeros(3, native.NODE_DTYPE)
+            nodes[0] = (2 + i, 1, 0.5 * i, 3, 1, 2, 0, 10, 1.0)
+            nodes[1] = (-1, -1, 0, -1, -1, -1, 0.25 + i, 4, 0)
+            nodes[2] = (-1, -1, 0, -1, -1, -1, -1.0, 6, 0)
+            e = R.Ensemble()
+            e.add(R.RegressionTree(nodes), 0.1)
+            texts.append(e.toString())
+            (d / f"bag{i}.txt").write_text("## Random Forests\n## No. of bags = 1\n\n" + e.toString() + "\n")
+        (d / "bag1.txt.progress").write_text("garbage")
+        out = tmp_path / "rf.txt"
+        R.Combiner().combine(str(d), str(out))
+        assert out.read_text() == "## Random Forests\n" + "".join(texts)
+        rf = R.RFRanker()
+        rf.loadFromString(out.read_text())
+        assert len(rf.ensembles) == 3 and list(rf.features) == [2, 3, 4] and rf.toString() == "".join(t + "\n" for t in texts)
+    finally:
+        R.RFRanker.nBag = saved
