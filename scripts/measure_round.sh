@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # measure_round.sh — everything profiles/ needs from ONE gpurun call (1 GPU):
 #
-#   gpurun --timeout 900 -- 'bash scripts/measure_round.sh r2'
+#   gpurun --timeout 1800 -- 'bash scripts/measure_round.sh r2'
 #
 #   1. pytest -m gpu                                   -> gpurun_out/<tag>_tests.log
 #   2. python bench.py (default K/W)                   -> gpurun_out/<tag>_bench_default.json   (the judged line; NOT under a profiler)
@@ -9,6 +9,7 @@
 #   4. ncu launch list of a short bench run            -> gpurun_out/<tag>_launches.csv + <tag>_launch_summary.txt
 #   5. ncu --set full of the dominant kernels          -> gpurun_out/<tag>_full.ncu-rep + <tag>_ncu_full.txt + hist_root_traffic.json
 #   6. event timeline without a profiler               -> gpurun_out/<tag>_event_timeline.txt
+#   7. compute-sanitizer memcheck + racecheck (small)  -> gpurun_out/<tag>_memcheck.log, <tag>_racecheck.log
 # Afterwards, here:  cp gpurun_out/<tag>_{bench_default.json,bench_reference.json,launches.csv,launch_summary.txt,ncu_full.txt,event_timeline.txt} profiles/
 #                    cp gpurun_out/hist_root_traffic.json profiles/
 # Every step is bounded by its own timeout so that one hanging step cannot take the box (and a strike) with it.
@@ -32,4 +33,7 @@ RLB_NO_GRAPH=1 timeout 420 ncu --set full --clock-control none --import-source o
     -f -o "$OUT/${TAG}_full" python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_ncu_f.log" 2>&1
 python scripts/summarise_ncu.py "$OUT/${TAG}_full.ncu-rep" "$OUT/${TAG}_ncu_full.txt" "$OUT/hist_root_traffic.json" > /dev/null 2>&1
 step "6 timeline";   timeout 200 python scripts/trace_iter.py > "$OUT/${TAG}_event_timeline.txt" 2>&1; head -12 "$OUT/${TAG}_event_timeline.txt"
+step "7 compute-sanitizer (memcheck, then racecheck; small run, graph off)"
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_small.py > "$OUT/${TAG}_memcheck.log" 2>&1; echo "memcheck rc=$?"; tail -3 "$OUT/${TAG}_memcheck.log"
+timeout 420 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize_small.py > "$OUT/${TAG}_racecheck.log" 2>&1; echo "racecheck rc=$?"; tail -3 "$OUT/${TAG}_racecheck.log"
 step done

@@ -1,0 +1,44 @@
+"""A short run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
+
+    compute-sanitizer --tool memcheck  python scripts/sanitize_small.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_small.py
+
+C1 (1k docs x 50 features, private-histogram path) and a 12k-doc MSLR-shaped slice (tiled root-histogram kernel), two
+LambdaMART iterations each without the CUDA graph, one MART iteration, ERR as a second metric, Ensemble.eval, the metric
+scorer and the float-chain hook.  Prints SANITIZE_SMALL DONE when every call returned RLB_OK."""
+import os
+import sys
+
+os.environ.setdefault("RLB_NO_GRAPH", "1")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+from ranklib_b200.host import native, synth  # noqa: E402
+
+
+def run(X, label, qoff, iters, **kw):
+    g = native.Context(0)
+    g.load_dense(X, label, qoff)
+    g.init(native.make_params(**kw))
+    trees = []
+    for _ in range(iters):
+        nodes, m = g.boost_iter()
+        trees.append(nodes)
+    Xe = np.zeros((X.shape[0], X.shape[1] + 1), np.float32)
+    Xe[:, 1:] = X
+    off = np.cumsum([0] + [len(t) for t in trees]).astype(np.int32)
+    s = g.ensemble_eval(np.concatenate(trees), off, np.full(len(trees), 0.1, np.float32), Xe)
+    g.score_metric(s.astype(np.float64), label, qoff)
+    g.float_chain(np.random.default_rng(1).normal(size=5000))
+    g.close()
+    return m
+
+
+X, label, qoff = synth.c1()
+print("c1 LambdaMART", run(X, label, qoff, 2))
+print("c1 MART", run(X, label, qoff, 1, kind=native.KIND_MART))
+print("c1 ERR@10", run(X, label, qoff, 1, metric=native.METRIC_ERR))
+X, label, qoff = synth.c2(0.01)
+print("mslr slice", run(X, label, qoff, 2))
+print("SANITIZE_SMALL DONE")
