@@ -88,6 +88,7 @@ public class B200LambdaMART extends LambdaMART {
         final int[] qoff = new int[samples.size() + 1];
         martSamples = new DataPoint[n];
         modelScores = new double[n];
+        impacts = new double[nf]; // never updated by the reference either (SURVEY.md Q1); RFRanker.learn reads it
         int at = 0;
         for (int q = 0; q < samples.size(); q++) {
             final RankList rl = samples.get(q);
@@ -142,6 +143,7 @@ public class B200LambdaMART extends LambdaMART {
             }
         }
         modelScores = new double[dims[0]];
+        impacts = new double[features.length];
         NativeBridge.init(handle, nTreeLeaves, minLeafSupport, learningRate, nThreshold, kind(), metricCode(scorer),
                 scorer.getK(), FeatureHistogram.samplingRate, seed);
     }
