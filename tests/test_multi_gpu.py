@@ -137,3 +137,14 @@ def test_gloo_world2_rf_bag_parallel_equals_single_process():
         assert p.exitcode == 0
     for rank, text, ids in got:
         assert ids == list(range(7)) and text == single.toString(), rank
+
+
+@pytest.mark.gpu
+def test_two_gpus_rf_bag_parallel_equals_one_process(built):
+    if native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29655", os.path.join(ROOT, "scripts", "rf_bag_parallel.py"), "--scale", "0.01", "--bags", "6", "--leaves", "20",
+           "--check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert "RF_BAG_PARALLEL CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
