@@ -65,6 +65,36 @@ def read_letor(path, must_have_rel_doc=False, nthreads=0):
     return RankLists(X, label, qoff, fids, qids)
 
 
+def read_feature(featureDefFile):
+    """FeatureManager.readFeature (R/features/FeatureManager.java:267-292): the -feature file — one feature id per line
+    (anything after a TAB is a comment), blank lines and lines starting with '#' skipped."""
+    try:
+        with open(featureDefFile, encoding="utf-8") as fh:
+            lines = [ln.strip(" \t\n\r\x0b\x0c") for ln in fh.read().replace("\r\n", "\n").replace("\r", "\n").split("\n")]
+    except OSError as e:
+        raise RankLibError(f"Error in FeatureManager::readFeature(): {e}")
+    fids = [ln.split("\t")[0].strip() for ln in lines if ln and not ln.startswith("#")]
+    try:
+        return np.array([int(f) for f in fids], np.int32)
+    except ValueError as e:          # Integer.parseInt -> NumberFormatException (unchecked in the reference)
+        raise RankLibError(f"Error in FeatureManager::readFeature(): {e}")
+
+
+def read_letor_files(paths, must_have_rel_doc=False):
+    """FeatureManager.readInput(List<String>) (R/features/FeatureManager.java:247-258): the rank lists of several files
+    appended in order."""
+    sets = [read_letor(p, must_have_rel_doc) for p in paths]
+    F = max(s.X.shape[1] for s in sets)
+    X = np.full((sum(s.X.shape[0] for s in sets), F), np.nan, np.float32)
+    at, qoff, qids = 0, [0], []
+    for s in sets:
+        X[at:at + s.X.shape[0], :s.X.shape[1]] = s.X
+        qoff.extend((s.qoff[1:] + at).tolist())
+        qids.extend(s.qids)
+        at += s.X.shape[0]
+    return RankLists(X, np.concatenate([s.label for s in sets]), np.array(qoff, np.int32), None, qids)
+
+
 # ---------------------------------------------------------------------------------------------------
 # java.util.Random (JDK specification) — replaces the reference's unseeded `new Random()` (SURVEY.md F7)
 # ---------------------------------------------------------------------------------------------------

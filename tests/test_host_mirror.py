@@ -144,3 +144,20 @@ def test_combiner_assembles_per_bag_files(tmp_path):
         assert len(rf.ensembles) == 3 and list(rf.features) == [2, 3, 4] and rf.toString() == "".join(t + "\n" for t in texts)
     finally:
         R.RFRanker.nBag = saved
+
+
+def test_read_feature_file_and_multiple_inputs(tmp_path):
+    f = tmp_path / "features.txt"
+    f.write_text("# features to use\n3\tdescription of three\n\n 1 \r\n12\n")
+    assert list(R.read_feature(str(f))) == [3, 1, 12]
+    f.write_text("3\nabc\n")
+    with pytest.raises(R.RankLibError, match="readFeature"):
+        R.read_feature(str(f))
+    with pytest.raises(R.RankLibError, match="readFeature"):
+        R.read_feature(str(tmp_path / "missing.txt"))
+    (tmp_path / "a.txt").write_text("1 qid:1 1:0.5 2:1\n0 qid:1 1:0.25\n")
+    (tmp_path / "b.txt").write_text("2 qid:7 3:4\n")
+    rl = R.read_letor_files([str(tmp_path / "a.txt"), str(tmp_path / "b.txt")])
+    assert rl.size() == 2 and rl.qids == ["1", "7"] and list(rl.qoff) == [0, 2, 3] and rl.X.shape == (3, 3)
+    assert rl.X[0, 1] == 1 and np.isnan(rl.X[1, 1]) and np.isnan(rl.X[0, 2]) and rl.X[2, 2] == 4 and np.isnan(rl.X[2, 0])
+    assert list(rl.label) == [1, 0, 2]
