@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # measure_round.sh — everything profiles/ needs from ONE gpurun call (1 GPU):
 #
-#   gpurun --timeout 1800 -- 'bash scripts/measure_round.sh r2'
+#   gpurun --timeout 2700 -- 'bash scripts/measure_round.sh r2'
 #
 #   1. pytest -m gpu                                   -> gpurun_out/<tag>_tests.log
 #   2. python bench.py (default K/W)                   -> gpurun_out/<tag>_bench_default.json   (the judged line; NOT under a profiler)
@@ -10,6 +10,7 @@
 #   5. ncu --set full of the dominant kernels          -> gpurun_out/<tag>_full.ncu-rep + <tag>_ncu_full.txt + hist_root_traffic.json
 #   6. event timeline without a profiler               -> gpurun_out/<tag>_event_timeline.txt
 #   7. compute-sanitizer memcheck + racecheck (small)  -> gpurun_out/<tag>_memcheck.log, <tag>_racecheck.log
+#   8. GPU vs oracle in lockstep on the FULL workload  -> gpurun_out/<tag>_full_size_parity.txt
 # Afterwards, here:  cp gpurun_out/<tag>_{bench_default.json,bench_reference.json,launches.csv,launch_summary.txt,ncu_full.txt,event_timeline.txt} profiles/
 #                    cp gpurun_out/hist_root_traffic.json profiles/
 # Every step is bounded by its own timeout so that one hanging step cannot take the box (and a strike) with it.
@@ -36,4 +37,6 @@ step "6 timeline";   timeout 200 python scripts/trace_iter.py > "$OUT/${TAG}_eve
 step "7 compute-sanitizer (memcheck, then racecheck; small run, graph off)"
 timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_small.py > "$OUT/${TAG}_memcheck.log" 2>&1; echo "memcheck rc=$?"; tail -3 "$OUT/${TAG}_memcheck.log"
 timeout 420 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize_small.py > "$OUT/${TAG}_racecheck.log" 2>&1; echo "racecheck rc=$?"; tail -3 "$OUT/${TAG}_racecheck.log"
+step "8 full-size lockstep with the oracle (north_star acceptance line)"
+timeout 900 python scripts/full_size_parity.py --trees 10 > "$OUT/${TAG}_full_size_parity.txt" 2>&1; tail -4 "$OUT/${TAG}_full_size_parity.txt"
 step done
