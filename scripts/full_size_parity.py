@@ -6,7 +6,7 @@ The tests compare the two at sizes the oracle finishes in seconds and check the 
 this script is the direct check of north_star's acceptance line — "NDCG@10 within 1e-4 of the reference on identical
 synthetic input" — at the size the bench runs.  Per tree: same partition of the training samples into leaves, identical
 (feature, threshold) of every split, leaf outputs <= 1e-5 relative, NDCG@10-T equal at 4 decimals.  About 1 s of oracle time
-per tree on 16 cores plus ~1 min of oracle init.  Prints FULL_SIZE_PARITY PASS / FAIL.
+per tree and ~10 s of oracle init on 8-16 cores.  Prints FULL_SIZE_PARITY PASS / FAIL.
 """
 import argparse
 import os
