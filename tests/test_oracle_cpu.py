@@ -271,3 +271,32 @@ def test_lambda_known_answers_from_the_published_formulas(built):
     lr = float(np.float32(0.1))
     np.testing.assert_array_equal(o.read("SCORE"), [2 * lr, -2 * lr, 2 * lr, -2 * lr])
     assert metric == np.float32(1.0)
+
+
+def test_metric_scores_known_answers(built):
+    """score() of every MetricScorer on ranked label lists, against values worked out by hand from the published
+    definitions (ERR: Chapelle et al. 2009 with R = (2^l - 1) / 16; AP; P@k; RR@k; Best@k; DCG / NDCG with RankLib's
+    gain 2^l - 1 and discount 1 / log2(rank + 2))."""
+    from math import log2
+    from ranklib_b200.host import native as N
+    ms = orc.metric_score
+    # ERR@10 of (1, 0, 2): 1/16 at rank 1, nothing at rank 2, (3/16)(15/16) / 3 at rank 3
+    assert ms([1, 0, 2], N.METRIC_ERR, 10) == 1 / 16 + (3 / 16) * (15 / 16) / 3
+    assert ms([1, 0, 2], N.METRIC_ERR, 2) == 1 / 16                              # the cut-off drops rank 3
+    assert ms([4], N.METRIC_ERR, 10) == 15 / 16
+    # MAP of (1, 0, 1): (1/1 + 2/3) / 2; no relevant document -> 0
+    assert ms([1, 0, 1], N.METRIC_MAP, 0) == (1 / 1 + 2 / 3) / 2
+    assert ms([0, 0], N.METRIC_MAP, 0) == 0.0
+    # P@k counts labels > 0 among the first min(k, n); k larger than the list -> the list length
+    assert ms([1, 0, 1], N.METRIC_PRECISION, 2) == 0.5
+    assert ms([1, 0, 1], N.METRIC_PRECISION, 10) == 2 / 3
+    # RR@k: 1 / rank of the first relevant document within the cut-off (a float division in the reference)
+    assert ms([0, 0, 3], N.METRIC_RR, 10) == float(np.float32(1.0) / np.float32(3))
+    assert ms([0, 0, 3], N.METRIC_RR, 2) == 0.0
+    # Best@k: the highest label among the first k
+    assert ms([1, 3, 2], N.METRIC_BEST, 2) == 3.0 and ms([1, 3, 4], N.METRIC_BEST, 2) == 3.0 and ms([1, 3, 4], N.METRIC_BEST, 10) == 4.0
+    # DCG@2 and NDCG@2 of (1, 2, 0): gains 1, 3; ideal order (2, 1, 0)
+    dcg = 1 / log2(2) + 3 / log2(3)
+    assert abs(ms([1, 2, 0], N.METRIC_DCG, 2) - dcg) < 1e-15
+    assert abs(ms([1, 2, 0], N.METRIC_NDCG, 2) - dcg / (3 / log2(2) + 1 / log2(3))) < 1e-15
+    assert ms([0, 0, 0], N.METRIC_NDCG, 10) == 0.0                                # ideal DCG 0 -> 0
