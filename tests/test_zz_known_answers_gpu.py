@@ -96,3 +96,29 @@ def test_load_letor_file_equals_load_dense(built, tmp_path):
             assert na.tobytes() == nb.tobytes() and ma == mb
         a.close()
         b.close()
+
+
+@pytest.mark.gpu
+def test_metric_scores_known_answers_on_the_device(built):
+    """rlb_score_metric against the hand-derived values of tests/test_oracle_cpu.py::test_metric_scores_known_answers
+    (one query per case, scores strictly descending so that the ranking is the given order)."""
+    g = native.Context(0)
+
+    def ms(label, metric, k):
+        n = len(label)
+        return g.score_metric(np.arange(n, 0, -1, dtype=np.float64), np.array(label, np.float32), np.array([0, n], np.int32), metric, k)
+
+    assert ms([1, 0, 2], native.METRIC_ERR, 10) == 1 / 16 + (3 / 16) * (15 / 16) / 3
+    assert ms([1, 0, 2], native.METRIC_ERR, 2) == 1 / 16
+    assert ms([1, 0, 1], native.METRIC_MAP, 0) == (1 / 1 + 2 / 3) / 2
+    assert ms([0, 0], native.METRIC_MAP, 0) == 0.0
+    assert ms([1, 0, 1], native.METRIC_PRECISION, 2) == 0.5
+    assert ms([1, 0, 1], native.METRIC_PRECISION, 10) == 2 / 3
+    assert ms([0, 0, 3], native.METRIC_RR, 10) == float(np.float32(1.0) / np.float32(3))
+    assert ms([0, 0, 3], native.METRIC_RR, 2) == 0.0
+    assert ms([1, 3, 4], native.METRIC_BEST, 2) == 3.0 and ms([1, 3, 4], native.METRIC_BEST, 10) == 4.0
+    dcg = 1 / log2(2) + 3 / log2(3)
+    assert abs(ms([1, 2, 0], native.METRIC_DCG, 2) - dcg) < 1e-15
+    assert abs(ms([1, 2, 0], native.METRIC_NDCG, 2) - dcg / (3 / log2(2) + 1 / log2(3))) < 1e-15
+    assert ms([0, 0, 0], native.METRIC_NDCG, 10) == 0.0
+    g.close()
