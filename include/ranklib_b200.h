@@ -100,6 +100,8 @@ typedef struct rlb_node {
 #define RLB_READ_ROOT_COUNT   7 /* int32[F][RLB_MAX_BINS]  cumulative root count (padded)   */
 #define RLB_READ_ROOT_STATS   8 /* double[2]  sumResponse, sqSumResponse of the root        */
 #define RLB_READ_NODE_ID      9 /* int32[N]   node index (rlb_node array) of each sample in the last tree */
+#define RLB_READ_SPLIT_S     10 /* double[(n_nodes-1)/2] S = sL^2/cL + sR^2/cR of every split of the last tree, in split
+                                   order (FeatureHistogram.java:253; the parity tests compare it with the oracle's) */
 
 const char* rlb_last_error(const rlb_ctx* ctx);
 int rlb_version(void);
@@ -125,6 +127,23 @@ int rlb_comm_init(rlb_ctx* ctx, int rank, int world, const uint8_t id[128]);
  * `samples` into martSamples in LambdaMART.init (R/learning/tree/LambdaMART.java:71-91). */
 int rlb_load_dense(rlb_ctx* ctx, const float* X, int64_t N, int32_t F, const int32_t* feature_ids,
                    const float* label, const int32_t* qoff, int32_t Q);
+
+/* Random Forests (R/learning/tree/RFRanker.java:80-85, R/learning/Sampler.java:21-38): make this context the bag that
+ * consists of the lists picks[0], picks[1], ... (indices into src's training set, repetitions allowed, in that order) by a
+ * device-to-device gather from `src`, a context on the same device that holds the whole training set (rlb_load_dense).
+ * Equivalent to rlb_load_dense on the gathered rows, without host work or a re-upload per bag; buffers of this context
+ * are reused from bag to bag.  rlb_lambdamart_init then derives the bag's own thresholds as LambdaMART.init does. */
+int rlb_load_bag(rlb_ctx* ctx, const rlb_ctx* src, const int32_t* picks, int32_t n_picks);
+
+/* Ranker.setValidationSet (R/learning/Ranker.java:67-69) + the cached modelScoresOnValidation of LambdaMART.init
+ * (R/learning/tree/LambdaMART.java:152-158): the validation lists (same F columns as the training set) stay on the
+ * device; every rlb_boost_iter then adds the new tree's outputs to their cached scores and evaluates the metric on them
+ * (LambdaMART.java:228-237, computeModelScoreOnValidation :485-518) with no host traffic.  Call after rlb_load_dense,
+ * before or after rlb_lambdamart_init (which zeroes the cached scores).  N GPUs: every rank loads the WHOLE validation set. */
+int rlb_load_validation(rlb_ctx* ctx, const float* X, int64_t N, int32_t F, const float* label,
+                        const int32_t* qoff, int32_t Q);
+/* the value of computeModelScoreOnValidation() after the last rlb_boost_iter (a Java float) */
+int rlb_valid_metric(rlb_ctx* ctx, float* out);
 
 /* Optional: impose candidate thresholds instead of deriving them from the loaded data (needed
  * when the data of this context is only a shard: thresholds must come from the whole set).
@@ -166,6 +185,16 @@ int rlb_boost_iter(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_no
 int rlb_boost_iters(rlb_ctx* ctx, int32_t n_iters, rlb_node* nodes_out, int32_t cap,
                     int32_t* n_nodes_out, float* train_metric_out);
 
+/* LambdaMART.learn's loop (LambdaMART.java:180-251) in ONE boundary crossing: up to n_trees iterations of rlb_boost_iter
+ * with the reference's best-model tracking (`score > bestScoreOnValidationData`, :240-243, only with a validation set) and
+ * early stop (`m - bestModelOnValidation > nRoundToStopEarly`, :248).  No roll-back: the caller drops the trees behind
+ * *best_model as :254-256 does.  nodes_out[n_trees][cap], n_nodes_out / train_metric_out / valid_metric_out[n_trees] (any
+ * may be NULL); *n_done = iterations run; *best_model = bestModelOnValidation (Integer.MAX_VALUE - 2 if never set);
+ * *best_valid = bestScoreOnValidationData as tracked inside the loop. */
+int rlb_learn(rlb_ctx* ctx, int32_t n_trees, int32_t n_round_to_stop_early, rlb_node* nodes_out, int32_t cap,
+              int32_t* n_nodes_out, float* train_metric_out, float* valid_metric_out, int32_t* n_done,
+              int32_t* best_model, double* best_valid);
+
 /* Copy internal state out for parity tests (see RLB_READ_*). `bytes` is the size of dst. */
 int rlb_read(rlb_ctx* ctx, int32_t what, void* dst, int64_t bytes);
 
@@ -194,6 +223,14 @@ int rlb_profile_read(rlb_ctx* ctx, double out[8]);
 int rlb_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* tree_off,
                       int32_t n_trees, const float* weights, const float* X, int64_t N,
                       int32_t n_cols, float* out);
+
+/* scorer.score(rank(samples)) (LambdaMART.java:259,263 -> Ranker.rank, R/learning/Ranker.java:88-103 ->
+ * Ensemble.eval; MetricScorer.score, R/metric/MetricScorer.java:46-52) on a set that is already RESIDENT on the device:
+ * which = 0 the training set, 1 the validation set.  The model is given as node arrays like rlb_ensemble_eval (split
+ * features by feature_id); the matrix is not uploaded again.  scores_out (float[N], may be NULL) receives Ensemble.eval
+ * of every document, *metric_out (may be NULL) the double mean of the context's metric@k over the lists. */
+int rlb_score_resident(rlb_ctx* ctx, int32_t which, const rlb_node* nodes, const int32_t* tree_off,
+                       int32_t n_trees, const float* weights, float* scores_out, double* metric_out);
 
 /* MetricScorer.score(List<RankList>) on caller-provided scores (R/metric/MetricScorer.java:46-52
  * + NDCGScorer.java:103-129): ranks each query by score (stable, descending) and returns the

@@ -127,6 +127,26 @@ class Oracle:
         assert self.lib.orc_read(self.h, w, _p(out), C.c_int64(out.nbytes)) == 0
         return out
 
+    def set_validation(self, X, label, qoff):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        label = np.ascontiguousarray(label, dtype=np.float32)
+        qoff = np.ascontiguousarray(qoff, dtype=np.int32)
+        assert self.lib.orc_set_validation(self.h, _p(X), C.c_int64(X.shape[0]), X.shape[1], _p(label), _p(qoff), len(qoff) - 1) == 0
+
+    def learn(self, n_trees, n_round_to_stop_early):
+        """LambdaMART.learn's loop (LambdaMART.java:180-251): (trees, train metrics, validation metrics, bestModelOnValidation,
+        bestScoreOnValidationData)."""
+        nodes = np.zeros((max(n_trees, 1), self.cap), NODE_DTYPE)
+        nn = np.zeros(max(n_trees, 1), np.int32)
+        tm = np.zeros(max(n_trees, 1), np.float32)
+        vm = np.zeros(max(n_trees, 1), np.float32)
+        done, best = C.c_int32(), C.c_int32()
+        bv = C.c_double()
+        assert self.lib.orc_learn(self.h, n_trees, n_round_to_stop_early, _p(nodes), self.cap, _p(nn), _p(tm), _p(vm),
+                                  C.byref(done), C.byref(best), C.byref(bv)) == 0
+        k = done.value
+        return [nodes[i, :nn[i]].copy() for i in range(k)], tm[:k].copy(), vm[:k].copy(), best.value, bv.value
+
     def split_S(self):
         out = np.zeros(self.cap, np.float64)
         n = self.lib.orc_split_S(self.h, _p(out), self.cap)

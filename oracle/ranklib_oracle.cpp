@@ -440,6 +440,13 @@ struct orc_ctx {
     std::vector<int> leaves;  // node indices, left-first DFS (Split.leaves, Split.java:100-113)
     std::vector<double> splitS;  // S of every successful split of the last tree, in split order
     int64_t rowsScanned = 0;
+    // validation set (Ranker.setValidationSet; LambdaMART.java:152-158): raw values in the training set's columns
+    bool haveValid = false;
+    int64_t Nv = 0;
+    int Qv = 0;
+    std::vector<float> VX, vlabel;
+    std::vector<int> vqoff;
+    std::vector<double> modelScoresOnValidation;
     float fval(int64_t k, int f) const {  // DenseDataPoint.getFeatureValue (DenseDataPoint.java:21-32)
         float v = X[(size_t)k * F + f];
         return std::isnan(v) ? 0.f : v;
@@ -926,6 +933,36 @@ static float train_metric(orc_ctx* c) {
     return s;
 }
 
+// RegressionTree.eval -> Split.eval (RegressionTree.java:93-95, Split.java:115-125) on a validation data point
+static double tree_eval_valid(const orc_ctx* c, int64_t k) {
+    int n = 0;
+    while (c->nodes[n].featureID != -1) {
+        float v = c->VX[(size_t)k * c->F + c->nodes[n].featureIdx];   // DenseDataPoint.getFeatureValue: NaN -> 0
+        if (std::isnan(v)) v = 0.f;
+        n = (v <= c->nodes[n].threshold) ? c->nodes[n].left : c->nodes[n].right;
+    }
+    return (double)(float)c->nodes[n].avgLabel;   // Split.avgLabel is a float
+}
+
+// LambdaMART.java:228-237: update the cached validation scores with the new tree, then computeModelScoreOnValidation
+// (:485-518): per list a stable descending sort of its cached scores, scorer.score, FLOAT running sum, / list count
+static float valid_step(orc_ctx* c) {
+    const float learningRate = c->prm.learning_rate;
+    for (int64_t k = 0; k < c->Nv; k++) c->modelScoresOnValidation[k] += learningRate * tree_eval_valid(c, k);
+    float score = 0;
+    std::vector<int> idx;
+    std::vector<float> rel;
+    for (int q = 0; q < c->Qv; q++) {
+        const int cur = c->vqoff[q];
+        const int n = c->vqoff[q + 1] - cur;
+        stable_argsort(c->modelScoresOnValidation.data(), cur, n, false, idx);
+        rel.resize(n);
+        for (int i = 0; i < n; i++) rel[i] = c->vlabel[idx[i]];
+        score = (float)((double)score + metric_score(rel, c->prm.metric, c->prm.metric_k));
+    }
+    return score / c->Qv;
+}
+
 static int export_nodes(orc_ctx* c, rlb_node* out, int cap, int* n_nodes) {
     const int n = (int)c->nodes.size();
     if (n_nodes) *n_nodes = n;
@@ -1011,6 +1048,57 @@ int orc_boost_iter(orc_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_node
     float m = train_metric(c);
     if (metric) *metric = m;
     return rc;
+}
+
+int orc_set_validation(orc_ctx* c, const float* X, int64_t N, int32_t F, const float* label, const int32_t* qoff, int32_t Q) {
+    if (F != c->F || N <= 0 || Q <= 0) return RLB_E_INVALID;
+    c->Nv = N;
+    c->Qv = Q;
+    c->VX.assign(X, X + (size_t)N * F);
+    c->vlabel.assign(label, label + N);
+    c->vqoff.assign(qoff, qoff + Q + 1);
+    c->modelScoresOnValidation.assign(N, 0.0);   // LambdaMART.java:152-158
+    c->haveValid = true;
+    return RLB_OK;
+}
+
+// LambdaMART.learn's loop (LambdaMART.java:180-251): boosting iterations with the validation-based best-model
+// tracking (:240-243) and the early stop (:248).  Same outputs as rlb_learn.
+int orc_learn(orc_ctx* c, int32_t n_trees, int32_t n_round_to_stop_early, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes_out,
+              float* train_metric_out, float* valid_metric_out, int32_t* n_done, int32_t* best_model, double* best_valid) {
+    int bestModelOnValidation = 2147483647 - 2;   // LambdaMART.java:50
+    double bestScoreOnValidationData = 0.0;       // Ranker.java:43
+    int m = 0;
+    for (; m < n_trees; m++) {
+        compute_pseudo_responses(c);
+        hist_update(c);
+        tree_fit(c);
+        update_tree_output(c);
+        update_scores(c);
+        int32_t n = 0;
+        if (nodes_out) {
+            if (int rc = export_nodes(c, nodes_out + (size_t)m * cap, cap, &n)) return rc;
+        }
+        if (n_nodes_out) n_nodes_out[m] = (int32_t)c->nodes.size();
+        const float tm = train_metric(c);
+        if (train_metric_out) train_metric_out[m] = tm;
+        if (c->haveValid) {
+            const double score = valid_step(c);
+            if (valid_metric_out) valid_metric_out[m] = (float)score;
+            if (score > bestScoreOnValidationData) {
+                bestScoreOnValidationData = score;
+                bestModelOnValidation = m;   // ensemble.treeCount() - 1
+            }
+        }
+        if ((long long)m - (long long)bestModelOnValidation > (long long)n_round_to_stop_early) {
+            m++;
+            break;
+        }
+    }
+    *n_done = m;
+    if (best_model) *best_model = bestModelOnValidation;
+    if (best_valid) *best_valid = bestScoreOnValidationData;
+    return RLB_OK;
 }
 
 // the timed CPU-baseline loop: n_iters passes of the boosting loop body with no export

@@ -295,6 +295,7 @@ int rlb_set_thresholds(rlb_ctx* c, const float* thr, const int32_t* n_thr) {
     c->h_thr.assign(thr, thr + (size_t)c->F * RLB_T);
     c->h_nthr.assign(n_thr, n_thr + c->F);
     c->have_thr = true;
+    c->thr_user = true;
     return RLB_OK;
 }
 
@@ -446,6 +447,65 @@ int rlb_boost_iter(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_node
     return RLB_OK;
 }
 
+int rlb_load_validation(rlb_ctx* c, const float* X, int64_t N, int32_t F, const float* label, const int32_t* qoff, int32_t Q) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_load_validation(c, X, N, F, label, qoff, Q);
+}
+
+int rlb_valid_metric(rlb_ctx* c, float* out) {
+    if (int rc = check_ready(c, "rlb_valid_metric")) return rc;
+    if (!c->have_valid || !out) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_valid_metric", "no validation set loaded");
+        return RLB_E_INVALID;
+    }
+    *out = c->hState->valid_metric;
+    return RLB_OK;
+}
+
+int rlb_score_resident(rlb_ctx* c, int32_t which, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees,
+                       const float* weights, float* scores_out, double* metric_out) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_score_resident(c, which, nodes, tree_off, n_trees, weights, scores_out, metric_out);
+}
+
+int rlb_load_bag(rlb_ctx* c, const rlb_ctx* src, const int32_t* picks, int32_t n_picks) {
+    if (!c) return RLB_E_INVALID;
+    return rlb_impl_load_bag(c, src, picks, n_picks);
+}
+
+// LambdaMART.learn's loop (LambdaMART.java:180-251) with the reference's best-model rule and early stop
+int rlb_learn(rlb_ctx* c, int32_t n_trees, int32_t n_round_to_stop_early, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes_out,
+              float* train_metric_out, float* valid_metric_out, int32_t* n_done, int32_t* best_model, double* best_valid) {
+    if (int rc = check_ready(c, "rlb_learn")) return rc;
+    if (n_trees < 0 || !n_done) return RLB_E_INVALID;
+    int bestModel = 2147483647 - 2;   // LambdaMART.bestModelOnValidation (LambdaMART.java:50)
+    double bestScore = 0.0;           // Ranker.bestScoreOnValidationData (Ranker.java:43)
+    int m = 0;
+    for (; m < n_trees; m++) {
+        int32_t n = 0;
+        float tm = 0.f;
+        if (int rc = rlb_boost_iter(c, nodes_out ? nodes_out + (size_t)m * cap : nullptr, cap, &n, &tm)) return rc;
+        if (n_nodes_out) n_nodes_out[m] = n;
+        if (train_metric_out) train_metric_out[m] = tm;
+        if (c->have_valid) {
+            const double score = (double)c->hState->valid_metric;   // `final double score = computeModelScoreOnValidation()` (a float)
+            if (valid_metric_out) valid_metric_out[m] = c->hState->valid_metric;
+            if (score > bestScore) {
+                bestScore = score;
+                bestModel = m;   // ensemble.treeCount() - 1
+            }
+        }
+        if ((long long)m - (long long)bestModel > (long long)n_round_to_stop_early) {   // LambdaMART.java:248
+            m++;
+            break;
+        }
+    }
+    *n_done = m;
+    if (best_model) *best_model = bestModel;
+    if (best_valid) *best_valid = bestScore;
+    return RLB_OK;
+}
+
 int rlb_boost_iters(rlb_ctx* c, int32_t n_iters, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes_out,
                     float* train_metric_out) {
     if (int rc = check_ready(c, "rlb_boost_iters")) return rc;
@@ -543,6 +603,21 @@ int rlb_read(rlb_ctx* c, int32_t what, void* dst, int64_t bytes) {
         case RLB_READ_ROOT_COUNT: {
             if (!need((int64_t)F * RLB_T * 4)) return RLB_E_INVALID;
             RLB_CUDA(c, cudaMemcpy(dst, c->dHistCnt, c->hist_stride * 4, cudaMemcpyDeviceToHost));
+            return RLB_OK;
+        }
+        case RLB_READ_SPLIT_S: {
+            // S of every successful split of the last tree in split order (split k created nodes 2k+1, 2k+2)
+            if (!c->tree_ready) {
+                rlb_set_error(c, RLB_E_INVALID, "rlb_read", "no fitted tree");
+                return RLB_E_INVALID;
+            }
+            RLB_CUDA(c, cudaMemcpy(c->hState, c->dState, sizeof(DevState), cudaMemcpyDeviceToHost));
+            const int n = c->hState->n_nodes;
+            if (!need((int64_t)((n - 1) / 2) * 8)) return RLB_E_INVALID;
+            for (int i = 0; i < n; i++) {
+                const NodeRec& r = c->hState->nodes[i];
+                if (r.feature_idx >= 0 && r.left >= 1 && (r.left - 1) / 2 < (n - 1) / 2) ((double*)dst)[(r.left - 1) / 2] = r.split_S;
+            }
             return RLB_OK;
         }
         case RLB_READ_ROOT_STATS: {

@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
                                                 const double* __restrict__ disc, const double* __restrict__ idealIn,
                                                 int32_t* __restrict__ rankDoc, double* __restrict__ lambda,
                                                 double* __restrict__ weight, double* __restrict__ qmetric,
-                                                DevState* __restrict__ st, const int32_t* __restrict__ qlist) {
+                                                DevState* __restrict__ st, const int32_t* __restrict__ qlist,
+                                                double* __restrict__ auxG, int auxCap) {
     __shared__ double sRaw[QCAP];
     __shared__ double sScore[QCAP];
     __shared__ float sLabel[QCAP];
@@ -390,6 +391,10 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
     const bool generic = metric > RLB_METRIC_DCG;
     const int kparam = cutoff;                       // MetricScorer.k as the scorer itself uses it
     const int cut = metric_cutoff(metric, cutoff);   // LambdaMART's loop guard (LambdaMART.java:362,375)
+    // queries above QCAP documents keep the metric_prologue arrays of the generic metrics in this CTA's slice of global
+    // memory (2 * auxCap doubles + auxCap ints) — swapChange has no size limit in the reference (ERRScorer.java:76-115)
+    double* const gAuxD = auxG ? auxG + (size_t)blockIdx.x * 3 * auxCap : nullptr;
+    int* const gAuxI = auxG ? reinterpret_cast<int*>(gAuxD + 2 * (size_t)auxCap) : nullptr;
     double thrMax = 0.0;
     for (int qi = blockIdx.x; qi < Q; qi += gridDim.x) {
         const int q = qlist ? qlist[qi] : qi;
@@ -461,9 +466,12 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
                     qmetric[q] = m;
                 }
             }
-            if (LAMBDA && generic && small) {
+            if (LAMBDA && generic && (small || gAuxD)) {
                 QAux ax;
-                metric_prologue(metric, cutoff, n, L, sAuxD, sAuxI, QCAP, ax);
+                if (small)
+                    metric_prologue(metric, cutoff, n, L, sAuxD, sAuxI, QCAP, ax);
+                else
+                    metric_prologue(metric, cutoff, n, L, gAuxD, gAuxI, auxCap, ax);
                 sAx = ax;
             }
         }
@@ -471,8 +479,11 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
             __syncthreads();
             const double ideal = sIdeal;
             const bool ndcg = (metric == RLB_METRIC_NDCG);
-            // generic metrics keep their per-query arrays in shared memory: queries above QCAP documents are refused at init
-            const bool have = generic ? small : (!ndcg || ideal > 0.0);
+            // generic metrics keep their per-query arrays in shared memory, or in global memory above QCAP documents
+            const bool have = generic ? (small || gAuxD != nullptr) : (!ndcg || ideal > 0.0);
+            const double* const pAuxD = small ? sAuxD : gAuxD;
+            const int* const pAuxI = small ? sAuxI : gAuxI;
+            const int pCap = small ? QCAP : auxCap;
             const int cutoff = cut;                        // shadows the parameter: the loop guard's value from here on
             const int size = generic ? sAx.rows : ((n > cutoff) ? cutoff : n);  // swapChange (NDCGScorer.java:133)
             for (int p = tid; p < n; p += blockDim.x) {
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(128) k_query(const double* __restrict__ score,
                     const double dp = disc[p];
                     // |changes[a][b]| for a < b, a < size
                     auto delta = [&](int a, int b, double ga, double gb) -> double {
-                        if (generic) return fabs(metric_change(metric, kparam, n, a, b, L, sAuxD, sAuxI, QCAP, sAx));
+                        if (generic) return fabs(metric_change(metric, kparam, n, a, b, L, pAuxD, pAuxI, pCap, sAx));
                         double ch = (disc[a] - disc[b]) * (ga - gb);
                         if (ndcg) ch = ch / ideal;
                         return fabs(ch);
@@ -1471,6 +1482,7 @@ __device__ void scan_and_decide(DevState* __restrict__ st, const TreeParams& tp,
                 sp.thr_idx = bestT;
                 sp.left = li;
                 sp.right = ri;
+                sp.split_S = bestS;
                 st->cur = -1;
             }
         }
@@ -3094,13 +3106,46 @@ __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st,
 
 // K9 tail: float chain over the per-query metric values (LambdaMART.java:474-483)
 __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
-                                                                      int Q, const float* __restrict__ carryIn, ChainBufs cb) {
+                                                                      int Q, const float* __restrict__ carryIn, ChainBufs cb, int slot) {
     const float s = chain_walk(cb.xs, Q, 0, chunk0[0], chunk0[1], 0, carryIn ? carryIn[0] : 0.f, cb, &st->chain_serial);
-    if (threadIdx.x == 0) st->chain_out[0] = s;
+    if (threadIdx.x == 0) st->chain_out[slot] = s;
 }
 
-__global__ void k_metric_final(DevState* st, long long Q_total) {
-    st->train_metric = st->chain_out[0] / (float)(int)Q_total;  // LambdaMART.java:470
+// slot 0: LambdaMART.java:470 (training), slot 1: LambdaMART.java:510 (validation): float sum / list count
+__global__ void k_metric_final(DevState* st, long long Q_total, int slot) {
+    const float v = st->chain_out[slot] / (float)(int)Q_total;
+    if (slot == 0)
+        st->train_metric = v;
+    else
+        st->valid_metric = v;
+}
+
+// LambdaMART.java:228-234: modelScoresOnValidation[i][j] += learningRate * rt.eval(dp) for the tree just fitted.
+// Split.eval (Split.java:115-125) walks `value <= threshold` on the raw value (NaN = unknown reads as 0,
+// DenseDataPoint.java:28-30); the tree comes straight from the controller's node records (children are adjacent:
+// right = left + 1).  One thread per validation document, the tree in shared memory.
+__global__ void __launch_bounds__(256) k_valid_update(const DevState* __restrict__ st, const float* __restrict__ VX, int F,
+                                                       const float* __restrict__ thr, int64_t Nv, float lr,
+                                                       double* __restrict__ vscore) {
+    extern __shared__ float4 sTree[];   // x = threshold, y = leaf output, z = feature index (int bits, -1 leaf), w = left child
+    if (st->n_leaves_out == 0) return;  // unfinished tree (k_tree_end): redone after the extra split steps
+    const int nn = st->n_nodes;
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        const NodeRec& r = st->nodes[i];
+        const int f = r.feature_idx;
+        sTree[i] = make_float4(f >= 0 ? thr[(size_t)f * RLB_T + r.thr_idx] : 0.f, r.output, __int_as_float(f), __int_as_float(r.left));
+    }
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const float* row = VX + i * F;
+        float4 nd = sTree[0];
+        while (__float_as_int(nd.z) >= 0) {
+            float v = row[__float_as_int(nd.z)];
+            if (v != v) v = 0.f;
+            nd = sTree[__float_as_int(nd.w) + ((v <= nd.x) ? 0 : 1)];
+        }
+        vscore[i] += (double)lr * (double)nd.y;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3121,16 +3166,40 @@ int rlb_impl_launch_rank_metric(rlb_ctx* c, const double* dScores, const float* 
     RLB_CUDA(c, cudaMalloc(&dRank, std::max<int64_t>(N, 1) * 4));
     const int grid = std::min(Q, 148 * 16);
     k_query<false><<<grid, 128, 0, c->stream>>>(dScores, dLabel, dQoff, Q, k, metric, dDisc, nullptr, dRank, nullptr, nullptr,
-                                                dOut, nullptr, nullptr);
-    RLB_CHECK_LAUNCH(c);
-    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dRank);
+                                                dOut, nullptr, nullptr, nullptr, 0);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dRank);   // also on the error paths
+    if (e != cudaSuccess) {
+        rlb_set_error(c, RLB_E_CUDA, "rlb_score_metric", cudaGetErrorString(e));
+        return RLB_E_CUDA;
+    }
     return RLB_OK;
 }
 
-// One pass over all training queries: NDCG@k per query (qmetric != null) and / or lambdas + weights
-// (want_lambda).  Queries are routed by size class (lists built at init).
-static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
+// the training set as a QuerySet view
+QuerySet rlb_train_set(const rlb_ctx* c) {
+    QuerySet q;
+    q.N = c->N;
+    q.Q = c->Q;
+    q.max_query = c->max_query;
+    q.dLabel = c->dLabel;
+    q.dQoff = c->dQoff;
+    q.dScore = c->dScore;
+    q.dIdeal = c->dIdeal;
+    q.dQMetric = c->dQMetric;
+    q.dRankDoc = c->dRankDoc;
+    q.dQList = c->dQList;
+    q.nqA = c->nqA; q.nqB0 = c->nqB0; q.nqB1 = c->nqB1; q.nqB2 = c->nqB2; q.nqC = c->nqC;
+    q.dAux = c->dQAux;
+    q.aux_ctas = c->qaux_ctas;
+    return q;
+}
+
+// One pass over all queries of a set: the metric per query (qmetric != null) and / or lambdas + weights
+// (want_lambda; training set only).  Queries are routed by size class (lists built at init / load).
+static int launch_queries(rlb_ctx* c, const QuerySet& qs, bool want_lambda, double* qmetric) {
     const int B0N = 128, B0T = 1280, B1N = 256, B1T = 2560, B2N = 1024, B2T = 10240;
     const size_t smA = (size_t)8 * QA_WARP_BYTES, smB0 = (size_t)B0N * 44 + (size_t)B0T * 16 + 64, smB1 = (size_t)B1N * 44 + (size_t)B1T * 16 + 64, smB2 = (size_t)B2N * 44 + (size_t)B2T * 16 + 64;
     double* lam = want_lambda ? c->dLambda : nullptr;
@@ -3140,58 +3209,60 @@ static int launch_queries(rlb_ctx* c, bool want_lambda, double* qmetric) {
     // capture this becomes parallel graph branches).  The warp-path kernel stays on the main stream.
     int nside = 0;
     const bool fork = !c->trace;
-    if (fork && (c->nqB0 > 0 || c->nqB1 > 0 || c->nqB2 > 0 || c->nqC > 0)) RLB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    if (fork && (qs.nqB0 > 0 || qs.nqB1 > 0 || qs.nqB2 > 0 || qs.nqC > 0)) RLB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
     auto branch = [&](int i) -> cudaStream_t {
         if (!fork) return c->stream;
         cudaStreamWaitEvent(c->side[i], c->ev_fork, 0);
         nside = std::max(nside, i + 1);
         return c->side[i];
     };
-    if (c->nqB0 > 0) {   // 65 .. 128 documents: two warps per query (a 128-thread CTA mostly waits at its barriers here)
-        const int grid = std::min(c->nqB0, c->sm_count * 8);
-        k_query_block<64><<<grid, 64, smB0, branch(3)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA, c->nqB0, k, m, c->dDisc,
-                                                         c->dIdeal, lam, wgt, qmetric, c->dState, B0N, B0T);
+    if (qs.nqB0 > 0) {   // 65 .. 128 documents: two warps per query (a 128-thread CTA mostly waits at its barriers here)
+        const int grid = std::min(qs.nqB0, c->sm_count * 8);
+        k_query_block<64><<<grid, 64, smB0, branch(3)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA, qs.nqB0, k, m, c->dDisc,
+                                                         qs.dIdeal, lam, wgt, qmetric, c->dState, B0N, B0T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[3], c->side[3]));
     }
-    if (c->nqB1 > 0) {
-        const int grid = std::min(c->nqB1, c->sm_count * 4);
-        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB0, c->nqB1, k, m, c->dDisc,
-                                                           c->dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
+    if (qs.nqB1 > 0) {
+        const int grid = std::min(qs.nqB1, c->sm_count * 4);
+        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0, qs.nqB1, k, m, c->dDisc,
+                                                           qs.dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
     }
-    if (c->nqB2 > 0) {
-        const int grid = std::min(c->nqB2, c->sm_count);
-        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(c->dScore, c->dLabel, c->dQoff, c->dQList + c->nqA + c->nqB0 + c->nqB1, c->nqB2, k, m,
-                                                           c->dDisc, c->dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
+    if (qs.nqB2 > 0) {
+        const int grid = std::min(qs.nqB2, c->sm_count);
+        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0 + qs.nqB1, qs.nqB2, k, m,
+                                                           c->dDisc, qs.dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
     }
-    if (c->nqC > 0) {
-        const int grid = std::min(c->nqC, c->sm_count * 8);
-        const int32_t* ql = c->dQList + c->nqA + c->nqB0 + c->nqB1 + c->nqB2;
+    if (qs.nqC > 0) {
+        // generic metrics on queries above QCAP documents: every CTA owns a slice of qs.dAux (see k_query)
+        const bool aux = qs.dAux != nullptr;
+        const int grid = aux ? std::min(qs.nqC, qs.aux_ctas) : std::min(qs.nqC, c->sm_count * 8);
+        const int32_t* ql = qs.dQList + qs.nqA + qs.nqB0 + qs.nqB1 + qs.nqB2;
         cudaStream_t sC = branch(2);
         if (want_lambda)
-            k_query<true><<<grid, 128, 0, sC>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, lam, wgt,
-                                                qmetric, c->dState, ql);
+            k_query<true><<<grid, 128, 0, sC>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.nqC, k, m, c->dDisc, qs.dIdeal, qs.dRankDoc, lam, wgt,
+                                                qmetric, c->dState, ql, qs.dAux, qs.max_query);
         else
-            k_query<false><<<grid, 128, 0, sC>>>(c->dScore, c->dLabel, c->dQoff, c->nqC, k, m, c->dDisc, c->dIdeal, c->dRankDoc, nullptr,
-                                                 nullptr, qmetric, c->dState, ql);
+            k_query<false><<<grid, 128, 0, sC>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.nqC, k, m, c->dDisc, qs.dIdeal, qs.dRankDoc, nullptr,
+                                                 nullptr, qmetric, c->dState, ql, nullptr, 0);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[2], c->side[2]));
     }
-    if (c->nqA > 0) {
-        const int grid = std::min((c->nqA + 7) / 8, c->sm_count * 2);
-        k_query_warp<<<grid, 256, smA, c->stream>>>(c->dScore, c->dLabel, c->dQoff, c->dQList, c->nqA, k, m, c->dDisc, c->dIdeal, lam, wgt,
+    if (qs.nqA > 0) {
+        const int grid = std::min((qs.nqA + 7) / 8, c->sm_count * 2);
+        k_query_warp<<<grid, 256, smA, c->stream>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList, qs.nqA, k, m, c->dDisc, qs.dIdeal, lam, wgt,
                                                     qmetric, c->dState);
         RLB_CHECK_LAUNCH(c);
     }
     if (fork) {
-        if (c->nqB0 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[3], 0));
-        if (c->nqB1 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
-        if (c->nqB2 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
-        if (c->nqC > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[2], 0));
+        if (qs.nqB0 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[3], 0));
+        if (qs.nqB1 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+        if (qs.nqB2 > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+        if (qs.nqC > 0) RLB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[2], 0));
     }
     return RLB_OK;
 }
@@ -3206,7 +3277,7 @@ int rlb_impl_pseudo(rlb_ctx* c) {
         RLB_CHECK_LAUNCH(c);
     } else {
         rlb_prof_begin(c, 2);
-        if (int rc = launch_queries(c, true, nullptr)) return rc;
+        if (int rc = launch_queries(c, rlb_train_set(c), true, nullptr)) return rc;
         rlb_prof_end(c);
     }
     if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
@@ -3377,6 +3448,7 @@ int rlb_impl_enqueue_iter(rlb_ctx* c) {
     if (int rc = rlb_impl_tree_output(c)) return rc;
     if (int rc = rlb_impl_update_scores(c)) return rc;
     if (int rc = rlb_impl_train_metric(c, true)) return rc;
+    if (int rc = rlb_impl_valid_step(c)) return rc;
     RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
     return RLB_OK;
 }
@@ -3393,6 +3465,7 @@ int rlb_impl_finish_iter(rlb_ctx* c) {
         if (int rc = rlb_impl_tree_output(c)) return rc;
         if (int rc = rlb_impl_update_scores(c)) return rc;
         if (int rc = rlb_impl_train_metric(c, true)) return rc;
+        if (int rc = rlb_impl_valid_step(c)) return rc;
         if (int rc = sync_state_header(c)) return rc;
     }
     c->tree_output_ready = false;
@@ -3495,6 +3568,45 @@ int rlb_impl_assign_nodes(rlb_ctx* c) {
 
 extern long long rlb_q_total(rlb_ctx* c);
 
+// float chain over per-list metric values (LambdaMART.java:474-483 / :508-516) and the division by the list count;
+// slot 0 = training set (continues across ranks on N GPUs), slot 1 = validation set
+static int metric_chain(rlb_ctx* c, const double* dQM, int Q, long long Q_total, int slot, bool multi) {
+    const int NT = 2 * (RLB_MAX_LEAVES + 1);
+    ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
+    if (multi) cb.tot = c->dChainTot;
+    int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2 + 2 * slot;  // static table of the metric chain: {0, ceil(Q / CK)}
+    const int gchunks = (Q + CK - 1) / CK;
+    k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, c->dState, ch0, 1, dQM, nullptr, nullptr, nullptr, Q, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, nullptr, cb);
+    RLB_CHECK_LAUNCH(c);
+    ChainBufs cbp = cb;
+    if (multi) {   // per-query values are >= 0 and the sum grows: the exact totals of the earlier ranks predict well enough
+        RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
+        cbp.gtot = c->dChainGTot;
+        cbp.rank = c->rank;
+    }
+    k_chain_sim<<<dim3((gchunks + SIM_WARPS - 1) / SIM_WARPS, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, c->dState, ch0, Q, nullptr, cbp);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, cb);
+    RLB_CHECK_LAUNCH(c);
+    k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, c->dState, ch0, cb);
+    RLB_CHECK_LAUNCH(c);
+    const float* carry = nullptr;
+    if (multi) {
+        if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
+        carry = c->dCarry;
+    }
+    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, Q, carry, cb, slot);
+    RLB_CHECK_LAUNCH(c);
+    if (multi) {
+        if (int rc = rlb_chain_carry_end(c, c->dState->chain_out, 1)) return rc;
+    }
+    k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, Q_total, slot);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
 // LambdaMART.computeModelScoreOnTraining (LambdaMART.java:442-483).  with_pseudo: the same ranking pass
 // also produces the pseudo responses of the NEXT iteration (both need the stable descending order of
 // the current scores), which saves one full pass over the queries per iteration.
@@ -3502,12 +3614,12 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
     if (with_pseudo && !c->lambda_fresh) {
         RLB_CUDA(c, cudaMemsetAsync(&c->dState->max_abs_bits, 0, sizeof(unsigned long long), c->stream));
         if (c->prm.kind == RLB_KIND_MART) {
-            if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
+            if (int rc = launch_queries(c, rlb_train_set(c), false, c->dQMetric)) return rc;
             k_mart_pseudo<<<c->grid_rows, 256, 0, c->stream>>>(c->dScore, c->dLabel, c->N, c->dLambda, c->dState);
             RLB_CHECK_LAUNCH(c);
         } else {
             rlb_prof_begin(c, 2);
-            if (int rc = launch_queries(c, true, c->dQMetric)) return rc;
+            if (int rc = launch_queries(c, rlb_train_set(c), true, c->dQMetric)) return rc;
             rlb_prof_end(c);
         }
         if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
@@ -3515,45 +3627,22 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
         RLB_CHECK_LAUNCH(c);
         c->lambda_fresh = true;
     } else {
-        if (int rc = launch_queries(c, false, c->dQMetric)) return rc;
+        if (int rc = launch_queries(c, rlb_train_set(c), false, c->dQMetric)) return rc;
     }
-    {
-        const bool multi = c->world > 1;
-        const int NT = 2 * (RLB_MAX_LEAVES + 1);
-        ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
-        if (multi) cb.tot = c->dChainTot;
-        int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2;  // static table of the metric chain: {0, ceil(Q / CK)}
-        const int gchunks = (c->Q + CK - 1) / CK;
-        k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, c->dState, ch0, 1, c->dQMetric, nullptr, nullptr, nullptr, c->Q, cb);
-        RLB_CHECK_LAUNCH(c);
-        k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, nullptr, cb);
-        RLB_CHECK_LAUNCH(c);
-        ChainBufs cbp = cb;
-        if (multi) {   // per-query values are >= 0 and the sum grows: the exact totals of the earlier ranks predict well enough
-            RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
-            cbp.gtot = c->dChainGTot;
-            cbp.rank = c->rank;
-        }
-        k_chain_sim<<<dim3((gchunks + SIM_WARPS - 1) / SIM_WARPS, 1), 32 * SIM_WARPS, 0, c->stream>>>(1, c->dState, ch0, c->Q, nullptr, cbp);
-        RLB_CHECK_LAUNCH(c);
-        k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, cb);
-        RLB_CHECK_LAUNCH(c);
-        k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, c->dState, ch0, cb);
-        RLB_CHECK_LAUNCH(c);
-        const float* carry = nullptr;
-        if (multi) {
-            if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
-            carry = c->dCarry;
-        }
-        k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, c->Q, carry, cb);
-        RLB_CHECK_LAUNCH(c);
-    }
-    if (c->world > 1) {
-        if (int rc = rlb_chain_carry_end(c, c->dState->chain_out, 1)) return rc;
-    }
-    k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, rlb_q_total(c));
+    return metric_chain(c, c->dQMetric, c->Q, rlb_q_total(c), 0, c->world > 1);
+}
+
+// LambdaMART.java:228-237 + computeModelScoreOnValidation (:485-518) for the resident validation set: update its
+// cached scores with the tree just fitted, the metric per list, float chain over the lists, / list count.
+// N GPUs: every rank holds the whole validation set and computes the same value (no exchange).
+int rlb_impl_valid_step(rlb_ctx* c) {
+    if (!c->have_valid) return RLB_OK;
+    const QuerySet& v = c->valid;
+    const size_t sm = (size_t)(2 * c->prm.n_leaves + 1) * sizeof(float4);
+    k_valid_update<<<c->grid_rows, 256, sm, c->stream>>>(c->dState, c->dVX, c->F, c->dThr, v.N, c->prm.learning_rate, v.dScore);
     RLB_CHECK_LAUNCH(c);
-    return RLB_OK;
+    if (int rc = launch_queries(c, v, false, v.dQMetric)) return rc;
+    return metric_chain(c, v.dQMetric, v.Q, v.Q, 1, false);
 }
 
 // Test hook (rlb_float_chain): the float32 accumulation chain  s = carry; s = (float)((double)s + x[i])  over n host
@@ -3606,7 +3695,7 @@ int rlb_impl_float_chain(rlb_ctx* c, const double* x, int64_t n, float carry, in
         k_chain_offsets<<<dim3(1, 1), 32, 0, c->stream>>>(1, dSt, dCh0, cb);
         k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, dSt, dCh0, cb);
     }
-    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(dSt, dCh0, (int)n, dCarry, cb);
+    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(dSt, dCh0, (int)n, dCarry, cb, 0);
     DevState* h = (DevState*)malloc(sizeof(DevState));
     cudaMemcpyAsync(h, dSt, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream);
     e = cudaStreamSynchronize(c->stream);

@@ -294,6 +294,28 @@ int rlb_p2p_setup(rlb_ctx* c) {
     return RLB_OK;
 }
 
+cudaError_t rlb_reserve_bytes(rlb_ctx* c, void** ptr, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    auto it = c->cap.find((void*)ptr);
+    if (*ptr && it != c->cap.end() && it->second >= bytes) return cudaSuccess;
+    const bool regrow = *ptr != nullptr;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    // a buffer that had to grow once gets headroom: the bags of a Random Forest differ in size by a few percent
+    size_t want = regrow ? bytes + bytes / 16 : bytes;
+    cudaError_t e = cudaMalloc(ptr, want);
+    if (e != cudaSuccess && want != bytes) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(ptr, want);
+    }
+    if (e == cudaSuccess)
+        c->cap[(void*)ptr] = want;
+    else
+        c->cap.erase((void*)ptr);
+    return e;
+}
+
 void rlb_impl_free(rlb_ctx* c) {
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) {
@@ -307,9 +329,17 @@ void rlb_impl_free(rlb_ctx* c) {
     fr(c->dHistCnt); fr(c->dHistCntL); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
     fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
     fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainTot); fr(c->dChainGTot); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
+    fr(c->dQAux);
+    fr(c->dVX); fr(c->valid.dLabel); fr(c->valid.dQoff); fr(c->valid.dScore); fr(c->valid.dIdeal); fr(c->valid.dQMetric);
+    fr(c->valid.dRankDoc); fr(c->valid.dQList); fr(c->valid.dAux);
+    for (int i = 0; i < 6; i++) {
+        fr(c->dEvalBuf[i]);
+        c->evalCap[i] = 0;
+    }
     if (c->hState) cudaFreeHost(c->hState);
     c->hState = nullptr;
-    c->loaded = c->inited = false;
+    c->cap.clear();
+    c->loaded = c->inited = c->have_valid = false;
 }
 
 int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
@@ -343,7 +373,9 @@ int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_
         }
     }
     RLB_CUDA(c, cudaSetDevice(c->device));
-    rlb_impl_free(c);
+    // buffers are grow-only (rlb_reserve): a context that is loaded again — the next bag of a Random Forest — reuses them
+    c->loaded = c->inited = false;
+    c->have_valid = false;   // a validation set belongs to the training set it was loaded after
     c->N = N;
     c->F = F;
     c->Fp = (F + 15) & ~15;  // rows of uint16 bins padded to whole 32-byte sectors: a 16-feature group never straddles two
@@ -351,9 +383,11 @@ int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_
     c->max_query = maxq;
     c->feature_ids.assign(feature_ids, feature_ids + F);
     c->have_thr = false;
-    RLB_CUDA(c, cudaMalloc(&c->dX, (size_t)N * F * sizeof(float)));
-    RLB_CUDA(c, cudaMalloc(&c->dLabel, (size_t)N * sizeof(float)));
-    RLB_CUDA(c, cudaMalloc(&c->dQoff, (size_t)(Q + 1) * sizeof(int32_t)));
+    c->thr_user = false;
+    c->h_qoff.assign(qoff, qoff + Q + 1);
+    RLB_CUDA(c, rlb_reserve(c, c->dX, (size_t)N * F * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dLabel, (size_t)N * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dQoff, (size_t)(Q + 1) * sizeof(int32_t)));
     RLB_CUDA(c, cudaMemcpyAsync(c->dX, X, (size_t)N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     RLB_CUDA(c, cudaMemcpyAsync(c->dLabel, label, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     RLB_CUDA(c, cudaMemcpyAsync(c->dQoff, qoff, (size_t)(Q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -385,6 +419,138 @@ static void build_thresholds(int nThreshold, int nDistinct, std::vector<float>& 
     }
 }
 
+// Routes the queries of a set to the per-query kernels by size (rlb_boost.cu launch_queries): the pair table of a query
+// has min(k, n) * n entries (MAP: n).  Uploads the grouped id list (qs.dQList, grow-only through &qs.dQList is not
+// possible for a by-value view, so the caller stores the pointer back).
+int rlb_build_query_classes(rlb_ctx* c, const int32_t* qoffh, QuerySet& qs) {
+    const rlb_params* p = &c->prm;
+    const int Q = qs.Q;
+    std::vector<int32_t> la, lb0, lb1, lb2, lc;
+    for (int q = 0; q < Q; q++) {
+        const int64_t n = qoffh[q + 1] - qoffh[q];
+        // rows of the pair table (query_fast): min(k, n); MAP visits only the pairs touching rank 0 (APScorer.k = 0)
+        const int64_t sz = (p->metric == RLB_METRIC_MAP) ? std::min<int64_t>(1, n)
+                                                          : ((p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0);
+        const int64_t terms = sz * n;
+        if (n <= 64 && terms <= 640) la.push_back(q);
+        else if (n <= 128 && terms <= 1280) lb0.push_back(q);
+        else if (n <= 256 && terms <= 2560) lb1.push_back(q);
+        else if (n <= 1024 && terms <= 10240) lb2.push_back(q);
+        else lc.push_back(q);
+    }
+    qs.nqA = (int)la.size(); qs.nqB0 = (int)lb0.size(); qs.nqB1 = (int)lb1.size(); qs.nqB2 = (int)lb2.size(); qs.nqC = (int)lc.size();
+    la.insert(la.end(), lb0.begin(), lb0.end());
+    la.insert(la.end(), lb1.begin(), lb1.end());
+    la.insert(la.end(), lb2.begin(), lb2.end());
+    la.insert(la.end(), lc.begin(), lc.end());
+    // the list lives in the owning context member (training: c->dQList, validation: c->valid.dQList)
+    int32_t*& owner = (qs.dQoff == c->dQoff) ? c->dQList : c->valid.dQList;
+    RLB_CUDA(c, rlb_reserve(c, owner, (size_t)std::max(Q, 1) * 4));
+    RLB_CUDA(c, cudaMemcpyAsync(owner, la.data(), (size_t)Q * 4, cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));   // `la` is pageable and dies here
+    qs.dQList = owner;
+    return RLB_OK;
+}
+
+// discount table 1 / log2(i + 2) (DCGScorer.java:24-27,106-123) for ranks up to the longest list of either set; computed
+// on the HOST with the same libm the oracle uses
+static int upload_discount(rlb_ctx* c) {
+    const int maxq = std::max(c->max_query, c->have_valid ? c->valid.max_query : 0);
+    std::vector<double> disc((size_t)maxq + 2);
+    const double LOG2 = std::log(2.0);
+    for (size_t i = 0; i < disc.size(); i++) disc[i] = 1.0 / (std::log((double)(i + 2)) / LOG2);
+    RLB_CUDA(c, rlb_reserve(c, c->dDisc, disc.size() * sizeof(double)));
+    RLB_CUDA(c, cudaMemcpyAsync(c->dDisc, disc.data(), disc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+// The part of the validation set's state that depends on the training parameters (metric, k): size classes, ideal DCG,
+// zeroed modelScoresOnValidation (LambdaMART.java:152-158).  Runs at the end of rlb_lambdamart_init, or at the end of
+// rlb_load_validation when the context is already initialised.
+static int valid_finalize(rlb_ctx* c, const int32_t* qoffh) {
+    QuerySet& v = c->valid;
+    if (int rc = rlb_build_query_classes(c, qoffh, v)) return rc;
+    RLB_CUDA(c, cudaMemsetAsync(v.dScore, 0, (size_t)v.N * sizeof(double), c->stream));
+    k_ideal_dcg<<<(v.Q + 127) / 128, 128, 0, c->stream>>>(v.dLabel, v.dQoff, v.Q, c->prm.metric_k, c->dDisc, v.dIdeal);
+    RLB_CHECK_LAUNCH(c);
+    if ((v.Q + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK + 2 > c->chain_max_chunks) {
+        rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_load_validation",
+                      "the validation set has more lists than the float-chain buffers of this training set cover: load it "
+                      "before rlb_lambdamart_init");
+        return RLB_E_UNSUPPORTED;
+    }
+    const int32_t mc[2] = {0, (v.Q + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK};
+    RLB_CUDA(c, cudaMemcpyAsync(c->dChunk0 + RLB_MAX_LEAVES + 4, mc, sizeof(mc), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+// Ranker.setValidationSet + LambdaMART.init's modelScoresOnValidation (Ranker.java:67-69, LambdaMART.java:152-158): the
+// validation lists stay on the device (raw values, labels, offsets, cached scores); rlb_boost_iter then scores every new
+// tree on them without any host traffic (LambdaMART.java:228-237).
+int rlb_impl_load_validation(rlb_ctx* c, const float* X, int64_t N, int32_t F, const float* label, const int32_t* qoff,
+                             int32_t Q) {
+    if (!c->loaded) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_load_validation", "load the training set first");
+        return RLB_E_INVALID;
+    }
+    if (!X || !label || !qoff || N <= 0 || Q <= 0 || N >= (1LL << 31) || F != c->F) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_load_validation", "null pointer, empty input, or a feature count that differs from the training set's");
+        return RLB_E_INVALID;
+    }
+    if (qoff[0] != 0 || qoff[Q] != N) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_load_validation", "qoff must start at 0 and end at N");
+        return RLB_E_INVALID;
+    }
+    int maxq = 0;
+    for (int q = 0; q < Q; q++) {
+        const int n = qoff[q + 1] - qoff[q];
+        if (n < 0) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_load_validation", "qoff must be non-decreasing");
+            return RLB_E_INVALID;
+        }
+        maxq = std::max(maxq, n);
+    }
+    for (int64_t i = 0; i < N; i++)
+        if (!(label[i] >= 0.f) || label[i] > (float)RLB_MAX_LABEL) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_load_validation", "Relevance label cannot be negative (or is above 30).");
+            return RLB_E_INVALID;
+        }
+    RLB_CUDA(c, cudaSetDevice(c->device));
+    QuerySet& v = c->valid;
+    v.N = N;
+    v.Q = Q;
+    v.max_query = maxq;
+    v.dAux = nullptr;
+    v.aux_ctas = 0;
+    RLB_CUDA(c, rlb_reserve(c, c->dVX, (size_t)N * F * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, v.dLabel, (size_t)N * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, v.dQoff, (size_t)(Q + 1) * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, v.dScore, (size_t)N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, v.dIdeal, (size_t)Q * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, v.dQMetric, (size_t)Q * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, v.dRankDoc, (size_t)N * sizeof(int32_t)));
+    RLB_CUDA(c, cudaMemcpyAsync(c->dVX, X, (size_t)N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaMemcpyAsync(v.dLabel, label, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaMemcpyAsync(v.dQoff, qoff, (size_t)(Q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h_vqoff.assign(qoff, qoff + Q + 1);
+    c->have_valid = true;
+    // the captured iteration does not contain the validation kernels yet
+    for (int i = 0; i < 2; i++)
+        if (c->iter_graph[i]) {
+            cudaGraphExecDestroy(c->iter_graph[i]);
+            c->iter_graph[i] = nullptr;
+        }
+    c->launches_per_iter = 0;
+    if (c->inited) {
+        if (int rc = upload_discount(c)) return rc;
+        return valid_finalize(c, c->h_vqoff.data());
+    }
+    return RLB_OK;
+}
+
 int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     if (!c->loaded) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_lambdamart_init", "no training set loaded");
@@ -400,12 +566,6 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         p->metric < 0 || p->metric >= RLB_METRIC_COUNT) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_lambdamart_init", "parameter out of range");
         return RLB_E_INVALID;
-    }
-    if (p->metric > RLB_METRIC_DCG && p->kind == RLB_KIND_LAMBDAMART && c->max_query > 1024) {
-        // ERR / MAP / P / RR / Best keep per-query arrays in shared memory (metric_prologue, rlb_boost.cu)
-        rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_lambdamart_init",
-                      "metrics other than NDCG / DCG support queries of up to 1024 documents");
-        return RLB_E_UNSUPPORTED;
     }
     RLB_CUDA(c, cudaSetDevice(c->device));
     c->prm = *p;
@@ -437,6 +597,9 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     }
 
     // ---- thresholds ----
+    // derived thresholds belong to (data, n_threshold): a re-init with another n_threshold rebuilds them; thresholds
+    // imposed through rlb_set_thresholds stay until the next rlb_load_dense
+    if (c->have_thr && !c->thr_user && c->thr_built_for != p->n_threshold) c->have_thr = false;
     if (!c->have_thr) {
         float *dMin, *dMax, *dDist;
         int* dND;
@@ -523,81 +686,75 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             build_thresholds(p->n_threshold, nd, merged, mn, mx, &c->h_thr[(size_t)f * RLB_T], &c->h_nthr[f]);
         }
         c->have_thr = true;
+        c->thr_user = false;
+        c->thr_built_for = p->n_threshold;
     }
-    if (!c->dThr) RLB_CUDA(c, cudaMalloc(&c->dThr, (size_t)F * RLB_T * sizeof(float)));
-    if (!c->dNThr) RLB_CUDA(c, cudaMalloc(&c->dNThr, F * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dThr, (size_t)F * RLB_T * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dNThr, F * sizeof(int32_t)));
     RLB_CUDA(c, cudaMemcpyAsync(c->dThr, c->h_thr.data(), (size_t)F * RLB_T * 4, cudaMemcpyHostToDevice, c->stream));
     RLB_CUDA(c, cudaMemcpyAsync(c->dNThr, c->h_nthr.data(), F * 4, cudaMemcpyHostToDevice, c->stream));
 
     // ---- allocations ----
     c->max_nodes = 2 * p->n_leaves;
     c->hist_stride = (size_t)F * RLB_T;
-    auto alloc = [&](auto*& ptr, size_t bytes) -> cudaError_t {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        return cudaMalloc(&ptr, bytes);
-    };
-    RLB_CUDA(c, alloc(c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
-    RLB_CUDA(c, alloc(c->dBinsT, (size_t)N * F * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dBinsT, (size_t)N * F * sizeof(uint16_t)));
     c->root_nb = (N + RLB_ROOT_R - 1) / RLB_ROOT_R;
-    RLB_CUDA(c, alloc(c->dBinsTile, (size_t)(Fp / 16) * c->root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
-    RLB_CUDA(c, alloc(c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
-    RLB_CUDA(c, alloc(c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
-    if (c->world > 1) RLB_CUDA(c, alloc(c->dHistCntL, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dBinsTile, (size_t)(Fp / 16) * c->root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
+    RLB_CUDA(c, rlb_reserve(c, c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
+    if (c->world > 1) RLB_CUDA(c, rlb_reserve(c, c->dHistCntL, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
     c->stage_elems = c->hist_stride + (c->hist_stride + 1) / 2 + 2;
     rlb_p2p_close(c);   // mappings of an earlier init point at buffers that are about to be freed
-    RLB_CUDA(c, alloc(c->dStage, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dStage, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long)));
     RLB_CUDA(c, cudaMemsetAsync(c->dStage, 0, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long), c->stream));
-    RLB_CUDA(c, alloc(c->dScore, N * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dLambda, N * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dWeight, N * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dQMetric, (size_t)Q * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dScore, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dLambda, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dWeight, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dQMetric, (size_t)Q * sizeof(double)));
     // the root histogram reads responses in whole tiles of RLB_ROOT_R rows: pad with zeros (added to bin 0, harmless)
-    RLB_CUDA(c, alloc(c->dVfix, ((size_t)c->root_nb * RLB_ROOT_R + 2) * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dVfix, ((size_t)c->root_nb * RLB_ROOT_R + 2) * sizeof(long long)));
     RLB_CUDA(c, cudaMemsetAsync(c->dVfix, 0, ((size_t)c->root_nb * RLB_ROOT_R + 2) * sizeof(long long), c->stream));
-    RLB_CUDA(c, alloc(c->dVfixC, (N + 2) * sizeof(long long)));
-    RLB_CUDA(c, alloc(c->dSqfix, N * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dVfixC, (N + 2) * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSqfix, N * sizeof(long long)));
     if (const char* e = getenv("RLB_HIST_MIN_ROWS")) c->hist_min_rows = atoi(e);
-    RLB_CUDA(c, alloc(c->dIdeal, (size_t)Q * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dRankDoc, N * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dSamples[0], N * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dSamples[1], N * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dNodeOf, N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dIdeal, (size_t)Q * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dRankDoc, N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSamples[0], N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSamples[1], N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dNodeOf, N * sizeof(int32_t)));
     c->n_tiles = (int)((N + RLB_PART_TILE - 1) / RLB_PART_TILE) + 1;
-    RLB_CUDA(c, alloc(c->dTileCnt, (size_t)c->n_tiles * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dTileState, (size_t)c->n_tiles * sizeof(unsigned long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dTileCnt, (size_t)c->n_tiles * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dTileState, (size_t)c->n_tiles * sizeof(unsigned long long)));
     RLB_CUDA(c, cudaMemsetAsync(c->dTileState, 0xff, (size_t)c->n_tiles * sizeof(unsigned long long), c->stream));
-    RLB_CUDA(c, alloc(c->dNodeFeatS, (size_t)c->max_nodes * F * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dNodeFeatT, (size_t)c->max_nodes * F * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dFeatS, F * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dFeatT, F * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dUsed, 2 * F * sizeof(int32_t)));  // usedFeatures + sampling pool
-    RLB_CUDA(c, alloc(c->dState, sizeof(DevState)));
-    RLB_CUDA(c, alloc(c->dCarry, 4 * (RLB_MAX_LEAVES + 1) * sizeof(float)));
-    c->chain_max_chunks = (int)(std::max<int64_t>(N, Q) / RLB_CHAIN_CK) + RLB_MAX_LEAVES + 2;
-    RLB_CUDA(c, alloc(c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainXs, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_CK * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainRSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainTot, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
-    RLB_CUDA(c, alloc(c->dChainGTot, (size_t)2 * std::max(c->world, 1) * 2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dNodeFeatS, (size_t)c->max_nodes * F * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dNodeFeatT, (size_t)c->max_nodes * F * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dFeatS, F * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dFeatT, F * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dUsed, 2 * F * sizeof(int32_t)));  // usedFeatures + sampling pool
+    RLB_CUDA(c, rlb_reserve(c, c->dState, sizeof(DevState)));
+    RLB_CUDA(c, rlb_reserve(c, c->dCarry, 4 * (RLB_MAX_LEAVES + 1) * sizeof(float)));
+    c->chain_max_chunks = (int)(std::max<int64_t>(std::max<int64_t>(N, Q), c->have_valid ? c->valid.Q : 0) / RLB_CHAIN_CK) + RLB_MAX_LEAVES + 2;
+    RLB_CUDA(c, rlb_reserve(c, c->dChainSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainXs, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_CK * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainRSum, (size_t)2 * c->chain_max_chunks * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainTot, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainGTot, (size_t)2 * std::max(c->world, 1) * 2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
     RLB_CUDA(c, cudaMemsetAsync(c->dChainTot, 0, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double), c->stream));
     c->chain_gtot_world = std::max(c->world, 1);
     if (int rc = rlb_p2p_setup(c)) return rc;
     {
-        void* p = c->dChainItems;   // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu)
-        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));
-        c->dChainItems = (struct ChainItem*)p;
-        p = c->dChainStream;        // the same + one marker per chunk (CH_STREAM)
-        RLB_CUDA(c, alloc(p, (size_t)2 * c->chain_max_chunks * (RLB_CHAIN_ITEMS + 1) * 16));
-        c->dChainStream = (struct ChainItem*)p;
+        // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu); the stream: the same + one marker per chunk
+        RLB_CUDA(c, rlb_reserve(c, c->dChainItems, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));
+        RLB_CUDA(c, rlb_reserve(c, c->dChainStream, (size_t)2 * c->chain_max_chunks * (RLB_CHAIN_ITEMS + 1) * 16));
     }
-    RLB_CUDA(c, alloc(c->dChainIPos, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dChainITot, (size_t)2 * (RLB_MAX_LEAVES + 2) * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dChainNItems, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
-    RLB_CUDA(c, alloc(c->dChainSimS, (size_t)2 * c->chain_max_chunks * sizeof(float)));
-    RLB_CUDA(c, alloc(c->dChainSimE, (size_t)2 * c->chain_max_chunks * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainIPos, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainITot, (size_t)2 * (RLB_MAX_LEAVES + 2) * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainNItems, (size_t)2 * c->chain_max_chunks * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainSimS, (size_t)2 * c->chain_max_chunks * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainSimE, (size_t)2 * c->chain_max_chunks * sizeof(float)));
     if (const char* e = getenv("RLB_CHAIN_PASSES")) c->chain_passes = std::max(1, atoi(e));
-    RLB_CUDA(c, alloc(c->dChunk0, (size_t)(RLB_MAX_LEAVES + 4) * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChunk0, (size_t)(RLB_MAX_LEAVES + 8) * sizeof(int32_t)));   // leaf chains | training metric | validation metric
     {
         const int32_t mc[2] = {0, (Q + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK};
         RLB_CUDA(c, cudaMemcpyAsync(c->dChunk0 + RLB_MAX_LEAVES + 2, mc, sizeof(mc), cudaMemcpyHostToDevice, c->stream));
@@ -632,46 +789,33 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCnt, F);
     RLB_CHECK_LAUNCH(c);
 
-    // ---- metric tables: discount on the HOST with the same libm the oracle uses ----
-    {
-        int maxq = c->max_query;
-        std::vector<double> disc((size_t)maxq + 2);
-        const double LOG2 = std::log(2.0);
-        for (size_t i = 0; i < disc.size(); i++) disc[i] = 1.0 / (std::log((double)(i + 2)) / LOG2);
-        RLB_CUDA(c, alloc(c->dDisc, disc.size() * sizeof(double)));
-        RLB_CUDA(c, cudaMemcpyAsync(c->dDisc, disc.data(), disc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
+    // ---- metric tables ----
+    if (int rc = upload_discount(c)) return rc;
     // ---- query size classes of the lambda / NDCG kernels (table = min(k, n) * n pair terms) ----
     {
-        std::vector<int32_t> qoffh((size_t)Q + 1);
-        RLB_CUDA(c, cudaMemcpy(qoffh.data(), c->dQoff, ((size_t)Q + 1) * 4, cudaMemcpyDeviceToHost));
-        std::vector<int32_t> la, lb0, lb1, lb2, lc;
-        for (int q = 0; q < Q; q++) {
-            const int64_t n = qoffh[q + 1] - qoffh[q];
-            // rows of the pair table (query_fast): min(k, n); MAP visits only the pairs touching rank 0 (APScorer.k = 0)
-            const int64_t sz = (p->metric == RLB_METRIC_MAP) ? std::min<int64_t>(1, n)
-                                                              : ((p->metric_k > 0) ? std::min<int64_t>(p->metric_k, n) : 0);
-            const int64_t terms = sz * n;
-            if (n <= 64 && terms <= 640) la.push_back(q);
-            else if (n <= 128 && terms <= 1280) lb0.push_back(q);
-            else if (n <= 256 && terms <= 2560) lb1.push_back(q);
-            else if (n <= 1024 && terms <= 10240) lb2.push_back(q);
-            else lc.push_back(q);
+        QuerySet qs = rlb_train_set(c);
+        if (int rc = rlb_build_query_classes(c, c->h_qoff.data(), qs)) return rc;
+        c->dQList = qs.dQList;
+        c->nqA = qs.nqA; c->nqB0 = qs.nqB0; c->nqB1 = qs.nqB1; c->nqB2 = qs.nqB2; c->nqC = qs.nqC;
+        // generic metrics (ERR, MAP, P, RR, Best) on queries above 1024 documents: per-CTA prologue arrays in global memory
+        c->qaux_ctas = 0;
+        if (p->metric > RLB_METRIC_DCG && p->kind == RLB_KIND_LAMBDAMART && c->max_query > 1024 && c->nqC > 0) {
+            c->qaux_ctas = std::min(c->nqC, c->sm_count * 2);
+            RLB_CUDA(c, rlb_reserve(c, c->dQAux, (size_t)c->qaux_ctas * 3 * c->max_query * sizeof(double)));
+        } else if (c->dQAux) {
+            cudaFree(c->dQAux);
+            c->dQAux = nullptr;
+            c->cap.erase((void*)&c->dQAux);
         }
-        c->nqA = (int)la.size(); c->nqB0 = (int)lb0.size(); c->nqB1 = (int)lb1.size(); c->nqB2 = (int)lb2.size(); c->nqC = (int)lc.size();
-        la.insert(la.end(), lb0.begin(), lb0.end());
-        la.insert(la.end(), lb1.begin(), lb1.end());
-        la.insert(la.end(), lb2.begin(), lb2.end());
-        la.insert(la.end(), lc.begin(), lc.end());
-        RLB_CUDA(c, alloc(c->dQList, (size_t)Q * 4));
-        RLB_CUDA(c, cudaMemcpy(c->dQList, la.data(), (size_t)Q * 4, cudaMemcpyHostToDevice));
     }
     k_ideal_dcg<<<(Q + 127) / 128, 128, 0, c->stream>>>(c->dLabel, c->dQoff, Q, p->metric_k, c->dDisc, c->dIdeal);
     RLB_CHECK_LAUNCH(c);
     k_iota<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], N);
     RLB_CHECK_LAUNCH(c);
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->have_valid) {
+        if (int rc = valid_finalize(c, c->h_vqoff.data())) return rc;
+    }
     c->inited = true;
     c->tree_ready = c->tree_output_ready = false;
     c->lambda_fresh = false;
@@ -679,32 +823,100 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ensemble.eval (R/learning/tree/Ensemble.java:110-116) + Split.eval (R/learning/tree/Split.java:115-125)
-// One thread per data point walks every tree in order with a float accumulator:
-//   s = (float)((double)s + (double)leaf * (double)weight)
+// K10 — Ensemble.eval (R/learning/tree/Ensemble.java:110-116) + Split.eval (R/learning/tree/Split.java:115-125) for a
+// batch of data points:   s = (float)((double)s + (double)leaf_t(x) * (double)weight_t)   over the trees in order.
+//
+// A CTA scores a tile of TD documents.  The tile's rows are read from global memory once, coalesced, and kept in shared
+// memory TRANSPOSED ([column][document], document index XOR-swizzled by the column so that both the row-major fill and
+// the per-document reads are bank-conflict free): whatever node each lane of a warp has reached, lane d reads bank
+// (d ^ column) — different documents never collide on the same column, and a warp that sits on one node reads 32
+// consecutive words.  The trees stream through shared memory in chunks of 8-byte nodes
+//     { float threshold | leaf output ; uint16 column (0xFFFF leaf, 0xFFFE "feature absent: value 0") ; uint16 left }
+// with right = left + 1 (the host lays every tree out with adjacent children); thread d walks every tree of the chunk
+// for its document with the float accumulator in a register.  X is touched once: N * n_cols * 4 bytes + N * 4 out.
 // ------------------------------------------------------------------------------------------------
-struct EvalNode {
-    int32_t fid;   // -1 leaf
-    float thr;     // threshold, or the leaf output
-    int32_t left, right;
+struct ENode {
+    float thr;         // threshold, or the leaf output
+    uint32_t cl;       // column | left << 16
 };
+#define EV_LEAF 0xFFFFu
+#define EV_ZERO 0xFFFEu
+#define EV_CHUNK_NODES 4096   // nodes per tree chunk in shared memory (32 KB)
+#define EV_CHUNK_TREES 512    // trees per chunk (offsets u16 + weights: 3 KB)
 
-__global__ void __launch_bounds__(256) k_ensemble_eval(const EvalNode* __restrict__ nodes, const int32_t* __restrict__ tree_off,
-                                                        int n_trees, const float* __restrict__ weights,
-                                                        const float* __restrict__ X, int64_t N, int n_cols,
-                                                        float* __restrict__ out) {
+// colmap == nullptr: X rows are indexed by the node's column directly (host matrices indexed by feature id);
+// X row pitch = n_cols floats.  TD = documents per tile = threads per CTA.
+template <int TD>
+__global__ void __launch_bounds__(TD) k_ensemble_eval_tiled(const ENode* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                                             const int32_t* __restrict__ chunk_t, int n_chunks,
+                                                             const float* __restrict__ weights,
+                                                             const float* __restrict__ X, int64_t N, int n_cols,
+                                                             float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char ev_smem[];
+    float* sX = reinterpret_cast<float*>(ev_smem);                         // [n_cols][TD], swizzled
+    ENode* sN = reinterpret_cast<ENode*>(sX + (size_t)n_cols * TD);         // EV_CHUNK_NODES
+    float* sW = reinterpret_cast<float*>(sN + EV_CHUNK_NODES);              // EV_CHUNK_TREES
+    unsigned short* sOff = reinterpret_cast<unsigned short*>(sW + EV_CHUNK_TREES);   // EV_CHUNK_TREES + 1 (relative to the chunk)
+    const int d = threadIdx.x;
+    const int64_t nTiles = (N + TD - 1) / TD;
+    for (int64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TD;
+        const int rows = (int)min((int64_t)TD, N - r0);
+        __syncthreads();   // the previous tile's reads are done
+        {   // coalesced fill: element e = (row, col) of the contiguous row block
+            const float* src = X + r0 * n_cols;
+            const int total = rows * n_cols;
+            for (int e = d; e < total; e += TD) {
+                const int row = e / n_cols, col = e - row * n_cols;
+                float v = src[e];
+                if (v != v) v = 0.f;   // DenseDataPoint.getFeatureValue: NaN (unknown) reads as 0
+                sX[col * TD + (row ^ (col & 31))] = v;
+            }
+        }
+        float s = 0.f;
+        for (int ci = 0; ci < n_chunks; ci++) {
+            // chunk = as many whole trees as fit EV_CHUNK_NODES / EV_CHUNK_TREES (cut by the host: chunk_t)
+            const int t0 = chunk_t[ci], t1 = chunk_t[ci + 1];
+            const int base = tree_off[t0];
+            __syncthreads();   // the previous chunk (and the tile fill) are done
+            const int nn = tree_off[t1] - base;
+            for (int i = d; i < nn; i += TD) sN[i] = nodes[base + i];
+            for (int i = d; i <= t1 - t0; i += TD) sOff[i] = (unsigned short)(tree_off[t0 + i] - base);
+            for (int i = d; i < t1 - t0; i += TD) sW[i] = weights[t0 + i];
+            __syncthreads();
+            if (d < rows) {
+                for (int t = 0; t < t1 - t0; t++) {
+                    const int o = sOff[t];
+                    ENode nd = sN[o];
+                    while ((nd.cl & 0xFFFFu) != EV_LEAF) {
+                        const uint32_t col = nd.cl & 0xFFFFu;
+                        const float v = (col == EV_ZERO) ? 0.f : sX[col * TD + (d ^ (col & 31))];
+                        nd = sN[o + (nd.cl >> 16) + ((v <= nd.thr) ? 0 : 1)];
+                    }
+                    s = (float)((double)s + (double)nd.thr * (double)sW[t]);
+                }
+            }
+        }
+        if (d < rows) out[r0 + d] = s;
+    }
+}
+
+// rows wider than the tiled kernel's shared memory takes: one thread per data point straight from global memory
+__global__ void __launch_bounds__(256) k_ensemble_eval_wide(const ENode* __restrict__ nodes, const int32_t* __restrict__ tree_off,
+                                                             int n_trees, const float* __restrict__ weights,
+                                                             const float* __restrict__ X, int64_t N, int n_cols,
+                                                             float* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const float* row = X + i * n_cols;
         float s = 0.f;
         for (int t = 0; t < n_trees; t++) {
-            const EvalNode* tn = nodes + tree_off[t];
-            int n = 0;
-            EvalNode nd = tn[0];
-            while (nd.fid != -1) {
-                float v = (nd.fid <= 0 || nd.fid >= n_cols) ? 0.f : row[nd.fid];
+            const ENode* tn = nodes + tree_off[t];
+            ENode nd = tn[0];
+            while ((nd.cl & 0xFFFFu) != EV_LEAF) {
+                const uint32_t col = nd.cl & 0xFFFFu;
+                float v = (col == EV_ZERO) ? 0.f : row[col];
                 if (v != v) v = 0.f;
-                n = (v <= nd.thr) ? nd.left : nd.right;
-                nd = tn[n];
+                nd = tn[(nd.cl >> 16) + ((v <= nd.thr) ? 0 : 1)];
             }
             s = (float)((double)s + (double)nd.thr * (double)weights[t]);
         }
@@ -712,40 +924,297 @@ __global__ void __launch_bounds__(256) k_ensemble_eval(const EvalNode* __restric
     }
 }
 
+static size_t eval_smem(int n_cols, int TD) {
+    return (size_t)n_cols * TD * 4 + (size_t)EV_CHUNK_NODES * sizeof(ENode) + (size_t)EV_CHUNK_TREES * 4 + (size_t)(EV_CHUNK_TREES + 2) * 2;
+}
+
+// grow-only scratch slot of the evaluation paths
+static int eval_buf(rlb_ctx* c, int slot, size_t bytes, void** out) {
+    if (c->evalCap[slot] < bytes || !c->dEvalBuf[slot]) {
+        if (c->dEvalBuf[slot]) cudaFree(c->dEvalBuf[slot]);
+        c->dEvalBuf[slot] = nullptr;
+        c->evalCap[slot] = 0;
+        RLB_CUDA(c, cudaMalloc(&c->dEvalBuf[slot], std::max<size_t>(bytes, 256)));
+        c->evalCap[slot] = std::max<size_t>(bytes, 256);
+    }
+    *out = c->dEvalBuf[slot];
+    return RLB_OK;
+}
+
+// Validates a model that crosses the ABI (a malformed one must not send a GPU thread out of bounds or into a cycle) and lays
+// every tree out breadth-first with adjacent children.  col_of(feature_id) gives the matrix column of a split's feature
+// (EV_ZERO when the matrix does not have it).
+template <typename ColFn>
+static int flatten_model(rlb_ctx* c, const char* fn, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees, ColFn col_of,
+                         std::vector<ENode>& en, std::vector<int32_t>& off) {
+    if (n_trees < 0 || tree_off[0] != 0) {
+        rlb_set_error(c, RLB_E_INVALID, fn, "tree_off must start at 0");
+        return RLB_E_INVALID;
+    }
+    en.clear();
+    off.assign(1, 0);
+    std::vector<int32_t> order, newid;
+    for (int t = 0; t < n_trees; t++) {
+        const int b = tree_off[t], e = tree_off[t + 1];
+        const int n = e - b;
+        if (n <= 0 || n > EV_CHUNK_NODES) {
+            rlb_set_error(c, RLB_E_INVALID, fn, n <= 0 ? "tree_off must be strictly increasing (empty tree)" : "a tree has more than 4096 nodes");
+            return RLB_E_INVALID;
+        }
+        const rlb_node* tn = nodes + b;
+        // breadth-first order from the root; every node must be reached exactly once (no cycles, no sharing, no strays)
+        order.clear();
+        newid.assign(n, -1);
+        order.push_back(0);
+        newid[0] = 0;
+        for (size_t h = 0; h < order.size(); h++) {
+            const rlb_node& nd = tn[order[h]];
+            if (nd.feature_id == -1) continue;
+            const int l = nd.left, r = nd.right;
+            if (l <= 0 || r <= 0 || l >= n || r >= n || l == r || newid[l] != -1 || newid[r] != -1) {
+                rlb_set_error(c, RLB_E_INVALID, fn, "malformed tree: child index out of range, shared or cyclic");
+                return RLB_E_INVALID;
+            }
+            newid[l] = (int)order.size();
+            order.push_back(l);
+            newid[r] = (int)order.size();
+            order.push_back(r);
+        }
+        const int base = (int)en.size();
+        for (size_t h = 0; h < order.size(); h++) {
+            const rlb_node& nd = tn[order[h]];
+            ENode o;
+            if (nd.feature_id == -1) {
+                o.thr = nd.output;
+                o.cl = EV_LEAF;
+            } else {
+                o.thr = nd.threshold;
+                o.cl = (uint32_t)col_of(nd.feature_id) | ((uint32_t)newid[nd.left] << 16);   // right = left + 1 by construction
+            }
+            en.push_back(o);
+        }
+        (void)base;
+        off.push_back((int32_t)en.size());
+    }
+    return RLB_OK;
+}
+
+template <int TD>
+static int launch_eval_td(rlb_ctx* c, size_t sm, int grid, const ENode* dN, const int32_t* dOff, const int32_t* dChunk, int n_chunks,
+                          const float* dW, const float* dX, int64_t N, int32_t n_cols, float* dOut) {
+    RLB_CUDA(c, cudaFuncSetAttribute(k_ensemble_eval_tiled<TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_ensemble_eval_tiled<TD><<<grid, TD, sm, c->stream>>>(dN, dOff, dChunk, n_chunks, dW, dX, N, n_cols, dOut);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
+// X (device) -> scores (device).  Chooses the widest tile of which at least two CTAs fit an SM (else the widest that fits).
+static int launch_eval(rlb_ctx* c, const std::vector<ENode>& en, const std::vector<int32_t>& off, int32_t n_trees, const float* weights,
+                       const float* dX, int64_t N, int32_t n_cols, float* dOut) {
+    // tree chunks of the shared-memory staging
+    std::vector<int32_t> chunk(1, 0);
+    for (int t0 = 0; t0 < n_trees;) {
+        int t1 = t0;
+        while (t1 < n_trees && t1 - t0 < EV_CHUNK_TREES && off[t1 + 1] - off[t0] <= EV_CHUNK_NODES) t1++;
+        chunk.push_back(t1);
+        t0 = t1;
+    }
+    const int n_chunks = (int)chunk.size() - 1;
+    std::vector<int32_t> offc(off);
+    offc.insert(offc.end(), chunk.begin(), chunk.end());   // one upload: tree offsets | chunk table
+    void *dN = nullptr, *dOff = nullptr, *dW = nullptr;
+    if (int rc = eval_buf(c, 0, std::max<size_t>(en.size(), 1) * sizeof(ENode), &dN)) return rc;
+    if (int rc = eval_buf(c, 1, offc.size() * 4, &dOff)) return rc;
+    if (int rc = eval_buf(c, 2, (size_t)std::max(n_trees, 1) * 4, &dW)) return rc;
+    RLB_CUDA(c, cudaMemcpyAsync(dN, en.data(), en.size() * sizeof(ENode), cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaMemcpyAsync(dOff, offc.data(), offc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaMemcpyAsync(dW, weights, (size_t)n_trees * 4, cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));   // the host vectors above are pageable and local
+    const int32_t* dChunk = (const int32_t*)dOff + off.size();
+    int dev_sm = 0, max_smem = 0;
+    RLB_CUDA(c, cudaDeviceGetAttribute(&dev_sm, cudaDevAttrMultiProcessorCount, c->device));
+    RLB_CUDA(c, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const size_t cap = (size_t)max_smem;
+    auto grid_of = [&](int TD, size_t sm) {
+        const int per_sm = std::max(1, (int)(cap / (sm + 1024)));
+        return (int)std::min<int64_t>((N + TD - 1) / TD, (int64_t)dev_sm * per_sm);
+    };
+    const ENode* pN = (const ENode*)dN;
+    const int32_t* pO = (const int32_t*)dOff;
+    const float* pW = (const float*)dW;
+    const size_t s256 = eval_smem(n_cols, 256), s128 = eval_smem(n_cols, 128), s64 = eval_smem(n_cols, 64), s32 = eval_smem(n_cols, 32);
+    if (2 * (s128 + 1024) <= cap) return launch_eval_td<128>(c, s128, grid_of(128, s128), pN, pO, dChunk, n_chunks, pW, dX, N, n_cols, dOut);
+    if (s256 <= cap) return launch_eval_td<256>(c, s256, grid_of(256, s256), pN, pO, dChunk, n_chunks, pW, dX, N, n_cols, dOut);
+    if (s128 <= cap) return launch_eval_td<128>(c, s128, grid_of(128, s128), pN, pO, dChunk, n_chunks, pW, dX, N, n_cols, dOut);
+    if (s64 <= cap) return launch_eval_td<64>(c, s64, grid_of(64, s64), pN, pO, dChunk, n_chunks, pW, dX, N, n_cols, dOut);
+    if (s32 <= cap) return launch_eval_td<32>(c, s32, grid_of(32, s32), pN, pO, dChunk, n_chunks, pW, dX, N, n_cols, dOut);
+    const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)dev_sm * 8);
+    k_ensemble_eval_wide<<<grid, 256, 0, c->stream>>>(pN, pO, n_trees, pW, dX, N, n_cols, dOut);
+    RLB_CHECK_LAUNCH(c);
+    return RLB_OK;
+}
+
 int rlb_impl_ensemble_eval(rlb_ctx* c, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees, const float* weights,
                            const float* X, int64_t N, int32_t n_cols, float* out) {
-    if (!nodes || !tree_off || !weights || !X || !out || N < 0 || n_trees < 0 || n_cols <= 0) {
+    if (!nodes || !tree_off || !weights || !X || !out || N < 0 || n_trees < 0 || n_cols <= 0 || n_cols > 0xFFF0) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_ensemble_eval", "bad argument");
         return RLB_E_INVALID;
     }
     if (N == 0) return RLB_OK;
     RLB_CUDA(c, cudaSetDevice(c->device));
-    const int total = tree_off[n_trees];
-    std::vector<EvalNode> en(std::max(total, 1));
-    for (int i = 0; i < total; i++) {
-        en[i].fid = nodes[i].feature_id;
-        en[i].thr = (nodes[i].feature_id == -1) ? nodes[i].output : nodes[i].threshold;
-        en[i].left = nodes[i].left;
-        en[i].right = nodes[i].right;
-    }
-    EvalNode* dN = nullptr;
-    int32_t* dOff = nullptr;
-    float *dW = nullptr, *dX = nullptr, *dOut = nullptr;
-    RLB_CUDA(c, cudaMalloc(&dN, en.size() * sizeof(EvalNode)));
-    RLB_CUDA(c, cudaMalloc(&dOff, (size_t)(n_trees + 1) * 4));
-    RLB_CUDA(c, cudaMalloc(&dW, (size_t)std::max(n_trees, 1) * 4));
-    RLB_CUDA(c, cudaMalloc(&dX, (size_t)N * n_cols * 4));
-    RLB_CUDA(c, cudaMalloc(&dOut, (size_t)N * 4));
-    RLB_CUDA(c, cudaMemcpyAsync(dN, en.data(), en.size() * sizeof(EvalNode), cudaMemcpyHostToDevice, c->stream));
-    RLB_CUDA(c, cudaMemcpyAsync(dOff, tree_off, (size_t)(n_trees + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    RLB_CUDA(c, cudaMemcpyAsync(dW, weights, (size_t)n_trees * 4, cudaMemcpyHostToDevice, c->stream));
+    std::vector<ENode> en;
+    std::vector<int32_t> off;
+    // X is indexed by feature id directly; an id outside the matrix reads 0 like -missingZero (DenseDataPoint.java:21-32)
+    auto col_of = [&](int fid) -> uint32_t { return (fid <= 0 || fid >= n_cols) ? EV_ZERO : (uint32_t)fid; };
+    if (int rc = flatten_model(c, "rlb_ensemble_eval", nodes, tree_off, n_trees, col_of, en, off)) return rc;
+    void *dX = nullptr, *dOut = nullptr;
+    if (int rc = eval_buf(c, 3, (size_t)N * n_cols * 4, &dX)) return rc;
+    if (int rc = eval_buf(c, 4, (size_t)N * 4, &dOut)) return rc;
     RLB_CUDA(c, cudaMemcpyAsync(dX, X, (size_t)N * n_cols * 4, cudaMemcpyHostToDevice, c->stream));
-    int grid = (int)std::min<int64_t>((N + 255) / 256, 148 * 16);
-    k_ensemble_eval<<<grid, 256, 0, c->stream>>>(dN, dOff, n_trees, dW, dX, N, n_cols, dOut);
-    RLB_CHECK_LAUNCH(c);
+    if (int rc = launch_eval(c, en, off, n_trees, weights, (const float*)dX, N, n_cols, (float*)dOut)) return rc;
     RLB_CUDA(c, cudaMemcpyAsync(out, dOut, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dN); cudaFree(dOff); cudaFree(dW); cudaFree(dX); cudaFree(dOut);
+    return RLB_OK;
+}
+
+__global__ void k_f32_to_f64(const float* __restrict__ a, double* __restrict__ b, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = (double)a[i];
+}
+
+// scorer.score(rank(samples)) (LambdaMART.java:259,263; Ranker.rank, Ranker.java:88-103; MetricScorer.score,
+// MetricScorer.java:46-52) on a set that is RESIDENT on the device — which = 0 the training set, 1 the validation set —
+// for a model given as node arrays: Ensemble.eval of every document from the raw values already in HBM (no upload of
+// the matrix), the metric of every list from those float scores, double mean in list order on the host.
+int rlb_impl_score_resident(rlb_ctx* c, int32_t which, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees,
+                            const float* weights, float* scores_out, double* metric_out) {
+    if (!c->loaded || (which != 0 && which != 1) || !nodes || !tree_off || !weights || n_trees < 0) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_score_resident", "bad argument, or no set loaded");
+        return RLB_E_INVALID;
+    }
+    if (which == 1 && !c->have_valid) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_score_resident", "no validation set loaded");
+        return RLB_E_INVALID;
+    }
+    RLB_CUDA(c, cudaSetDevice(c->device));
+    const float* dX = which ? c->dVX : c->dX;
+    const int64_t N = which ? c->valid.N : c->N;
+    const int32_t Q = which ? c->valid.Q : c->Q;
+    const float* dLabel = which ? c->valid.dLabel : c->dLabel;
+    const int32_t* dQoff = which ? c->valid.dQoff : c->dQoff;
+    std::vector<ENode> en;
+    std::vector<int32_t> off;
+    std::map<int, int> colmap;   // feature id -> column of the resident matrix
+    for (int j = 0; j < c->F; j++) colmap.emplace(c->feature_ids[j], j);
+    auto col_of = [&](int fid) -> uint32_t {
+        auto it = colmap.find(fid);
+        return it == colmap.end() ? EV_ZERO : (uint32_t)it->second;
+    };
+    if (int rc = flatten_model(c, "rlb_score_resident", nodes, tree_off, n_trees, col_of, en, off)) return rc;
+    void *dOut = nullptr, *dS = nullptr, *dQM = nullptr;
+    if (int rc = eval_buf(c, 4, (size_t)N * 4, &dOut)) return rc;
+    if (int rc = launch_eval(c, en, off, n_trees, weights, dX, N, c->F, (float*)dOut)) return rc;
+    if (scores_out) RLB_CUDA(c, cudaMemcpyAsync(scores_out, dOut, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (metric_out) {
+        if (!c->inited) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_score_resident", "the metric needs rlb_lambdamart_init (scorer, k)");
+            return RLB_E_INVALID;
+        }
+        if (int rc = eval_buf(c, 3, (size_t)N * 8, &dS)) return rc;
+        if (int rc = eval_buf(c, 5, (size_t)Q * 8, &dQM)) return rc;
+        k_f32_to_f64<<<c->grid_rows, 256, 0, c->stream>>>((const float*)dOut, (double*)dS, N);
+        RLB_CHECK_LAUNCH(c);
+        if (int rc = rlb_impl_launch_rank_metric(c, (const double*)dS, dLabel, dQoff, Q, N, c->prm.metric, c->prm.metric_k, c->dDisc,
+                                                 (double*)dQM))
+            return rc;
+        std::vector<double> per(Q);
+        RLB_CUDA(c, cudaMemcpyAsync(per.data(), dQM, (size_t)Q * 8, cudaMemcpyDeviceToHost, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        double score = 0.0;
+        for (int q = 0; q < Q; q++) score += per[q];
+        *metric_out = score / Q;
+    }
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Random Forests: Sampler.doSampling (R/learning/Sampler.java:21-38) on the device.  `src` holds the whole training set
+// (rlb_load_dense); this context becomes the bag — the lists src picks[0], picks[1], ... in that order — by a device-to-
+// device gather of their rows: no host gather, no re-upload of the matrix per bag (RFRanker.java:80-85).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_lists(const float* __restrict__ srcX, const float* __restrict__ srcLabel,
+                                                       const int32_t* __restrict__ srcStart, const int32_t* __restrict__ dstQoff,
+                                                       int nq, int F, float* __restrict__ dstX, float* __restrict__ dstLabel) {
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int64_t s0 = srcStart[q], d0 = dstQoff[q];
+        const int n = dstQoff[q + 1] - dstQoff[q];
+        const float* sp = srcX + s0 * F;
+        float* dp = dstX + d0 * F;
+        const int total = n * F;   // the rows of a list are contiguous in both matrices
+        for (int e = threadIdx.x; e < total; e += blockDim.x) dp[e] = sp[e];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) dstLabel[d0 + e] = srcLabel[s0 + e];
+    }
+}
+
+int rlb_impl_load_bag(rlb_ctx* c, const rlb_ctx* src, const int32_t* picks, int32_t n_picks) {
+    if (!src || !src->loaded || !picks || n_picks <= 0 || src->device != c->device || src == c) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_load_bag", "the source context must hold a training set on the same device");
+        return RLB_E_INVALID;
+    }
+    RLB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int32_t> start(n_picks), qoff((size_t)n_picks + 1);
+    int64_t N = 0;
+    int maxq = 0;
+    qoff[0] = 0;
+    for (int i = 0; i < n_picks; i++) {
+        const int q = picks[i];
+        if (q < 0 || q >= src->Q) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_load_bag", "list index out of range");
+            return RLB_E_INVALID;
+        }
+        const int n = src->h_qoff[q + 1] - src->h_qoff[q];
+        start[i] = src->h_qoff[q];
+        N += n;
+        if (N >= (1LL << 31)) {
+            rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_load_bag", "more than 2^31-1 samples in the bag");
+            return RLB_E_UNSUPPORTED;
+        }
+        qoff[i + 1] = (int32_t)N;
+        maxq = std::max(maxq, n);
+    }
+    if (N <= 0) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_load_bag", "empty bag");
+        return RLB_E_INVALID;
+    }
+    c->loaded = c->inited = false;
+    c->have_valid = false;
+    c->N = N;
+    c->F = src->F;
+    c->Fp = (c->F + 15) & ~15;
+    c->Q = n_picks;
+    c->max_query = maxq;
+    c->feature_ids = src->feature_ids;
+    c->have_thr = false;
+    c->thr_user = false;
+    c->h_qoff = qoff;
+    int32_t* dStart = nullptr;
+    void* tmp = nullptr;
+    if (int rc = eval_buf(c, 1, (size_t)n_picks * 4, &tmp)) return rc;
+    dStart = (int32_t*)tmp;
+    RLB_CUDA(c, rlb_reserve(c, c->dX, (size_t)N * c->F * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dLabel, (size_t)N * sizeof(float)));
+    RLB_CUDA(c, rlb_reserve(c, c->dQoff, (size_t)(n_picks + 1) * sizeof(int32_t)));
+    RLB_CUDA(c, cudaMemcpyAsync(dStart, start.data(), (size_t)n_picks * 4, cudaMemcpyHostToDevice, c->stream));
+    RLB_CUDA(c, cudaMemcpyAsync(c->dQoff, qoff.data(), (size_t)(n_picks + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    // the source context's stream may still be uploading: order behind it
+    RLB_CUDA(c, cudaStreamSynchronize(src->stream));
+    int dev_sm = 0;
+    RLB_CUDA(c, cudaDeviceGetAttribute(&dev_sm, cudaDevAttrMultiProcessorCount, c->device));
+    k_gather_lists<<<std::min(n_picks, dev_sm * 16), 256, 0, c->stream>>>(src->dX, src->dLabel, dStart, c->dQoff, n_picks, c->F, c->dX,
+                                                                           c->dLabel);
+    RLB_CHECK_LAUNCH(c);
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));   // `start` / `qoff` are pageable host vectors
+    c->loaded = true;
     return RLB_OK;
 }
 
@@ -753,37 +1222,49 @@ int rlb_impl_ensemble_eval(rlb_ctx* c, const rlb_node* nodes, const int32_t* tre
 // the device, double mean in query order on the host.
 int rlb_impl_score_metric(rlb_ctx* c, const double* scores, const float* label, const int32_t* qoff, int32_t Q,
                           int32_t metric, int32_t k, double* out) {
-    if (!scores || !label || !qoff || !out || Q <= 0) {
+    if (!scores || !label || !qoff || !out || Q <= 0 || metric < 0 || metric >= RLB_METRIC_COUNT) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_score_metric", "bad argument");
         return RLB_E_INVALID;
     }
+    if (qoff[0] != 0) {
+        rlb_set_error(c, RLB_E_INVALID, "rlb_score_metric", "qoff must start at 0");
+        return RLB_E_INVALID;
+    }
+    int maxq = 0;
+    for (int q = 0; q < Q; q++) {
+        if (qoff[q + 1] < qoff[q]) {
+            rlb_set_error(c, RLB_E_INVALID, "rlb_score_metric", "qoff must be non-decreasing");
+            return RLB_E_INVALID;
+        }
+        maxq = std::max(maxq, qoff[q + 1] - qoff[q]);
+    }
     RLB_CUDA(c, cudaSetDevice(c->device));
     const int64_t N = qoff[Q];
-    int maxq = 0;
-    for (int q = 0; q < Q; q++) maxq = std::max(maxq, qoff[q + 1] - qoff[q]);
     std::vector<double> disc((size_t)maxq + 2);
     const double LOG2 = std::log(2.0);
     for (size_t i = 0; i < disc.size(); i++) disc[i] = 1.0 / (std::log((double)(i + 2)) / LOG2);
-    double *dS = nullptr, *dDisc = nullptr, *dOut = nullptr;
-    float* dL = nullptr;
-    int32_t* dQ = nullptr;
-    RLB_CUDA(c, cudaMalloc(&dS, std::max<int64_t>(N, 1) * 8));
-    RLB_CUDA(c, cudaMalloc(&dL, std::max<int64_t>(N, 1) * 4));
-    RLB_CUDA(c, cudaMalloc(&dQ, (size_t)(Q + 1) * 4));
-    RLB_CUDA(c, cudaMalloc(&dDisc, disc.size() * 8));
-    RLB_CUDA(c, cudaMalloc(&dOut, (size_t)Q * 8));
-    RLB_CUDA(c, cudaMemcpyAsync(dS, scores, N * 8, cudaMemcpyHostToDevice, c->stream));
-    RLB_CUDA(c, cudaMemcpyAsync(dL, label, N * 4, cudaMemcpyHostToDevice, c->stream));
-    RLB_CUDA(c, cudaMemcpyAsync(dQ, qoff, (size_t)(Q + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    RLB_CUDA(c, cudaMemcpyAsync(dDisc, disc.data(), disc.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    int rc = rlb_impl_launch_rank_metric(c, dS, dL, dQ, Q, N, metric, k, dDisc, dOut);
-    if (rc) return rc;
+    // one scratch block, released on every path
+    const size_t oS = 0, oD = oS + (size_t)std::max<int64_t>(N, 1) * 8, oO = oD + disc.size() * 8, oL = oO + (size_t)Q * 8,
+                 oQ = oL + (((size_t)std::max<int64_t>(N, 1) * 4 + 7) & ~(size_t)7), total = oQ + (size_t)(Q + 1) * 4;
+    unsigned char* blk = nullptr;
+    RLB_CUDA(c, cudaMalloc(&blk, total));
     std::vector<double> per(Q);
-    RLB_CUDA(c, cudaMemcpyAsync(per.data(), dOut, (size_t)Q * 8, cudaMemcpyDeviceToHost, c->stream));
-    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int rc = [&]() -> int {
+        RLB_CUDA(c, cudaMemcpyAsync(blk + oS, scores, N * 8, cudaMemcpyHostToDevice, c->stream));
+        RLB_CUDA(c, cudaMemcpyAsync(blk + oL, label, N * 4, cudaMemcpyHostToDevice, c->stream));
+        RLB_CUDA(c, cudaMemcpyAsync(blk + oQ, qoff, (size_t)(Q + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        RLB_CUDA(c, cudaMemcpyAsync(blk + oD, disc.data(), disc.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        if (int r = rlb_impl_launch_rank_metric(c, (const double*)(blk + oS), (const float*)(blk + oL), (const int32_t*)(blk + oQ), Q, N,
+                                                metric, k, (const double*)(blk + oD), (double*)(blk + oO)))
+            return r;
+        RLB_CUDA(c, cudaMemcpyAsync(per.data(), blk + oO, (size_t)Q * 8, cudaMemcpyDeviceToHost, c->stream));
+        RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+        return RLB_OK;
+    }();
+    cudaFree(blk);
+    if (rc) return rc;
     double score = 0.0;
     for (int q = 0; q < Q; q++) score += per[q];
     *out = score / Q;
-    cudaFree(dS); cudaFree(dL); cudaFree(dQ); cudaFree(dDisc); cudaFree(dOut);
     return RLB_OK;
 }

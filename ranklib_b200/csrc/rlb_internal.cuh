@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -68,6 +69,7 @@ struct NodeRec {
     double deviance;
     float output;
     int32_t leaf_ord;      // ordinal in leaves() order once the tree is finished, else -1
+    double split_S;        // S = sL^2/cL + sR^2/cR of the split taken at this node (FeatureHistogram.java:253); parity tests
 };
 
 // peer-memory view of the staging blocks and hand-shake flags of every rank (own entries = local pointers)
@@ -112,7 +114,8 @@ struct DevState {
     long long chain_prof[64][4]; // RLB_CHAIN_DEBUG: per chain (leaf*2+which): walk cycles, fallback cycles, fallbacks, chunks
     long long small_sq_fix; // scratch: squared-sum of the rows going LEFT (local, then all-reduced)
     float train_metric;
-    float chain_out[4];
+    float valid_metric;     // score of the current model on the validation set (LambdaMART.java:236)
+    float chain_out[4];     // [0] training-metric chain, [1] validation-metric chain
     int32_t queue[RLB_MAX_NODES];
     int32_t qcnt[RLB_MAX_NODES];             // sample count of every queued node (kept next to the queue: the controller
     double qdev[RLB_MAX_NODES];              // is one thread chasing global memory, so its data sits in few cache lines)
@@ -120,6 +123,23 @@ struct DevState {
     int32_t leaf_lo[RLB_MAX_LEAVES + 1];      // their segment starts (ascending) + N sentinel
     float leaf_s1[RLB_MAX_LEAVES + 1], leaf_s2[RLB_MAX_LEAVES + 1];
     NodeRec nodes[RLB_MAX_NODES];
+};
+
+// One List<RankList> resident on the device as the per-query kernels see it: the training set, or the validation set
+// (LambdaMART.java:152-158).  Queries are routed to kernels by size class (lists built once, rlb_build_query_classes).
+struct QuerySet {
+    int64_t N = 0;
+    int32_t Q = 0, max_query = 0;
+    float* dLabel = nullptr;
+    int32_t* dQoff = nullptr;
+    double* dScore = nullptr;
+    double* dIdeal = nullptr;       // ideal DCG@k per query
+    double* dQMetric = nullptr;     // per-query metric of the last pass
+    int32_t* dRankDoc = nullptr;    // ranking scratch of the table-free kernel
+    int32_t* dQList = nullptr;      // query ids grouped [A: warp | B0 | B1 | B2: CTA | C: table-free]
+    int32_t nqA = 0, nqB0 = 0, nqB1 = 0, nqB2 = 0, nqC = 0;
+    double* dAux = nullptr;         // generic metrics, queries above QCAP documents: per-CTA prologue arrays (global memory)
+    int32_t aux_ctas = 0;           // CTAs of the table-free kernel when dAux is in use
 };
 
 struct rlb_ctx {
@@ -135,6 +155,8 @@ struct rlb_ctx {
     int64_t N = 0, N_total = 0, Q_total = 0;
     int32_t F = 0, Fp = 0, Q = 0, max_query = 0;
     bool loaded = false, inited = false, have_thr = false, tree_ready = false, tree_output_ready = false;
+    bool thr_user = false;          // h_thr was imposed by rlb_set_thresholds (kept across re-inits); else derived from the data
+    int32_t thr_built_for = 0;      // n_threshold the derived thresholds were built with
     bool lambda_fresh = false;      // dLambda / dWeight / scales belong to the current dScore
     rlb_params prm{};
     std::vector<int32_t> feature_ids;
@@ -163,6 +185,21 @@ struct rlb_ctx {
     int32_t hist_min_rows = 4096;   // nodes with fewer local rows use the direct-atomics histogram kernel
     // per-query ranking scratch (positions inside the query, sorted by score)
     int32_t* dRankDoc = nullptr;
+    double* dQAux = nullptr;        // generic metrics on queries above QCAP documents (see QuerySet::dAux)
+    int32_t qaux_ctas = 0;
+    // validation set, resident (LambdaMART.java:152-158,228-237): raw values (a tree walk compares v <= thresholds[f][t]
+    // exactly as Split.eval does), labels, offsets, modelScoresOnValidation
+    bool have_valid = false;
+    float* dVX = nullptr;           // [Nv][F], columns as the training set's
+    QuerySet valid;
+    // capacity of every buffer obtained through rlb_reserve (key: address of the pointer member): buffers are grow-only,
+    // so a context that is re-loaded / re-initialised (one Random-Forest bag after the other) reuses its allocations
+    std::map<void*, size_t> cap;
+    std::vector<int32_t> h_vqoff;   // ... and of the validation set's
+    std::vector<int32_t> h_qoff;    // host copy of the training set's query offsets (rlb_load_bag of another context reads it)
+    // scratch of rlb_ensemble_eval / rlb_score_resident (grow-only)
+    void* dEvalBuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t evalCap[6] = {0, 0, 0, 0, 0, 0};
     // query ids grouped by size class: [A: warp path | B0: 64-thread CTA | B1: 128-thread CTA | B2: 256-thread CTA | C: fallback]
     int32_t* dQList = nullptr;
     int32_t nqA = 0, nqB0 = 0, nqB1 = 0, nqB2 = 0, nqC = 0;
@@ -272,7 +309,19 @@ int rlb_impl_ensemble_eval(rlb_ctx* ctx, const rlb_node* nodes, const int32_t* t
                            const float* weights, const float* X, int64_t N, int32_t n_cols, float* out);
 int rlb_impl_score_metric(rlb_ctx* ctx, const double* scores, const float* label, const int32_t* qoff, int32_t Q,
                           int32_t metric, int32_t k, double* out);
+int rlb_impl_load_validation(rlb_ctx* ctx, const float* X, int64_t N, int32_t F, const float* label, const int32_t* qoff,
+                             int32_t Q);
+int rlb_impl_score_resident(rlb_ctx* ctx, int32_t which, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees,
+                            const float* weights, float* scores_out, double* metric_out);
 void rlb_impl_free(rlb_ctx* ctx);
+// grow-only device allocation: keeps *ptr when its capacity covers `bytes`, else frees it and allocates anew
+cudaError_t rlb_reserve_bytes(rlb_ctx* ctx, void** ptr, size_t bytes);
+template <typename T>
+static inline cudaError_t rlb_reserve(rlb_ctx* ctx, T*& ptr, size_t bytes) {
+    return rlb_reserve_bytes(ctx, reinterpret_cast<void**>(&ptr), bytes);
+}
+int rlb_build_query_classes(rlb_ctx* ctx, const int32_t* qoff_host, QuerySet& qs);
+int rlb_impl_load_bag(rlb_ctx* ctx, const rlb_ctx* src, const int32_t* picks, int32_t n_picks);
 int rlb_p2p_setup(rlb_ctx* ctx);
 void rlb_p2p_close(rlb_ctx* ctx);
 
@@ -286,6 +335,8 @@ int rlb_impl_finish_iter(rlb_ctx* ctx);
 int rlb_impl_tree_output(rlb_ctx* ctx);
 int rlb_impl_update_scores(rlb_ctx* ctx);
 int rlb_impl_train_metric(rlb_ctx* ctx, bool with_pseudo);
+int rlb_impl_valid_step(rlb_ctx* ctx);
+QuerySet rlb_train_set(const rlb_ctx* ctx);
 int rlb_impl_assign_nodes(rlb_ctx* ctx);
 int rlb_impl_export_tree(rlb_ctx* ctx, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes);
 int rlb_impl_float_chain(rlb_ctx* ctx, const double* x, int64_t n, float carry, int32_t passes, float* out, int64_t* info);

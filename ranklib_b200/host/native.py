@@ -17,7 +17,7 @@ KIND_LAMBDAMART, KIND_MART = 0, 1
 METRIC_NDCG, METRIC_DCG, METRIC_ERR, METRIC_MAP, METRIC_PRECISION, METRIC_RR, METRIC_BEST = range(7)
 MAX_BINS = 257
 
-READ = dict(LAMBDA=1, WEIGHT=2, SCORE=3, LEAF_ID=4, BINS=5, ROOT_SUM=6, ROOT_COUNT=7, ROOT_STATS=8, NODE_ID=9)
+READ = dict(LAMBDA=1, WEIGHT=2, SCORE=3, LEAF_ID=4, BINS=5, ROOT_SUM=6, ROOT_COUNT=7, ROOT_STATS=8, NODE_ID=9, SPLIT_S=10)
 
 # every symbol include/ranklib_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "rlb_destroy", "rlb_comm_unique_id",
@@ -26,7 +26,7 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
            "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain",
            "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_write_binary", "rlb_load_letor", "rlb_letor_qid", "rlb_letor_free",
-           "rlb_parse_java_float"]
+           "rlb_parse_java_float", "rlb_load_validation", "rlb_valid_metric", "rlb_score_resident", "rlb_load_bag", "rlb_learn"]
 
 
 class RankLibError(RuntimeError):
@@ -170,6 +170,7 @@ class Context:
                 else np.ascontiguousarray(feature_ids, np.int32))
         self._ck(self.lib.rlb_load_dense(self.h, _p(X), C.c_int64(N), F, _p(fids), _p(label), _p(qoff), len(qoff) - 1))
         self.N, self.F, self.Q = N, F, len(qoff) - 1
+        self.qoff_host = qoff.copy()
 
     def load_letor(self, path, must_have_rel_doc=False, features=None, nthreads=0):
         """FeatureManager.readInput + the flattening of LambdaMART.init in one native step: file -> device."""
@@ -184,6 +185,53 @@ class Context:
             self.N, self.F, self.Q = n.value, (mf.value if fids is None else len(fids)), q.value
         finally:
             self.lib.rlb_letor_free(h)
+
+    def load_validation(self, X, label, qoff):
+        """Ranker.setValidationSet: the validation lists stay on the device (same feature columns as the training set)."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        label = np.ascontiguousarray(label, dtype=np.float32)
+        qoff = np.ascontiguousarray(qoff, dtype=np.int32)
+        self._ck(self.lib.rlb_load_validation(self.h, _p(X), C.c_int64(X.shape[0]), X.shape[1], _p(label), _p(qoff), len(qoff) - 1))
+        self.Nv, self.Qv = X.shape[0], len(qoff) - 1
+
+    def load_bag(self, src, picks):
+        """Sampler.doSampling on the device: this context becomes the bag of src's lists picks[0], picks[1], ..."""
+        picks = np.ascontiguousarray(picks, np.int32)
+        self._ck(self.lib.rlb_load_bag(self.h, src.h, _p(picks), len(picks)))
+        qo = np.asarray(src.qoff_host)
+        sizes = qo[picks + 1] - qo[picks]
+        self.N, self.F, self.Q = int(sizes.sum()), src.F, len(picks)
+        self.qoff_host = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+
+    def valid_metric(self):
+        m = C.c_float()
+        self._ck(self.lib.rlb_valid_metric(self.h, C.byref(m)))
+        return m.value
+
+    def learn(self, n_trees, n_round_to_stop_early):
+        """LambdaMART.learn's loop in one call: (trees, train metrics, validation metrics, bestModelOnValidation, best score)."""
+        nodes = np.zeros((max(n_trees, 1), self.cap), NODE_DTYPE)
+        nn = np.zeros(max(n_trees, 1), np.int32)
+        tm = np.zeros(max(n_trees, 1), np.float32)
+        vm = np.zeros(max(n_trees, 1), np.float32)
+        done, best = C.c_int32(), C.c_int32()
+        bv = C.c_double()
+        self._ck(self.lib.rlb_learn(self.h, n_trees, n_round_to_stop_early, _p(nodes), self.cap, _p(nn), _p(tm), _p(vm),
+                                    C.byref(done), C.byref(best), C.byref(bv)))
+        k = done.value
+        return [nodes[i, :nn[i]].copy() for i in range(k)], tm[:k].copy(), vm[:k].copy(), best.value, bv.value
+
+    def score_resident(self, which, nodes, tree_off, weights, want_scores=False, want_metric=True):
+        """scorer.score(rank(samples)) on the resident training (0) / validation (1) set: (scores or None, metric or None)."""
+        nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+        tree_off = np.ascontiguousarray(tree_off, np.int32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        n = self.N if which == 0 else self.Nv
+        out = np.zeros(n, np.float32) if want_scores else None
+        m = C.c_double()
+        self._ck(self.lib.rlb_score_resident(self.h, which, _p(nodes), _p(tree_off), len(tree_off) - 1, _p(weights),
+                                             _p(out) if want_scores else None, C.byref(m) if want_metric else None))
+        return out, (m.value if want_metric else None)
 
     def set_thresholds(self, thr, n_thr):
         thr = np.ascontiguousarray(thr, np.float32)
@@ -249,7 +297,7 @@ class Context:
         N, F = self.N, self.F
         shape, dt = {1: ((N,), np.float64), 2: ((N,), np.float64), 3: ((N,), np.float64), 4: ((N,), np.int32),
                      5: ((F, N), np.int32), 6: ((F, MAX_BINS), np.float64), 7: ((F, MAX_BINS), np.int32),
-                     8: ((2,), np.float64), 9: ((N,), np.int32)}[w]
+                     8: ((2,), np.float64), 9: ((N,), np.int32), 10: ((self.cap,), np.float64)}[w]
         out = np.zeros(shape, dt)
         self._ck(self.lib.rlb_read(self.h, w, _p(out), C.c_int64(out.nbytes)))
         return out

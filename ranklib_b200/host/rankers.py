@@ -427,21 +427,40 @@ class LambdaMART(Ranker):
         self.features = s.features[cols]
         self.ctx = native.Context(self.device)
         self.ctx.load_dense(s.X[:, cols], s.label, s.qoff, self.features)
+        self.init_loaded()
+
+    def init_loaded(self):
+        """The rest of LambdaMART.init for a context that already holds its training set (rlb_load_dense / rlb_load_bag)."""
+        self._load_validation()
         self.ctx.init(native.make_params(n_leaves=type(self).nTreeLeaves, mls=type(self).minLeafSupport,
                                          lr=type(self).learningRate, n_threshold=type(self).nThreshold, kind=self.KIND,
                                          metric=self.scorer.metric, k=self.scorer.getK(), frate=type(self).samplingRate,
                                          seed=type(self).seed))
         self.ensemble = Ensemble()
         self.trainLog = []
+        self.bestModelOnValidation = (1 << 31) - 3      # Integer.MAX_VALUE - 2 (LambdaMART.java:50)
+
+    def _load_validation(self):
+        """modelScoresOnValidation of LambdaMART.init (LambdaMART.java:152-158): the validation lists go to the device once,
+        in the training set's feature columns (a feature the validation file does not list is unknown = NaN -> 0)."""
+        v = self.validationSamples
+        if v is None:
+            return
+        Xv = np.full((v.X.shape[0], len(self.features)), np.nan, np.float32)
+        pos = {int(f): j for j, f in enumerate(v.features)}
+        for j, f in enumerate(self.features):
+            if int(f) in pos:
+                Xv[:, j] = v.X[:, pos[int(f)]]
+        self.ctx.load_validation(Xv, v.label, v.qoff)
 
     def learn(self):
         """LambdaMART.learn (LambdaMART.java:169-272): boosting loop, validation-based best-model tracking and early
-        stopping, roll-back, final score on the training data from Ensemble.eval."""
+        stopping, roll-back, final score on the training data from Ensemble.eval.  The validation lists are resident on
+        the device: every rlb_boost_iter updates their cached scores and evaluates the metric there (:228-237), and the
+        final scores (:259,263) come from the resident matrices too — nothing is uploaded inside the loop."""
         cls = type(self)
         v = self.validationSamples
-        best_model, best_v = (1 << 31) - 3, -1.0
-        v_scores = None if v is None else np.zeros(v.X.shape[0], np.float64)
-        v_fid = None if v is None else v.dense_with_fid_columns()
+        self.bestScoreOnValidationData = 0.0                 # Ranker.java:43
         for m in range(cls.nTrees):
             nodes, metric = self.ctx.boost_iter()
             rt = RegressionTree(nodes)
@@ -449,23 +468,25 @@ class LambdaMART(Ranker):
             self.scoreOnTrainingData = metric
             row = [m + 1, round(float(metric), 4)]
             if v is not None:
-                # modelScoresOnValidation += learningRate * rt.eval(dp) (LambdaMART.java:228-234), double accumulation
-                leaf = self.ctx.ensemble_eval(nodes, [0, len(nodes)], [1.0], v_fid).astype(np.float64)
-                v_scores += float(np.float32(cls.learningRate)) * leaf
-                score = np.float32(self.ctx.score_metric(v_scores, v.label, v.qoff, self.scorer.metric, self.scorer.getK()))
-                row.append(round(float(score), 4))
-                if score > best_v:
-                    best_v, best_model = float(score), self.ensemble.treeCount() - 1
+                score = float(np.float32(self.ctx.valid_metric()))   # computeModelScoreOnValidation(): a float (:485-518)
+                row.append(round(score, 4))
+                if score > self.bestScoreOnValidationData:           # :240-243
+                    self.bestScoreOnValidationData = score
+                    self.bestModelOnValidation = self.ensemble.treeCount() - 1
             self.trainLog.append(row)
-            if m - best_model > cls.nRoundToStopEarly:
+            if m - self.bestModelOnValidation > cls.nRoundToStopEarly:   # :248
                 break
-        while self.ensemble.treeCount() > best_model + 1:
+        while self.ensemble.treeCount() > self.bestModelOnValidation + 1:   # :254-256
             self.ensemble.remove(self.ensemble.treeCount() - 1)
-        self.scoreOnTrainingData = self._score(self.samples)
+        self.scoreOnTrainingData = self._score_resident(0)
         if v is not None:
-            self.bestScoreOnValidationData = self._score(v)
+            self.bestScoreOnValidationData = self._score_resident(1)
 
-    def _score(self, rl):  # scorer.score(rank(samples)) (LambdaMART.java:259, Ranker.java:88-103)
+    def _score_resident(self, which):  # scorer.score(rank(samples)) (LambdaMART.java:259,263) without re-uploading the set
+        nodes, offs, w = self.ensemble.flat()
+        return self.ctx.score_resident(which, nodes, offs, w)[1]
+
+    def _score(self, rl):  # scorer.score(rank(rl)) for a set that is not on the device (Ranker.java:88-103)
         s = self.ensemble.eval(self.ctx, rl.dense_with_fid_columns()).astype(np.float64)
         return self.ctx.score_metric(s, rl.label, rl.qoff, self.scorer.metric, self.scorer.getK())
 
@@ -523,6 +544,19 @@ class RFRanker(Ranker):
 
     def init(self):
         self.ensembles = []
+        self._base = None
+
+    def _base_ctx(self):
+        """The whole training set, uploaded ONCE; every bag is gathered from it on the device (rlb_load_bag)."""
+        if self._base is None:
+            s = self.samples
+            cols = np.arange(s.X.shape[1]) if self.features is None else \
+                np.array([int(np.nonzero(s.features == f)[0][0]) for f in self.features])
+            self.features = s.features[cols]
+            self._base = native.Context(self.device)
+            self._base.load_dense(s.X[:, cols], s.label, s.qoff, self.features)
+            self._bagctx = native.Context(self.device)
+        return self._base
 
     def bag_queries(self, rnd):
         """Sampler.doSampling(samples, subSamplingRate, withReplacement=true) (R/learning/Sampler.java:21-38)."""
@@ -548,11 +582,15 @@ class RFRanker(Ranker):
             nRoundToStopEarly = (1 << 30)
             samplingRate, seed = cls.featureSamplingRate, cls.seed + 1 + i
 
-        r = _Bag(self.samples.select(picks), self.features, self.scorer)
+        base = self._base_ctx()
+        r = _Bag(None, self.features, self.scorer)
         r.device = self.device
-        r.init()
+        r.ctx = self._bagctx                       # one context for all bags: its buffers are reused (grow-only)
+        r.ctx.load_bag(base, picks)                # Sampler.doSampling on the device (no host gather, no re-upload)
+        r.init_loaded()
         r.learn()
         self._ctx = r.ctx
+        self.bagScores.append(r.getScoreOnTrainingData())
         return r.getEnsemble()
 
     def learn(self, bags=None):
@@ -560,7 +598,20 @@ class RFRanker(Ranker):
         plan = self.bag_plan()
         todo = range(type(self).nBag) if bags is None else sorted(bags)
         self.bag_ids = list(todo)
+        self.bagScores = []
         self.ensembles = [self._train_bag(i, plan[i]) for i in todo]
+        if bags is None:
+            self._finish()
+
+    def _finish(self):
+        """RFRanker.learn's tail (RFRanker.java:97-103): scorer.score(rank(samples)) on the training / validation data."""
+        s = self.eval(self.samples)
+        self.scoreOnTrainingData = self._ctx.score_metric(s, self.samples.label, self.samples.qoff, self.scorer.metric,
+                                                          self.scorer.getK())
+        v = self.validationSamples
+        if v is not None:
+            self.bestScoreOnValidationData = self._ctx.score_metric(self.eval(v), v.label, v.qoff, self.scorer.metric,
+                                                                    self.scorer.getK())
 
     def learn_bag_parallel(self, rank, world, dist=None):
         """Config C5: replicas + bag parallelism.  Every process holds the whole training set, trains
@@ -576,6 +627,12 @@ class RFRanker(Ranker):
             assert [i for i, _ in merged] == list(range(type(self).nBag)), "every bag exactly once"
             self.ensembles = [Ensemble(text) for _, text in merged]
             self.bag_ids = list(range(type(self).nBag))
+        self._finish()
+
+    def rank(self, rl):
+        """Ranker.rank (Ranker.java:88-103): per list, stable descending order of RFRanker.eval."""
+        s = self.eval(rl)
+        return [rl.qoff[q] + np.argsort(-s[rl.qoff[q]:rl.qoff[q + 1]], kind="stable") for q in range(rl.size())]
 
     def eval(self, rl):
         """RFRanker.eval (RFRanker.java:117-123): double mean of the bag ensembles' float scores."""

@@ -594,6 +594,19 @@ class LambdaMART : public Ranker {
         ctx.reset();
         NativeContext& c = context();
         c.check(rlb_load_dense(c.get(), xp, s.N, F, features.data(), s.label.data(), s.qoff.data(), s.size()));
+        if (validationSamples) {
+            // modelScoresOnValidation of LambdaMART.init (LambdaMART.java:152-158): the validation lists go to the device once,
+            // in the training set's feature columns (a feature the validation set does not have is unknown = NaN -> 0)
+            const RankLists& v = *validationSamples;
+            std::vector<float> Xv((size_t)v.N * (size_t)F, std::numeric_limits<float>::quiet_NaN());
+            for (int32_t j = 0; j < F; j++) {
+                auto it = std::find(v.features.begin(), v.features.end(), features[(size_t)j]);
+                if (it == v.features.end()) continue;
+                const size_t col = (size_t)(it - v.features.begin());
+                for (int64_t i = 0; i < v.N; i++) Xv[(size_t)i * (size_t)F + (size_t)j] = v.X[(size_t)i * (size_t)v.F + col];
+            }
+            c.check(rlb_load_validation(c.get(), Xv.data(), v.N, F, v.label.data(), v.qoff.data(), v.size()));
+        }
         rlb_params p{};
         p.n_leaves = nTreeLeaves;
         p.min_leaf_support = minLeafSupport;
@@ -617,13 +630,7 @@ class LambdaMART : public Ranker {
         const int cap = 2 * nTreeLeaves + 1;
         std::vector<rlb_node> buf((size_t)cap);
         const RankLists* v = validationSamples.get();
-        std::vector<double> vScores;
-        std::vector<float> vFid;
-        int32_t vCols = 0;
-        if (v) {
-            vScores.assign((size_t)v->N, 0.0);
-            vFid = v->denseWithFidColumns(&vCols);
-        }
+        bestScoreOnValidationData = 0.0;   // Ranker.java:43
         for (int m = 0; m < nTrees; m++) {
             int32_t n = 0;
             float metric = 0.f;
@@ -633,12 +640,9 @@ class LambdaMART : public Ranker {
             scoreOnTrainingData = metric;
             LogRow row{m + 1, (double)metric, std::numeric_limits<double>::quiet_NaN()};
             if (v) {
-                // modelScoresOnValidation[i][j] += learningRate * rt.eval(dp) (LambdaMART.java:228-234): double accumulation
-                Ensemble one;
-                one.add(rt, 1.0f);
-                const std::vector<float> leaf = one.eval(c.get(), vFid, v->N, vCols);
-                for (size_t i = 0; i < vScores.size(); i++) vScores[i] += (double)learningRate * (double)leaf[i];
-                const float score = (float)c.scoreMetric(vScores, *v, scorer);  // computeModelScoreOnValidation returns float
+                // LambdaMART.java:228-237 ran on the device inside rlb_boost_iter (resident validation lists)
+                float score = 0.f;
+                c.check(rlb_valid_metric(c.get(), &score));
                 row.validation = score;
                 if (score > bestScoreOnValidationData) {
                     bestScoreOnValidationData = score;
@@ -649,8 +653,20 @@ class LambdaMART : public Ranker {
             if (m - bestModelOnValidation > nRoundToStopEarly) break;
         }
         while (ensemble.treeCount() > bestModelOnValidation + 1) ensemble.remove(ensemble.treeCount() - 1);
-        scoreOnTrainingData = score(*samples);
-        if (v) bestScoreOnValidationData = score(*v);
+        scoreOnTrainingData = scoreResident(0);
+        if (v) bestScoreOnValidationData = scoreResident(1);
+    }
+
+    // scorer.score(rank(samples)) (LambdaMART.java:259,263) from the matrices already on the device
+    double scoreResident(int which) {
+        std::vector<rlb_node> nodes;
+        std::vector<int32_t> off;
+        std::vector<float> w;
+        ensemble.flat(&nodes, &off, &w);
+        double out = 0.0;
+        NativeContext& c = context();
+        c.check(rlb_score_resident(c.get(), which, nodes.data(), off.data(), ensemble.treeCount(), w.data(), nullptr, &out));
+        return out;
     }
 
     std::vector<double> eval(const RankLists& rl) override {

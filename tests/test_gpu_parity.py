@@ -10,7 +10,7 @@ import pytest
 
 from oracle import oracle as orc
 from ranklib_b200.host import native, synth
-from tests.util import compare_tree, rel_err
+from tests.util import ParityTally, compare_tree, rel_err, split_S_error
 
 pytestmark = pytest.mark.gpu
 
@@ -77,22 +77,27 @@ def test_stagewise_first_iterations_c1(built):
         assert round(mo, 4) == round(mg, 4), (mo, mg)
 
 
+S_TOL = 1e-9   # |S_gpu - S_oracle| / S per split (H1): fixed-point sums vs doubles in sample order, both ~1e-11 of rounding
+
+
 def _run_lockstep(X, label, qoff, n_trees, **kw):
     o, g = _pair(X, label, qoff, **kw)
-    n_ident = n_equiv = 0
+    tally = ParityTally()
     for it in range(n_trees):
         on, mo = o.boost_iter()
         gn, mg = g.boost_iter()
         ng, no = g.read("NODE_ID"), o.read("NODE_ID")
         identical, equivalent = compare_tree(gn, on, ng, no)
         assert equivalent, f"tree {it}: partitions differ"
-        n_ident += identical
-        n_equiv += equivalent
+        s_err = split_S_error(g.read("SPLIT_S")[:(len(gn) - 1) // 2], o.split_S())
+        assert s_err <= S_TOL, f"tree {it}: split S differs by {s_err:.2e}"
+        tally.add(identical, equivalent, s_err)
         assert np.max(rel_err(gn["output"][ng], on["output"][no])) <= 1e-5, f"tree {it}"
         assert abs(mo - mg) <= 5e-5 and round(mo, 4) == round(mg, 4), (it, mo, mg)
     so, sg = o.read("SCORE"), g.read("SCORE")
     assert np.max(rel_err(sg, so, floor=1e-9)) <= 1e-5
-    return n_ident, n_equiv, o, g
+    print("PARITY", tally)
+    return tally.identical, tally.equivalent, o, g
 
 
 def test_c1_20_trees_lockstep(built):

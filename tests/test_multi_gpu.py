@@ -86,6 +86,9 @@ def _stub_rf(samples):
             e.add(R.RegressionTree(nodes), 0.1)
             return e
 
+        def _finish(self):   # the final scorer.score(rank(samples)) is GPU work (covered by the -m gpu tests)
+            pass
+
     rf = StubRF(samples, None, R.NDCGScorer(10))
     rf.init()
     return rf

@@ -300,3 +300,38 @@ def test_metric_scores_known_answers(built):
     assert abs(ms([1, 2, 0], N.METRIC_DCG, 2) - dcg) < 1e-15
     assert abs(ms([1, 2, 0], N.METRIC_NDCG, 2) - dcg / (3 / log2(2) + 1 / log2(3))) < 1e-15
     assert ms([0, 0, 0], N.METRIC_NDCG, 10) == 0.0                                # ideal DCG 0 -> 0
+
+
+def test_oracle_validation_early_stop_and_best_model_rule():
+    """orc_learn restates LambdaMART.java:180-256: the validation metric of every iteration is the float chain over the lists of
+    scorer.score on the cached scores (modelScoresOnValidation += (double)0.1f * rt.eval), re-derived here from the returned
+    trees alone; best = first strict maximum above 0.0; the loop stops when m - best > nRoundToStopEarly."""
+    X, label, qoff = synth.c1()
+    tr = (X[:800], label[:800], qoff[:21])
+    va = (X[800:], label[800:], (qoff[20:] - qoff[20]).astype(np.int32))
+    o = orc.Oracle(*tr, orc.make_params())
+    o.set_validation(*va)
+    trees, tm, vm, best, bv = o.learn(40, 5)
+    assert len(trees) == min(40, best + 5 + 2) and len(vm) == len(trees)
+    Xf = np.zeros((va[0].shape[0], va[0].shape[1] + 1), np.float32)
+    Xf[:, 1:] = va[0]
+    scores = np.zeros(va[0].shape[0], np.float64)
+    lr = float(np.float32(0.1))
+    running_best, running_arg = 0.0, (1 << 31) - 3
+    for m, t in enumerate(trees):
+        leaf = orc.ensemble_eval(t, [0, len(t)], np.ones(1, np.float32), Xf)      # rt.eval(dp): the leaf's float output
+        scores += lr * leaf.astype(np.float64)
+        s = np.float32(0)
+        for q in range(len(va[2]) - 1):
+            a, b = va[2][q], va[2][q + 1]
+            order = np.argsort(-scores[a:b], kind="stable")
+            s = np.float32(np.float64(s) + orc.metric_score(va[1][a:b][order], 0, 10))
+        s = np.float32(s / np.float32(len(va[2]) - 1))
+        assert s == vm[m], (m, s, vm[m])
+        if float(s) > running_best:
+            running_best, running_arg = float(s), m
+    assert (running_arg, running_best) == (best, bv)
+    # no validation set: nothing is tracked, nothing stops the loop
+    o2 = orc.Oracle(*tr, orc.make_params())
+    t2, _, _, best2, bv2 = o2.learn(7, 2)
+    assert len(t2) == 7 and best2 == (1 << 31) - 3 and bv2 == 0.0

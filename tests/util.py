@@ -21,12 +21,42 @@ def compare_tree(gn, on, g_node_of_doc, o_node_of_doc):
     is the robust integer criterion of SURVEY.md H1/F10: where two candidate splits induce the same
     (or the mirrored) partition their S values are equal in exact arithmetic, the reference's choice
     among them is decided by double rounding noise of its summation order, and ours by the lowest
-    (feature, threshold) because fixed-point sums are exact."""
+    (feature, threshold) because fixed-point sums are exact.  The second half of H1's definition — the
+    two S agree — is checked by split_S_error below."""
     identical = trees_identical(gn, on)
     gl = np.sort(gn["count"][gn["feature_idx"] == -1])
     ol = np.sort(on["count"][on["feature_idx"] == -1])
     equivalent = len(gn) == len(on) and np.array_equal(gl, ol) and same_partition(g_node_of_doc, o_node_of_doc)
     return identical, bool(equivalent)
+
+
+def split_S_error(g_S, o_S):
+    """Largest relative difference between the S = sL^2/cL + sR^2/cR values (FeatureHistogram.java:253) of the splits
+    of two equivalent trees, in split order.  The device's sums are 2^-39-relative fixed point, the oracle's are
+    doubles in sample order: both carry ~1e-11 of rounding, which is what this number measures."""
+    g_S, o_S = np.asarray(g_S, np.float64), np.asarray(o_S, np.float64)
+    n = min(len(g_S), len(o_S))
+    if n == 0:
+        return 0.0
+    return float(np.max(rel_err(g_S[:n], o_S[:n])))
+
+
+class ParityTally:
+    """identity / equivalence rates and the largest S disagreement over a run (SURVEY.md H1 asks for both rates)."""
+
+    def __init__(self):
+        self.trees = self.identical = self.equivalent = 0
+        self.max_S_err = 0.0
+
+    def add(self, identical, equivalent, s_err=0.0):
+        self.trees += 1
+        self.identical += int(bool(identical))
+        self.equivalent += int(bool(equivalent))
+        self.max_S_err = max(self.max_S_err, float(s_err))
+
+    def __str__(self):
+        return (f"{self.trees} trees: split ids identical {self.identical}/{self.trees}, same partition "
+                f"{self.equivalent}/{self.trees}, max |S_gpu - S_oracle| / S = {self.max_S_err:.2e}")
 
 
 def rel_err(a, b, floor=0.0):
