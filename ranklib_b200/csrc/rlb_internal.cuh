@@ -72,11 +72,46 @@ struct NodeRec {
     double split_S;        // S = sL^2/cL + sR^2/cR of the split taken at this node (FeatureHistogram.java:253); parity tests
 };
 
-// peer-memory view of the staging blocks and hand-shake flags of every rank (own entries = local pointers)
+// ------------------------------------------------------------------------------------------------------------------
+// N GPUs, one process each: the EXCHANGE WINDOW.  Every rank owns one device allocation (made in rlb_comm_init, mapped
+// into every peer process with CUDA IPC once per communicator) that carries all data-path communication of a boosting
+// iteration — no NCCL call and no host involvement between the first and the last kernel of an iteration, so the whole
+// iteration is one CUDA graph on N GPUs as on one:
+//   pulled by the peers (they read it over NVLink):  the raw root histogram of this rank's rows, the raw histogram of
+//       the scanned child of the current split (two blocks alternating with the split ordinal), their squared sums;
+//   pushed by the peers (they write it over NVLink): max|lambda| of the iteration, the per-chain totals that predict the
+//       float-chain starts, the running value of every float chain when the previous rank hands it over, the final value
+//       of every chain from the last rank;
+//   flags[kind][source rank]: "source has completed exchange `kind` up to epoch e" (st.release.sys / ld.acquire.sys).
+// Epoch counters live in DevState and advance identically on every rank; a rank can never be a whole exchange ahead of
+// a peer that still reads, because every exchange is a barrier (see the notes at each use in rlb_boost.cu).
+// ------------------------------------------------------------------------------------------------------------------
+#define XW_SPLIT 0    // staging block of split `part_epoch` complete
+#define XW_ROOT 1     // raw root histogram + squared sum complete
+#define XW_SCALE 2    // max|lambda| pushed
+#define XW_TOT1 3     // leaf-chain totals (exact sums) pushed
+#define XW_TOT2 4     // leaf-chain totals (rounded increments) pushed
+#define XW_MTOT 5     // metric-chain total pushed
+#define XW_KINDS 8
+#define XW_NCHAIN (2 * (RLB_MAX_LEAVES + 1))   // leaf chains: which * (RLB_MAX_LEAVES + 1) + leaf
+#define XW_METRIC_CHAIN XW_NCHAIN               // the training-metric chain's slot in carry[] / final_[]
+
+struct XWin {
+    unsigned int flags[XW_KINDS][RLB_MAX_RANKS];
+    unsigned long long scale_bits[2][RLB_MAX_RANKS];          // [epoch parity][source rank]
+    double chain_tot[3][RLB_MAX_RANKS][XW_NCHAIN];             // [XW_TOT1 | XW_TOT2 | XW_MTOT][source rank][chain]
+    unsigned long long carry[XW_NCHAIN + 2];                   // epoch << 32 | float bits, from rank - 1
+    unsigned long long final_[XW_NCHAIN + 2];                  // epoch << 32 | float bits, from the last rank
+    long long root_sq;                                         // this rank's root squared sum (pulled)
+    long long pad_[7];
+};
+#define XW_HEADER_BYTES ((sizeof(XWin) + 255) & ~(size_t)255)
+
 struct PeerTab {
-    long long* stage[RLB_MAX_RANKS];
-    unsigned int* flags[RLB_MAX_RANKS];
+    char* win[RLB_MAX_RANKS];      // every rank's window in THIS process's address space (own entry = local pointer)
     int32_t world, rank;
+    unsigned long long off_root;   // byte offset of the raw root histogram (i64[F * RLB_T])
+    unsigned long long off_stage;  // byte offset of the two per-split staging blocks (i64[2][stage_elems])
 };
 
 struct DevState {
@@ -100,6 +135,8 @@ struct DevState {
     // last-block tickets
     uint32_t ticket_scan, ticket_part, ticket_finish;
     uint32_t part_epoch;    // split counter that is never reset: epoch of the one-pass partition's tile states
+    uint32_t xe[XW_KINDS];  // exchange epochs (N GPUs): advanced by k_xbump / single-block kernels, identical on every rank
+    uint32_t chain_epoch;   // epoch of the float-chain hand-over slots (carry / final), advanced once per chain run
     // feature sampling (FeatureHistogram.java:271-294)
     long long rng_seed;     // java.util.Random state
     int32_t n_used;
@@ -214,9 +251,11 @@ struct rlb_ctx {
     // N GPUs: the per-split all-reduce is done by k_finish itself over peer memory (NVLink loads of every rank's staging
     // block, flags for the hand-shake); NCCL stays as the fallback when the IPC mapping is not available (RLB_P2P=0)
     struct PeerTab* dPeers = nullptr;
-    unsigned int* dXFlags = nullptr;      // [RLB_MAX_RANKS] written by the peers: their split epoch
-    void* peer_maps[2 * 16] = {nullptr};  // cudaIpcOpenMemHandle results (to close)
-    bool p2p = false;
+    char* dWin = nullptr;                 // this rank's exchange window (header XWin + root block + 2 staging blocks)
+    size_t win_bytes = 0;
+    void* peer_maps[RLB_MAX_RANKS] = {nullptr};   // cudaIpcOpenMemHandle results (to close)
+    bool p2p = false;                     // the window is mapped on every rank: exchanges run inside the kernels
+    long long* dRootRaw = nullptr;        // raw root histogram accumulation target (window on N GPUs, dHistSum on one)
     int32_t* dSamples[2] = {nullptr, nullptr};
     int32_t* dNodeOf = nullptr;     // node id of each doc in the last tree
     int32_t* dTileCnt = nullptr;    // partition tile counts / offsets
@@ -322,8 +361,9 @@ static inline cudaError_t rlb_reserve(rlb_ctx* ctx, T*& ptr, size_t bytes) {
 }
 int rlb_build_query_classes(rlb_ctx* ctx, const int32_t* qoff_host, QuerySet& qs);
 int rlb_impl_load_bag(rlb_ctx* ctx, const rlb_ctx* src, const int32_t* picks, int32_t n_picks);
-int rlb_p2p_setup(rlb_ctx* ctx);
+int rlb_p2p_setup(rlb_ctx* ctx);      // rlb_comm_init: allocate the window, exchange IPC handles, map the peers
 void rlb_p2p_close(rlb_ctx* ctx);
+int rlb_p2p_layout(rlb_ctx* ctx);     // rlb_lambdamart_init: place the F-dependent blocks, reset the header (collective)
 
 // ---- rlb_boost.cu ----
 int rlb_impl_pseudo(rlb_ctx* ctx);
