@@ -198,8 +198,10 @@ int rlb_learn(rlb_ctx* ctx, int32_t n_trees, int32_t n_round_to_stop_early, rlb_
 /* Copy internal state out for parity tests (see RLB_READ_*). `bytes` is the size of dst. */
 int rlb_read(rlb_ctx* ctx, int32_t what, void* dst, int64_t bytes);
 
-/* Counters of the last rlb_tree_fit/rlb_boost_iter: [0] rows fed to child-histogram builds,
- * [1] splits done, [2] leaf float-chain segments that took the serial path, [3] reserved. */
+/* Counters of the last rlb_tree_fit/rlb_boost_iter: [0] rows fed to child-histogram builds, [1] splits done,
+ * [2] float chains: elements applied one by one (bits 0-31) | chunks redone exactly (bits 32-47) | chunks whose end value
+ * was taken from their simulation because the walk arrived with the predicted start (bits 48-63),
+ * [3] kernels launched by the context so far. */
 int rlb_stats(rlb_ctx* ctx, int64_t out[4]);
 
 /* Measurement hooks (no reference counterpart; RankerTrainer only prints wall time,

@@ -263,17 +263,26 @@ int rlb_comm_init(rlb_ctx* c, int rank, int world, const uint8_t id[128]) {
     RLB_NCCL(c, ncclCommInitRank(&c->comm, world, nid, rank));
     c->rank = rank;
     c->world = world;
-    // connect the rings now (first collective) rather than inside the first training call
-    int* d = nullptr;
-    RLB_CUDA(c, cudaMalloc(&d, 4));
+    // connect the channels of every collective shape rlb_lambdamart_init uses now (first use of each is tens of
+    // milliseconds) rather than inside the first training job
+    // (NCCL connects per algorithm / protocol, which it picks by message size: warm a tiny, a medium and a large message)
+    long long* d = nullptr;
+    const size_t big = (size_t)1 << 18;   // 2 MB of int64
+    RLB_CUDA(c, cudaMalloc(&d, 8 * big * (size_t)(world + 1)));
     const int rc = [&]() -> int {
-        RLB_CUDA(c, cudaMemsetAsync(d, 0, 4, c->stream));
-        RLB_NCCL(c, ncclAllReduce(d, d, 1, ncclInt32, ncclSum, c->comm, c->stream));
+        RLB_CUDA(c, cudaMemsetAsync(d, 0, 8 * big * (size_t)(world + 1), c->stream));
+        for (size_t n : {(size_t)1, (size_t)4096, big}) {
+            RLB_NCCL(c, ncclAllReduce(d, d, n, ncclInt32, ncclSum, c->comm, c->stream));
+            RLB_NCCL(c, ncclAllReduce(d, d, n, ncclInt64, ncclMax, c->comm, c->stream));
+            RLB_NCCL(c, ncclAllGather(d, d + big, n, ncclInt64, c->comm, c->stream));
+        }
         RLB_CUDA(c, cudaStreamSynchronize(c->stream));
         return RLB_OK;
     }();
     cudaFree(d);  // also on the error paths
-    return rc;
+    if (rc) return rc;
+    // the exchange window of the iteration's in-kernel exchanges: allocated and mapped on every peer once per communicator
+    return rlb_p2p_setup(c);
 }
 
 int rlb_load_dense(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
@@ -394,7 +403,9 @@ int rlb_train_metric(rlb_ctx* c, float* out) {
 // One iteration = one CUDA-graph launch (captured on first use) + one stream synchronisation.
 static int boost_one(rlb_ctx* c) {
     const int gi = c->profile ? 1 : 0;
-    if (!c->use_graph || (c->world > 1 && !c->graph_multi)) {
+    // N GPUs: with the exchange window every exchange of the iteration happens inside a kernel, so the iteration is a plain
+    // launch sequence that can be captured like the single-GPU one; the NCCL path is captured only on request
+    if (!c->use_graph || (c->world > 1 && !c->p2p && !c->graph_multi)) {
         if (int rc = rlb_impl_enqueue_iter(c)) return rc;
     } else {
         if (!c->lambda_fresh) {  // the captured sequence is the steady state: pseudo responses already fresh
@@ -645,10 +656,11 @@ int rlb_stats(rlb_ctx* c, int64_t out[4]) {
     out[3] = c->launches;
     if (c->inited) {
         long long s = 0;
-        long long fb = 0;
+        long long fb = 0, sk = 0;
         if (cudaMemcpy(&s, &c->dState->chain_serial, 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
-            cudaMemcpy(&fb, &c->dState->chain_fallback, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
-            out[2] = s + (fb << 32);
+            cudaMemcpy(&fb, &c->dState->chain_fallback, 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+            cudaMemcpy(&sk, &c->dState->chain_dbg[0], 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            out[2] = (s & 0xffffffffLL) + ((fb & 0xffff) << 32) + (sk << 48);
 #ifdef RLB_CHAIN_DEBUG
         long long dbg[3];
         cudaMemcpy(dbg, c->dState->chain_dbg, 24, cudaMemcpyDeviceToHost);

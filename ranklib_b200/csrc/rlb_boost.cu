@@ -88,6 +88,64 @@ __device__ __forceinline__ size_t stage_offset(const DevState* st, size_t stageS
     return (size_t)(st->part_epoch & 1u) * stageStride;
 }
 
+// ---- exchange window primitives (N GPUs; rlb_internal.cuh XWin) ------------------------------------------------------
+__device__ __forceinline__ XWin* xw_of(const PeerTab* p, int r) { return reinterpret_cast<XWin*>(p->win[r]); }
+__device__ __forceinline__ long long* xw_stage(const PeerTab* p, int r) { return reinterpret_cast<long long*>(p->win[r] + p->off_stage); }
+__device__ __forceinline__ long long* xw_root(const PeerTab* p, int r) { return reinterpret_cast<long long*>(p->win[r] + p->off_root); }
+__device__ __forceinline__ void st_release_sys(unsigned int* a, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* a) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys64(unsigned long long* a, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys64(const unsigned long long* a) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+    return v;
+}
+#define XW_SPIN_LIMIT (1LL << 22)   // polls of a local flag before a wait gives up (seconds): reported through st->p2p_timeout
+
+// "exchange `kind` of this rank has reached `epoch`": one flag store into every peer's window.  Call from ONE thread once the
+// data the flag stands for is globally visible (earlier kernels of the stream, or a __threadfence_system of the writers + a
+// block barrier).
+__device__ __forceinline__ void xw_signal(const PeerTab* p, int kind, unsigned int epoch) {
+    __threadfence_system();
+    for (int r = 0; r < p->world; r++)
+        if (r != p->rank) st_release_sys(&xw_of(p, r)->flags[kind][p->rank], epoch);
+}
+// wait until every peer has signalled `kind` >= epoch (ONE thread; the caller follows with a block barrier)
+__device__ __forceinline__ void xw_wait(const PeerTab* p, int kind, unsigned int epoch, DevState* st) {
+    const XWin* me = xw_of(p, p->rank);
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank) continue;
+        unsigned int v;
+        long long spins = 0;
+        do {
+            v = ld_acquire_sys(&me->flags[kind][r]);
+        } while ((int)(v - epoch) < 0 && ++spins < XW_SPIN_LIMIT);
+        if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
+    }
+}
+// a float handed over through a 64-bit slot: epoch << 32 | bits (one atomic store, no separate flag)
+__device__ __forceinline__ void xw_put_float(unsigned long long* slot, unsigned int epoch, float v) {
+    __threadfence_system();
+    st_release_sys64(slot, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v));
+}
+__device__ __forceinline__ float xw_get_float(const unsigned long long* slot, unsigned int epoch, DevState* st) {
+    unsigned long long v;
+    long long spins = 0;
+    do {
+        v = ld_acquire_sys64(slot);
+    } while ((unsigned int)(v >> 32) != epoch && ++spins < XW_SPIN_LIMIT);
+    if ((unsigned int)(v >> 32) != epoch) st->p2p_timeout = 1;
+    return __uint_as_float((unsigned int)(v & 0xffffffffull));
+}
+
 // RegressionTree.insert (RegressionTree.java:147-157)
 __device__ void queue_insert(DevState* st, int node) {
     int i = 0;
@@ -788,8 +846,50 @@ __global__ void __launch_bounds__(256) k_mart_pseudo(const double* __restrict__ 
     if ((threadIdx.x & 31) == 0 && b) atomicMax(&st->max_abs_bits, b);
 }
 
-// fixed-point scales of the iteration from max|lambda| and the global sample count
-__global__ void k_scale(DevState* st, long long n_total) {
+// fixed-point scales of the iteration from max|lambda| and the global sample count.  N GPUs (peers != null): the
+// all-reduce(max) of max|lambda| happens here — lane r pushes this rank's value into rank r's window, then every rank takes
+// the maximum of what it received.  One warp.
+__global__ void __launch_bounds__(32) k_scale(DevState* st, long long n_total, const PeerTab* peers) {
+    if (peers) {
+        const int lane = threadIdx.x;
+        const unsigned int epoch = st->xe[XW_SCALE] + 1;
+        const int par = epoch & 1;
+        const unsigned long long mine = st->max_abs_bits;
+        __syncwarp();
+        if (lane < peers->world) {
+            unsigned long long* dst = &xw_of(peers, lane)->scale_bits[par][peers->rank];
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(mine) : "memory");
+            if (lane != peers->rank) {
+                __threadfence_system();
+                st_release_sys(&xw_of(peers, lane)->flags[XW_SCALE][peers->rank], epoch);
+            }
+        }
+        unsigned long long got = 0;
+        if (lane < peers->world) {
+            const XWin* me = xw_of(peers, peers->rank);
+            if (lane != peers->rank) {
+                unsigned int v;
+                long long spins = 0;
+                do {
+                    v = ld_acquire_sys(&me->flags[XW_SCALE][lane]);
+                } while ((int)(v - epoch) < 0 && ++spins < XW_SPIN_LIMIT);
+                if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&me->scale_bits[par][lane]) : "memory");
+            } else {
+                got = mine;
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, got, d);
+            got = o > got ? o : got;
+        }
+        if (lane == 0) {
+            st->max_abs_bits = got;
+            st->xe[XW_SCALE] = epoch;
+        }
+        __syncwarp();
+    }
+    if (threadIdx.x != 0) return;
     const double m = __longlong_as_double((long long)st->max_abs_bits);
     int nb = 64 - __clzll(n_total);
     int se = 0, s2 = 0;
@@ -1359,10 +1459,20 @@ __device__ __forceinline__ void feature_best(long long cumS, int cumC, int t, in
 
 // per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan; also the root's
 // best threshold of this feature (the split scan of every node is done where its histogram is produced)
+// N GPUs: "my raw root histogram and its squared sum are complete" (all earlier kernels of the stream have finished)
+__global__ void k_root_publish(DevState* st, const PeerTab* peers) {
+    const unsigned int epoch = st->xe[XW_ROOT] + 1;
+    xw_of(peers, peers->rank)->root_sq = st->root_sq_fix;
+    st->xe[XW_ROOT] = epoch;
+    xw_signal(peers, XW_ROOT, epoch);
+}
+
+// raw: the root histogram to prefix (one GPU: `sum` itself; N GPUs with the exchange window: every rank's raw block is read
+// over NVLink and added here — the root all-reduce, fused)
 __global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum, const int32_t* __restrict__ cnt,
-                                                      const int32_t* __restrict__ nthr, const DevState* __restrict__ st, int mls,
+                                                      const int32_t* __restrict__ nthr, DevState* __restrict__ st, int mls,
                                                       long long N_total, double* __restrict__ nodeFeatS,
-                                                      int32_t* __restrict__ nodeFeatT) {
+                                                      int32_t* __restrict__ nodeFeatT, const PeerTab* __restrict__ peers) {
     __shared__ long long wt[9];
     __shared__ double sS[9];
     __shared__ int sT[9];
@@ -1370,7 +1480,20 @@ __global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum
     const int f = blockIdx.x;
     long long* s = sum + (size_t)f * RLB_T;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    long long v = (t < RLB_T) ? s[t] : 0;
+    long long v = 0;
+    if (peers) {
+        if (t == 0) xw_wait(peers, XW_ROOT, st->xe[XW_ROOT], st);   // the epoch k_root_publish just set
+        __syncthreads();
+        if (t < RLB_T)
+            for (int r = 0; r < peers->world; r++) v += __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t);
+        if (f == 0 && t == 0) {
+            long long sq = 0;
+            for (int r = 0; r < peers->world; r++) sq += __ldcv(&xw_of(peers, r)->root_sq);
+            st->root_sq_fix = sq;
+        }
+    } else if (t < RLB_T) {
+        v = s[t];
+    }
     v = warp_incl_scan_ll(v, lane);
     if (lane == 31) wt[w] = v;
     __syncthreads();
@@ -1519,6 +1642,7 @@ __global__ void __launch_bounds__(288) k_tree_begin(DevState* st, TreeParams tp,
     st->n_splits = 0;
     st->chain_serial = 0;
     st->chain_fallback = 0;
+    st->chain_dbg[0] = 0;
     st->small_sq_fix = 0;
     st->ticket_scan = st->ticket_part = st->ticket_finish = 0;
     draw_features(st, tp, used, pool);
@@ -2012,22 +2136,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         // hundred CTAs of 288 threads), so spinning is safe; the spin is bounded and reports through st->p2p_timeout.
         const unsigned int epoch = st->part_epoch;
         if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) {
-                __threadfence_system();
-                for (int r = 0; r < peers->world; r++)
-                    if (r != peers->rank)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers->flags[r] + peers->rank), "r"(epoch) : "memory");
-            }
-            for (int r = 0; r < peers->world; r++) {
-                if (r == peers->rank) continue;
-                const unsigned int* fl = peers->flags[peers->rank] + r;
-                unsigned int v;
-                long long spins = 0;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
-                } while ((int)(v - epoch) < 0 && ++spins < (1LL << 22));
-                if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
-            }
+            if (blockIdx.x == 0) xw_signal(peers, XW_SPLIT, epoch);
+            xw_wait(peers, XW_SPLIT, epoch, st);
         }
         __syncthreads();
     }
@@ -2048,8 +2158,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
             lC = stageCnt[o];
             // rank order: the same integer additions on every rank (fixed point: any order gives the same bits anyway)
             for (int r = 0; r < peers->world; r++) {
-                const long long* ps = peers->stage[r] + so;
-                const int32_t* pc = reinterpret_cast<const int32_t*>(peers->stage[r] + so + hist_stride);
+                const long long* ps = xw_stage(peers, r) + so;
+                const int32_t* pc = reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride);
                 vS += __ldcv(ps + o);   // peer memory: never through L1
                 vC += __ldcv(pc + o);
             }
@@ -2124,7 +2234,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         if (peers) {
             sqAcc = 0;
             const size_t sqo = hist_stride + (hist_stride + 1) / 2;
-            for (int r = 0; r < peers->world; r++) sqAcc += __ldcv(peers->stage[r] + so + sqo);
+            for (int r = 0; r < peers->world; r++) sqAcc += __ldcv(xw_stage(peers, r) + so + sqo);
             // the OTHER block is free again (every peer has finished the previous split, or it could not have sent this
             // split's flag): clear its scalar for the next split; its histogram part is cleared by the partition
             *(stageSq - so + (stageStride - so)) = 0;
@@ -2396,6 +2506,10 @@ struct ChainBufs {
     double* tot = nullptr;           // [2][RLB_MAX_LEAVES + 1] this rank's total per chain (written by k_chain_pred / pred2)
     const double* gtot = nullptr;    // [world][2][RLB_MAX_LEAVES + 1] the totals of every rank (null on one GPU)
     int32_t rank = 0;
+    // exchange window (N GPUs): gtot points into this rank's window and is filled by the peers (k_chain_push); a kernel that
+    // reads it first waits for exchange `wait_kind` of the current epoch
+    const PeerTab* peers = nullptr;
+    int32_t wait_kind = -1;
 };
 
 // predicted value in front of this rank's part of chain (l, which): the totals of the ranks before it
@@ -2403,7 +2517,7 @@ __device__ __forceinline__ double chain_rank_prefix(const ChainBufs& cb, int mod
     if (!cb.gtot) return 0.0;
     const int ch = (mode == 1) ? 0 : which * (RLB_MAX_LEAVES + 1) + l;
     double s = 0.0;
-    for (int r = 0; r < cb.rank; r++) s += cb.gtot[(size_t)r * 2 * (RLB_MAX_LEAVES + 1) + ch];
+    for (int r = 0; r < cb.rank; r++) s += __ldcv(&cb.gtot[(size_t)r * 2 * (RLB_MAX_LEAVES + 1) + ch]);   // written by the peers
     return s;
 }
 
@@ -2592,6 +2706,10 @@ __global__ void __launch_bounds__(CK / 4) k_chain_round(int mode, const DevState
     const int nCh = (mode == 1) ? 1 : st->n_leaves_out;
     const int b = blockIdx.x, which = blockIdx.y;
     if (b >= chunk0[nCh]) return;
+    if (cb.peers && cb.wait_kind >= 0) {
+        if (threadIdx.x == 0) xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));
+        __syncthreads();
+    }
     const size_t o = (size_t)which * cb.maxChunks + b;
     const double* xg = cb.xs + o * CK;
     __shared__ double wT[8];
@@ -2676,6 +2794,10 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * SIM_WARPS + wid, which = blockIdx.y;
     if (b >= chunk0[nCh]) return;   // whole warp; nothing below synchronises across warps
+    if (cb.peers && cb.wait_kind >= 0) {
+        if (lane == 0) xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));
+        __syncwarp();
+    }
     const int l = chain_of_chunk(chunk0, nCh, b);
     int64_t n;
     if (mode == 1) {
@@ -3050,23 +3172,81 @@ __device__ float chain_walk(const double* __restrict__ xsAll, int64_t n, int cha
     return r;
 }
 
+// N GPUs: the all-gather of this rank's per-chain totals (k_chain_pred / k_chain_pred2 left them in `tot`), pushed into every
+// rank's window, then the flag.  kind = XW_TOT1 / XW_TOT2 (leaf chains: nw x n_leaves_out entries) or XW_MTOT (entry 0).
+// One block; the consumers (k_chain_round, k_chain_sim) wait for every peer's flag of this epoch.
+__global__ void __launch_bounds__(256) k_chain_push(DevState* __restrict__ st, const PeerTab* __restrict__ peers, int kind,
+                                                     const double* __restrict__ tot, int nw) {
+    const unsigned int epoch = st->xe[kind] + 1;
+    const int nl = (kind == XW_MTOT) ? 1 : st->n_leaves_out;
+    const int n = (kind == XW_MTOT) ? 1 : nw * nl;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ch = (kind == XW_MTOT) ? 0 : (i / nl) * (RLB_MAX_LEAVES + 1) + (i % nl);
+        const double v = tot[ch];
+        for (int r = 0; r < peers->world; r++) {
+            double* dst = &xw_of(peers, r)->chain_tot[kind - XW_TOT1][peers->rank][ch];
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->xe[kind] = epoch;
+        xw_signal(peers, kind, epoch);
+    }
+}
+
+// Hand-over of a float chain between ranks (the chains run in GLOBAL document / list order: rank r continues where rank
+// r - 1 stopped).  carry-in: rank 0 starts from 0, the others wait for the slot rank - 1 writes; carry-out: to rank + 1's
+// slot, or — last rank — the final value into EVERY rank's final_ slot.  epoch: of the totals exchange that preceded.
+__device__ __forceinline__ float chain_carry_in(const PeerTab* peers, int slot, unsigned int epoch, DevState* st) {
+    if (!peers || peers->rank == 0) return 0.f;
+    return xw_get_float(&xw_of(peers, peers->rank)->carry[slot], epoch, st);
+}
+__device__ __forceinline__ void chain_carry_out(const PeerTab* peers, int slot, unsigned int epoch, float v) {
+    if (!peers) return;
+    if (peers->rank + 1 < peers->world) {
+        xw_put_float(&xw_of(peers, peers->rank + 1)->carry[slot], epoch, v);
+    } else {
+        for (int r = 0; r < peers->world; r++) xw_put_float(&xw_of(peers, r)->final_[slot], epoch, v);
+    }
+}
+
 // K7: LambdaMART.updateTreeOutput (LambdaMART.java:398-415) / MART.updateTreeOutput (MART.java:54-65):
 // blockIdx.x = leaf ordinal, blockIdx.y = 0 -> sum of pseudo responses, 1 -> sum of weights.
 __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                                     const float* __restrict__ carryIn, ChainBufs cb) {
+    __shared__ float sCarry;
     const int l = blockIdx.x;
     if (l >= st->n_leaves_out) return;
     const int which = blockIdx.y;
     const NodeRec& r = st->nodes[st->leaf_nodes[l]];
-    const float c0 = carryIn ? carryIn[which * (RLB_MAX_LEAVES + 1) + l] : 0.f;
+    const int slot = which * (RLB_MAX_LEAVES + 1) + l;
+    float c0 = carryIn ? carryIn[slot] : 0.f;
+    unsigned int epoch = 0;
+    if (cb.peers) {
+        epoch = st->xe[XW_TOT1];
+        if (threadIdx.x == 0) sCarry = chain_carry_in(cb.peers, slot, epoch, st);
+        __syncthreads();
+        c0 = sCarry;
+    }
     const float s = chain_walk(cb.xs, r.hi - r.lo, l, chunk0[l], chunk0[l + 1], which, c0, cb, &st->chain_serial);
-    if (threadIdx.x == 0) (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
+    if (threadIdx.x == 0) {
+        (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
+        chain_carry_out(cb.peers, slot, epoch, s);
+    }
 }
 
-__global__ void k_leaf_finalize(DevState* st, int kind) {
+__global__ void k_leaf_finalize(DevState* st, int kind, const PeerTab* peers) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= st->n_leaves_out) return;
     NodeRec& r = st->nodes[st->leaf_nodes[l]];
+    if (peers) {   // the chains ended on the last rank: its values, identical on every rank
+        const unsigned int epoch = st->xe[XW_TOT1];
+        const XWin* me = xw_of(peers, peers->rank);
+        st->leaf_s1[l] = xw_get_float(&me->final_[l], epoch, st);
+        if (kind != RLB_KIND_MART) st->leaf_s2[l] = xw_get_float(&me->final_[(RLB_MAX_LEAVES + 1) + l], epoch, st);
+    }
     const float s1 = st->leaf_s1[l];
     float out;
     if (kind == RLB_KIND_MART) {
@@ -3107,12 +3287,25 @@ __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st,
 // K9 tail: float chain over the per-query metric values (LambdaMART.java:474-483)
 __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __restrict__ st, const int32_t* __restrict__ chunk0,
                                                                       int Q, const float* __restrict__ carryIn, ChainBufs cb, int slot) {
-    const float s = chain_walk(cb.xs, Q, 0, chunk0[0], chunk0[1], 0, carryIn ? carryIn[0] : 0.f, cb, &st->chain_serial);
-    if (threadIdx.x == 0) st->chain_out[slot] = s;
+    __shared__ float sCarry;
+    float c0 = carryIn ? carryIn[0] : 0.f;
+    unsigned int epoch = 0;
+    if (cb.peers) {
+        epoch = st->xe[XW_MTOT];
+        if (threadIdx.x == 0) sCarry = chain_carry_in(cb.peers, XW_METRIC_CHAIN, epoch, st);
+        __syncthreads();
+        c0 = sCarry;
+    }
+    const float s = chain_walk(cb.xs, Q, 0, chunk0[0], chunk0[1], 0, c0, cb, &st->chain_serial);
+    if (threadIdx.x == 0) {
+        st->chain_out[slot] = s;
+        chain_carry_out(cb.peers, XW_METRIC_CHAIN, epoch, s);
+    }
 }
 
 // slot 0: LambdaMART.java:470 (training), slot 1: LambdaMART.java:510 (validation): float sum / list count
-__global__ void k_metric_final(DevState* st, long long Q_total, int slot) {
+__global__ void k_metric_final(DevState* st, long long Q_total, int slot, const PeerTab* peers) {
+    if (peers) st->chain_out[slot] = xw_get_float(&xw_of(peers, peers->rank)->final_[XW_METRIC_CHAIN], st->xe[XW_MTOT], st);
     const float v = st->chain_out[slot] / (float)(int)Q_total;
     if (slot == 0)
         st->train_metric = v;
@@ -3280,8 +3473,10 @@ int rlb_impl_pseudo(rlb_ctx* c) {
         if (int rc = launch_queries(c, rlb_train_set(c), true, nullptr)) return rc;
         rlb_prof_end(c);
     }
-    if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
-    k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
+    if (!c->p2p) {
+        if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
+    }
+    k_scale<<<1, 32, 0, c->stream>>>(c->dState, (long long)c->N_total, c->p2p ? c->dPeers : nullptr);
     RLB_CHECK_LAUNCH(c);
     c->lambda_fresh = true;
     return RLB_OK;
@@ -3303,26 +3498,33 @@ static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
 static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
 
 int rlb_impl_hist_update(rlb_ctx* c) {
-    RLB_CUDA(c, cudaMemsetAsync(c->dHistSum, 0, c->hist_stride * sizeof(long long), c->stream));
+    // the raw root histogram accumulates in dRootRaw: node 0's slot of dHistSum on one GPU (and on the NCCL path), the root
+    // block of the exchange window on N GPUs, where k_root_cumsum adds up every rank's block over NVLink
+    RLB_CUDA(c, cudaMemsetAsync(c->dRootRaw, 0, c->hist_stride * sizeof(long long), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
     k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dVfixC, c->dSqfix, c->dState);
     RLB_CHECK_LAUNCH(c);
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
         k_hist_root<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
-                                                                                    hist_groups(c), c->dHistSum);
+                                                                                    hist_groups(c), c->dRootRaw);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
     } else {
         k_hist_rows<false><<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, c->Fp, c->F, c->dVfix, c->dSqfix, c->N, nullptr, nullptr,
-                                                                c->dHistSum, c->dHistCnt, c->dState, 0);
+                                                                c->dRootRaw, c->dHistCnt, c->dState, 0);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
     }
-    if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
-    if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
+    if (c->p2p) {
+        k_root_publish<<<1, 1, 0, c->stream>>>(c->dState, c->dPeers);
+        RLB_CHECK_LAUNCH(c);
+    } else {
+        if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;
+        if (int rc = rlb_allreduce_i64(c, &c->dState->root_sq_fix, 1)) return rc;
+    }
     k_root_cumsum<<<c->F, 288, 0, c->stream>>>(c->dHistSum, c->dHistCnt, c->dNThr, c->dState, c->prm.min_leaf_support,
-                                               (long long)c->N_total, c->dNodeFeatS, c->dNodeFeatT);
+                                               (long long)c->N_total, c->dNodeFeatS, c->dNodeFeatT, c->p2p ? c->dPeers : nullptr);
     RLB_CHECK_LAUNCH(c);
     return RLB_OK;
 }
@@ -3490,6 +3692,8 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     const int nw = c->prm.kind == RLB_KIND_MART ? 1 : 2;
     ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
     if (multi) cb.tot = c->dChainTot;
+    const bool xw = multi && c->p2p;   // exchanges inside the kernels over the exchange window; else NCCL calls in between
+    XWin* win = xw ? reinterpret_cast<XWin*>(c->dWin) : nullptr;
     const int gchunks = (int)(c->N / CK) + nl + 1;
     k_chain_sum<<<dim3(gchunks, nw), CK / 4, 0, c->stream>>>(0, c->dState, c->dChunk0, nl, c->dLambda, c->dWeight, c->dSamples[0],
                                                           c->dSamples[1], 0, cb);
@@ -3499,7 +3703,14 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     k_chain_pred<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, nullptr, cb);
     RLB_CHECK_LAUNCH(c);
     ChainBufs cbp = cb;   // the view with the other ranks' totals
-    if (multi) {
+    if (xw) {
+        k_chain_push<<<1, 256, 0, c->stream>>>(c->dState, c->dPeers, XW_TOT1, c->dChainTot, nw);
+        RLB_CHECK_LAUNCH(c);
+        cbp.gtot = &win->chain_tot[XW_TOT1 - XW_TOT1][0][0];
+        cbp.rank = c->rank;
+        cbp.peers = c->dPeers;
+        cbp.wait_kind = XW_TOT1;
+    } else if (multi) {
         RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
         cbp.gtot = c->dChainGTot;
         cbp.rank = c->rank;
@@ -3510,7 +3721,12 @@ int rlb_impl_tree_output(rlb_ctx* c) {
         RLB_CHECK_LAUNCH(c);
         k_chain_pred2<<<dim3(nl, nw), 32, 0, c->stream>>>(0, c->dState, c->dChunk0, nullptr, cb);
         RLB_CHECK_LAUNCH(c);
-        if (multi) {
+        if (xw) {
+            k_chain_push<<<1, 256, 0, c->stream>>>(c->dState, c->dPeers, XW_TOT2, c->dChainTot, nw);
+            RLB_CHECK_LAUNCH(c);
+            cbp.gtot = &win->chain_tot[XW_TOT2 - XW_TOT1][0][0];
+            cbp.wait_kind = XW_TOT2;
+        } else if (multi) {
             RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot + (size_t)c->world * NT, NT, ncclDouble, c->comm, c->stream));
             cbp.gtot = c->dChainGTot + (size_t)c->world * NT;
         }
@@ -3528,17 +3744,20 @@ int rlb_impl_tree_output(rlb_ctx* c) {
     k_chain_compact<<<dim3(gchunks, nw), 128, 0, c->stream>>>(0, c->dState, c->dChunk0, cb);
     RLB_CHECK_LAUNCH(c);
     const float* carry = nullptr;
-    if (multi) {
+    ChainBufs cbw = cb;   // the walk's view: with the window the hand-over between ranks happens inside k_leaf_chain
+    if (xw) {
+        cbw.peers = c->dPeers;
+    } else if (multi) {
         if (int rc = rlb_chain_carry_begin(c, 2 * (RLB_MAX_LEAVES + 1))) return rc;
         carry = c->dCarry;
     }
-    k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, carry, cb);
+    k_leaf_chain<<<dim3(nl, nw), RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, c->dChunk0, carry, cbw);
     RLB_CHECK_LAUNCH(c);
-    if (c->world > 1) {
+    if (multi && !xw) {
         // leaf_s1 and leaf_s2 are adjacent in DevState: one carry message
         if (int rc = rlb_chain_carry_end(c, c->dState->leaf_s1, 2 * (RLB_MAX_LEAVES + 1))) return rc;
     }
-    k_leaf_finalize<<<(nl + 127) / 128, 128, 0, c->stream>>>(c->dState, c->prm.kind);
+    k_leaf_finalize<<<(nl + 127) / 128, 128, 0, c->stream>>>(c->dState, c->prm.kind, xw ? c->dPeers : nullptr);
     RLB_CHECK_LAUNCH(c);
     c->tree_output_ready = true;
     return RLB_OK;
@@ -3574,6 +3793,7 @@ static int metric_chain(rlb_ctx* c, const double* dQM, int Q, long long Q_total,
     const int NT = 2 * (RLB_MAX_LEAVES + 1);
     ChainBufs cb{c->dChainSum, c->dChainXs, c->dChainItems, c->dChainNItems, c->dChainIPos, c->dChainITot, c->dChainStream, c->dChainRSum, c->dChainSimS, c->dChainSimE, c->chain_max_chunks};
     if (multi) cb.tot = c->dChainTot;
+    const bool xw = multi && c->p2p;
     int32_t* ch0 = c->dChunk0 + RLB_MAX_LEAVES + 2 + 2 * slot;  // static table of the metric chain: {0, ceil(Q / CK)}
     const int gchunks = (Q + CK - 1) / CK;
     k_chain_sum<<<dim3(gchunks, 1), CK / 4, 0, c->stream>>>(1, c->dState, ch0, 1, dQM, nullptr, nullptr, nullptr, Q, cb);
@@ -3581,7 +3801,14 @@ static int metric_chain(rlb_ctx* c, const double* dQM, int Q, long long Q_total,
     k_chain_pred<<<dim3(1, 1), 32, 0, c->stream>>>(1, c->dState, ch0, nullptr, cb);
     RLB_CHECK_LAUNCH(c);
     ChainBufs cbp = cb;
-    if (multi) {   // per-query values are >= 0 and the sum grows: the exact totals of the earlier ranks predict well enough
+    if (xw) {      // per-query values are >= 0 and the sum grows: the exact totals of the earlier ranks predict well enough
+        k_chain_push<<<1, 256, 0, c->stream>>>(c->dState, c->dPeers, XW_MTOT, c->dChainTot, 1);
+        RLB_CHECK_LAUNCH(c);
+        cbp.gtot = &reinterpret_cast<XWin*>(c->dWin)->chain_tot[XW_MTOT - XW_TOT1][0][0];
+        cbp.rank = c->rank;
+        cbp.peers = c->dPeers;
+        cbp.wait_kind = XW_MTOT;
+    } else if (multi) {
         RLB_NCCL(c, ncclAllGather(c->dChainTot, c->dChainGTot, NT, ncclDouble, c->comm, c->stream));
         cbp.gtot = c->dChainGTot;
         cbp.rank = c->rank;
@@ -3593,16 +3820,19 @@ static int metric_chain(rlb_ctx* c, const double* dQM, int Q, long long Q_total,
     k_chain_compact<<<dim3(gchunks, 1), 128, 0, c->stream>>>(1, c->dState, ch0, cb);
     RLB_CHECK_LAUNCH(c);
     const float* carry = nullptr;
-    if (multi) {
+    ChainBufs cbw = cb;
+    if (xw) {
+        cbw.peers = c->dPeers;
+    } else if (multi) {
         if (int rc = rlb_chain_carry_begin(c, 1)) return rc;
         carry = c->dCarry;
     }
-    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, Q, carry, cb, slot);
+    k_metric_chain<<<1, RLB_CHAIN_THREADS, 0, c->stream>>>(c->dState, ch0, Q, carry, cbw, slot);
     RLB_CHECK_LAUNCH(c);
-    if (multi) {
+    if (multi && !xw) {
         if (int rc = rlb_chain_carry_end(c, c->dState->chain_out, 1)) return rc;
     }
-    k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, Q_total, slot);
+    k_metric_final<<<1, 1, 0, c->stream>>>(c->dState, Q_total, slot, xw ? c->dPeers : nullptr);
     RLB_CHECK_LAUNCH(c);
     return RLB_OK;
 }
@@ -3622,8 +3852,10 @@ int rlb_impl_train_metric(rlb_ctx* c, bool with_pseudo) {
             if (int rc = launch_queries(c, rlb_train_set(c), true, c->dQMetric)) return rc;
             rlb_prof_end(c);
         }
-        if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
-        k_scale<<<1, 1, 0, c->stream>>>(c->dState, (long long)c->N_total);
+        if (!c->p2p) {
+            if (int rc = rlb_allreduce_max_u64(c, &c->dState->max_abs_bits, 1)) return rc;
+        }
+        k_scale<<<1, 32, 0, c->stream>>>(c->dState, (long long)c->N_total, c->p2p ? c->dPeers : nullptr);
         RLB_CHECK_LAUNCH(c);
         c->lambda_fresh = true;
     } else {

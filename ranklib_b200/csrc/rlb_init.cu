@@ -205,9 +205,10 @@ __global__ void k_iota(int32_t* a, int64_t n) {
 // host side
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
-// N GPUs, one process each: map every rank's staging block and hand-shake flags into this process (CUDA IPC) so that
-// k_finish can reduce the scanned child's histogram over NVLink itself (rlb_boost.cu).  Collective: every rank calls it
-// from rlb_lambdamart_init; if any rank cannot map its peers all of them keep the NCCL all-reduce.
+// N GPUs, one process each: the exchange window (rlb_internal.cuh XWin).  rlb_p2p_setup runs ONCE per communicator
+// (rlb_comm_init): allocate the window, exchange CUDA IPC handles with one ncclAllGather, map every peer's window —
+// the mapping enables peer access lazily, ~0.1-0.2 s per peer the first time, which therefore never lands inside a
+// training job's init.  If any rank cannot map its peers all of them keep the NCCL collectives (c->p2p stays false).
 // ------------------------------------------------------------------------------------------------
 void rlb_p2p_close(rlb_ctx* c) {
     for (void*& m : c->peer_maps) {
@@ -222,22 +223,34 @@ int rlb_p2p_setup(rlb_ctx* c) {
     if (c->world <= 1 || c->world > RLB_MAX_RANKS || !c->comm) return RLB_OK;
     int want = 1;
     if (const char* e = getenv("RLB_P2P")) want = atoi(e) != 0;
+    size_t mb = 64;   // header ~0.6 MB + (F * 257) * (8 + 2 * 12) bytes: 64 MB covers F up to ~7000 features
+    if (const char* e = getenv("RLB_XWIN_MB")) mb = (size_t)std::max(8, atoi(e));
     struct Rec {
-        cudaIpcMemHandle_t stage, flags;
+        cudaIpcMemHandle_t win;
         int ok;
         int pad[15];
     };
     static_assert(sizeof(Rec) % 8 == 0, "record size");
-    if (!c->dXFlags) RLB_CUDA(c, cudaMalloc(&c->dXFlags, RLB_MAX_RANKS * sizeof(unsigned int)));
-    RLB_CUDA(c, cudaMemsetAsync(c->dXFlags, 0, RLB_MAX_RANKS * sizeof(unsigned int), c->stream));
     Rec mine;
     memset(&mine, 0, sizeof(mine));
-    mine.ok = want && cudaIpcGetMemHandle(&mine.stage, c->dStage) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.flags, c->dXFlags) == cudaSuccess;
+    if (want && !c->dWin) {
+        c->win_bytes = mb << 20;
+        if (cudaMalloc(&c->dWin, c->win_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            c->dWin = nullptr;
+            c->win_bytes = 0;
+        }
+    }
+    if (c->dWin) RLB_CUDA(c, cudaMemsetAsync(c->dWin, 0, XW_HEADER_BYTES, c->stream));
+    mine.ok = want && c->dWin && cudaIpcGetMemHandle(&mine.win, c->dWin) == cudaSuccess;
     cudaGetLastError();
     Rec *dSend = nullptr, *dRecv = nullptr;
     RLB_CUDA(c, cudaMalloc(&dSend, sizeof(Rec)));
-    RLB_CUDA(c, cudaMalloc(&dRecv, sizeof(Rec) * c->world));
+    if (cudaMalloc(&dRecv, sizeof(Rec) * c->world) != cudaSuccess) {
+        cudaFree(dSend);
+        rlb_set_error(c, RLB_E_CUDA, "rlb_comm_init", "cudaMalloc");
+        return RLB_E_CUDA;
+    }
     std::vector<Rec> all(c->world);
     auto gather = [&]() -> int {
         RLB_CUDA(c, cudaMemcpyAsync(dSend, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
@@ -256,22 +269,17 @@ int rlb_p2p_setup(rlb_ctx* c) {
     if (ok) {
         for (int r = 0; r < c->world; r++) {
             if (r == c->rank) {
-                tab.stage[r] = c->dStage;
-                tab.flags[r] = c->dXFlags;
+                tab.win[r] = c->dWin;
                 continue;
             }
-            void *ps = nullptr, *pf = nullptr;
-            if (cudaIpcOpenMemHandle(&ps, all[r].stage, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-                cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            void* pw = nullptr;
+            if (cudaIpcOpenMemHandle(&pw, all[r].win, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
-                if (ps) cudaIpcCloseMemHandle(ps);
                 ok = false;
                 break;
             }
-            c->peer_maps[2 * r] = ps;
-            c->peer_maps[2 * r + 1] = pf;
-            tab.stage[r] = (long long*)ps;
-            tab.flags[r] = (unsigned int*)pf;
+            c->peer_maps[r] = pw;
+            tab.win[r] = (char*)pw;
         }
     }
     // second round: everybody must have mapped everybody, or nobody uses the mappings
@@ -282,15 +290,47 @@ int rlb_p2p_setup(rlb_ctx* c) {
     cudaFree(dRecv);
     if (rc != RLB_OK) return rc;
     if (getenv("RLB_P2P_VERBOSE"))
-        fprintf(stderr, "ranklib_b200 rank %d: per-split all-reduce %s\n", c->rank,
-                ok ? "fused into k_finish over peer memory" : "through NCCL (peer mapping unavailable or RLB_P2P=0)");
+        fprintf(stderr, "ranklib_b200 rank %d: iteration exchanges %s\n", c->rank,
+                ok ? "inside the kernels over peer memory (exchange window mapped on every rank)"
+                   : "through NCCL (peer mapping unavailable or RLB_P2P=0)");
     if (!ok) {
         rlb_p2p_close(c);
         return RLB_OK;
     }
     if (!c->dPeers) RLB_CUDA(c, cudaMalloc(&c->dPeers, sizeof(PeerTab)));
     RLB_CUDA(c, cudaMemcpy(c->dPeers, &tab, sizeof(PeerTab), cudaMemcpyHostToDevice));
+    // touch every peer's window once (a 4-byte read): the lazily enabled peer access and the first NVLink transaction
+    // of each pair happen here, not in the first training iteration
+    for (int r = 0; r < c->world; r++)
+        if (r != c->rank) {
+            unsigned int probe = 0;
+            RLB_CUDA(c, cudaMemcpy(&probe, tab.win[r], 4, cudaMemcpyDeviceToHost));
+        }
     c->p2p = true;
+    return RLB_OK;
+}
+
+// rlb_lambdamart_init (collective): place the F-dependent blocks behind the header and reset the header.  The caller
+// issues an NCCL collective on the same stream right after, which is the barrier that keeps any rank from signalling
+// into a window that is still to be cleared.
+int rlb_p2p_layout(rlb_ctx* c) {
+    if (!c->p2p) return RLB_OK;
+    const size_t off_root = XW_HEADER_BYTES;
+    const size_t off_stage = (off_root + c->hist_stride * 8 + 255) & ~(size_t)255;
+    const size_t need = off_stage + 2 * c->stage_elems * 8;
+    if (need > c->win_bytes) {
+        rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_lambdamart_init",
+                      "the exchange window is too small for this many features: set RLB_XWIN_MB (before rlb_comm_init) to a larger value");
+        return RLB_E_UNSUPPORTED;
+    }
+    RLB_CUDA(c, cudaMemsetAsync(c->dWin, 0, need, c->stream));
+    PeerTab tab;
+    RLB_CUDA(c, cudaMemcpy(&tab, c->dPeers, sizeof(PeerTab), cudaMemcpyDeviceToHost));
+    tab.off_root = off_root;
+    tab.off_stage = off_stage;
+    RLB_CUDA(c, cudaMemcpy(c->dPeers, &tab, sizeof(PeerTab), cudaMemcpyHostToDevice));
+    c->dStage = reinterpret_cast<long long*>(c->dWin + off_stage);
+    c->dRootRaw = reinterpret_cast<long long*>(c->dWin + off_root);
     return RLB_OK;
 }
 
@@ -323,11 +363,18 @@ void rlb_impl_free(rlb_ctx* c) {
         p = nullptr;
     };
     rlb_p2p_close(c);
-    fr(c->dPeers); fr(c->dXFlags);
+    fr(c->dPeers);
+    if (c->dWin) {
+        cudaFree(c->dWin);
+        c->dWin = nullptr;
+        c->win_bytes = 0;
+    }
     fr(c->dX); fr(c->dLabel); fr(c->dQoff); fr(c->dQidOfDoc); fr(c->dBins); fr(c->dBinsT); fr(c->dBinsTile); fr(c->dThr); fr(c->dNThr); fr(c->dDisc);
     fr(c->dIdeal); fr(c->dScore); fr(c->dLambda); fr(c->dWeight); fr(c->dQMetric); fr(c->dRankDoc); fr(c->dHistSum);
     fr(c->dHistCnt); fr(c->dHistCntL); fr(c->dSamples[0]); fr(c->dSamples[1]); fr(c->dNodeOf); fr(c->dTileCnt); fr(c->dFeatS);
-    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStage); fr(c->dTileState);
+    fr(c->dFeatT); fr(c->dUsed); fr(c->dState); fr(c->dCarry); fr(c->dVfix); fr(c->dVfixC); fr(c->dSqfix); fr(c->dQList); fr(c->dNodeFeatS); fr(c->dNodeFeatT); fr(c->dStageOwn); fr(c->dTileState);
+    c->dStage = nullptr;
+    c->dRootRaw = nullptr;
     fr(c->dChainSum); fr(c->dChainRSum); fr(c->dChainTot); fr(c->dChainGTot); fr(c->dChainXs); fr(c->dChainItems); fr(c->dChainStream); fr(c->dChainNItems); fr(c->dChainIPos); fr(c->dChainITot); fr(c->dChainSimS); fr(c->dChainSimE); fr(c->dChunk0);
     fr(c->dQAux);
     fr(c->dVX); fr(c->valid.dLabel); fr(c->valid.dQoff); fr(c->valid.dScore); fr(c->valid.dIdeal); fr(c->valid.dQMetric);
@@ -576,6 +623,11 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     c->sm_count = prop.multiProcessorCount;
     c->grid_rows = c->sm_count * 8;
 
+    // N GPUs: place and clear the exchange window BEFORE the first collective of this init (the collective is the barrier
+    // behind which every rank's window is known to be clear)
+    c->hist_stride = (size_t)F * RLB_T;
+    c->stage_elems = c->hist_stride + (c->hist_stride + 1) / 2 + 2;
+    if (int rc = rlb_p2p_layout(c)) return rc;
     // global sizes
     {
         long long tot[2] = {(long long)N, (long long)c->max_query};
@@ -704,10 +756,12 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, rlb_reserve(c, c->dHistSum, (c->max_nodes + 1) * c->hist_stride * sizeof(long long)));  // +1: staging slot
     RLB_CUDA(c, rlb_reserve(c, c->dHistCnt, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
     if (c->world > 1) RLB_CUDA(c, rlb_reserve(c, c->dHistCntL, (c->max_nodes + 1) * c->hist_stride * sizeof(int32_t)));
-    c->stage_elems = c->hist_stride + (c->hist_stride + 1) / 2 + 2;
-    rlb_p2p_close(c);   // mappings of an earlier init point at buffers that are about to be freed
-    RLB_CUDA(c, rlb_reserve(c, c->dStage, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long)));
-    RLB_CUDA(c, cudaMemsetAsync(c->dStage, 0, (c->world > 1 ? 2 : 1) * c->stage_elems * sizeof(long long), c->stream));
+    if (!c->p2p) {   // with the exchange window mapped (N GPUs) the staging blocks live inside it: rlb_p2p_layout above
+        RLB_CUDA(c, rlb_reserve(c, c->dStageOwn, c->stage_elems * sizeof(long long)));
+        RLB_CUDA(c, cudaMemsetAsync(c->dStageOwn, 0, c->stage_elems * sizeof(long long), c->stream));
+        c->dStage = c->dStageOwn;
+        c->dRootRaw = c->dHistSum;
+    }
     RLB_CUDA(c, rlb_reserve(c, c->dScore, N * sizeof(double)));
     RLB_CUDA(c, rlb_reserve(c, c->dLambda, N * sizeof(double)));
     RLB_CUDA(c, rlb_reserve(c, c->dWeight, N * sizeof(double)));
@@ -742,7 +796,6 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     RLB_CUDA(c, rlb_reserve(c, c->dChainGTot, (size_t)2 * std::max(c->world, 1) * 2 * (RLB_MAX_LEAVES + 1) * sizeof(double)));
     RLB_CUDA(c, cudaMemsetAsync(c->dChainTot, 0, (size_t)2 * (RLB_MAX_LEAVES + 1) * sizeof(double), c->stream));
     c->chain_gtot_world = std::max(c->world, 1);
-    if (int rc = rlb_p2p_setup(c)) return rc;
     {
         // RLB_CHAIN_ITEMS items of 16 bytes per chunk (ChainItem: rlb_boost.cu); the stream: the same + one marker per chunk
         RLB_CUDA(c, rlb_reserve(c, c->dChainItems, (size_t)2 * c->chain_max_chunks * RLB_CHAIN_ITEMS * 16));

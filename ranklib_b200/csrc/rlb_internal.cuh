@@ -246,7 +246,9 @@ struct rlb_ctx {
     long long* dHistSum = nullptr;  // [max_nodes][F][RLB_T]
     int32_t* dHistCnt = nullptr;    // [max_nodes][F][RLB_T]
     int32_t* dHistCntL = nullptr;   // N GPUs: the same from this rank's rows only (cumulative), for the one-pass partition
-    long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum (two of them on N GPUs)
+    long long* dStage = nullptr;    // staging block of the scanned child: sums | counts | left squared-sum (two of them, inside the
+                                    // exchange window, on N GPUs)
+    long long* dStageOwn = nullptr; // its own allocation when there is no window
     size_t stage_elems = 0;         // i64 elements of one staging block
     // N GPUs: the per-split all-reduce is done by k_finish itself over peer memory (NVLink loads of every rank's staging
     // block, flags for the hand-shake); NCCL stays as the fallback when the IPC mapping is not available (RLB_P2P=0)

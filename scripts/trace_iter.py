@@ -14,7 +14,8 @@ native.lib().rlb_trace_dump(g.h, b"/tmp/trace0.txt")   # discard warm-up
 for _ in range(4):
     g.boost_iter(want_tree=False)
     st = g.stats()
-    print("rows_hist", st[0], "splits", st[1], "chain serial elements", st[2] & 0xffffffff, "chain fallback chunks", st[2] >> 32)
+    print("rows_hist", st[0], "splits", st[1], "chain serial elements", st[2] & 0xffffffff, "chain fallback chunks", (st[2] >> 32) & 0xffff,
+          "chain chunks skipped (start predicted exactly)", st[2] >> 48)
 out = os.path.join("gpurun_out", "trace.txt")
 os.makedirs("gpurun_out", exist_ok=True)
 native.lib().rlb_trace_dump(g.h, out.encode())
