@@ -416,7 +416,6 @@ def run_train(args):
     for _ in range(max(args.warmup, 3)):
         ctx.boost_iter(want_tree=False)
     ext, e0, e1 = env.events(ctx)
-    ctx.profile(True)
     launches0 = int(ctx.stats()[3])
     env.barrier()
     e0.record(ext)
@@ -425,13 +424,27 @@ def run_train(args):
         _, metric = ctx.boost_iter(want_tree=False)
     e1.record(ext)
     env.barrier()
-    clocks = sampler.stop()
     ms = env.max_over_ranks(e0.elapsed_time(e1))
+    launches = int(ctx.stats()[3]) - launches0
+    value = args.steps / (ms / 1000.0)
+    # the same K steps again with CUDA events recorded around every histogram / lambda launch (event nodes inside the
+    # iteration graph): per-kernel durations for the roofline.  Kept out of `value`: the event nodes cost a few percent.
+    ctx.profile(True)
+    ctx.boost_iter(want_tree=False)
+    ctx.profile_read()
+    ctx.profile(True)
+    ext, p0, p1 = env.events(ctx)
+    env.barrier()
+    p0.record(ext)
+    for _ in range(args.steps):
+        ctx.boost_iter(want_tree=False)
+    p1.record(ext)
+    env.barrier()
+    clocks = sampler.stop()
+    ms_prof = env.max_over_ranks(p0.elapsed_time(p1))
     prof = ctx.profile_read()
     ctx.profile(False)
-    launches = int(ctx.stats()[3]) - launches0
     rows_child = prof[5] / max(args.steps, 1)
-    value = args.steps / (ms / 1000.0)
     comm = ctx.comm_stats() if hasattr(ctx, "comm_stats") else None
     ctx.close()
 
@@ -457,7 +470,8 @@ def run_train(args):
     roofline = {"bound": "hbm", "kernel": "k_hist_root (FeatureHistogram.update)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": root_ms,
-                "share_of_step": (prof[0] / ms) if ms > 0 else None,
+                "share_of_step": (prof[0] / ms_prof) if ms_prof > 0 else None,
+                "ms_per_step_with_event_nodes": ms_prof / args.steps,
                 "child_hist_ms_per_step": child_ms, "child_hist_rows_per_step": rows_child,
                 "child_hist_frac": (child_bytes / (child_ms * 1e-3) / 1e9 / peak) if child_ms > 0 else None,
                 "lambda_ms_per_step": prof[6] / max(args.steps, 1)}

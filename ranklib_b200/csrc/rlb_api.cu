@@ -205,6 +205,14 @@ int rlb_create(int device, rlb_ctx** out) {
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    {   // keep freed blocks cached in the device's default memory pool (see rlb_dev_alloc, rlb_init.cu)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return RLB_OK;
 }
@@ -329,6 +337,7 @@ int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
     }
     c->Q_total = q;
     if (const char* e = getenv("RLB_NO_GRAPH")) c->use_graph = (atoi(e) == 0);
+    if (const char* e = getenv("RLB_PDL")) c->pdl = (atoi(e) != 0);
     if (const char* e = getenv("RLB_GRAPH_MULTI")) c->graph_multi = (atoi(e) != 0);
     if (const char* e = getenv("RLB_TRACE")) {
         c->trace = atoi(e) != 0;

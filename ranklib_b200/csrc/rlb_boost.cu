@@ -24,6 +24,13 @@
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): the kernels of a split step are launched with the programmatic-stream-serialization
+// attribute, so the next kernel's CTAs may be scheduled while this one still runs.  pdl_trigger() at the top lets the
+// dependents start launching as soon as every CTA of this grid is resident; pdl_wait() blocks until the preceding grid has
+// COMPLETED and its memory is visible — nothing produced by the predecessor may be read before it.  Without the launch
+// attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ double fix2d(long long v, int scale_exp) { return scalbn((double)v, -scale_exp); }
 
 __device__ __forceinline__ long long warp_incl_scan_ll(long long v, int lane) {
@@ -1268,6 +1275,20 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     unsigned long long* empty = full + HSTAGES;
     int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
+    // everything that does not depend on the partition happens before pdl_wait(): the 197 KB of private histograms are
+    // cleared and the barriers initialised while the partition kernel is still running
+    pdl_trigger();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < HSTAGES; s2++) {
+            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
+            mbar_init(&empty[s2], (uint32_t)CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();
+    __syncthreads();
     if (!st->split_active) return;
     {
         const size_t so = stage_offset(st, stageStride);
@@ -1279,25 +1300,14 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     const int32_t* samples = r.buf ? samples1 : samples0;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x % nGroups;
     const int idx = blockIdx.x / nGroups;
     const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
     const int64_t n = hi - lo;
     const int64_t r0 = lo + n * idx / nCta, r1 = lo + n * (idx + 1) / nCta;
     const int nst = (int)((r1 - r0 + R - 1) / R);
-    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
+    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows)
     const int nfull = (int)((r1 - r0) / R);
-
-    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
-    if (tid == 0) {
-        for (int s2 = 0; s2 < HSTAGES; s2++) {
-            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
-            mbar_init(&empty[s2], (uint32_t)CW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
 
     if (warp == CW) {
         // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
@@ -1807,6 +1817,8 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
                                                      int32_t* __restrict__ stageCnt, size_t hist_stride,
                                                      const long long* __restrict__ sqfix, long long* __restrict__ stageSq,
                                                      size_t stageStride, int localCounts) {
+    pdl_trigger();
+    pdl_wait();
     if (!st->split_active) return;
     {
         const size_t so = stage_offset(st, stageStride);
@@ -2123,6 +2135,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
                                                  int32_t* __restrict__ nodeFeatT, long long* __restrict__ stageSq, int sqIsSmall,
                                                  size_t stageStride, const PeerTab* __restrict__ peers,
                                                  int32_t* __restrict__ histCntL) {
+    pdl_trigger();
+    pdl_wait();
     if (!st->split_active) return;
     const size_t so = stage_offset(st, stageStride);
     stageSum += so;
@@ -3344,6 +3358,24 @@ __global__ void __launch_bounds__(256) k_valid_update(const DevState* __restrict
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Kernel launch with the programmatic-stream-serialization attribute (PDL): a dependent of the previous kernel of the
+// stream that may be scheduled before that kernel has drained; the kernel itself calls pdl_wait() before it reads anything
+// the predecessor wrote.  Captured into the iteration graph as a programmatic edge.  c->pdl = false: a plain launch.
+template <typename... KA, typename... A>
+static inline void launch_pdl(const rlb_ctx* c, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);   // errors surface through RLB_CHECK_LAUNCH (cudaGetLastError)
+}
+
 static TreeParams tree_params(const rlb_ctx* c) {
     TreeParams tp;
     tp.F = c->F;
@@ -3544,9 +3576,8 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         if (c->world == 1 || c->p2p) {
             // one pass: the number of this rank's rows going left is known beforehand (N GPUs: from the rank's own cumulative
             // counts, which the peer-memory path keeps per node)
-            k_part_fused<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1], c->dTileState,
-                                                              stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride,
-                                                              c->p2p ? 1 : 0);
+            launch_pdl(c, k_part_fused, dim3(c->grid_rows), dim3(256), 0, c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1],
+                       c->dTileState, stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride, c->p2p ? 1 : 0);
             RLB_CHECK_LAUNCH(c);
         } else {  // NCCL path: local left counts are not known in advance: count pass + scatter pass
             k_part_count<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dBins, c->Fp, c->dSamples[0], c->dSamples[1], c->dTileCnt,
@@ -3556,9 +3587,8 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             RLB_CHECK_LAUNCH(c);
         }
         rlb_prof_begin(c, 1);
-        k_hist_child<<<hist_grid(c), hist_threads(), hist_smem_child(), c->stream>>>(c->dBins, c->Fp, c->F, c->dVfixC, c->dSamples[0],
-                                                                                      c->dSamples[1], stageSum, stageCnt, c->dState,
-                                                                                      hist_groups(c), stageStride);
+        launch_pdl(c, k_hist_child, dim3(hist_grid(c)), dim3(hist_threads()), hist_smem_child(), c->dBins, c->Fp, c->F, c->dVfixC,
+                   c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState, hist_groups(c), stageStride);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
         if (c->world > 1 && !c->p2p) {
@@ -3566,10 +3596,9 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             // and its squared-sum scalar, at fixed addresses
             if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
-        k_finish<<<c->F, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt, c->dUsed,
-                                              c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq,
-                                              (c->world == 1 || c->p2p) ? 1 : 0, stageStride, c->p2p ? c->dPeers : nullptr,
-                                              c->p2p ? c->dHistCntL : nullptr);
+        launch_pdl(c, k_finish, dim3(c->F), dim3(288), 0, c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt,
+                   c->dUsed, c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, (c->world == 1 || c->p2p) ? 1 : 0,
+                   stageStride, c->p2p ? c->dPeers : nullptr, c->p2p ? c->dHistCntL : nullptr);
         RLB_CHECK_LAUNCH(c);
     }
     return RLB_OK;

@@ -7,6 +7,7 @@
 // (b) fmin/fmax, (c) the bin of every value.  (a)+(b) come from one pass with a shared-memory hash
 // set per feature, (c) from a lower_bound per value — no sort, no int[F][N] index arrays.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cfloat>
 #include <cmath>
@@ -132,8 +133,26 @@ __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, in
         }
         bins[i] = (uint16_t)lo;
         binsT[(size_t)f * N + k] = (uint16_t)lo;
-        atomicAdd(&rootCnt[(size_t)f * RLB_T + lo], 1);
     }
+    (void)rootCnt;
+}
+
+// raw root counts (FeatureHistogram.java:106 before the prefix): CTA = (feature, slice of rows) of the feature-major bins,
+// shared-memory counters (32-bit shared atomics are native), one global atomic per non-empty (feature, bin) and CTA —
+// instead of one global atomic per value in the binning kernel (163 M of them at the MSLR shape)
+__global__ void __launch_bounds__(256) k_root_counts(const uint16_t* __restrict__ binsT, int64_t N, int F, int slices,
+                                                      int* __restrict__ rootCnt) {
+    __shared__ int sc[RLB_T];
+    const int f = blockIdx.x / slices, sl = blockIdx.x % slices;
+    if (f >= F) return;
+    for (int i = threadIdx.x; i < RLB_T; i += blockDim.x) sc[i] = 0;
+    __syncthreads();
+    const int64_t r0 = N * sl / slices, r1 = N * (sl + 1) / slices;
+    const uint16_t* col = binsT + (size_t)f * N;
+    for (int64_t k = r0 + threadIdx.x; k < r1; k += blockDim.x) atomicAdd(&sc[col[k]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RLB_T; i += blockDim.x)
+        if (sc[i]) atomicAdd(&rootCnt[(size_t)f * RLB_T + i], sc[i]);
 }
 
 // Root-histogram layout (k_hist_root, rlb_boost.cu): tile (g, B) = [16 features of group g][RLB_ROOT_R rows], the 8 rows
@@ -334,20 +353,42 @@ int rlb_p2p_layout(rlb_ctx* c) {
     return RLB_OK;
 }
 
+// Device memory of a context comes from the device's stream-ordered memory pool (cudaMallocAsync on the context's stream;
+// rlb_create raises the pool's release threshold so that freed blocks stay cached): the ~60 buffers of a training job
+// (2.5 GB at the MSLR shape) cost ~7 ms of cudaMalloc in a fresh process and next to nothing for every later context of
+// the process (the next bag, the next fold, the next model).  RLB_POOL=0: plain cudaMalloc / cudaFree.
+static bool use_pool() {
+    static const bool on = [] {
+        const char* e = getenv("RLB_POOL");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+cudaError_t rlb_dev_alloc(rlb_ctx* c, void** ptr, size_t bytes) {
+    return use_pool() ? cudaMallocAsync(ptr, bytes, c->stream) : cudaMalloc(ptr, bytes);
+}
+void rlb_dev_free(rlb_ctx* c, void* ptr) {
+    if (!ptr) return;
+    if (use_pool())
+        cudaFreeAsync(ptr, c->stream);
+    else
+        cudaFree(ptr);
+}
+
 cudaError_t rlb_reserve_bytes(rlb_ctx* c, void** ptr, size_t bytes) {
     if (bytes == 0) bytes = 8;
     auto it = c->cap.find((void*)ptr);
     if (*ptr && it != c->cap.end() && it->second >= bytes) return cudaSuccess;
     const bool regrow = *ptr != nullptr;
-    if (*ptr) cudaFree(*ptr);
+    if (*ptr) rlb_dev_free(c, *ptr);
     *ptr = nullptr;
     // a buffer that had to grow once gets headroom: the bags of a Random Forest differ in size by a few percent
     size_t want = regrow ? bytes + bytes / 16 : bytes;
-    cudaError_t e = cudaMalloc(ptr, want);
+    cudaError_t e = rlb_dev_alloc(c, ptr, want);
     if (e != cudaSuccess && want != bytes) {
         cudaGetLastError();
         want = bytes;
-        e = cudaMalloc(ptr, want);
+        e = rlb_dev_alloc(c, ptr, want);
     }
     if (e == cudaSuccess)
         c->cap[(void*)ptr] = want;
@@ -358,8 +399,8 @@ cudaError_t rlb_reserve_bytes(rlb_ctx* c, void** ptr, size_t bytes) {
 
 void rlb_impl_free(rlb_ctx* c) {
     cudaSetDevice(c->device);
-    auto fr = [](auto*& p) {
-        if (p) cudaFree(p);
+    auto fr = [c](auto*& p) {
+        if (p) rlb_dev_free(c, (void*)p);
         p = nullptr;
     };
     rlb_p2p_close(c);
@@ -598,7 +639,23 @@ int rlb_impl_load_validation(rlb_ctx* c, const float* X, int64_t N, int32_t F, c
     return RLB_OK;
 }
 
+// RLB_INIT_PROFILE=1: wall time of the phases of rlb_lambdamart_init on stderr (development aid)
+struct InitTimer {
+    bool on;
+    rlb_ctx* c;
+    std::chrono::steady_clock::time_point t0;
+    explicit InitTimer(rlb_ctx* ctx) : on(getenv("RLB_INIT_PROFILE") != nullptr), c(ctx), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(c->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "  init %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
+    InitTimer tm(c);
     if (!c->loaded) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_lambdamart_init", "no training set loaded");
         return RLB_E_INVALID;
@@ -618,9 +675,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     c->prm = *p;
     const int64_t N = c->N;
     const int F = c->F, Fp = c->Fp, Q = c->Q;
-    cudaDeviceProp prop;
-    RLB_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
-    c->sm_count = prop.multiProcessorCount;
+    RLB_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));   // (cudaGetDeviceProperties costs ~2.5 ms)
     c->grid_rows = c->sm_count * 8;
 
     // N GPUs: place and clear the exchange window BEFORE the first collective of this init (the collective is the barrier
@@ -648,26 +703,29 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         }
     }
 
+    tm.mark("sizes + window");
     // ---- thresholds ----
     // derived thresholds belong to (data, n_threshold): a re-init with another n_threshold rebuilds them; thresholds
     // imposed through rlb_set_thresholds stay until the next rlb_load_dense
     if (c->have_thr && !c->thr_user && c->thr_built_for != p->n_threshold) c->have_thr = false;
     if (!c->have_thr) {
-        float *dMin, *dMax, *dDist;
-        int* dND;
-        RLB_CUDA(c, cudaMalloc(&dMin, F * sizeof(float)));
-        RLB_CUDA(c, cudaMalloc(&dMax, F * sizeof(float)));
-        RLB_CUDA(c, cudaMalloc(&dND, F * sizeof(int)));
-        RLB_CUDA(c, cudaMalloc(&dDist, (size_t)F * RLB_T * sizeof(float)));
+        // one scratch block (from the pool) instead of eight allocations: [min | max | nDistinct | distinct values | hash sets |
+        // min bits | max bits | counters]
+        const size_t oMin = 0, oMax = oMin + (size_t)F * 4, oND = oMax + (size_t)F * 4, oDist = oND + (size_t)F * 4,
+                     oTab = oDist + (size_t)F * RLB_T * 4, oMinB = oTab + (size_t)F * HASH_CAP * 4, oMaxB = oMinB + (size_t)F * 4,
+                     oCnt = oMaxB + (size_t)F * 4, scratchBytes = oCnt + (size_t)F * 4;
+        unsigned char* scratch = nullptr;
+        RLB_CUDA(c, rlb_dev_alloc(c, (void**)&scratch, scratchBytes));
+        float* dMin = (float*)(scratch + oMin);
+        float* dMax = (float*)(scratch + oMax);
+        int* dND = (int*)(scratch + oND);
+        float* dDist = (float*)(scratch + oDist);
         {
-            unsigned int *dTab = nullptr, *dMinB = nullptr, *dMaxB = nullptr;
-            int* dCnt = nullptr;
-            RLB_CUDA(c, cudaMalloc(&dTab, (size_t)F * HASH_CAP * 4));
-            RLB_CUDA(c, cudaMalloc(&dMinB, F * 4));
-            RLB_CUDA(c, cudaMalloc(&dMaxB, F * 4));
-            RLB_CUDA(c, cudaMalloc(&dCnt, F * 4));
-            // EMPTY_KEY = 0x7fc00001 is not a byte pattern: fill with a kernel-free trick (memset32 via driver API
-            // is not in the runtime) -> cudaMemset2D on 4-byte rows is overkill; use a tiny fill kernel instead
+            unsigned int* dTab = (unsigned int*)(scratch + oTab);
+            unsigned int* dMinB = (unsigned int*)(scratch + oMinB);
+            unsigned int* dMaxB = (unsigned int*)(scratch + oMaxB);
+            int* dCnt = (int*)(scratch + oCnt);
+            // EMPTY_KEY = 0x7fc00001 is not a byte pattern: a tiny fill kernel
             extern void rlb_fill_u32(unsigned int*, size_t, unsigned int, cudaStream_t);
             rlb_fill_u32(dTab, (size_t)F * HASH_CAP, EMPTY_KEY, c->stream);
             rlb_fill_u32(dMinB, F, 0xffffffffu, c->stream);
@@ -677,8 +735,6 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             RLB_CHECK_LAUNCH(c);
             k_colstats_finish<<<(F + 127) / 128, 128, 0, c->stream>>>(dTab, dCnt, F, p->n_threshold, dMinB, dMaxB, dMin, dMax, dND, dDist);
             RLB_CHECK_LAUNCH(c);
-            RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(dTab); cudaFree(dMinB); cudaFree(dMaxB); cudaFree(dCnt);
         }
         const int W = c->world;
         std::vector<float> hMin((size_t)F * W), hMax((size_t)F * W), hDist((size_t)F * RLB_T * W);
@@ -686,10 +742,10 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         if (W > 1) {
             float *gMin, *gMax, *gDist;
             int* gND;
-            RLB_CUDA(c, cudaMalloc(&gMin, (size_t)F * W * sizeof(float)));
-            RLB_CUDA(c, cudaMalloc(&gMax, (size_t)F * W * sizeof(float)));
-            RLB_CUDA(c, cudaMalloc(&gND, (size_t)F * W * sizeof(int)));
-            RLB_CUDA(c, cudaMalloc(&gDist, (size_t)F * RLB_T * W * sizeof(float)));
+            RLB_CUDA(c, rlb_dev_alloc(c, (void**)&gMin, (size_t)F * W * sizeof(float)));
+            RLB_CUDA(c, rlb_dev_alloc(c, (void**)&gMax, (size_t)F * W * sizeof(float)));
+            RLB_CUDA(c, rlb_dev_alloc(c, (void**)&gND, (size_t)F * W * sizeof(int)));
+            RLB_CUDA(c, rlb_dev_alloc(c, (void**)&gDist, (size_t)F * RLB_T * W * sizeof(float)));
             RLB_NCCL(c, ncclGroupStart());
             RLB_NCCL(c, ncclAllGather(dMin, gMin, F, ncclFloat, c->comm, c->stream));
             RLB_NCCL(c, ncclAllGather(dMax, gMax, F, ncclFloat, c->comm, c->stream));
@@ -701,7 +757,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             RLB_CUDA(c, cudaMemcpyAsync(hND.data(), gND, hND.size() * 4, cudaMemcpyDeviceToHost, c->stream));
             RLB_CUDA(c, cudaMemcpyAsync(hDist.data(), gDist, hDist.size() * 4, cudaMemcpyDeviceToHost, c->stream));
             RLB_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(gMin); cudaFree(gMax); cudaFree(gND); cudaFree(gDist);
+            rlb_dev_free(c, gMin); rlb_dev_free(c, gMax); rlb_dev_free(c, gND); rlb_dev_free(c, gDist);
         } else {
             RLB_CUDA(c, cudaMemcpyAsync(hMin.data(), dMin, hMin.size() * 4, cudaMemcpyDeviceToHost, c->stream));
             RLB_CUDA(c, cudaMemcpyAsync(hMax.data(), dMax, hMax.size() * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -709,7 +765,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             RLB_CUDA(c, cudaMemcpyAsync(hDist.data(), dDist, hDist.size() * 4, cudaMemcpyDeviceToHost, c->stream));
             RLB_CUDA(c, cudaStreamSynchronize(c->stream));
         }
-        cudaFree(dMin); cudaFree(dMax); cudaFree(dND); cudaFree(dDist);
+        rlb_dev_free(c, scratch);
         c->h_thr.assign((size_t)F * RLB_T, FLT_MAX);
         c->h_nthr.assign(F, 0);
         std::vector<float> merged;
@@ -741,6 +797,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         c->thr_user = false;
         c->thr_built_for = p->n_threshold;
     }
+    tm.mark("thresholds");
     RLB_CUDA(c, rlb_reserve(c, c->dThr, (size_t)F * RLB_T * sizeof(float)));
     RLB_CUDA(c, rlb_reserve(c, c->dNThr, F * sizeof(int32_t)));
     RLB_CUDA(c, cudaMemcpyAsync(c->dThr, c->h_thr.data(), (size_t)F * RLB_T * 4, cudaMemcpyHostToDevice, c->stream));
@@ -828,9 +885,15 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
                                     c->stream));
     }
 
+    tm.mark("allocations + clears");
     // ---- binning + root counts ----
     k_binning<<<c->grid_rows, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, c->dHistCnt);
     RLB_CHECK_LAUNCH(c);
+    {
+        const int slices = std::max(1, (c->sm_count * 8 + F - 1) / F);
+        k_root_counts<<<F * slices, 256, 0, c->stream>>>(c->dBinsT, N, F, slices, c->dHistCnt);
+        RLB_CHECK_LAUNCH(c);
+    }
     k_tile_bins<<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, Fp, F, N, c->root_nb, c->dBinsTile);
     RLB_CHECK_LAUNCH(c);
     if (c->world > 1) {   // this rank's own root counts, kept next to the global ones
@@ -842,6 +905,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCnt, F);
     RLB_CHECK_LAUNCH(c);
 
+    tm.mark("binning + tiles + counts");
     // ---- metric tables ----
     if (int rc = upload_discount(c)) return rc;
     // ---- query size classes of the lambda / NDCG kernels (table = min(k, n) * n pair terms) ----
@@ -856,7 +920,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             c->qaux_ctas = std::min(c->nqC, c->sm_count * 2);
             RLB_CUDA(c, rlb_reserve(c, c->dQAux, (size_t)c->qaux_ctas * 3 * c->max_query * sizeof(double)));
         } else if (c->dQAux) {
-            cudaFree(c->dQAux);
+            rlb_dev_free(c, c->dQAux);
             c->dQAux = nullptr;
             c->cap.erase((void*)&c->dQAux);
         }
@@ -869,6 +933,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     if (c->have_valid) {
         if (int rc = valid_finalize(c, c->h_vqoff.data())) return rc;
     }
+    tm.mark("metric tables + query classes");
     c->inited = true;
     c->tree_ready = c->tree_output_ready = false;
     c->lambda_fresh = false;
@@ -984,10 +1049,10 @@ static size_t eval_smem(int n_cols, int TD) {
 // grow-only scratch slot of the evaluation paths
 static int eval_buf(rlb_ctx* c, int slot, size_t bytes, void** out) {
     if (c->evalCap[slot] < bytes || !c->dEvalBuf[slot]) {
-        if (c->dEvalBuf[slot]) cudaFree(c->dEvalBuf[slot]);
+        if (c->dEvalBuf[slot]) rlb_dev_free(c, c->dEvalBuf[slot]);
         c->dEvalBuf[slot] = nullptr;
         c->evalCap[slot] = 0;
-        RLB_CUDA(c, cudaMalloc(&c->dEvalBuf[slot], std::max<size_t>(bytes, 256)));
+        RLB_CUDA(c, rlb_dev_alloc(c, &c->dEvalBuf[slot], std::max<size_t>(bytes, 256)));
         c->evalCap[slot] = std::max<size_t>(bytes, 256);
     }
     *out = c->dEvalBuf[slot];

@@ -50,7 +50,7 @@ bool rlb_nccl_load(std::string* why);
 #define RLB_MAX_LABEL 30             // gain(rel) = (1<<rel)-1 must fit a Java int (DCGScorer.java:28-31)
 #define RLB_PART_TILE 2048           // rows per partition tile (256 threads x 8)
 #define RLB_ROOT_R 192               // rows per tile of the root-histogram layout (dBinsTile)
-#define RLB_CHAIN_CK 512             // float-chain elements per chunk (rlb_boost.cu: one warp compiles a chunk's item program)
+#define RLB_CHAIN_CK 1024            // float-chain elements per chunk (rlb_boost.cu: one warp compiles a chunk's item program)
 #define RLB_CHAIN_ITEMS (RLB_CHAIN_CK + 88)   // item capacity of a chunk's program
 #define RLB_CHAIN_THREADS 256
 #define RLB_CHAIN_PER_THREAD 4
@@ -300,6 +300,7 @@ struct rlb_ctx {
     int graph_events[2] = {0, 0};
     bool capturing = false;
     bool use_graph = true;
+    bool pdl = false;               // programmatic dependent launch between the kernels of a split step (RLB_PDL=0: off)
     bool graph_multi = false;       // capture NCCL collectives into the iteration graph (multi-GPU)
     int64_t launches_per_iter = 0;
     // development trace: one event after every kernel launch (RLB_TRACE=1, disables the graph)
@@ -355,6 +356,8 @@ int rlb_impl_load_validation(rlb_ctx* ctx, const float* X, int64_t N, int32_t F,
 int rlb_impl_score_resident(rlb_ctx* ctx, int32_t which, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees,
                             const float* weights, float* scores_out, double* metric_out);
 void rlb_impl_free(rlb_ctx* ctx);
+cudaError_t rlb_dev_alloc(rlb_ctx* ctx, void** ptr, size_t bytes);   // from the device's stream-ordered pool (rlb_init.cu)
+void rlb_dev_free(rlb_ctx* ctx, void* ptr);
 // grow-only device allocation: keeps *ptr when its capacity covers `bytes`, else frees it and allocates anew
 cudaError_t rlb_reserve_bytes(rlb_ctx* ctx, void** ptr, size_t bytes);
 template <typename T>
