@@ -153,39 +153,46 @@ __device__ __forceinline__ float xw_get_float(const unsigned long long* slot, un
     return __uint_as_float((unsigned int)(v & 0xffffffffull));
 }
 
+// The deviance-ordered queue of RegressionTree.fit as the controller thread sees it: the arrays live in DevState (global
+// memory); k_finish works on a shared-memory copy (one thread chasing global memory pays an L2 round trip per access).
+struct QueueView {
+    int32_t* q;
+    double* dev;
+    int32_t* cnt;
+    int ql, taken;
+};
+
 // RegressionTree.insert (RegressionTree.java:147-157)
-__device__ void queue_insert(DevState* st, int node) {
+__device__ void queue_insert_v(QueueView& v, int node, double d, int cnt) {
     int i = 0;
-    const double d = st->nodes[node].deviance;
-    const int cnt = st->nodes[node].count;
-    const int ql = st->qlen;
+    const int ql = v.ql;
     while (i < ql) {
-        if (st->qdev[i] > d)
+        if (v.dev[i] > d)
             i++;
         else
             break;
     }
     for (int j = ql; j > i; j--) {
-        st->queue[j] = st->queue[j - 1];
-        st->qdev[j] = st->qdev[j - 1];
-        st->qcnt[j] = st->qcnt[j - 1];
+        v.q[j] = v.q[j - 1];
+        v.dev[j] = v.dev[j - 1];
+        v.cnt[j] = v.cnt[j - 1];
     }
-    st->queue[i] = node;
-    st->qdev[i] = d;
-    st->qcnt[i] = cnt;
-    st->qlen = ql + 1;
+    v.q[i] = node;
+    v.dev[i] = d;
+    v.cnt[i] = cnt;
+    v.ql = ql + 1;
 }
 
 // the head of RegressionTree.fit's while loop (RegressionTree.java:69-77) up to the point where a
 // histogram scan is needed; the cheap rejections are consumed here.
-__device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, int32_t* pool) {
-    int head = 0, ql = st->qlen, taken = st->taken;
+__device__ void select_next_v(DevState* st, QueueView& v, const TreeParams& tp, int32_t* used, int32_t* pool) {
+    int head = 0, ql = v.ql, taken = v.taken;
     int chosen = -1;
     while (true) {
         if (!(taken + (ql - head) < tp.n_leaves) || ql - head == 0) break;
-        const int leaf = st->queue[head];
-        const int cnt = st->qcnt[head];
-        const double dev = st->qdev[head];
+        const int leaf = v.q[head];
+        const int cnt = v.cnt[head];
+        const double dev = v.dev[head];
         head++;
         if (cnt < 2 * tp.mls) {
             taken++;
@@ -200,13 +207,13 @@ __device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, i
     }
     if (head > 0) {  // drop the popped entries
         for (int j = head; j < ql; j++) {
-            st->queue[j - head] = st->queue[j];
-            st->qdev[j - head] = st->qdev[j];
-            st->qcnt[j - head] = st->qcnt[j];
+            v.q[j - head] = v.q[j];
+            v.dev[j - head] = v.dev[j];
+            v.cnt[j - head] = v.cnt[j];
         }
     }
-    st->qlen = ql - head;
-    st->taken = taken;
+    v.ql = ql - head;
+    v.taken = taken;
     if (chosen < 0) {
         st->cur = -1;
         st->done = 1;
@@ -214,6 +221,19 @@ __device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, i
     }
     draw_features(st, tp, used, pool);
     st->cur = chosen;
+}
+
+__device__ void queue_insert(DevState* st, int node) {
+    QueueView v{st->queue, st->qdev, st->qcnt, st->qlen, st->taken};
+    queue_insert_v(v, node, st->nodes[node].deviance, st->nodes[node].count);
+    st->qlen = v.ql;
+}
+
+__device__ void select_next(DevState* st, const TreeParams& tp, int32_t* used, int32_t* pool) {
+    QueueView v{st->queue, st->qdev, st->qcnt, st->qlen, st->taken};
+    select_next_v(st, v, tp, used, pool);
+    st->qlen = v.ql;
+    st->taken = v.taken;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,66 +728,99 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
         const int size = generic ? ax.rows : ((n > cutoff) ? cutoff : n);
         const bool have = !ndcg || ideal > 0.0;
         const int np = size > 0 ? size * n : 0;
-        for (int e = gt; e < np; e += G) {
-            const int a = e / n, b = e - a * n;
+        // Only pairs (a, b), a < size, b > a with DIFFERENT labels are ever read back (the loops below test the labels): the
+        // others are not evaluated at all.  Each warp compacts its share of the pairs into a small queue (a << 16 | b; the
+        // raw-score array is free after the ranking) and evaluates them 32 at a time, so that every lane is busy through
+        // the exp / divide chains — with MSLR-like label marginals 39 % of all pairs have equal labels.
+        uint32_t* wq = reinterpret_cast<uint32_t*>(sRaw) + (gt >> 5) * 64;
+        const int lane = gt & 31;
+        auto eval_pair = [&](int a, int b) {
+            const float la = sLabel[a], lb = sLabel[b];
+            double ch;
+            if (generic) {
+                ch = metric_change(metric, cutoff, n, a, b, labf, auxD, auxI, capN, ax);
+            } else {
+                ch = (disc[a] - disc[b]) * ((double)((1 << (int)la) - 1) - (double)((1 << (int)lb) - 1));
+                if (ndcg) ch = ch / ideal;
+            }
+            const double d = fabs(ch);
             double l = 0.0, w = 0.0;
-            if (b > a && have) {
-                const float la = sLabel[a], lb = sLabel[b];
-                if (la != lb) {
-                    double ch;
-                    if (generic) {
-                        ch = metric_change(metric, cutoff, n, a, b, labf, auxD, auxI, capN, ax);
-                    } else {
-                        ch = (disc[a] - disc[b]) * ((double)((1 << (int)la) - 1) - (double)((1 << (int)lb) - 1));
-                        if (ndcg) ch = ch / ideal;
-                    }
-                    const double d = fabs(ch);
-                    if (d > 0) {
-                        const double diff = (la > lb) ? (sScore[a] - sScore[b]) : (sScore[b] - sScore[a]);
-                        const double rho = 1.0 / (1 + exp(diff));
-                        l = rho * d;
-                        w = rho * (1.0 - rho) * d;
-                    }
+            if (d > 0) {
+                const double diff = (la > lb) ? (sScore[a] - sScore[b]) : (sScore[b] - sScore[a]);
+                const double rho = 1.0 / (1 + exp(diff));
+                l = rho * d;
+                w = rho * (1.0 - rho) * d;
+            }
+            tL[a * n + b] = l;
+            tW[a * n + b] = w;
+        };
+        {
+            int a = gt / n, b = gt - a * n;            // element e = gt + i * G of the size x n table, kept incrementally
+            const int da = G / n, db = G - da * n;
+            int qn = 0;                                // queued pairs of this warp (uniform across the warp)
+            for (int e0 = 0; e0 < np; e0 += G) {
+                const bool valid = (e0 + gt < np) && b > a && have && (sLabel[a] != sLabel[b]);
+                const unsigned int m = __ballot_sync(0xffffffffu, valid);
+                if (valid) wq[qn + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)a << 16) | (uint32_t)b;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const uint32_t pr = wq[lane];
+                    const uint32_t tail = (lane < qn - 32) ? wq[32 + lane] : 0u;
+                    __syncwarp();
+                    if (lane < qn - 32) wq[lane] = tail;
+                    qn -= 32;
+                    eval_pair((int)(pr >> 16), (int)(pr & 0xffffu));
+                    __syncwarp();
+                }
+                a += da;
+                b += db;
+                if (b >= n) {
+                    b -= n;
+                    a++;
                 }
             }
-            tL[e] = l;
-            tW[e] = w;
+            if (lane < qn) {
+                const uint32_t pr = wq[lane];
+                eval_pair((int)(pr >> 16), (int)(pr & 0xffffu));
+            }
         }
         group_sync<G>();
-        for (int p = gt; p < n; p += G) {
+        // Two threads per document: one accumulates its lambda, the other its weight — two independent chains of double
+        // additions, each in the reference's visit order.  lambda -= t is lambda += -t exactly.
+        for (int c2 = gt; c2 < 2 * n; c2 += G) {
+            const int p = c2 >> 1;
+            const bool isW = (c2 & 1) != 0;
+            const double* T = isW ? tW : tL;
             const float lp = sLabel[p];
-            double lam = 0.0, w = 0.0;
+            double acc = 0.0;
             if (size > 0) {
                 const int j1 = min(p, size);
                 for (int j = 0; j < j1; j++)  // (1) outer j < p: p loses to every better-labelled j in the top `size`
                     if (sLabel[j] > lp) {
-                        lam -= tL[j * n + p];
-                        w += tW[j * n + p];
+                        const double t = T[j * n + p];
+                        acc += isW ? t : -t;
                     }
                 if (p < size) {
                     for (int k = 0; k < n; k++)  // (2) outer j == p: p wins over every worse-labelled k
-                        if (lp > sLabel[k]) {
-                            const int t = (k < p) ? k * n + p : p * n + k;
-                            lam += tL[t];
-                            w += tW[t];
-                        }
+                        if (lp > sLabel[k]) acc += T[(k < p) ? k * n + p : p * n + k];
                     for (int j = p + 1; j < n; j++)  // (3) outer j > p
                         if (sLabel[j] > lp) {
-                            lam -= tL[p * n + j];
-                            w += tW[p * n + j];
+                            const double t = T[p * n + j];
+                            acc += isW ? t : -t;
                         }
                 } else {
                     for (int k = 0; k < size; k++)
-                        if (lp > sLabel[k]) {
-                            lam += tL[k * n + p];
-                            w += tW[k * n + p];
-                        }
+                        if (lp > sLabel[k]) acc += T[k * n + p];
                 }
             }
             const int doc = lo + sDoc[p];
-            lambda[doc] = lam;
-            weight[doc] = w;
-            thrMax = fmax(thrMax, fabs(lam));
+            if (isW) {
+                weight[doc] = acc;
+            } else {
+                lambda[doc] = acc;
+                thrMax = fmax(thrMax, fabs(acc));
+            }
         }
     }
     group_sync<G>();
@@ -1106,7 +1159,7 @@ __device__ __forceinline__ void hist_rmw8(HChunk& c) {
 
 // Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
 // per non-empty entry and clear the private copies.  Consumer threads only (named barrier 1).
-template <bool CHILD, int PH>
+template <bool CHILD, int PH, bool CLEAR = true>
 __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, long long* __restrict__ sum,
                                            int32_t* __restrict__ cnt) {
     constexpr int T = HG * PH;
@@ -1120,7 +1173,7 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 #pragma unroll
         for (int q = 0; q < PH; q++) {
             const long long pk = H[bin * T + q * HG + ff];
-            H[bin * T + q * HG + ff] = 0;
+            if (CLEAR) H[bin * T + q * HG + ff] = 0;   // the kernel's last flush leaves the copies as they are
             if (CHILD) {
                 const long long sv = ((pk + (1LL << (CNT_SHIFT - 1))) & (CNT_ONE - 1)) - (1LL << (CNT_SHIFT - 1));
                 sacc += sv;
@@ -1239,7 +1292,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 cur = nxt;
             }
         }
-        hist_flush<false, PH>(H, tid, g, F, sum, nullptr);
+        hist_flush<false, PH, false>(H, tid, g, F, sum, nullptr);
     }
 }
 
@@ -1275,20 +1328,8 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     unsigned long long* empty = full + HSTAGES;
     int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
-    // everything that does not depend on the partition happens before pdl_wait(): the 197 KB of private histograms are
-    // cleared and the barriers initialised while the partition kernel is still running
     pdl_trigger();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
-    if (tid == 0) {
-        for (int s2 = 0; s2 < HSTAGES; s2++) {
-            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
-            mbar_init(&empty[s2], (uint32_t)CW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     pdl_wait();
-    __syncthreads();
     if (!st->split_active) return;
     {
         const size_t so = stage_offset(st, stageStride);
@@ -1300,14 +1341,25 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     const int32_t* samples = r.buf ? samples1 : samples0;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->rows_hist += (hi - lo);
 
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x % nGroups;
     const int idx = blockIdx.x / nGroups;
     const int nCta = (gridDim.x - g + nGroups - 1) / nGroups;  // CTAs working on this feature group
     const int64_t n = hi - lo;
     const int64_t r0 = lo + n * idx / nCta, r1 = lo + n * (idx + 1) / nCta;
     const int nst = (int)((r1 - r0 + R - 1) / R);
-    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows)
+    if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
     const int nfull = (int)((r1 - r0) / R);
+
+    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if (tid == 0) {
+        for (int s2 = 0; s2 < HSTAGES; s2++) {
+            mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
+            mbar_init(&empty[s2], (uint32_t)CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     if (warp == CW) {
         // ===== producer warp: 16-byte cp.async (LDGSTS) straight into the stage, no register staging =====
@@ -1417,7 +1469,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 }
             }
         }
-        hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+        hist_flush<true, PH, false>(H, tid, g, F, sum, cnt);
     }
 }
 
@@ -2239,6 +2291,21 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     __syncthreads();
     if (!amLast) return;
     __threadfence();
+    // the queue in shared memory (up to QCACHE entries; longer queues are worked on in place)
+    constexpr int QCACHE = 256;
+    __shared__ int32_t sQ[QCACHE];
+    __shared__ double sQd[QCACHE];
+    __shared__ int32_t sQc[QCACHE];
+    __shared__ int sQl;
+    const int ql0 = ((volatile DevState*)st)->qlen;
+    const bool cached = ql0 + 2 <= QCACHE;
+    if (cached)
+        for (int i = t; i < ql0; i += blockDim.x) {
+            sQ[i] = __ldcg(&st->queue[i]);
+            sQd[i] = __ldcg(&st->qdev[i]);
+            sQc[i] = __ldcg(&st->qcnt[i]);
+        }
+    __syncthreads();
     if (t == 0) {
         st->ticket_finish = 0;
         volatile NodeRec* ns = &st->nodes[small];
@@ -2262,20 +2329,30 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         ns->sq_fix = sqS;
         no->sq_fix = sqP - sqS;
         const int se = st->scale_exp, s2 = st->scale2_exp;
-        {
-            const double sv = fix2d(ns->sum_fix, se);
-            ns->deviance = fix2d(sqS, s2) - sv * sv / ns->count;
-        }
-        {
-            const double sv = fix2d(no->sum_fix, se);
-            no->deviance = fix2d(sqP - sqS, s2) - sv * sv / no->count;
-        }
+        const int cntS = ns->count, cntO = no->count;
+        const double svS = fix2d(ns->sum_fix, se), svO = fix2d(no->sum_fix, se);
+        const double devS = fix2d(sqS, s2) - svS * svS / cntS;
+        const double devO = fix2d(sqP - sqS, s2) - svO * svO / cntO;
+        ns->deviance = devS;
+        no->deviance = devO;
         __threadfence();
-        queue_insert(st, st->nodes[parent].left);   // RegressionTree.java:82-83: left first, then right
-        queue_insert(st, st->nodes[parent].right);
+        QueueView v = cached ? QueueView{sQ, sQd, sQc, ql0, st->taken} : QueueView{st->queue, st->qdev, st->qcnt, ql0, st->taken};
+        const int li = st->nodes[parent].left, ri = st->nodes[parent].right;   // RegressionTree.java:82-83: left first, then right
+        queue_insert_v(v, li, (li == small) ? devS : devO, (li == small) ? cntS : cntO);
+        queue_insert_v(v, ri, (ri == small) ? devS : devO, (ri == small) ? cntS : cntO);
         st->split_active = 0;
-        select_next(st, tp, used, pool);
+        select_next_v(st, v, tp, used, pool);
+        st->qlen = v.ql;
+        st->taken = v.taken;
+        sQl = v.ql;
     }
+    __syncthreads();
+    if (cached)
+        for (int i = t; i < sQl; i += blockDim.x) {
+            st->queue[i] = sQ[i];
+            st->qdev[i] = sQd[i];
+            st->qcnt[i] = sQc[i];
+        }
     __syncthreads();
     // the scan of the node just selected, by this (last) CTA: the next step starts with its partition
     scan_and_decide(st, tp, histCnt, hist_stride, nodeFeatS, nodeFeatT, used, pool, peers ? histCntL : nullptr);
