@@ -214,6 +214,12 @@ int rlb_stats(rlb_ctx* ctx, int64_t out[4]);
  *   (FeatureHistogram.construct(parent, soi, labels)); out[6] ms inside the lambda kernel, out[7]
  *   its launches. */
 int rlb_stream(rlb_ctx* ctx, void** stream_out);
+/* N GPUs: milliseconds (SM cycles / the device's nominal SM clock) one representative thread of this rank has spent WAITING
+ * for its peers since rlb_lambdamart_init, per exchange of the iteration: out[0] per-split histogram hand-shake, [1] root
+ * histogram, [2] max|lambda|, [3] / [4] leaf-chain totals (two rounds), [5] metric-chain total, [6] / [7] unused,
+ * [8] float-chain hand-over from the previous rank, [9] final chain values from the last rank.  Waiting = skew between the
+ * ranks + NVLink latency; the data volume is negligible.  All zeros on one GPU. */
+int rlb_comm_stats(rlb_ctx* ctx, double out[10]);
 int rlb_profile(rlb_ctx* ctx, int32_t enable);
 int rlb_profile_read(rlb_ctx* ctx, double out[8]);
 

@@ -105,18 +105,58 @@ public class B200LambdaMART extends LambdaMART {
         }
         qoff[samples.size()] = at;
 
-        if (validationSamples != null) {
-            modelScoresOnValidation = new double[validationSamples.size()][];
-            for (int i = 0; i < validationSamples.size(); i++) {
-                modelScoresOnValidation[i] = new double[validationSamples.get(i).size()];
-            }
-        }
-
         release();
         handle = NativeBridge.create(device);
         NativeBridge.loadDense(handle, x, n, nf, features, labels, qoff);
+        uploadValidation();
         NativeBridge.init(handle, nTreeLeaves, minLeafSupport, learningRate, nThreshold, kind(), metricCode(scorer),
                 scorer.getK(), FeatureHistogram.samplingRate, seed);
+    }
+
+    /**
+     * init() for a bag of a Random Forest (B200RFRanker): the training set of this ranker is gathered on the device from
+     * the context `source`, which holds the forest's whole training set — Sampler.doSampling without host work.
+     */
+    void initFromBag(final long source, final int[] picks, final int nDocs) {
+        release();
+        handle = NativeBridge.create(device);
+        NativeBridge.loadBag(handle, source, picks);
+        modelScores = new double[nDocs];
+        impacts = new double[features.length];
+        NativeBridge.init(handle, nTreeLeaves, minLeafSupport, learningRate, nThreshold, kind(), metricCode(scorer),
+                scorer.getK(), FeatureHistogram.samplingRate, seed);
+    }
+
+    /**
+     * modelScoresOnValidation of LambdaMART.init (LambdaMART.java:152-158): the validation lists go to the device once, in
+     * the training set's feature columns; the per-tree update and metric (LambdaMART.java:228-237) then run there.
+     */
+    protected void uploadValidation() {
+        if (validationSamples == null) {
+            return;
+        }
+        int n = 0;
+        for (final RankList rl : validationSamples) {
+            n += rl.size();
+        }
+        final int nf = features.length;
+        final float[] x = new float[Math.multiplyExact(n, nf)];
+        final float[] labels = new float[n];
+        final int[] qoff = new int[validationSamples.size() + 1];
+        int at = 0;
+        for (int q = 0; q < validationSamples.size(); q++) {
+            final RankList rl = validationSamples.get(q);
+            qoff[q] = at;
+            for (int j = 0; j < rl.size(); j++, at++) {
+                final DataPoint dp = rl.get(j);
+                labels[at] = dp.getLabel();
+                for (int c = 0; c < nf; c++) {
+                    x[at * nf + c] = dp.getFeatureValue(features[c]);
+                }
+            }
+        }
+        qoff[validationSamples.size()] = at;
+        NativeBridge.loadValidation(handle, x, n, nf, labels, qoff);
     }
 
     /**
@@ -126,12 +166,6 @@ public class B200LambdaMART extends LambdaMART {
      * data (scoreOnTrainingData keeps the last NDCG@k-T); validation sets still go through setValidationSet.
      */
     public void initFromFile(final String trainingFile, final boolean mustHaveRelDoc) {
-        if (validationSamples != null) {
-            modelScoresOnValidation = new double[validationSamples.size()][];
-            for (int i = 0; i < validationSamples.size(); i++) {
-                modelScoresOnValidation[i] = new double[validationSamples.get(i).size()];
-            }
-        }
         release();
         handle = NativeBridge.create(device);
         final int[] dims = new int[3];
@@ -144,8 +178,36 @@ public class B200LambdaMART extends LambdaMART {
         }
         modelScores = new double[dims[0]];
         impacts = new double[features.length];
+        uploadValidation();
         NativeBridge.init(handle, nTreeLeaves, minLeafSupport, learningRate, nThreshold, kind(), metricCode(scorer),
                 scorer.getK(), FeatureHistogram.samplingRate, seed);
+    }
+
+    /** Flat node arrays of every tree of the ensemble, as NativeBridge.boostIter returned them (Split keeps its feature id and
+     * threshold private, so the arrays the device path needs are kept beside the Split objects). */
+    protected final java.util.List<int[]> treeInts = new java.util.ArrayList<>();
+    protected final java.util.List<float[]> treeFloats = new java.util.ArrayList<>();
+
+    /** scorer.score(rank(samples)) from the set resident on the device: which = 0 training, 1 validation; the first
+     * ensemble.treeCount() trees (the roll-back of LambdaMART.java:254-256 has already dropped the others). */
+    protected double scoreResident(final int which) {
+        final int nt = ensemble.treeCount();
+        final int[] off = new int[nt + 1];
+        final float[] w = new float[nt];
+        int total = 0;
+        for (int t = 0; t < nt; t++) {
+            off[t] = total;
+            w[t] = ensemble.getWeight(t);
+            total += treeInts.get(t).length / 7;
+        }
+        off[nt] = total;
+        final int[] ni = new int[7 * total];
+        final float[] nf = new float[2 * total];
+        for (int t = 0; t < nt; t++) {
+            System.arraycopy(treeInts.get(t), 0, ni, 7 * off[t], treeInts.get(t).length);
+            System.arraycopy(treeFloats.get(t), 0, nf, 2 * off[t], treeFloats.get(t).length);
+        }
+        return NativeBridge.scoreResident(handle, which, ni, nf, off, w);
     }
 
     /** Split objects (Split.java:44-83) from the flat node arrays of NativeBridge.boostIter. */
@@ -170,6 +232,8 @@ public class B200LambdaMART extends LambdaMART {
     @Override
     public void learn() {
         ensemble = new Ensemble();
+        treeInts.clear();
+        treeFloats.clear();
         final int cap = NativeBridge.nodeCapacity(nTreeLeaves);
         final int[] ni = new int[7 * cap];
         final float[] nf = new float[2 * cap];
@@ -189,16 +253,13 @@ public class B200LambdaMART extends LambdaMART {
                 scoreOnTrainingData = NativeBridge.boostIter(handle, ni, nf, nd, nn);
                 final RegressionTree rt = new RegressionTree(treeFromFlat(ni, nf, nd, 0));
                 ensemble.add(rt, learningRate);
+                treeInts.add(java.util.Arrays.copyOf(ni, 7 * nn[0]));
+                treeFloats.add(java.util.Arrays.copyOf(nf, 2 * nn[0]));
                 printLog(new int[] { 9 }, new String[] { Double.toString(SimpleMath.round(scoreOnTrainingData, 4)) });
 
                 if (validationSamples != null) {
-                    for (int i = 0; i < modelScoresOnValidation.length; i++) {
-                        final RankList rl = validationSamples.get(i);
-                        for (int j = 0; j < modelScoresOnValidation[i].length; j++) {
-                            modelScoresOnValidation[i][j] += learningRate * rt.eval(rl.get(j));
-                        }
-                    }
-                    final double v = computeModelScoreOnValidation();
+                    // LambdaMART.java:228-237 ran on the device inside boostIter (resident validation lists)
+                    final double v = NativeBridge.validMetric(handle);
                     printLog(new int[] { 9 }, new String[] { Double.toString(SimpleMath.round(v, 4)) });
                     if (v > bestScoreOnValidationData) {
                         bestScoreOnValidationData = v;
@@ -212,19 +273,17 @@ public class B200LambdaMART extends LambdaMART {
                 }
             }
             NativeBridge.readScores(handle, modelScores);
+
+            while (ensemble.treeCount() > bestModelOnValidation + 1) {
+                ensemble.remove(ensemble.treeCount() - 1);
+            }
+            // scorer.score(rank(samples)) (LambdaMART.java:259,263) from the matrices already on the device
+            scoreOnTrainingData = scoreResident(0);
+            if (validationSamples != null) {
+                bestScoreOnValidationData = scoreResident(1);
+            }
         } finally {
             release();
-        }
-
-        while (ensemble.treeCount() > bestModelOnValidation + 1) {
-            ensemble.remove(ensemble.treeCount() - 1);
-        }
-
-        if (!samples.isEmpty()) { // initFromFile leaves no Java-side copy of the training set
-            scoreOnTrainingData = scorer.score(rank(samples));
-        }
-        if (validationSamples != null) {
-            bestScoreOnValidationData = scorer.score(rank(validationSamples));
         }
     }
 

@@ -62,4 +62,35 @@ final class NativeBridge {
 
     static native int ensembleEval(long handle, int[] nodeInts, float[] nodeFloats, int[] treeOff, float[] weights,
             float[] X, long N, int nCols, float[] out);
+
+    /**
+     * Ranker.setValidationSet + modelScoresOnValidation of LambdaMART.init (LambdaMART.java:152-158): the validation lists,
+     * in the training set's feature columns, stay on the device; every boostIter then updates their cached scores and
+     * evaluates the metric there (LambdaMART.java:228-237).
+     */
+    static native int loadValidation(long handle, float[] X, long N, int F, float[] labels, int[] qoff);
+
+    /** computeModelScoreOnValidation() (LambdaMART.java:485-518) of the iteration boostIter just ran. */
+    static native float validMetric(long handle);
+
+    /**
+     * scorer.score(rank(samples)) (LambdaMART.java:259,263) on the training (which = 0) / validation (1) set that is
+     * resident on the device, for the model given as flat node arrays.
+     */
+    static native double scoreResident(long handle, int which, int[] nodeInts, float[] nodeFloats, int[] treeOff,
+            float[] weights);
+
+    /**
+     * Sampler.doSampling on the device (RFRanker.java:80, Sampler.java:21-38): the context `handle` becomes the bag of the
+     * lists picks[0], picks[1], ... of the context `source`, which holds the whole training set (loadDense).
+     */
+    static native int loadBag(long handle, long source, int[] picks);
+
+    /**
+     * Query-sharded training on the GPUs of one box, one JVM per GPU: rank 0 calls commUniqueId and ships the 128 bytes
+     * to the other ranks; every rank calls commInit before loadDense of ITS shard of the lists.
+     */
+    static native int commUniqueId(byte[] id128);
+
+    static native int commInit(long handle, int rank, int world, byte[] id128);
 }

@@ -24,14 +24,20 @@
 
 #define BRIDGE(name) Java_ciir_umass_edu_learning_tree_NativeBridge_##name
 
-static void throw_ranklib_error(JNIEnv* env, rlb_ctx* ctx) {
+/* RankLibError.create(String) (R/utilities/RankLibError.java:25-42) + Throw.  A failed lookup leaves the JVM's own
+ * NoClassDefFoundError / NoSuchMethodError pending, which is the right thing to surface. */
+static void throw_message(JNIEnv* env, const char* text) {
     jclass cls = (*env)->FindClass(env, "ciir/umass/edu/utilities/RankLibError");
     if (!cls) return;
     jmethodID create = (*env)->GetStaticMethodID(env, cls, "create", "(Ljava/lang/String;)Lciir/umass/edu/utilities/RankLibError;");
-    jstring msg = (*env)->NewStringUTF(env, rlb_last_error(ctx));
+    if (!create) return;
+    jstring msg = (*env)->NewStringUTF(env, text ? text : "ranklib_b200: unknown error");
+    if (!msg) return; /* OutOfMemoryError pending */
     jobject err = (*env)->CallStaticObjectMethod(env, cls, create, msg);
     if (err) (*env)->Throw(env, (jthrowable)err);
 }
+
+static void throw_ranklib_error(JNIEnv* env, rlb_ctx* ctx) { throw_message(env, rlb_last_error(ctx)); }
 
 #define CHECK(ctx, call)                          \
     do {                                          \
@@ -58,6 +64,12 @@ JNIEXPORT jint JNICALL BRIDGE(loadDense)(JNIEnv* env, jclass c, jlong h, jfloatA
                                           jfloatArray labels, jintArray qoff) {
     rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
     jint Q = (*env)->GetArrayLength(env, qoff) - 1;
+    /* the native side reads N*F values, N labels, F ids and Q+1 offsets: the Java arrays must hold them */
+    if (N < 0 || F <= 0 || Q < 1 || (int64_t)(*env)->GetArrayLength(env, X) < (int64_t)N * F ||
+        (int64_t)(*env)->GetArrayLength(env, labels) < (int64_t)N || (*env)->GetArrayLength(env, features) < F) {
+        throw_message(env, "NativeBridge.loadDense: array lengths do not match N, F and the number of lists");
+        return 0;
+    }
     float* x = (*env)->GetPrimitiveArrayCritical(env, X, NULL);
     int32_t* f = (*env)->GetPrimitiveArrayCritical(env, features, NULL);
     float* l = (*env)->GetPrimitiveArrayCritical(env, labels, NULL);
@@ -139,13 +151,19 @@ JNIEXPORT jfloat JNICALL BRIDGE(boostIter)(JNIEnv* env, jclass c, jlong h, jintA
     rlb_node* nodes;
     int32_t n = 0;
     float metric = 0.f;
-    /* the three arrays must agree: cap nodes of 7 ints, 2 floats, 1 double */
+    /* the three arrays must agree: cap nodes of 7 ints, 2 floats, 1 double.  Checked BEFORE the library runs: a boosting
+     * iteration that has run cannot be taken back, and the ensemble on the Java side would be out of step with the device. */
     if (cap < 1 || (*env)->GetArrayLength(env, nodeInts) < 7 * cap || (*env)->GetArrayLength(env, nodeFloats) < 2 * cap ||
-        (*env)->GetArrayLength(env, nNodes) < 1)
-        cap = 0;
-    nodes = (rlb_node*)malloc(sizeof(rlb_node) * (size_t)(cap > 0 ? cap : 1));
-    if (!nodes) return 0.f;
-    if (rlb_boost_iter(ctx, nodes, cap, &n, &metric) != RLB_OK) { /* cap == 0 ends here: "node buffer too small" */
+        (*env)->GetArrayLength(env, nNodes) < 1) {
+        throw_message(env, "NativeBridge.boostIter: node arrays of inconsistent lengths (7 ints, 2 floats, 1 double per node)");
+        return 0.f;
+    }
+    nodes = (rlb_node*)malloc(sizeof(rlb_node) * (size_t)cap);
+    if (!nodes) {
+        throw_message(env, "NativeBridge.boostIter: out of memory");
+        return 0.f;
+    }
+    if (rlb_boost_iter(ctx, nodes, cap, &n, &metric) != RLB_OK) {
         free(nodes);
         throw_ranklib_error(env, ctx);
         return 0.f;
@@ -184,18 +202,29 @@ JNIEXPORT jint JNICALL BRIDGE(readScores)(JNIEnv* env, jclass c, jlong h, jdoubl
     return 0;
 }
 
-/* int ensembleEval(long h, int[] nodeInts, float[] nodeFloats, int[] treeOff, float[] weights, float[] X, long N, int nCols, float[] out)
- * Ensemble.eval for a batch (R/learning/tree/Ensemble.java:110-116): Ranker.rank / Evaluator.score call this once per
- * file instead of once per DataPoint. */
-JNIEXPORT jint JNICALL BRIDGE(ensembleEval)(JNIEnv* env, jclass c, jlong h, jintArray nodeInts, jfloatArray nodeFloats,
-                                             jintArray treeOff, jfloatArray weights, jfloatArray X, jlong N, jint nCols,
-                                             jfloatArray out) {
-    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+/* rlb_node array from the flat Java arrays (feature id, children, threshold, output); NULL + pending exception on
+ * inconsistent lengths or exhausted memory */
+static rlb_node* unpack_nodes(JNIEnv* env, jintArray nodeInts, jfloatArray nodeFloats, jintArray treeOff, jfloatArray weights,
+                              jsize* nTreesOut) {
     jsize nTrees = (*env)->GetArrayLength(env, weights);
     jsize nNodes = (*env)->GetArrayLength(env, nodeInts) / 7;
+    if ((*env)->GetArrayLength(env, nodeFloats) < 2 * nNodes || (*env)->GetArrayLength(env, treeOff) != nTrees + 1) {
+        throw_message(env, "NativeBridge: model arrays of inconsistent lengths (7 ints + 2 floats per node, nTrees + 1 offsets)");
+        return NULL;
+    }
+    rlb_node* nodes = (rlb_node*)malloc(sizeof(rlb_node) * (size_t)(nNodes > 0 ? nNodes : 1));
+    if (!nodes) {
+        throw_message(env, "NativeBridge: out of memory");
+        return NULL;
+    }
     jint* ni = (*env)->GetIntArrayElements(env, nodeInts, NULL);
     jfloat* nf = (*env)->GetFloatArrayElements(env, nodeFloats, NULL);
-    rlb_node* nodes = (rlb_node*)malloc(sizeof(rlb_node) * (size_t)(nNodes > 0 ? nNodes : 1));
+    if (!ni || !nf) {
+        if (ni) (*env)->ReleaseIntArrayElements(env, nodeInts, ni, JNI_ABORT);
+        if (nf) (*env)->ReleaseFloatArrayElements(env, nodeFloats, nf, JNI_ABORT);
+        free(nodes);
+        return NULL; /* OutOfMemoryError pending */
+    }
     for (jsize i = 0; i < nNodes; i++) {
         memset(&nodes[i], 0, sizeof(rlb_node));
         nodes[i].feature_id = ni[7 * i + 0];
@@ -206,6 +235,25 @@ JNIEXPORT jint JNICALL BRIDGE(ensembleEval)(JNIEnv* env, jclass c, jlong h, jint
     }
     (*env)->ReleaseIntArrayElements(env, nodeInts, ni, JNI_ABORT);
     (*env)->ReleaseFloatArrayElements(env, nodeFloats, nf, JNI_ABORT);
+    *nTreesOut = nTrees;
+    return nodes;
+}
+
+/* int ensembleEval(long h, int[] nodeInts, float[] nodeFloats, int[] treeOff, float[] weights, float[] X, long N, int nCols, float[] out)
+ * Ensemble.eval for a batch (R/learning/tree/Ensemble.java:110-116): Ranker.rank / Evaluator.score call this once per
+ * file instead of once per DataPoint.  The library validates the model itself (child indices, offsets). */
+JNIEXPORT jint JNICALL BRIDGE(ensembleEval)(JNIEnv* env, jclass c, jlong h, jintArray nodeInts, jfloatArray nodeFloats,
+                                             jintArray treeOff, jfloatArray weights, jfloatArray X, jlong N, jint nCols,
+                                             jfloatArray out) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    jsize nTrees = 0;
+    if (N < 0 || nCols <= 0 || (int64_t)(*env)->GetArrayLength(env, X) < (int64_t)N * nCols ||
+        (int64_t)(*env)->GetArrayLength(env, out) < (int64_t)N) {
+        throw_message(env, "NativeBridge.ensembleEval: X / out shorter than N x nCols / N");
+        return 0;
+    }
+    rlb_node* nodes = unpack_nodes(env, nodeInts, nodeFloats, treeOff, weights, &nTrees);
+    if (!nodes) return 0;
     jint* to = (*env)->GetPrimitiveArrayCritical(env, treeOff, NULL);
     jfloat* w = (*env)->GetPrimitiveArrayCritical(env, weights, NULL);
     jfloat* x = (*env)->GetPrimitiveArrayCritical(env, X, NULL);
@@ -217,6 +265,93 @@ JNIEXPORT jint JNICALL BRIDGE(ensembleEval)(JNIEnv* env, jclass c, jlong h, jint
     (*env)->ReleasePrimitiveArrayCritical(env, treeOff, to, JNI_ABORT);
     free(nodes);
     CHECK(ctx, rc);
+    return 0;
+}
+
+/* int loadValidation(long h, float[] X (N x F, the training set's feature columns), long N, int F, float[] labels, int[] qoff)
+ * Ranker.setValidationSet + modelScoresOnValidation of LambdaMART.init (LambdaMART.java:152-158): the validation lists stay
+ * on the device; every boostIter then scores the new tree on them (LambdaMART.java:228-237) without host traffic. */
+JNIEXPORT jint JNICALL BRIDGE(loadValidation)(JNIEnv* env, jclass c, jlong h, jfloatArray X, jlong N, jint F, jfloatArray labels,
+                                               jintArray qoff) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    jint Q = (*env)->GetArrayLength(env, qoff) - 1;
+    if (N < 0 || F <= 0 || Q < 1 || (int64_t)(*env)->GetArrayLength(env, X) < (int64_t)N * F ||
+        (int64_t)(*env)->GetArrayLength(env, labels) < (int64_t)N) {
+        throw_message(env, "NativeBridge.loadValidation: array lengths do not match N, F and the number of lists");
+        return 0;
+    }
+    float* x = (*env)->GetPrimitiveArrayCritical(env, X, NULL);
+    float* l = (*env)->GetPrimitiveArrayCritical(env, labels, NULL);
+    int32_t* q = (*env)->GetPrimitiveArrayCritical(env, qoff, NULL);
+    int rc = rlb_load_validation(ctx, x, (int64_t)N, F, l, q, Q);
+    (*env)->ReleasePrimitiveArrayCritical(env, qoff, q, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, labels, l, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, X, x, JNI_ABORT);
+    CHECK(ctx, rc);
+    return 0;
+}
+
+/* float validMetric(long h) — computeModelScoreOnValidation() of the iteration boostIter just ran (LambdaMART.java:236) */
+JNIEXPORT jfloat JNICALL BRIDGE(validMetric)(JNIEnv* env, jclass c, jlong h) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    float v = 0.f;
+    CHECK(ctx, rlb_valid_metric(ctx, &v));
+    return v;
+}
+
+/* double scoreResident(long h, int which, int[] nodeInts, float[] nodeFloats, int[] treeOff, float[] weights)
+ * scorer.score(rank(samples)) (LambdaMART.java:259,263) on the training (0) / validation (1) set resident on the device */
+JNIEXPORT jdouble JNICALL BRIDGE(scoreResident)(JNIEnv* env, jclass c, jlong h, jint which, jintArray nodeInts, jfloatArray nodeFloats,
+                                                 jintArray treeOff, jfloatArray weights) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    jsize nTrees = 0;
+    double metric = 0.0;
+    rlb_node* nodes = unpack_nodes(env, nodeInts, nodeFloats, treeOff, weights, &nTrees);
+    if (!nodes) return 0.0;
+    jint* to = (*env)->GetPrimitiveArrayCritical(env, treeOff, NULL);
+    jfloat* w = (*env)->GetPrimitiveArrayCritical(env, weights, NULL);
+    int rc = rlb_score_resident(ctx, which, nodes, to, nTrees, w, NULL, &metric);
+    (*env)->ReleasePrimitiveArrayCritical(env, weights, w, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, treeOff, to, JNI_ABORT);
+    free(nodes);
+    CHECK(ctx, rc);
+    return metric;
+}
+
+/* int loadBag(long h, long src, int[] picks) — Sampler.doSampling on the device (RFRanker.java:80, Sampler.java:21-38): this
+ * context becomes the bag of src's lists picks[0], picks[1], ... */
+JNIEXPORT jint JNICALL BRIDGE(loadBag)(JNIEnv* env, jclass c, jlong h, jlong src, jintArray picks) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    jsize n = (*env)->GetArrayLength(env, picks);
+    jint* p = (*env)->GetPrimitiveArrayCritical(env, picks, NULL);
+    int rc = rlb_load_bag(ctx, (const rlb_ctx*)(intptr_t)src, (const int32_t*)p, n);
+    (*env)->ReleasePrimitiveArrayCritical(env, picks, p, JNI_ABORT);
+    CHECK(ctx, rc);
+    return 0;
+}
+
+/* int commUniqueId(byte[] id128) / int commInit(long h, int rank, int world, byte[] id128): query-sharded training on the
+ * GPUs of one box, one process (JVM) per GPU (include/ranklib_b200.h rlb_comm_*); rank 0 creates the id and ships it. */
+JNIEXPORT jint JNICALL BRIDGE(commUniqueId)(JNIEnv* env, jclass c, jbyteArray id) {
+    uint8_t buf[128];
+    if ((*env)->GetArrayLength(env, id) < 128) {
+        throw_message(env, "NativeBridge.commUniqueId: the id array must hold 128 bytes");
+        return 0;
+    }
+    CHECK(NULL, rlb_comm_unique_id(buf));
+    (*env)->SetByteArrayRegion(env, id, 0, 128, (const jbyte*)buf);
+    return 0;
+}
+
+JNIEXPORT jint JNICALL BRIDGE(commInit)(JNIEnv* env, jclass c, jlong h, jint rank, jint world, jbyteArray id) {
+    rlb_ctx* ctx = (rlb_ctx*)(intptr_t)h;
+    uint8_t buf[128];
+    if ((*env)->GetArrayLength(env, id) < 128) {
+        throw_message(env, "NativeBridge.commInit: the id array must hold 128 bytes");
+        return 0;
+    }
+    (*env)->GetByteArrayRegion(env, id, 0, 128, (jbyte*)buf);
+    CHECK(ctx, rlb_comm_init(ctx, rank, world, buf));
     return 0;
 }
 #endif /* RLB_HAVE_JNI */

@@ -705,6 +705,18 @@ int rlb_trace_dump(rlb_ctx* c, const char* path) {
     return RLB_OK;
 }
 
+int rlb_comm_stats(rlb_ctx* c, double out[10]) {
+    if (int rc = check_ready(c, "rlb_comm_stats")) return rc;
+    if (!out) return RLB_E_INVALID;
+    long long cyc[XW_KINDS + 2];
+    RLB_CUDA(c, cudaStreamSynchronize(c->stream));
+    RLB_CUDA(c, cudaMemcpy(cyc, c->dState->xwait, sizeof(cyc), cudaMemcpyDeviceToHost));
+    int khz = 0;
+    RLB_CUDA(c, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device));   // clock64 ticks at the SM clock
+    for (int i = 0; i < XW_KINDS + 2; i++) out[i] = khz > 0 ? (double)cyc[i] / (double)khz : 0.0;
+    return RLB_OK;
+}
+
 int rlb_stream(rlb_ctx* c, void** stream_out) {
     if (!c || !stream_out) return RLB_E_INVALID;
     *stream_out = (void*)c->stream;

@@ -128,6 +128,7 @@ __device__ __forceinline__ void xw_signal(const PeerTab* p, int kind, unsigned i
 // wait until every peer has signalled `kind` >= epoch (ONE thread; the caller follows with a block barrier)
 __device__ __forceinline__ void xw_wait(const PeerTab* p, int kind, unsigned int epoch, DevState* st) {
     const XWin* me = xw_of(p, p->rank);
+    const long long t0 = clock64();
     for (int r = 0; r < p->world; r++) {
         if (r == p->rank) continue;
         unsigned int v;
@@ -137,19 +138,22 @@ __device__ __forceinline__ void xw_wait(const PeerTab* p, int kind, unsigned int
         } while ((int)(v - epoch) < 0 && ++spins < XW_SPIN_LIMIT);
         if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
     }
+    if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd((unsigned long long*)&st->xwait[kind], (unsigned long long)(clock64() - t0));
 }
 // a float handed over through a 64-bit slot: epoch << 32 | bits (one atomic store, no separate flag)
 __device__ __forceinline__ void xw_put_float(unsigned long long* slot, unsigned int epoch, float v) {
     __threadfence_system();
     st_release_sys64(slot, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v));
 }
-__device__ __forceinline__ float xw_get_float(const unsigned long long* slot, unsigned int epoch, DevState* st) {
+__device__ __forceinline__ float xw_get_float(const unsigned long long* slot, unsigned int epoch, DevState* st, int acct = -1) {
     unsigned long long v;
     long long spins = 0;
+    const long long t0 = clock64();
     do {
         v = ld_acquire_sys64(slot);
     } while ((unsigned int)(v >> 32) != epoch && ++spins < XW_SPIN_LIMIT);
     if ((unsigned int)(v >> 32) != epoch) st->p2p_timeout = 1;
+    if (acct >= 0) atomicAdd((unsigned long long*)&st->xwait[acct], (unsigned long long)(clock64() - t0));
     return __uint_as_float((unsigned int)(v & 0xffffffffull));
 }
 
@@ -925,6 +929,7 @@ __global__ void __launch_bounds__(32) k_scale(DevState* st, long long n_total, c
             }
         }
         unsigned long long got = 0;
+        const long long t0 = clock64();
         if (lane < peers->world) {
             const XWin* me = xw_of(peers, peers->rank);
             if (lane != peers->rank) {
@@ -946,6 +951,7 @@ __global__ void __launch_bounds__(32) k_scale(DevState* st, long long n_total, c
         if (lane == 0) {
             st->max_abs_bits = got;
             st->xe[XW_SCALE] = epoch;
+            st->xwait[XW_SCALE] += clock64() - t0;
         }
         __syncwarp();
     }
@@ -1958,42 +1964,34 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
             if (k < w) off += sw[k];
             tot += sw[k];
         }
-        if (w == 0) {
-            // warp 0: publish the aggregate, look back 32 predecessors at a time for the exclusive prefix,
-            // publish the inclusive prefix (decoupled look-back)
+        // Exclusive prefix of the tile's left count over the preceding tiles: the tile publishes its aggregate, then ALL its
+        // threads read the aggregates of the tiles before it in parallel (thread i takes tiles i, i + 256, ...; an entry that
+        // is not there yet is polled) and the block adds them up — one memory round trip whatever the tile's ordinal.  (A
+        // chained look-back needs an inclusive prefix from some predecessor, which makes tile t wait on a chain of ~t / 32
+        // round trips: 18 of them at 586 tiles, the whole cost of this kernel on the root split.)  Tiles are handed out by
+        // ticket, so every tile a thread waits for has been started: no deadlock whatever the grid.
+        {
             volatile unsigned long long* ts = tileState;
-            int excl = 0;
-            if (tile > 0) {
-                if (lane == 0) {
-                    ts[tile] = (epoch << 34) | (1ull << 32) | (unsigned long long)(unsigned int)tot;
-                    __threadfence();
-                }
-                int p = tile - 1;  // lane l inspects tile p - l
-                while (true) {
-                    const int q = p - lane;
-                    unsigned long long v = 0;
-                    bool ready = true;
-                    if (q >= 0) {
-                        do {
-                            v = ts[q];
-                        } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0ull);
-                    }
-                    (void)ready;
-                    const bool isPrefix = (q >= 0) && (((v >> 32) & 3ull) == 2ull);
-                    const unsigned int pm = __ballot_sync(0xffffffffu, isPrefix);
-                    // tiles p .. p-k where k is the first lane holding an inclusive prefix (or all 32 / down to tile 0)
-                    const int k = pm ? (__ffs(pm) - 1) : 31;
-                    int val = (q >= 0 && lane <= k) ? (int)(unsigned int)(v & 0xffffffffull) : 0;
-                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                    excl += val;
-                    if (pm || p - 31 <= 0) break;
-                    p -= 32;
-                }
-            }
-            if (lane == 0) {
-                ts[tile] = (epoch << 34) | (2ull << 32) | (unsigned long long)(unsigned int)(excl + tot);
+            if (threadIdx.x == 0) {
+                ts[tile] = (epoch << 34) | (1ull << 32) | (unsigned long long)(unsigned int)tot;
                 __threadfence();
-                sExcl = excl;
+            }
+            int part = 0;
+            for (int q = threadIdx.x; q < tile; q += blockDim.x) {
+                unsigned long long v;
+                do {
+                    v = ts[q];
+                } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0ull);
+                part += (int)(unsigned int)(v & 0xffffffffull);
+            }
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            __syncthreads();              // sw[] (the warps' left counts) has been read by everybody
+            if (lane == 0) sw[w] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int e = 0;
+                for (int k = 0; k < 8; k++) e += sw[k];
+                sExcl = e;
             }
         }
         __syncthreads();
@@ -3292,7 +3290,7 @@ __global__ void __launch_bounds__(256) k_chain_push(DevState* __restrict__ st, c
 // slot, or — last rank — the final value into EVERY rank's final_ slot.  epoch: of the totals exchange that preceded.
 __device__ __forceinline__ float chain_carry_in(const PeerTab* peers, int slot, unsigned int epoch, DevState* st) {
     if (!peers || peers->rank == 0) return 0.f;
-    return xw_get_float(&xw_of(peers, peers->rank)->carry[slot], epoch, st);
+    return xw_get_float(&xw_of(peers, peers->rank)->carry[slot], epoch, st, (slot == 0 || slot == XW_METRIC_CHAIN) ? XW_KINDS : -1);
 }
 __device__ __forceinline__ void chain_carry_out(const PeerTab* peers, int slot, unsigned int epoch, float v) {
     if (!peers) return;
@@ -3335,7 +3333,7 @@ __global__ void k_leaf_finalize(DevState* st, int kind, const PeerTab* peers) {
     if (peers) {   // the chains ended on the last rank: its values, identical on every rank
         const unsigned int epoch = st->xe[XW_TOT1];
         const XWin* me = xw_of(peers, peers->rank);
-        st->leaf_s1[l] = xw_get_float(&me->final_[l], epoch, st);
+        st->leaf_s1[l] = xw_get_float(&me->final_[l], epoch, st, l == 0 ? XW_KINDS + 1 : -1);
         if (kind != RLB_KIND_MART) st->leaf_s2[l] = xw_get_float(&me->final_[(RLB_MAX_LEAVES + 1) + l], epoch, st);
     }
     const float s1 = st->leaf_s1[l];
@@ -3396,7 +3394,7 @@ __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __
 
 // slot 0: LambdaMART.java:470 (training), slot 1: LambdaMART.java:510 (validation): float sum / list count
 __global__ void k_metric_final(DevState* st, long long Q_total, int slot, const PeerTab* peers) {
-    if (peers) st->chain_out[slot] = xw_get_float(&xw_of(peers, peers->rank)->final_[XW_METRIC_CHAIN], st->xe[XW_MTOT], st);
+    if (peers) st->chain_out[slot] = xw_get_float(&xw_of(peers, peers->rank)->final_[XW_METRIC_CHAIN], st->xe[XW_MTOT], st, XW_KINDS + 1);
     const float v = st->chain_out[slot] / (float)(int)Q_total;
     if (slot == 0)
         st->train_metric = v;

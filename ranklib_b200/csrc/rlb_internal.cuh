@@ -137,6 +137,8 @@ struct DevState {
     uint32_t part_epoch;    // split counter that is never reset: epoch of the one-pass partition's tile states
     uint32_t xe[XW_KINDS];  // exchange epochs (N GPUs): advanced by k_xbump / single-block kernels, identical on every rank
     uint32_t chain_epoch;   // epoch of the float-chain hand-over slots (carry / final), advanced once per chain run
+    long long xwait[XW_KINDS + 2];   // SM cycles one representative thread spent waiting for the peers, per exchange kind
+                                     // (+0 .. XW_KINDS-1: flags; XW_KINDS: chain carry-in; XW_KINDS+1: chain finals); since init
     // feature sampling (FeatureHistogram.java:271-294)
     long long rng_seed;     // java.util.Random state
     int32_t n_used;

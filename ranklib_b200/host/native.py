@@ -26,7 +26,8 @@ SYMBOLS = ["rlb_last_error", "rlb_version", "rlb_device_count", "rlb_create", "r
            "rlb_update_scores", "rlb_train_metric", "rlb_boost_iter", "rlb_boost_iters", "rlb_read", "rlb_stats",
            "rlb_ensemble_eval", "rlb_score_metric", "rlb_stream", "rlb_profile", "rlb_profile_read", "rlb_float_chain",
            "rlb_letor_read", "rlb_letor_dims", "rlb_letor_fill", "rlb_letor_write_binary", "rlb_load_letor", "rlb_letor_qid", "rlb_letor_free",
-           "rlb_parse_java_float", "rlb_load_validation", "rlb_valid_metric", "rlb_score_resident", "rlb_load_bag", "rlb_learn"]
+           "rlb_parse_java_float", "rlb_load_validation", "rlb_valid_metric", "rlb_score_resident", "rlb_load_bag", "rlb_learn",
+           "rlb_comm_stats"]
 
 
 class RankLibError(RuntimeError):
@@ -285,10 +286,14 @@ class Context:
         self._ck(self.lib.rlb_boost_iter(self.h, None, 0, C.byref(n), C.byref(m)))
         return None, m.value
 
-    def boost_iters(self, n_iters):
-        nodes = np.zeros((n_iters, self.cap), NODE_DTYPE)
+    def boost_iters(self, n_iters, want_trees=True):
+        """n_iters passes of the loop body in one boundary crossing; want_trees=False: only the training metrics come back."""
         nn = np.zeros(n_iters, np.int32)
         mm = np.zeros(n_iters, np.float32)
+        if not want_trees:
+            self._ck(self.lib.rlb_boost_iters(self.h, n_iters, None, 0, _p(nn), _p(mm)))
+            return None, mm
+        nodes = np.zeros((n_iters, self.cap), NODE_DTYPE)
         self._ck(self.lib.rlb_boost_iters(self.h, n_iters, _p(nodes), self.cap, _p(nn), _p(mm)))
         return [nodes[i, :nn[i]].copy() for i in range(n_iters)], mm
 
@@ -320,6 +325,14 @@ class Context:
         out = np.zeros(8, np.float64)
         self._ck(self.lib.rlb_profile_read(self.h, _p(out)))
         return out
+
+    def comm_stats(self):
+        """N GPUs: ms spent waiting for the peers since init, per exchange (see rlb_comm_stats)."""
+        out = np.zeros(10, np.float64)
+        self._ck(self.lib.rlb_comm_stats(self.h, _p(out)))
+        names = ["split_handshake", "root_hist", "max_lambda", "chain_totals_1", "chain_totals_2", "metric_total", "-", "-",
+                 "chain_handover", "chain_finals"]
+        return {n: round(float(v), 3) for n, v in zip(names, out) if n != "-"}
 
     def float_chain(self, x, carry=0.0, passes=2):
         """Test hook: float s = carry; for v in x: s += v  (Java compound assignment), on the device."""

@@ -23,6 +23,7 @@ typedef int64_t jlong;
 typedef float jfloat;
 typedef double jdouble;
 typedef uint8_t jboolean;
+typedef int8_t jbyte;
 typedef jint jsize;
 
 struct mock_object;
@@ -34,6 +35,7 @@ typedef jobject jarray;
 typedef jarray jintArray;
 typedef jarray jfloatArray;
 typedef jarray jdoubleArray;
+typedef jarray jbyteArray;
 struct mock_method;
 typedef struct mock_method* jmethodID;
 
@@ -56,6 +58,8 @@ struct JNINativeInterface_ {
     void (*SetIntArrayRegion)(JNIEnv* env, jintArray a, jsize start, jsize len, const jint* buf);
     const char* (*GetStringUTFChars)(JNIEnv* env, jstring s, jboolean* isCopy);
     void (*ReleaseStringUTFChars)(JNIEnv* env, jstring s, const char* utf);
+    void (*SetByteArrayRegion)(JNIEnv* env, jbyteArray a, jsize start, jsize len, const jbyte* buf);
+    void (*GetByteArrayRegion)(JNIEnv* env, jbyteArray a, jsize start, jsize len, jbyte* buf);
 };
 
 #endif

@@ -121,6 +121,23 @@ static void m_SetIntArrayRegion(JNIEnv* env, jintArray a, jsize start, jsize len
     memcpy((jint*)a->data + start, buf, (size_t)len * sizeof(jint));
 }
 
+static void m_SetByteArrayRegion(JNIEnv* env, jbyteArray a, jsize start, jsize len, const jbyte* buf) {
+    (void)env;
+    if (start < 0 || len < 0 || start + len > a->len || a->elem != 1) {
+        J.pin_errors++;
+        return;
+    }
+    memcpy((jbyte*)a->data + start, buf, (size_t)len);
+}
+static void m_GetByteArrayRegion(JNIEnv* env, jbyteArray a, jsize start, jsize len, jbyte* buf) {
+    (void)env;
+    if (start < 0 || len < 0 || start + len > a->len || a->elem != 1) {
+        J.pin_errors++;
+        return;
+    }
+    memcpy(buf, (jbyte*)a->data + start, (size_t)len);
+}
+
 static const char* m_GetStringUTFChars(JNIEnv* env, jstring s, jboolean* isCopy) {
     (void)env;
     if (isCopy) *isCopy = 1;
@@ -146,7 +163,8 @@ static void m_ReleaseStringUTFChars(JNIEnv* env, jstring s, const char* utf) {
 static const struct JNINativeInterface_ table = {
     m_FindClass, m_GetStaticMethodID, m_CallStaticObjectMethod, m_NewStringUTF, m_Throw, m_GetArrayLength,
     m_GetPrimitiveArrayCritical, m_ReleasePrimitiveArrayCritical, m_GetIntArrayElements, m_ReleaseIntArrayElements,
-    m_GetFloatArrayElements, m_ReleaseFloatArrayElements, m_SetIntArrayRegion, m_GetStringUTFChars, m_ReleaseStringUTFChars};
+    m_GetFloatArrayElements, m_ReleaseFloatArrayElements, m_SetIntArrayRegion, m_GetStringUTFChars, m_ReleaseStringUTFChars,
+    m_SetByteArrayRegion, m_GetByteArrayRegion};
 static JNIEnv the_env = &table;
 
 static jarray new_array(int elem, jsize len, const void* init) {
@@ -175,6 +193,12 @@ jint BRIDGE(loadLetorFile)(JNIEnv*, jclass, jlong, jstring, jboolean, jintArray,
 jfloat BRIDGE(boostIter)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jdoubleArray, jintArray);
 jint BRIDGE(readScores)(JNIEnv*, jclass, jlong, jdoubleArray);
 jint BRIDGE(ensembleEval)(JNIEnv*, jclass, jlong, jintArray, jfloatArray, jintArray, jfloatArray, jfloatArray, jlong, jint, jfloatArray);
+jint BRIDGE(loadValidation)(JNIEnv*, jclass, jlong, jfloatArray, jlong, jint, jfloatArray, jintArray);
+jfloat BRIDGE(validMetric)(JNIEnv*, jclass, jlong);
+jdouble BRIDGE(scoreResident)(JNIEnv*, jclass, jlong, jint, jintArray, jfloatArray, jintArray, jfloatArray);
+jint BRIDGE(loadBag)(JNIEnv*, jclass, jlong, jlong, jintArray);
+jint BRIDGE(commUniqueId)(JNIEnv*, jclass, jbyteArray);
+jint BRIDGE(commInit)(JNIEnv*, jclass, jlong, jint, jint, jbyteArray);
 
 /* --- what the Python test reads back --- */
 int mock_thrown(void) { return J.thrown; }
@@ -325,5 +349,146 @@ done:
     if (h) BRIDGE(destroy)(env, NULL, h);
     free_array(jf); free_array(jd); free_array(jni_); free_array(jnf); free_array(jnd); free_array(jnn);
     if (jpath) { free(jpath->pinned); free(jpath->data); free(jpath); }
+    return rc;
+}
+
+/*
+ * B200LambdaMART.init() + learn() WITH a validation set, as jni/java/.../B200LambdaMART.java drives it: create, loadDense,
+ * loadValidation, init, n_trees x (boostIter, validMetric), scoreResident(training), scoreResident(validation), destroy.
+ * With picks != NULL the training context is a bag gathered on the device from a base context (B200RFRanker): create x 2,
+ * loadDense(base), loadBag.
+ *   out: node arrays as mock_train, valid_out[n_trees], final_scores[2] (training, validation)
+ * Returns 0, or the ordinal of the native call after which a Java exception was pending.
+ */
+int mock_train_valid(int device, const float* X, long long N, int F, const float* labels, const int* qoff, int Q, const float* VX,
+                     long long NV, const float* vlabels, const int* vqoff, int QV, const int* picks, int n_picks, int n_leaves,
+                     int kind, int n_trees, int* node_ints, float* node_floats, int* n_nodes, float* metric_out, float* valid_out,
+                     double* final_scores) {
+    JNIEnv* env = &the_env;
+    int step = 0, rc = 0;
+    int cap = 2 * n_leaves + 1;
+    jlong h = 0, base = 0;
+    jarray jx = NULL, jf = NULL, jl = NULL, jq = NULL, jvx = NULL, jvl = NULL, jvq = NULL, jp = NULL;
+    jarray jni_ = NULL, jnf = NULL, jnd = NULL, jnn = NULL, ani = NULL, anf = NULL, ato = NULL, aw = NULL;
+    int* fids = malloc(sizeof(int) * (size_t)F);
+    for (int j = 0; j < F; j++) fids[j] = j + 1;
+    step++;
+    h = BRIDGE(create)(env, NULL, device);
+    if (J.thrown) { rc = step; goto done; }
+    jx = new_array(4, (jsize)(N * F), X);
+    jf = new_array(4, F, fids);
+    jl = new_array(4, (jsize)N, labels);
+    jq = new_array(4, Q + 1, qoff);
+    if (picks) {
+        step++;
+        base = BRIDGE(create)(env, NULL, device);
+        if (J.thrown) { rc = step; goto done; }
+        step++;
+        BRIDGE(loadDense)(env, NULL, base, jx, N, F, jf, jl, jq);
+        if (J.thrown) { rc = step; goto done; }
+        jp = new_array(4, n_picks, picks);
+        step++;
+        BRIDGE(loadBag)(env, NULL, h, base, jp);
+        if (J.thrown) { rc = step; goto done; }
+    } else {
+        step++;
+        BRIDGE(loadDense)(env, NULL, h, jx, N, F, jf, jl, jq);
+        if (J.thrown) { rc = step; goto done; }
+    }
+    if (VX) {
+        jvx = new_array(4, (jsize)(NV * F), VX);
+        jvl = new_array(4, (jsize)NV, vlabels);
+        jvq = new_array(4, QV + 1, vqoff);
+        step++;
+        BRIDGE(loadValidation)(env, NULL, h, jvx, NV, F, jvl, jvq);
+        if (J.thrown) { rc = step; goto done; }
+    }
+    step++;
+    BRIDGE(init)(env, NULL, h, n_leaves, 1, 0.1f, 256, kind, 0, 10, 1.0f, 0);
+    if (J.thrown) { rc = step; goto done; }
+    jni_ = new_array(4, cap * 7, NULL);
+    jnf = new_array(4, cap * 2, NULL);
+    jnd = new_array(8, cap, NULL);
+    jnn = new_array(4, 1, NULL);
+    for (int t = 0; t < n_trees; t++) {
+        step++;
+        metric_out[t] = BRIDGE(boostIter)(env, NULL, h, jni_, jnf, jnd, jnn);
+        if (J.thrown) { rc = step; goto done; }
+        n_nodes[t] = ((int*)jnn->data)[0];
+        memcpy(node_ints + (size_t)t * cap * 7, jni_->data, sizeof(int) * (size_t)cap * 7);
+        memcpy(node_floats + (size_t)t * cap * 2, jnf->data, sizeof(float) * (size_t)cap * 2);
+        if (VX) {
+            step++;
+            valid_out[t] = BRIDGE(validMetric)(env, NULL, h);
+            if (J.thrown) { rc = step; goto done; }
+        }
+    }
+    {
+        int total = 0;
+        for (int t = 0; t < n_trees; t++) total += n_nodes[t];
+        int* ci = calloc((size_t)total * 7 + 1, sizeof(int));
+        float* cf = calloc((size_t)total * 2 + 1, sizeof(float));
+        int* off = calloc((size_t)n_trees + 1, sizeof(int));
+        float* w = calloc((size_t)n_trees + 1, sizeof(float));
+        int at = 0;
+        for (int t = 0; t < n_trees; t++) {
+            off[t] = at;
+            w[t] = 0.1f;
+            memcpy(ci + (size_t)at * 7, node_ints + (size_t)t * cap * 7, sizeof(int) * (size_t)n_nodes[t] * 7);
+            memcpy(cf + (size_t)at * 2, node_floats + (size_t)t * cap * 2, sizeof(float) * (size_t)n_nodes[t] * 2);
+            at += n_nodes[t];
+        }
+        off[n_trees] = at;
+        ani = new_array(4, total * 7, ci);
+        anf = new_array(4, total * 2, cf);
+        ato = new_array(4, n_trees + 1, off);
+        aw = new_array(4, n_trees, w);
+        free(ci); free(cf); free(off); free(w);
+        step++;
+        final_scores[0] = BRIDGE(scoreResident)(env, NULL, h, 0, ani, anf, ato, aw);
+        if (J.thrown) { rc = step; goto done; }
+        if (VX) {
+            step++;
+            final_scores[1] = BRIDGE(scoreResident)(env, NULL, h, 1, ani, anf, ato, aw);
+            if (J.thrown) { rc = step; goto done; }
+        }
+    }
+done:
+    if (h) BRIDGE(destroy)(env, NULL, h);
+    if (base) BRIDGE(destroy)(env, NULL, base);
+    free(fids);
+    free_array(jx); free_array(jf); free_array(jl); free_array(jq); free_array(jvx); free_array(jvl); free_array(jvq); free_array(jp);
+    free_array(jni_); free_array(jnf); free_array(jnd); free_array(jnn); free_array(ani); free_array(anf); free_array(ato); free_array(aw);
+    return rc;
+}
+
+/* NativeBridge.commUniqueId(byte[128]) then commInit(handle, 0, 1, id) on a fresh context (world size 1: no NCCL needed for
+ * commInit; commUniqueId needs libnccl).  Also: boostIter with node arrays of inconsistent lengths must throw BEFORE the
+ * library runs.  Returns 0 or the ordinal of the failing step; *id_nonzero = the id is not all zeros. */
+int mock_comm_and_checks(int device, int* id_nonzero, int* bad_lengths_thrown) {
+    JNIEnv* env = &the_env;
+    int rc = 0, step = 0;
+    jlong h = 0;
+    jarray id = new_array(1, 128, NULL), ni = NULL, nf = NULL, nd = NULL, nn = NULL;
+    step++;
+    BRIDGE(commUniqueId)(env, NULL, id);
+    if (J.thrown) { rc = step; goto done; }
+    *id_nonzero = 0;
+    for (int i = 0; i < 128; i++) *id_nonzero |= ((unsigned char*)id->data)[i] != 0;
+    step++;
+    h = BRIDGE(create)(env, NULL, device);
+    if (J.thrown) { rc = step; goto done; }
+    step++;
+    BRIDGE(commInit)(env, NULL, h, 0, 1, id);
+    if (J.thrown) { rc = step; goto done; }
+    ni = new_array(4, 7 * 5, NULL);
+    nf = new_array(4, 2 * 5, NULL);
+    nd = new_array(8, 21, NULL);   /* 21 nodes of deviance but only 5 nodes of ints / floats */
+    nn = new_array(4, 1, NULL);
+    BRIDGE(boostIter)(env, NULL, h, ni, nf, nd, nn);
+    *bad_lengths_thrown = J.thrown;
+done:
+    if (h) BRIDGE(destroy)(env, NULL, h);
+    free_array(id); free_array(ni); free_array(nf); free_array(nd); free_array(nn);
     return rc;
 }

@@ -65,7 +65,8 @@ def test_shim_exports_every_native_of_the_bridge_class(shim):
     java = open(os.path.join(ROOT, "jni", "java", "ciir", "umass", "edu", "learning", "tree", "NativeBridge.java")).read()
     import re
     natives = re.findall(r"static native \w+ (\w+)\(", java)
-    assert sorted(natives) == ["boostIter", "create", "destroy", "ensembleEval", "init", "loadDense", "loadLetorFile", "readScores"]
+    assert sorted(natives) == ["boostIter", "commInit", "commUniqueId", "create", "destroy", "ensembleEval", "init", "loadBag", "loadDense",
+                               "loadLetorFile", "loadValidation", "readScores", "scoreResident", "validMetric"]
     for n in natives:
         assert hasattr(shim, "Java_ciir_umass_edu_learning_tree_NativeBridge_" + n), n
 
@@ -174,3 +175,79 @@ def test_shim_training_from_a_letor_file(shim, tmp_path):
     (tmp_path / "bad.txt").write_text("1 qid:1 0:1\n")
     rc, _ = _train_from_file(shim, 0, tmp_path / "bad.txt")
     assert rc == 2 and "less than or equal to zero" in shim.mock_message().decode()
+
+
+def _train_valid(lib, device, tr, va=None, picks=None, n_leaves=6, kind=0, n_trees=4):
+    X, label, qoff = (np.ascontiguousarray(a, t) for a, t in zip(tr, (np.float32, np.float32, np.int32)))
+    cap = 2 * n_leaves + 1
+    out = dict(ni=np.zeros((n_trees, cap, 7), np.int32), nf=np.zeros((n_trees, cap, 2), np.float32), nn=np.zeros(n_trees, np.int32),
+               m=np.zeros(n_trees, np.float32), vm=np.zeros(n_trees, np.float32), final=np.zeros(2, np.float64))
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    if va is not None:
+        VX, vl, vq = (np.ascontiguousarray(a, t) for a, t in zip(va, (np.float32, np.float32, np.int32)))
+    else:
+        VX = vl = vq = None
+    pk = None if picks is None else np.ascontiguousarray(picks, np.int32)
+    lib.mock_reset()
+    rc = lib.mock_train_valid(C.c_int(device), p(X), C.c_longlong(X.shape[0]), C.c_int(X.shape[1]), p(label), p(qoff), C.c_int(len(qoff) - 1),
+                              p(VX), C.c_longlong(0 if VX is None else VX.shape[0]), p(vl), p(vq), C.c_int(0 if vq is None else len(vq) - 1),
+                              p(pk), C.c_int(0 if pk is None else len(pk)), C.c_int(n_leaves), C.c_int(kind), C.c_int(n_trees),
+                              p(out["ni"]), p(out["nf"]), p(out["nn"]), p(out["m"]), p(out["vm"]), p(out["final"]))
+    return rc, out
+
+
+@pytest.mark.gpu
+def test_shim_validation_and_resident_scores_equal_ctypes_binding(shim):
+    """loadValidation / validMetric / scoreResident through the shim == the same calls through ctypes (which the parity tests
+    compare with the oracle's restatement of LambdaMART.java:228-263)."""
+    from ranklib_b200.host import native
+    X, label, qoff = _tiny(Q=40, n=25, F=9)
+    tr = (X[:750], label[:750], qoff[:31])
+    va = (X[750:], label[750:], (qoff[30:] - 750).astype(np.int32))
+    rc, out = _train_valid(shim, 0, tr, va)
+    assert rc == 0, shim.mock_message()
+    assert shim.mock_thrown() == 0 and shim.mock_outstanding_pins() == 0 and shim.mock_pin_errors() == 0
+    g = native.Context(0)
+    g.load_dense(*tr)
+    g.load_validation(*va)
+    g.init(native.make_params(n_leaves=6))
+    trees = []
+    for t in range(4):
+        nodes, m = g.boost_iter()
+        trees.append(nodes)
+        assert np.float32(m) == out["m"][t] and np.float32(g.valid_metric()) == out["vm"][t]
+        assert np.array_equal(out["ni"][t, :len(nodes), 2], nodes["threshold_idx"])
+    off = np.cumsum([0] + [len(t) for t in trees]).astype(np.int32)
+    w = np.full(4, 0.1, np.float32)
+    assert out["final"][0] == g.score_resident(0, np.concatenate(trees), off, w)[1]
+    assert out["final"][1] == g.score_resident(1, np.concatenate(trees), off, w)[1]
+
+
+@pytest.mark.gpu
+def test_shim_device_side_bag_equals_ctypes_binding(shim):
+    """B200RFRanker's per-bag sequence (create x 2, loadDense(base), loadBag, init kind = MART, boostIter) through the shim."""
+    from ranklib_b200.host import native
+    X, label, qoff = _tiny(Q=40, n=25, F=9)
+    picks = np.random.default_rng(3).integers(0, 40, 40).astype(np.int32)
+    rc, out = _train_valid(shim, 0, (X, label, qoff), None, picks, n_leaves=8, kind=1, n_trees=1)
+    assert rc == 0, shim.mock_message()
+    assert shim.mock_outstanding_pins() == 0 and shim.mock_pin_errors() == 0
+    base, bag = native.Context(0), native.Context(0)
+    base.load_dense(X, label, qoff)
+    bag.load_bag(base, picks)
+    bag.init(native.make_params(n_leaves=8, kind=1))
+    nodes, m = bag.boost_iter()
+    n = int(out["nn"][0])
+    assert n == len(nodes) and np.float32(m) == out["m"][0]
+    assert np.array_equal(out["ni"][0, :n, 0], nodes["feature_id"]) and np.array_equal(out["nf"][0, :n, 1], nodes["output"])
+
+
+@pytest.mark.gpu
+def test_shim_comm_natives_and_length_checks(shim):
+    idnz, bad = C.c_int(0), C.c_int(0)
+    shim.mock_reset()
+    rc = shim.mock_comm_and_checks(0, C.byref(idnz), C.byref(bad))
+    assert rc == 0, shim.mock_message()
+    assert idnz.value == 1, "ncclGetUniqueId left the 128 bytes untouched"
+    assert bad.value == 1 and b"inconsistent lengths" in shim.mock_message()
+    assert shim.mock_outstanding_pins() == 0 and shim.mock_pin_errors() == 0
