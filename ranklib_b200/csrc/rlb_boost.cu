@@ -117,32 +117,35 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys64(const unsigned lo
 }
 #define XW_SPIN_LIMIT (1LL << 22)   // polls of a local flag before a wait gives up (seconds): reported through st->p2p_timeout
 
-// "exchange `kind` of this rank has reached `epoch`": one flag store into every peer's window.  Call from ONE thread once the
-// data the flag stands for is globally visible (earlier kernels of the stream, or a __threadfence_system of the writers + a
-// block barrier).
+// "exchange `kind` of this rank has reached `epoch`": one flag store into every peer's window.  WARP-COOPERATIVE (all 32
+// lanes of one warp call it): lane r stores into rank r's window, so the world - 1 release stores — each a system-scope
+// fence that waits for the acknowledgement of the NVLink writes before it — are in flight together (one thread issuing them
+// one after the other pays the NVLink round trip world - 1 times: 20 us per signal at 8 GPUs).  The release is cumulative:
+// it covers the data other threads wrote before the barrier / kernel boundary this warp has passed.
 __device__ __forceinline__ void xw_signal(const PeerTab* p, int kind, unsigned int epoch) {
-    __threadfence_system();
-    for (int r = 0; r < p->world; r++)
-        if (r != p->rank) st_release_sys(&xw_of(p, r)->flags[kind][p->rank], epoch);
+    const int lane = threadIdx.x & 31;
+    if (lane < p->world && lane != p->rank) st_release_sys(&xw_of(p, lane)->flags[kind][p->rank], epoch);
+    __syncwarp();
 }
-// wait until every peer has signalled `kind` >= epoch (ONE thread; the caller follows with a block barrier)
+// wait until every peer has signalled `kind` >= epoch.  WARP-COOPERATIVE: lane r polls rank r's flag (in this rank's own
+// window); the caller follows with a block barrier.
 __device__ __forceinline__ void xw_wait(const PeerTab* p, int kind, unsigned int epoch, DevState* st) {
     const XWin* me = xw_of(p, p->rank);
+    const int lane = threadIdx.x & 31;
     const long long t0 = clock64();
-    for (int r = 0; r < p->world; r++) {
-        if (r == p->rank) continue;
+    if (lane < p->world && lane != p->rank) {
         unsigned int v;
         long long spins = 0;
         do {
-            v = ld_acquire_sys(&me->flags[kind][r]);
+            v = ld_acquire_sys(&me->flags[kind][lane]);
         } while ((int)(v - epoch) < 0 && ++spins < XW_SPIN_LIMIT);
         if ((int)(v - epoch) < 0) st->p2p_timeout = 1;
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd((unsigned long long*)&st->xwait[kind], (unsigned long long)(clock64() - t0));
+    __syncwarp();
+    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd((unsigned long long*)&st->xwait[kind], (unsigned long long)(clock64() - t0));
 }
 // a float handed over through a 64-bit slot: epoch << 32 | bits (one atomic store, no separate flag)
 __device__ __forceinline__ void xw_put_float(unsigned long long* slot, unsigned int epoch, float v) {
-    __threadfence_system();
     st_release_sys64(slot, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v));
 }
 __device__ __forceinline__ float xw_get_float(const unsigned long long* slot, unsigned int epoch, DevState* st, int acct = -1) {
@@ -923,10 +926,7 @@ __global__ void __launch_bounds__(32) k_scale(DevState* st, long long n_total, c
         if (lane < peers->world) {
             unsigned long long* dst = &xw_of(peers, lane)->scale_bits[par][peers->rank];
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(mine) : "memory");
-            if (lane != peers->rank) {
-                __threadfence_system();
-                st_release_sys(&xw_of(peers, lane)->flags[XW_SCALE][peers->rank], epoch);
-            }
+            if (lane != peers->rank) st_release_sys(&xw_of(peers, lane)->flags[XW_SCALE][peers->rank], epoch);   // orders the store above
         }
         unsigned long long got = 0;
         const long long t0 = clock64();
@@ -1528,10 +1528,15 @@ __device__ __forceinline__ void feature_best(long long cumS, int cumC, int t, in
 // per-feature serial-in-t prefix over the bins (FeatureHistogram.java:141-145), as a block scan; also the root's
 // best threshold of this feature (the split scan of every node is done where its histogram is produced)
 // N GPUs: "my raw root histogram and its squared sum are complete" (all earlier kernels of the stream have finished)
-__global__ void k_root_publish(DevState* st, const PeerTab* peers) {
+__global__ void __launch_bounds__(32) k_root_publish(DevState* st, const PeerTab* peers) {
     const unsigned int epoch = st->xe[XW_ROOT] + 1;
-    xw_of(peers, peers->rank)->root_sq = st->root_sq_fix;
-    st->xe[XW_ROOT] = epoch;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        xw_of(peers, peers->rank)->root_sq = st->root_sq_fix;
+        st->xe[XW_ROOT] = epoch;
+        __threadfence_system();
+    }
+    __syncwarp();
     xw_signal(peers, XW_ROOT, epoch);
 }
 
@@ -1550,13 +1555,22 @@ __global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     long long v = 0;
     if (peers) {
-        if (t == 0) xw_wait(peers, XW_ROOT, st->xe[XW_ROOT], st);   // the epoch k_root_publish just set
+        if (t < 32) xw_wait(peers, XW_ROOT, st->xe[XW_ROOT], st);   // the epoch k_root_publish just set
         __syncthreads();
-        if (t < RLB_T)
-            for (int r = 0; r < peers->world; r++) v += __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t);
+        if (t < RLB_T) {
+            long long lv[RLB_MAX_RANKS];   // all NVLink loads in flight together (see k_finish)
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) lv[r] = (r < peers->world) ? __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t) : 0LL;
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) v += lv[r];
+        }
         if (f == 0 && t == 0) {
+            long long lq[RLB_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) lq[r] = (r < peers->world) ? __ldcv(&xw_of(peers, r)->root_sq) : 0LL;
             long long sq = 0;
-            for (int r = 0; r < peers->world; r++) sq += __ldcv(&xw_of(peers, r)->root_sq);
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) sq += lq[r];
             st->root_sq_fix = sq;
         }
     } else if (t < RLB_T) {
@@ -2199,7 +2213,7 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         // performed); then wait until every peer has said the same.  All CTAs of this kernel are co-resident (F <= a few
         // hundred CTAs of 288 threads), so spinning is safe; the spin is bounded and reports through st->p2p_timeout.
         const unsigned int epoch = st->part_epoch;
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             if (blockIdx.x == 0) xw_signal(peers, XW_SPLIT, epoch);
             xw_wait(peers, XW_SPLIT, epoch, st);
         }
@@ -2220,12 +2234,27 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     if (t < RLB_T) {
         if (peers) {
             lC = stageCnt[o];
-            // rank order: the same integer additions on every rank (fixed point: any order gives the same bits anyway)
-            for (int r = 0; r < peers->world; r++) {
-                const long long* ps = xw_stage(peers, r) + so;
-                const int32_t* pc = reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride);
-                vS += __ldcv(ps + o);   // peer memory: never through L1
-                vC += __ldcv(pc + o);
+            // every rank's value of this (feature, bin): ALL the NVLink loads are issued before the first one is used (a loop
+            // that adds as it loads pays one round trip per peer: 7 x ~1.5 us at 8 GPUs); then rank order — the same integer
+            // additions on every rank (fixed point: any order gives the same bits anyway)
+            long long ls[RLB_MAX_RANKS];
+            int lc[RLB_MAX_RANKS];
+            const int W = peers->world;
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) {
+                ls[r] = 0;
+                lc[r] = 0;
+                if (r < W) {
+                    const long long* ps = xw_stage(peers, r) + so;
+                    const int32_t* pc = reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride);
+                    ls[r] = __ldcv(ps + o);   // peer memory: never through L1
+                    lc[r] = __ldcv(pc + o);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) {
+                vS += ls[r];
+                vC += lc[r];
             }
         } else {
             vS = stageSum[o];
@@ -2313,7 +2342,11 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         if (peers) {
             sqAcc = 0;
             const size_t sqo = hist_stride + (hist_stride + 1) / 2;
-            for (int r = 0; r < peers->world; r++) sqAcc += __ldcv(xw_stage(peers, r) + so + sqo);
+            long long lq[RLB_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) lq[r] = (r < peers->world) ? __ldcv(xw_stage(peers, r) + so + sqo) : 0LL;
+#pragma unroll
+            for (int r = 0; r < RLB_MAX_RANKS; r++) sqAcc += lq[r];
             // the OTHER block is free again (every peer has finished the previous split, or it could not have sent this
             // split's flag): clear its scalar for the next split; its histogram part is cleared by the partition
             *(stageSq - so + (stageStride - so)) = 0;
@@ -2796,7 +2829,7 @@ __global__ void __launch_bounds__(CK / 4) k_chain_round(int mode, const DevState
     const int b = blockIdx.x, which = blockIdx.y;
     if (b >= chunk0[nCh]) return;
     if (cb.peers && cb.wait_kind >= 0) {
-        if (threadIdx.x == 0) xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));
+        if (threadIdx.x < 32) xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));
         __syncthreads();
     }
     const size_t o = (size_t)which * cb.maxChunks + b;
@@ -2884,8 +2917,7 @@ __global__ void __launch_bounds__(32 * SIM_WARPS) k_chain_sim(int mode, const De
     const int b = blockIdx.x * SIM_WARPS + wid, which = blockIdx.y;
     if (b >= chunk0[nCh]) return;   // whole warp; nothing below synchronises across warps
     if (cb.peers && cb.wait_kind >= 0) {
-        if (lane == 0) xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));
-        __syncwarp();
+        xw_wait(cb.peers, cb.wait_kind, st->xe[cb.wait_kind], const_cast<DevState*>(st));   // the whole warp
     }
     const int l = chain_of_chunk(chunk0, nCh, b);
     int64_t n;
@@ -3277,12 +3309,9 @@ __global__ void __launch_bounds__(256) k_chain_push(DevState* __restrict__ st, c
             asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st->xe[kind] = epoch;
-        xw_signal(peers, kind, epoch);
-    }
+    __syncthreads();   // the release stores of warp 0 below are cumulative over the stores every thread issued before this barrier
+    if (threadIdx.x == 0) st->xe[kind] = epoch;
+    if (threadIdx.x < 32) xw_signal(peers, kind, epoch);
 }
 
 // Hand-over of a float chain between ranks (the chains run in GLOBAL document / list order: rank r continues where rank
@@ -3292,12 +3321,14 @@ __device__ __forceinline__ float chain_carry_in(const PeerTab* peers, int slot, 
     if (!peers || peers->rank == 0) return 0.f;
     return xw_get_float(&xw_of(peers, peers->rank)->carry[slot], epoch, st, (slot == 0 || slot == XW_METRIC_CHAIN) ? XW_KINDS : -1);
 }
+// WARP-COOPERATIVE (warp 0 of the chain's CTA): the last rank's final value goes to every rank, lane r -> rank r
 __device__ __forceinline__ void chain_carry_out(const PeerTab* peers, int slot, unsigned int epoch, float v) {
     if (!peers) return;
+    const int lane = threadIdx.x & 31;
     if (peers->rank + 1 < peers->world) {
-        xw_put_float(&xw_of(peers, peers->rank + 1)->carry[slot], epoch, v);
-    } else {
-        for (int r = 0; r < peers->world; r++) xw_put_float(&xw_of(peers, r)->final_[slot], epoch, v);
+        if (lane == 0) xw_put_float(&xw_of(peers, peers->rank + 1)->carry[slot], epoch, v);
+    } else if (lane < peers->world) {
+        xw_put_float(&xw_of(peers, lane)->final_[slot], epoch, v);
     }
 }
 
@@ -3320,10 +3351,8 @@ __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_leaf_chain(DevState* __re
         c0 = sCarry;
     }
     const float s = chain_walk(cb.xs, r.hi - r.lo, l, chunk0[l], chunk0[l + 1], which, c0, cb, &st->chain_serial);
-    if (threadIdx.x == 0) {
-        (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
-        chain_carry_out(cb.peers, slot, epoch, s);
-    }
+    if (threadIdx.x == 0) (which ? st->leaf_s2 : st->leaf_s1)[l] = s;
+    if (threadIdx.x < 32) chain_carry_out(cb.peers, slot, epoch, s);
 }
 
 __global__ void k_leaf_finalize(DevState* st, int kind, const PeerTab* peers) {
@@ -3386,10 +3415,8 @@ __global__ void __launch_bounds__(RLB_CHAIN_THREADS) k_metric_chain(DevState* __
         c0 = sCarry;
     }
     const float s = chain_walk(cb.xs, Q, 0, chunk0[0], chunk0[1], 0, c0, cb, &st->chain_serial);
-    if (threadIdx.x == 0) {
-        st->chain_out[slot] = s;
-        chain_carry_out(cb.peers, XW_METRIC_CHAIN, epoch, s);
-    }
+    if (threadIdx.x == 0) st->chain_out[slot] = s;
+    if (threadIdx.x < 32) chain_carry_out(cb.peers, XW_METRIC_CHAIN, epoch, s);
 }
 
 // slot 0: LambdaMART.java:470 (training), slot 1: LambdaMART.java:510 (validation): float sum / list count
@@ -3624,7 +3651,7 @@ int rlb_impl_hist_update(rlb_ctx* c) {
         RLB_CHECK_LAUNCH(c);
     }
     if (c->p2p) {
-        k_root_publish<<<1, 1, 0, c->stream>>>(c->dState, c->dPeers);
+        k_root_publish<<<1, 32, 0, c->stream>>>(c->dState, c->dPeers);
         RLB_CHECK_LAUNCH(c);
     } else {
         if (int rc = rlb_allreduce_i64(c, c->dHistSum, c->hist_stride)) return rc;

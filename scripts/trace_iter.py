@@ -31,8 +31,8 @@ for ln in open(out):
     # kernel name: search backwards from the CHECK line for '<<<'
     name = "?"
     for k in range(int(line) - 1, max(0, int(line) - 12), -1):
-        m = re.search(r"(k_\w+)(<[^<>]*>)?<<<", src[f][k])
-        if m:
+        m = re.search(r"(k_\w+)(<[^<>]*>)?(<<<|,)", src[f][k])
+        if m and ("<<<" in src[f][k] or "launch_pdl" in src[f][k]):
             name = m.group(1) + (m.group(2) or "")
             break
     agg.setdefault(name, [0, 0.0])
