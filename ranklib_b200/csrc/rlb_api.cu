@@ -205,14 +205,6 @@ int rlb_create(int device, rlb_ctx** out) {
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-    {   // keep freed blocks cached in the device's default memory pool (see rlb_dev_alloc, rlb_init.cu)
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
     *out = c;
     return RLB_OK;
 }

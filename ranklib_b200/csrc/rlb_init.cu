@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -353,26 +355,93 @@ int rlb_p2p_layout(rlb_ctx* c) {
     return RLB_OK;
 }
 
-// Device memory of a context comes from the device's stream-ordered memory pool (cudaMallocAsync on the context's stream;
-// rlb_create raises the pool's release threshold so that freed blocks stay cached): the ~60 buffers of a training job
-// (2.5 GB at the MSLR shape) cost ~7 ms of cudaMalloc in a fresh process and next to nothing for every later context of
-// the process (the next bag, the next fold, the next model).  RLB_POOL=0: plain cudaMalloc / cudaFree.
-static bool use_pool() {
+// Device memory of a context: plain cudaMalloc, with a process-wide cache of freed blocks per device.  The ~60 buffers of a
+// training job (2.5 GB at the MSLR shape) cost ~7 ms of cudaMalloc in a fresh process; a context that is destroyed hands
+// its blocks to the cache instead of cudaFree (which costs about as much again), and every later context of the process —
+// the next bag, the next fold, the next model — takes blocks of a fitting size (>= the request, <= 1.25 x) from there.
+// (cudaMallocAsync's pool was tried: the first large job of a process paid 50-280 ms for the pool's growth.)
+// RLB_POOL=0 disables the cache; RLB_POOL_MB bounds it (default 32768 MB per device).
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks[RLB_MAX_RANKS * 4];   // by device ordinal
+    std::map<void*, size_t> live;                                   // size of every block handed out
+    size_t cached[RLB_MAX_RANKS * 4] = {0};
+};
+BlockCache& cache() {
+    static BlockCache* c = new BlockCache();   // never destroyed: the driver may be gone at exit
+    return *c;
+}
+bool use_pool() {
     static const bool on = [] {
         const char* e = getenv("RLB_POOL");
         return !(e && atoi(e) == 0);
     }();
     return on;
 }
-cudaError_t rlb_dev_alloc(rlb_ctx* c, void** ptr, size_t bytes) {
-    return use_pool() ? cudaMallocAsync(ptr, bytes, c->stream) : cudaMalloc(ptr, bytes);
+size_t pool_limit() {
+    static const size_t lim = [] {
+        const char* e = getenv("RLB_POOL_MB");
+        return (size_t)(e ? std::max(0, atoi(e)) : 32768) << 20;
+    }();
+    return lim;
 }
+}  // namespace
+
+cudaError_t rlb_dev_alloc(rlb_ctx* c, void** ptr, size_t bytes) {
+    *ptr = nullptr;
+    if (bytes == 0) bytes = 8;
+    const int dev = c->device;
+    if (use_pool() && dev >= 0 && dev < RLB_MAX_RANKS * 4) {
+        BlockCache& bc = cache();
+        std::lock_guard<std::mutex> lk(bc.mu);
+        auto it = bc.free_blocks[dev].lower_bound(bytes);
+        if (it != bc.free_blocks[dev].end() && it->first <= bytes + bytes / 4 + 4096) {
+            *ptr = it->second;
+            bc.live[*ptr] = it->first;
+            bc.cached[dev] -= it->first;
+            bc.free_blocks[dev].erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess && use_pool() && dev >= 0 && dev < RLB_MAX_RANKS * 4) {   // out of memory: drop the cache and retry
+        cudaGetLastError();
+        BlockCache& bc = cache();
+        std::lock_guard<std::mutex> lk(bc.mu);
+        for (auto& kv : bc.free_blocks[dev]) cudaFree(kv.second);
+        bc.free_blocks[dev].clear();
+        bc.cached[dev] = 0;
+        e = cudaMalloc(ptr, bytes);
+    }
+    if (e == cudaSuccess && use_pool()) {
+        BlockCache& bc = cache();
+        std::lock_guard<std::mutex> lk(bc.mu);
+        bc.live[*ptr] = bytes;
+    }
+    return e;
+}
+
+// The caller guarantees that no work touching the block is still in flight (rlb_destroy synchronises the stream first;
+// rlb_reserve_bytes frees only between jobs).
 void rlb_dev_free(rlb_ctx* c, void* ptr) {
     if (!ptr) return;
-    if (use_pool())
-        cudaFreeAsync(ptr, c->stream);
-    else
-        cudaFree(ptr);
+    const int dev = c->device;
+    if (use_pool() && dev >= 0 && dev < RLB_MAX_RANKS * 4) {
+        BlockCache& bc = cache();
+        std::lock_guard<std::mutex> lk(bc.mu);
+        auto it = bc.live.find(ptr);
+        if (it != bc.live.end()) {
+            const size_t sz = it->second;
+            bc.live.erase(it);
+            if (bc.cached[dev] + sz <= pool_limit()) {
+                bc.free_blocks[dev].emplace(sz, ptr);
+                bc.cached[dev] += sz;
+                return;
+            }
+        }
+    }
+    cudaFree(ptr);
 }
 
 cudaError_t rlb_reserve_bytes(rlb_ctx* c, void** ptr, size_t bytes) {
