@@ -288,6 +288,7 @@ int rlb_comm_init(rlb_ctx* c, int rank, int world, const uint8_t id[128]) {
 int rlb_load_dense(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
                    const int32_t* qoff, int32_t Q) {
     if (!c) return RLB_E_INVALID;
+    RlbRange r("rlb_load_dense");
     return rlb_impl_load(c, X, N, F, feature_ids, label, qoff, Q);
 }
 
@@ -310,6 +311,7 @@ int rlb_set_thresholds(rlb_ctx* c, const float* thr, const int32_t* n_thr) {
 
 int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
     if (!c || !params) return RLB_E_INVALID;
+    RlbRange r("rlb_lambdamart_init");
     int rc = rlb_impl_init(c, params);
     if (rc) return rc;
     // global query count for the NDCG-T mean
@@ -444,6 +446,7 @@ static int boost_one(rlb_ctx* c) {
 
 int rlb_boost_iter(rlb_ctx* c, rlb_node* nodes_out, int32_t cap, int32_t* n_nodes, float* train_metric) {
     if (int rc = check_ready(c, "rlb_boost_iter")) return rc;
+    RlbRange r("rlb_boost_iter");
     const int64_t l0 = c->launches;
     if (int rc = boost_one(c)) return rc;
     if (c->launches == l0) c->launches += c->launches_per_iter; else if (c->launches_per_iter == 0) c->launches_per_iter = c->launches - l0;
@@ -737,6 +740,7 @@ int rlb_profile_read(rlb_ctx* c, double out[8]) {
 int rlb_ensemble_eval(rlb_ctx* c, const rlb_node* nodes, const int32_t* tree_off, int32_t n_trees, const float* weights,
                       const float* X, int64_t N, int32_t n_cols, float* out) {
     if (!c) return RLB_E_INVALID;
+    RlbRange r("rlb_ensemble_eval");
     return rlb_impl_ensemble_eval(c, nodes, tree_off, n_trees, weights, X, N, n_cols, out);
 }
 

@@ -981,7 +981,7 @@ __global__ void __launch_bounds__(32) k_scale(DevState* st, long long n_total, c
 
 __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lambda, int64_t N, long long* __restrict__ vfix,
                                                    long long* __restrict__ vfixc, long long* __restrict__ sqfix,
-                                                   DevState* __restrict__ st) {
+                                                   DevState* __restrict__ st, int32_t* __restrict__ identity) {
     const double sc = scalbn(1.0, st->scale_exp);
     const double sc2 = scalbn(1.0, st->scale2_exp);
     long long sq = 0;
@@ -993,6 +993,7 @@ __global__ void __launch_bounds__(256) k_quantise(const double* __restrict__ lam
         const long long q = __double2ll_rn((lam * lam) * sc2);
         sqfix[i] = q;
         sq += q;
+        identity[i] = (int32_t)i;   // every tree starts from the identity sample list (RegressionTree.java:49-52)
     }
     // one global reduction per CTA (one per warp serialises ~N/32 same-address atomics in L2: ~100 us at C2)
     __shared__ long long wsq[8];
@@ -2390,40 +2391,50 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
 }
 
 // end of RegressionTree.fit: leaves() in left-first DFS order (Split.java:100-113)
-__global__ void k_tree_end(DevState* st, int64_t N_local, int32_t* __restrict__ chunk0) {
+__global__ void __launch_bounds__(256) k_tree_end(DevState* st, int64_t N_local, int32_t* __restrict__ chunk0) {
+    // the node records the walk needs, staged in shared memory by the whole CTA (one thread chasing global memory pays an L2
+    // round trip per field); the explicit stack holds a whole degenerate tree (best-first growth can chain RLB_MAX_LEAVES deep)
+    __shared__ int16_t sLeft[RLB_MAX_NODES], sRight[RLB_MAX_NODES], sStack[RLB_MAX_NODES];
+    __shared__ int32_t sLo[RLB_MAX_NODES], sHi[RLB_MAX_NODES];
+    __shared__ int8_t sLeaf[RLB_MAX_NODES];
     if (!st->done && st->cur >= 0) {
-        st->incomplete = 1;
-        st->n_leaves_out = 0;  // the leaf / score kernels that follow become no-ops
-        chunk0[0] = 0;
+        if (threadIdx.x == 0) {
+            st->incomplete = 1;
+            st->n_leaves_out = 0;  // the leaf / score kernels that follow become no-ops
+            chunk0[0] = 0;
+        }
         return;
     }
+    const int nn = min(st->n_nodes, RLB_MAX_NODES);
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        const NodeRec& r = st->nodes[i];
+        sLeaf[i] = (r.feature_idx == -1) ? 1 : 0;
+        sLeft[i] = (int16_t)r.left;
+        sRight[i] = (int16_t)r.right;
+        sLo[i] = r.lo;
+        sHi[i] = r.hi;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     st->incomplete = 0;
-    int stack[64];
-    int sp = 0, nl = 0;
-    stack[sp++] = 0;
+    int sp = 0, nl = 0, run = 0;
+    sStack[sp++] = 0;
     while (sp > 0) {
-        const int n = stack[--sp];
-        NodeRec& r = st->nodes[n];
-        if (r.feature_idx == -1) {
-            r.leaf_ord = nl;
+        const int n = sStack[--sp];
+        if (sLeaf[n]) {
+            st->nodes[n].leaf_ord = nl;
             st->leaf_nodes[nl] = n;
-            st->leaf_lo[nl] = r.lo;
+            st->leaf_lo[nl] = sLo[n];
+            chunk0[nl] = run;   // chunk table of the leaf chains: chunk0[l] = first chunk of leaf l
+            run += (sHi[n] - sLo[n] + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK;
             nl++;
         } else {
-            if (sp + 2 > 64) break;  // depth bound: cannot happen for n_leaves <= RLB_MAX_LEAVES in practice
-            stack[sp++] = r.right;
-            stack[sp++] = r.left;
+            sStack[sp++] = sRight[n];
+            sStack[sp++] = sLeft[n];
         }
     }
     st->leaf_lo[nl] = (int32_t)N_local;
     st->n_leaves_out = nl;
-    // chunk table of the leaf chains: chunk0[l] = first chunk of leaf l
-    int run = 0;
-    for (int l = 0; l < nl; l++) {
-        chunk0[l] = run;
-        const NodeRec& r = st->nodes[st->leaf_nodes[l]];
-        run += (r.hi - r.lo + RLB_CHAIN_CK - 1) / RLB_CHAIN_CK;
-    }
     chunk0[nl] = run;
 }
 
@@ -3636,8 +3647,9 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     // block of the exchange window on N GPUs, where k_root_cumsum adds up every rank's block over NVLink
     RLB_CUDA(c, cudaMemsetAsync(c->dRootRaw, 0, c->hist_stride * sizeof(long long), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(&c->dState->root_sq_fix, 0, sizeof(long long), c->stream));
-    k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dVfixC, c->dSqfix, c->dState);
+    k_quantise<<<c->grid_rows, 256, 0, c->stream>>>(c->dLambda, c->N, c->dVfix, c->dVfixC, c->dSqfix, c->dState, c->dSamples[0]);
     RLB_CHECK_LAUNCH(c);
+    c->identity_fresh = true;
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
         k_hist_root<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
@@ -3721,14 +3733,17 @@ int rlb_impl_tree_enqueue(rlb_ctx* c) {
     if (c->p2p)
         RLB_CUDA(c, cudaMemsetAsync(c->dStage + c->stage_elems + c->hist_stride + (c->hist_stride + 1) / 2, 0, sizeof(long long),
                                     c->stream));
-    k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
-    RLB_CHECK_LAUNCH(c);
+    if (!c->identity_fresh) {   // rlb_hist_update's quantise pass has just refilled the identity list; a second rlb_tree_fit has not
+        k_identity<<<c->grid_rows, 256, 0, c->stream>>>(c->dSamples[0], c->N);
+        RLB_CHECK_LAUNCH(c);
+    }
+    c->identity_fresh = false;
     k_tree_begin<<<1, 288, 0, c->stream>>>(c->dState, tp, c->dHistSum, c->N, (long long)c->N_total, c->dUsed, c->dUsed + c->F,
                                            c->dHistCnt, c->hist_stride, c->dNodeFeatS, c->dNodeFeatT,
                                            c->p2p ? c->dHistCntL : nullptr);
     RLB_CHECK_LAUNCH(c);
     if (int rc = enqueue_split_steps(c, c->prm.n_leaves - 1)) return rc;
-    k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
+    k_tree_end<<<1, 256, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
     RLB_CHECK_LAUNCH(c);
     return RLB_OK;
 }
@@ -3739,7 +3754,7 @@ int rlb_impl_tree_check(rlb_ctx* c, int* recovered) {
     for (int round = 0; c->hState->incomplete && round < 4 * c->prm.n_leaves + 8; round++) {
         if (recovered) *recovered = 1;
         if (int rc = enqueue_split_steps(c, 2)) return rc;
-        k_tree_end<<<1, 1, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
+        k_tree_end<<<1, 256, 0, c->stream>>>(c->dState, c->N, c->dChunk0);
         RLB_CHECK_LAUNCH(c);
         if (int rc = sync_state_header(c)) return rc;
     }
@@ -3774,14 +3789,35 @@ int rlb_impl_prepare(rlb_ctx* c) {
 // the whole loop body of LambdaMART.learn (LambdaMART.java:180-251) as one launch sequence without
 // any host synchronisation; ends with the copy of the state header (tree size, NDCG-T, flags)
 int rlb_impl_enqueue_iter(rlb_ctx* c) {
-    if (int rc = rlb_impl_pseudo(c)) return rc;
-    if (int rc = rlb_impl_hist_update(c)) return rc;
-    if (int rc = rlb_impl_tree_enqueue(c)) return rc;
+    {
+        RlbRange r("computePseudoResponses");
+        if (int rc = rlb_impl_pseudo(c)) return rc;
+    }
+    {
+        RlbRange r("FeatureHistogram.update");
+        if (int rc = rlb_impl_hist_update(c)) return rc;
+    }
+    {
+        RlbRange r("RegressionTree.fit");
+        if (int rc = rlb_impl_tree_enqueue(c)) return rc;
+    }
     c->tree_ready = true;
-    if (int rc = rlb_impl_tree_output(c)) return rc;
-    if (int rc = rlb_impl_update_scores(c)) return rc;
-    if (int rc = rlb_impl_train_metric(c, true)) return rc;
-    if (int rc = rlb_impl_valid_step(c)) return rc;
+    {
+        RlbRange r("updateTreeOutput");
+        if (int rc = rlb_impl_tree_output(c)) return rc;
+    }
+    {
+        RlbRange r("score update");
+        if (int rc = rlb_impl_update_scores(c)) return rc;
+    }
+    {
+        RlbRange r("computeModelScoreOnTraining + next pseudo responses");
+        if (int rc = rlb_impl_train_metric(c, true)) return rc;
+    }
+    {
+        RlbRange r("validation");
+        if (int rc = rlb_impl_valid_step(c)) return rc;
+    }
     RLB_CUDA(c, cudaMemcpyAsync(c->hState, c->dState, offsetof(DevState, queue), cudaMemcpyDeviceToHost, c->stream));
     return RLB_OK;
 }

@@ -111,32 +111,52 @@ __global__ void k_colstats_finish(const unsigned int* __restrict__ table, const 
 // binning: bins[k][f] = first t with value <= thresholds[f][t]  (FeatureHistogram.java:89-103);
 // also the raw (non-cumulative) root counts.
 // ------------------------------------------------------------------------------------------------
+// CTA = a block of BIN_ROWS consecutive rows x all features.  The bins of the block are computed into shared memory (reads
+// of X coalesced along the row), then written twice, both times coalesced: row-major (`bins`, rows of Fp entries) and
+// feature-major (`binsT`: for every feature the BIN_ROWS consecutive rows are one contiguous run) — writing binsT element by
+// element from a row-major loop costs one 32-byte sector per 2-byte value (5 GB of write traffic at the MSLR shape).
+#define BIN_ROWS 64
 __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, int64_t N, int F, int Fp,
                                                   const float* __restrict__ thr, const int* __restrict__ nthr,
                                                   uint16_t* __restrict__ bins, uint16_t* __restrict__ binsT,
-                                                  int* __restrict__ rootCnt) {
-    const int64_t total = N * (int64_t)Fp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = i / Fp;
-        const int f = (int)(i - k * Fp);
-        if (f >= F) {
-            bins[i] = 0;
-            continue;
+                                                  int brows) {
+    extern __shared__ uint16_t sb[];   // [brows][Fp + 2]
+    const int pitch = Fp + 2;
+    const int64_t nBlocks = (N + brows - 1) / brows;
+    for (int64_t blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
+        const int64_t k0 = blk * brows;
+        const int rows = (int)min((int64_t)brows, N - k0);
+        __syncthreads();   // the previous block's tile has been written out
+        for (int e = threadIdx.x; e < rows * Fp; e += blockDim.x) {
+            const int r = e / Fp, f = e - r * Fp;
+            uint16_t b = 0;
+            if (f < F) {
+                const float v = canon_value(X[(k0 + r) * F + f]);
+                const float* th = thr + (size_t)f * RLB_T;
+                int lo = 0, hi = nthr[f] - 1;  // the last threshold is Float.MAX_VALUE: every finite value lands
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (v <= th[mid])
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+                b = (uint16_t)lo;
+            }
+            sb[r * pitch + f] = b;
         }
-        const float v = canon_value(X[k * F + f]);
-        const float* th = thr + (size_t)f * RLB_T;
-        int lo = 0, hi = nthr[f] - 1;  // the last threshold is Float.MAX_VALUE: every finite value lands
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (v <= th[mid])
-                hi = mid;
-            else
-                lo = mid + 1;
+        __syncthreads();
+        // row-major: the block's rows are contiguous in `bins`
+        for (int e = threadIdx.x; e < rows * Fp; e += blockDim.x) {
+            const int r = e / Fp, f = e - r * Fp;
+            bins[(k0 + r) * Fp + f] = sb[r * pitch + f];
         }
-        bins[i] = (uint16_t)lo;
-        binsT[(size_t)f * N + k] = (uint16_t)lo;
+        // feature-major: for feature f the rows k0 .. k0 + rows - 1 are contiguous in `binsT`
+        for (int e = threadIdx.x; e < F * brows; e += blockDim.x) {
+            const int f = e / brows, r = e - f * brows;
+            if (r < rows) binsT[(size_t)f * N + k0 + r] = sb[r * pitch + f];
+        }
     }
-    (void)rootCnt;
 }
 
 // raw root counts (FeatureHistogram.java:106 before the prefix): CTA = (feature, slice of rows) of the feature-major bins,
@@ -956,8 +976,14 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
 
     tm.mark("allocations + clears");
     // ---- binning + root counts ----
-    k_binning<<<c->grid_rows, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, c->dHistCnt);
-    RLB_CHECK_LAUNCH(c);
+    {
+        // rows per block: BIN_ROWS, fewer for very wide matrices (the block's bins must fit 96 KB of shared memory)
+        const int brows = (int)std::max<size_t>(1, std::min<size_t>(BIN_ROWS, (96 * 1024) / ((size_t)(Fp + 2) * sizeof(uint16_t))));
+        const size_t sm = (size_t)brows * (Fp + 2) * sizeof(uint16_t);
+        if (sm > 48 * 1024) RLB_CUDA(c, cudaFuncSetAttribute(k_binning, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_binning<<<c->grid_rows, 256, sm, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, brows);
+        RLB_CHECK_LAUNCH(c);
+    }
     {
         const int slices = std::max(1, (c->sm_count * 8 + F - 1) / F);
         k_root_counts<<<F * slices, 256, 0, c->stream>>>(c->dBinsT, N, F, slices, c->dHistCnt);
@@ -1006,6 +1032,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     c->inited = true;
     c->tree_ready = c->tree_output_ready = false;
     c->lambda_fresh = false;
+    c->identity_fresh = false;
     return RLB_OK;
 }
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <map>
@@ -197,6 +198,7 @@ struct rlb_ctx {
     bool thr_user = false;          // h_thr was imposed by rlb_set_thresholds (kept across re-inits); else derived from the data
     int32_t thr_built_for = 0;      // n_threshold the derived thresholds were built with
     bool lambda_fresh = false;      // dLambda / dWeight / scales belong to the current dScore
+    bool identity_fresh = false;    // dSamples[0] holds the identity list (filled by the quantise pass, consumed by a tree fit)
     rlb_params prm{};
     std::vector<int32_t> feature_ids;
     std::vector<float> h_thr;       // [F][RLB_T]
@@ -313,6 +315,15 @@ struct rlb_ctx {
 };
 
 const char* rlb_set_error(rlb_ctx* ctx, int code, const char* what, const char* detail);
+
+// NVTX range of one phase (the reference has no tracing at all).  Host-side: marks where the launches of a
+// phase are issued (or captured); with a profiler attached the ABI calls and the phases of an iteration show up by name.
+struct RlbRange {
+    explicit RlbRange(const char* name) { nvtxRangePushA(name); }
+    ~RlbRange() { nvtxRangePop(); }
+    RlbRange(const RlbRange&) = delete;
+    RlbRange& operator=(const RlbRange&) = delete;
+};
 
 #define RLB_CUDA(ctx, call)                                                              \
     do {                                                                                 \

@@ -355,3 +355,19 @@ def test_reinit_with_another_n_threshold_rebuilds_the_bins(built):
     assert len(g.thresholds(3)) == 2
     g.init(native.make_params(n_threshold=16))
     assert len(g.thresholds(3)) == 2
+
+
+@pytest.mark.parametrize("kind,leaves", [(1, 150), (0, 300)])
+def test_many_leaves_deep_trees_lockstep(built, kind, leaves):
+    """Random-Forest-sized trees (RFRanker.java:63: 100 leaves; more here): best-first growth chases outliers and chains deep,
+    which exercises the leaf enumeration's explicit stack and the long deviance queue of the controller."""
+    X, label, qoff = synth.c1()
+    tally, o, g = _lockstep(X, label, qoff, 2, kind=kind, n_leaves=leaves)
+    assert tally.equivalent == 2
+    nodes, _ = g.boost_iter()
+    depth = {0: 0}
+    for i in range(len(nodes)):
+        if nodes["feature_idx"][i] >= 0:
+            depth[int(nodes["left"][i])] = depth[i] + 1
+            depth[int(nodes["right"][i])] = depth[i] + 1
+    print("deepest leaf", max(depth.values()), "nodes", len(nodes))
