@@ -13,10 +13,12 @@ Default (what the driver runs): --workload c2 --op train.  A "step" is one pass 
   e2e       the same K iterations through the C ABI from HOST buffers: rlb_load_dense (H2D of the float matrix from
             pinned memory) + rlb_lambdamart_init + K x rlb_boost_iter, each call returning the fitted tree and NDCG@10-T
             to the host.  The upload happens once per training job in the reference too (LambdaMART.init); it is inside
-            the timed region (init_ms) and its bytes are reported per step (total / K).
+            the timed region (load_ms / init_ms) and its bytes are reported per step (total / K).  Three complete jobs
+            are run, the median is reported and all three totals are listed (runs_ms_total).
   roofline  the root-histogram kernel (FeatureHistogram.update): algorithmic bytes per launch N*(F*2+8) + F*257*8
             (b = 2 bytes per bin index) / its mean duration from CUDA events recorded around every launch
-            inside the timed region.
+            of a SECOND loop of K iterations (event nodes inside the iteration graph cost ~0.24 ms per iteration, so the
+            loop `value` is timed on carries none; both loops build the same trees).
   cpu_baseline  the CPU oracle (C++ restatement of the reference with its own thread decomposition; the real RankLib needs
             a JVM, which this image does not have) on all host cores, on the SAME full workload.
   parity    (N = 1) the first trees of the GPU path against the oracle's on the same data: same partition of the training
@@ -383,29 +385,39 @@ def run_train(args):
 
     # ---- e2e: host buffers -> C ABI -> trees on the host (first, on a clean allocator: it contains the one-time upload and
     # init of the job, which would otherwise be timed right behind the release of the previous context's 2.5 GB) ----
-    ctx = env.new_ctx(native)
-    ext, e0, e1 = env.events(ctx)
-    env.barrier()
-    e0.record(ext)
-    t0 = time.perf_counter()
-    ctx.load_dense(Xs.numpy(), ls.numpy(), qs)
-    ctx.init(params)
-    t_init = time.perf_counter()
-    d2h = 0
-    crc = 0
-    for _ in range(args.steps):
-        nodes, m2 = ctx.boost_iter(want_tree=True)
-        d2h += nodes.nbytes + 4
-        crc = tree_crc(crc, nodes)
-    e1.record(ext)
-    env.barrier()
-    wall_ms = (time.perf_counter() - t0) * 1000.0
-    init_ms = env.max_over_ranks((t_init - t0) * 1000.0)
-    e2e_ms = env.max_over_ranks(max(e0.elapsed_time(e1), wall_ms))   # host work between calls counts too
+    # Three complete jobs (fresh context each: upload, init, K iterations); the MEDIAN is reported and all three are listed.
+    # The upload + init of a job is ~25 ms of which 13 ms is the PCIe copy; on these shared hosts single runs have been seen at
+    # 2-4x that with no change of code, which would decide a 20-step number by itself.
     h2d = Xs.numel() * 4 + ls.numel() * 4 + qs.nbytes
+    e2e_runs = []
+    for rep in range(3):
+        ctx = env.new_ctx(native)
+        ext, e0, e1 = env.events(ctx)
+        env.barrier()
+        e0.record(ext)
+        t0 = time.perf_counter()
+        ctx.load_dense(Xs.numpy(), ls.numpy(), qs)
+        t_load = time.perf_counter()
+        ctx.init(params)
+        t_init = time.perf_counter()
+        d2h = 0
+        crc = 0
+        for _ in range(args.steps):
+            nodes, m2 = ctx.boost_iter(want_tree=True)
+            d2h += nodes.nbytes + 4
+            crc = tree_crc(crc, nodes)
+        e1.record(ext)
+        env.barrier()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        e2e_runs.append({"ms_total": env.max_over_ranks(max(e0.elapsed_time(e1), wall_ms)),   # host work between calls counts too
+                         "load_ms": env.max_over_ranks((t_load - t0) * 1000.0),
+                         "init_ms": env.max_over_ranks((t_init - t0) * 1000.0), "crc": crc})
+        ctx.close()
+        env.barrier()
+    assert len({r["crc"] for r in e2e_runs}) == 1, "the same job built different trees"
+    med = sorted(e2e_runs, key=lambda r: r["ms_total"])[1]
+    e2e_ms, init_ms, load_ms = med["ms_total"], med["init_ms"], med["load_ms"]
     e2e_value = args.steps / (e2e_ms / 1000.0)
-    ctx.close()
-    env.barrier()
 
     # ---- value: data resident in HBM ----
     ctx = env.new_ctx(native)
@@ -536,7 +548,8 @@ def run_train(args):
                        "ndcg_at_10_T": round(float(metric), 4)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                    "init_ms": init_ms, "ms_total": e2e_ms,
+                    "init_ms": init_ms, "load_ms": load_ms, "ms_total": e2e_ms,
+                    "runs_ms_total": [round(r["ms_total"], 2) for r in e2e_runs], "of_runs": "median of 3 complete jobs",
                     "includes": "rlb_load_dense + rlb_lambdamart_init once (init_ms), then K rlb_boost_iter calls returning tree + NDCG"},
             "gpu_launches": launches, "roofline": roofline, "tree_hash": f"{crc & 0xffffffff:08x}"}
     if comm is not None:

@@ -17,9 +17,11 @@ import numpy as np  # noqa: E402
 from ranklib_b200.host import native, synth  # noqa: E402
 
 
-def run(X, label, qoff, iters, **kw):
+def run(X, label, qoff, iters, valid=None, **kw):
     g = native.Context(0)
     g.load_dense(X, label, qoff)
+    if valid is not None:
+        g.load_validation(*valid)          # resident validation lists: k_valid_update + the validation metric chain
     g.init(native.make_params(**kw))
     trees = []
     for _ in range(iters):
@@ -28,7 +30,10 @@ def run(X, label, qoff, iters, **kw):
     Xe = np.zeros((X.shape[0], X.shape[1] + 1), np.float32)
     Xe[:, 1:] = X
     off = np.cumsum([0] + [len(t) for t in trees]).astype(np.int32)
-    s = g.ensemble_eval(np.concatenate(trees), off, np.full(len(trees), 0.1, np.float32), Xe)
+    s = g.ensemble_eval(np.concatenate(trees), off, np.full(len(trees), 0.1, np.float32), Xe)      # tiled Ensemble.eval kernel
+    g.score_resident(0, np.concatenate(trees), off, np.full(len(trees), 0.1, np.float32), want_scores=True)
+    if valid is not None:
+        g.score_resident(1, np.concatenate(trees), off, np.full(len(trees), 0.1, np.float32))
     g.score_metric(s.astype(np.float64), label, qoff)
     g.float_chain(np.random.default_rng(1).normal(size=5000))
     g.close()
@@ -39,6 +44,19 @@ X, label, qoff = synth.c1()
 print("c1 LambdaMART", run(X, label, qoff, 2))
 print("c1 MART", run(X, label, qoff, 1, kind=native.KIND_MART))
 print("c1 ERR@10", run(X, label, qoff, 1, metric=native.METRIC_ERR))
+X, label, qoff = synth.c1()
+print("c1 + validation", run(X[:800], label[:800], qoff[:21], 2, valid=(X[800:], label[800:], (qoff[20:] - qoff[20]).astype(np.int32))))
+# a list above 1024 documents with a generic metric (per-CTA prologue arrays in global memory)
+rng = np.random.default_rng(3)
+Xl = rng.standard_normal((1400, 6)).astype(np.float32)
+ll = rng.integers(0, 4, 1400).astype(np.float32)
+print("ERR, list of 1200", run(Xl, ll, np.array([0, 1200, 1400], np.int32), 1, metric=native.METRIC_ERR))
 X, label, qoff = synth.c2(0.01)
 print("mslr slice", run(X, label, qoff, 2))
+# Random-Forest bag gathered on the device, 40 leaves with feature sampling
+base, bag = native.Context(0), native.Context(0)
+base.load_dense(X, label, qoff)
+bag.load_bag(base, np.random.default_rng(4).integers(0, len(qoff) - 1, len(qoff) - 1).astype(np.int32))
+bag.init(native.make_params(n_leaves=40, kind=native.KIND_MART, frate=0.3, seed=5))
+print("device bag", bag.boost_iter()[1])
 print("SANITIZE_SMALL DONE")

@@ -8,13 +8,15 @@ import pytest
 
 from oracle import oracle as orc
 from ranklib_b200.host import native, rankers as R, synth
-from tests.util import ParityTally, compare_tree, rel_err, split_S_error
+from tests.util import ParityTally, compare_tree, first_divergence, rel_err, split_S_error
 
 pytestmark = pytest.mark.gpu
 S_TOL = 1e-8   # see tests/test_gpu_parity.py
 
 
-def _lockstep(X, label, qoff, n_trees, nthreads=1, **kw):
+def _lockstep(X, label, qoff, n_trees, nthreads=1, stop_at_tie=False, **kw):
+    """stop_at_tie: a tree whose partition differs is accepted iff the first differing split is a tie in S (1e-10; see
+    first_divergence) — the run then ends there, because the two models are different valid models from that tree on."""
     o = orc.Oracle(X, label, qoff, orc.make_params(**kw), nthreads=nthreads)
     g = native.Context(0)
     g.load_dense(X, label, qoff)
@@ -25,13 +27,20 @@ def _lockstep(X, label, qoff, n_trees, nthreads=1, **kw):
         gn, mg = g.boost_iter()
         ng, no = g.read("NODE_ID"), o.read("NODE_ID")
         identical, equivalent = compare_tree(gn, on, ng, no)
+        if not equivalent and stop_at_tie:
+            d = first_divergence(gn, on, g.read("SPLIT_S"), o.split_S())
+            assert d is not None and d[1] <= 1e-10, f"tree {it}: partitions differ and split {d} is not a tie"
+            print(f"tree {it}: split {d[0]} is a tie, device (node, f, t) {d[2]} vs oracle {d[3]}, |dS|/S = {d[1]:.1e}")
+            tally.ties = it
+            break
         assert equivalent, f"tree {it}: partitions differ"
         s_err = split_S_error(g.read("SPLIT_S")[:(len(gn) - 1) // 2], o.split_S())
         assert s_err <= S_TOL, (it, s_err)
         tally.add(identical, equivalent, s_err)
         assert np.max(rel_err(gn["output"][ng], on["output"][no])) <= 1e-5, f"tree {it}"
         assert round(float(mo), 4) == round(float(mg), 4) and abs(mo - mg) <= 1e-4, (it, mo, mg)
-    assert np.max(rel_err(g.read("SCORE"), o.read("SCORE"), floor=1e-9)) <= 1e-5
+    if tally.ties is None:
+        assert np.max(rel_err(g.read("SCORE"), o.read("SCORE"), floor=1e-9)) <= 1e-5
     print("PARITY", tally)
     return tally, o, g
 
@@ -362,8 +371,8 @@ def test_many_leaves_deep_trees_lockstep(built, kind, leaves):
     """Random-Forest-sized trees (RFRanker.java:63: 100 leaves; more here): best-first growth chases outliers and chains deep,
     which exercises the leaf enumeration's explicit stack and the long deviance queue of the controller."""
     X, label, qoff = synth.c1()
-    tally, o, g = _lockstep(X, label, qoff, 2, kind=kind, n_leaves=leaves)
-    assert tally.equivalent == 2
+    tally, o, g = _lockstep(X, label, qoff, 2, stop_at_tie=True, kind=kind, n_leaves=leaves)
+    assert tally.equivalent >= 1      # tree 0; a MART tree 1 over pure leaves is full of exact ties (equal pseudo-responses)
     nodes, _ = g.boost_iter()
     depth = {0: 0}
     for i in range(len(nodes)):

@@ -41,12 +41,35 @@ def split_S_error(g_S, o_S):
     return float(np.max(rel_err(g_S[:n], o_S[:n])))
 
 
+def first_divergence(gn, on, g_S, o_S):
+    """(k, relative S difference) of the first split, in growth order, where two trees disagree, or None.  Split k creates
+    nodes 2k+1 / 2k+2, so its parent is the node whose `left` is 2k+1.  A divergence whose S values agree to double
+    rounding is a tie between two maximisers of S: exact fixed-point sums resolve it to the lowest
+    (feature, threshold), the reference's doubles by the rounding of its summation order; both trees are valid."""
+    g_S, o_S = np.asarray(g_S, np.float64), np.asarray(o_S, np.float64)
+
+    def splits(nodes):
+        parent = {int(nodes["left"][i]): i for i in range(len(nodes)) if nodes["feature_idx"][i] >= 0}
+        out = []
+        for k in range((len(nodes) - 1) // 2):
+            i = parent[2 * k + 1]
+            out.append((i, int(nodes["feature_idx"][i]), int(nodes["threshold_idx"][i])))
+        return out
+
+    gs, os_ = splits(gn), splits(on)
+    for k in range(min(len(gs), len(os_))):
+        if gs[k] != os_[k]:
+            return k, float(rel_err(g_S[k:k + 1], o_S[k:k + 1])[0]), gs[k], os_[k]
+    return None
+
+
 class ParityTally:
     """identity / equivalence rates and the largest S disagreement over a run (SURVEY.md H1 asks for both rates)."""
 
     def __init__(self):
         self.trees = self.identical = self.equivalent = 0
         self.max_S_err = 0.0
+        self.ties = None          # the tree at which a tie-broken split ended a stop_at_tie run
 
     def add(self, identical, equivalent, s_err=0.0):
         self.trees += 1
