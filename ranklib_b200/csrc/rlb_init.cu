@@ -408,6 +408,29 @@ size_t pool_limit() {
 }
 }  // namespace
 
+// The pinned host copy of DevState: cudaMallocHost costs about a millisecond, so finished contexts hand theirs on (pinned
+// memory is not tied to a device).
+static std::mutex g_pinned_mu;
+static std::vector<DevState*> g_pinned_states;
+static DevState* pinned_state_get() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (use_pool() && !g_pinned_states.empty()) {
+            DevState* h = g_pinned_states.back();
+            g_pinned_states.pop_back();
+            return h;
+        }
+    }
+    DevState* h = nullptr;
+    if (cudaMallocHost(&h, sizeof(DevState)) != cudaSuccess) return nullptr;
+    return h;
+}
+static void pinned_state_put(DevState* h) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (use_pool() && g_pinned_states.size() < 16) g_pinned_states.push_back(h);
+    else cudaFreeHost(h);
+}
+
 cudaError_t rlb_dev_alloc(rlb_ctx* c, void** ptr, size_t bytes) {
     *ptr = nullptr;
     if (bytes == 0) bytes = 8;
@@ -513,10 +536,36 @@ void rlb_impl_free(rlb_ctx* c) {
         fr(c->dEvalBuf[i]);
         c->evalCap[i] = 0;
     }
-    if (c->hState) cudaFreeHost(c->hState);
+    if (c->hState) pinned_state_put(c->hState);
     c->hState = nullptr;
     c->cap.clear();
     c->loaded = c->inited = c->have_valid = false;
+}
+
+// The buffers of rlb_lambdamart_init whose size follows from (N, F, Q) alone.  rlb_impl_init reserves them again (a no-op
+// when they are large enough); calling this from the loaders only moves the allocation under the upload.
+static int reserve_row_buffers(rlb_ctx* c) {
+    const int64_t N = c->N;
+    const int F = c->F, Fp = c->Fp, Q = c->Q;
+    const int64_t root_nb = (N + RLB_ROOT_R - 1) / RLB_ROOT_R;
+    RLB_CUDA(c, rlb_reserve(c, c->dBins, (size_t)N * Fp * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dBinsT, (size_t)N * F * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dBinsTile, (size_t)(Fp / 16) * root_nb * RLB_ROOT_R * 16 * sizeof(uint16_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dScore, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dLambda, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dWeight, N * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dVfix, ((size_t)root_nb * RLB_ROOT_R + 2) * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dVfixC, (N + 2) * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSqfix, N * sizeof(long long)));
+    RLB_CUDA(c, rlb_reserve(c, c->dRankDoc, N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSamples[0], N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dSamples[1], N * sizeof(int32_t)));
+    RLB_CUDA(c, rlb_reserve(c, c->dNodeOf, N * sizeof(int32_t)));
+    const size_t chunks = (size_t)(std::max<int64_t>(N, Q) / RLB_CHAIN_CK) + RLB_MAX_LEAVES + 2;
+    RLB_CUDA(c, rlb_reserve(c, c->dChainXs, 2 * chunks * RLB_CHAIN_CK * sizeof(double)));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainItems, 2 * chunks * RLB_CHAIN_ITEMS * 16));
+    RLB_CUDA(c, rlb_reserve(c, c->dChainStream, 2 * chunks * (RLB_CHAIN_ITEMS + 1) * 16));
+    return RLB_OK;
 }
 
 int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_t* feature_ids, const float* label,
@@ -529,45 +578,51 @@ int rlb_impl_load(rlb_ctx* c, const float* X, int64_t N, int32_t F, const int32_
         rlb_set_error(c, RLB_E_INVALID, "rlb_load_dense", "qoff must start at 0 and end at N");
         return RLB_E_INVALID;
     }
-    int maxq = 0;
-    for (int q = 0; q < Q; q++) {
-        int n = qoff[q + 1] - qoff[q];
-        if (n < 0) {
-            rlb_set_error(c, RLB_E_INVALID, "rlb_load_dense", "qoff must be non-decreasing");
-            return RLB_E_INVALID;
-        }
-        maxq = std::max(maxq, n);
-    }
-    for (int64_t i = 0; i < N; i++) {
-        // DataPoint.parse rejects negative labels (R/learning/DataPoint.java:70-73)
-        if (!(label[i] >= 0.f)) {
-            rlb_set_error(c, RLB_E_INVALID, "rlb_load_dense", "Relevance label cannot be negative.");
-            return RLB_E_INVALID;
-        }
-        if (label[i] > (float)RLB_MAX_LABEL) {
-            rlb_set_error(c, RLB_E_UNSUPPORTED, "rlb_load_dense", "relevance label > 30 overflows gain = (1<<rel)-1");
-            return RLB_E_UNSUPPORTED;
-        }
-    }
     RLB_CUDA(c, cudaSetDevice(c->device));
     // buffers are grow-only (rlb_reserve): a context that is loaded again — the next bag of a Random Forest — reuses them
     c->loaded = c->inited = false;
     c->have_valid = false;   // a validation set belongs to the training set it was loaded after
+    c->have_thr = false;
+    c->thr_user = false;
+    // The matrix goes first: from pinned memory the copy is a DMA that runs while the host checks the labels and offsets
+    // and while the row-sized buffers of rlb_lambdamart_init are reserved (cudaMalloc of ~2 GB costs as much as the copy
+    // on a cold process; here it is hidden behind it).
+    RLB_CUDA(c, rlb_reserve(c, c->dX, (size_t)N * F * sizeof(float)));
+    RLB_CUDA(c, cudaMemcpyAsync(c->dX, X, (size_t)N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const char* bad = nullptr;
+    int bad_code = RLB_E_INVALID;
+    int maxq = 0;
+    for (int q = 0; q < Q && !bad; q++) {
+        int n = qoff[q + 1] - qoff[q];
+        if (n < 0) bad = "qoff must be non-decreasing";
+        maxq = std::max(maxq, n);
+    }
+    for (int64_t i = 0; i < N && !bad; i++) {
+        // DataPoint.parse rejects negative labels (R/learning/DataPoint.java:70-73)
+        if (!(label[i] >= 0.f)) {
+            bad = "Relevance label cannot be negative.";
+        } else if (label[i] > (float)RLB_MAX_LABEL) {
+            bad = "relevance label > 30 overflows gain = (1<<rel)-1";
+            bad_code = RLB_E_UNSUPPORTED;
+        }
+    }
+    if (bad) {
+        cudaStreamSynchronize(c->stream);
+        rlb_set_error(c, bad_code, "rlb_load_dense", bad);
+        return bad_code;
+    }
     c->N = N;
     c->F = F;
     c->Fp = (F + 15) & ~15;  // rows of uint16 bins padded to whole 32-byte sectors: a 16-feature group never straddles two
     c->Q = Q;
     c->max_query = maxq;
     c->feature_ids.assign(feature_ids, feature_ids + F);
-    c->have_thr = false;
-    c->thr_user = false;
     c->h_qoff.assign(qoff, qoff + Q + 1);
-    RLB_CUDA(c, rlb_reserve(c, c->dX, (size_t)N * F * sizeof(float)));
     RLB_CUDA(c, rlb_reserve(c, c->dLabel, (size_t)N * sizeof(float)));
     RLB_CUDA(c, rlb_reserve(c, c->dQoff, (size_t)(Q + 1) * sizeof(int32_t)));
-    RLB_CUDA(c, cudaMemcpyAsync(c->dX, X, (size_t)N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     RLB_CUDA(c, cudaMemcpyAsync(c->dLabel, label, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     RLB_CUDA(c, cudaMemcpyAsync(c->dQoff, qoff, (size_t)(Q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = reserve_row_buffers(c)) return rc;
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->loaded = true;
     return RLB_OK;
@@ -959,7 +1014,12 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         RLB_CUDA(c, cudaMemcpyAsync(c->dChunk0 + RLB_MAX_LEAVES + 2, mc, sizeof(mc), cudaMemcpyHostToDevice, c->stream));
         RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    if (!c->hState) RLB_CUDA(c, cudaMallocHost(&c->hState, sizeof(DevState)));
+    tm.mark("  reserves");
+    if (!c->hState) {
+        c->hState = pinned_state_get();
+        if (!c->hState) RLB_CUDA(c, cudaErrorMemoryAllocation);
+    }
+    tm.mark("  pinned state");
     RLB_CUDA(c, cudaMemsetAsync(c->dState, 0, sizeof(DevState), c->stream));
     RLB_CUDA(c, cudaMemsetAsync(c->dScore, 0, N * sizeof(double), c->stream));   // modelScores = 0 (LambdaMART.java:86)
     RLB_CUDA(c, cudaMemsetAsync(c->dLambda, 0, N * sizeof(double), c->stream));

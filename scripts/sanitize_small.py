@@ -51,7 +51,7 @@ rng = np.random.default_rng(3)
 Xl = rng.standard_normal((1400, 6)).astype(np.float32)
 ll = rng.integers(0, 4, 1400).astype(np.float32)
 print("ERR, list of 1200", run(Xl, ll, np.array([0, 1200, 1400], np.int32), 1, metric=native.METRIC_ERR))
-X, label, qoff = synth.c2(0.01)
+X, label, qoff = synth.c2(0.025)   # 30 000 rows: ~10 tiles per CTA of k_hist_root, so its shared-memory stages are reused (4 stages)
 print("mslr slice", run(X, label, qoff, 2))
 # Random-Forest bag gathered on the device, 40 leaves with feature sampling
 base, bag = native.Context(0), native.Context(0)
