@@ -1365,7 +1365,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     if (tid == 0) {
         for (int s2 = 0; s2 < HSTAGES; s2++) {
             mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
-            mbar_init(&empty[s2], (uint32_t)CW);
+            mbar_init(&empty[s2], (uint32_t)T);   // one release per consumer thread (as in k_hist_root)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1454,8 +1454,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                             mbar_wait(&full[s1], ((k + 1) / HSTAGES) & 1);
                             load(nxt, st0 + s1 * STAGE_BYTES, pp);
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[s2]);
+                        mbar_arrive(&empty[s2]);   // this thread's reads of stage s2 are behind it
                     }
                     hist_rmw8(cur);
                     cur = nxt;
@@ -1562,11 +1561,15 @@ __global__ void __launch_bounds__(288) k_root_cumsum(long long* __restrict__ sum
         if (t < 32) xw_wait(peers, XW_ROOT, st->xe[XW_ROOT], st);   // the epoch k_root_publish just set
         __syncthreads();
         if (t < RLB_T) {
-            long long lv[RLB_MAX_RANKS];   // all NVLink loads in flight together (see k_finish)
+            if (peers->seq_loads) {
+                for (int r = 0; r < peers->world; r++) v += __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t);
+            } else {
+                long long lv[RLB_MAX_RANKS];   // all NVLink loads in flight together (see k_finish)
 #pragma unroll
-            for (int r = 0; r < RLB_MAX_RANKS; r++) lv[r] = (r < peers->world) ? __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t) : 0LL;
+                for (int r = 0; r < RLB_MAX_RANKS; r++) lv[r] = (r < peers->world) ? __ldcv(xw_root(peers, r) + (size_t)f * RLB_T + t) : 0LL;
 #pragma unroll
-            for (int r = 0; r < RLB_MAX_RANKS; r++) v += lv[r];
+                for (int r = 0; r < RLB_MAX_RANKS; r++) v += lv[r];
+            }
         }
         if (f == 0 && t == 0) {
             long long lq[RLB_MAX_RANKS];
@@ -2241,24 +2244,31 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
             // every rank's value of this (feature, bin): ALL the NVLink loads are issued before the first one is used (a loop
             // that adds as it loads pays one round trip per peer: 7 x ~1.5 us at 8 GPUs); then rank order — the same integer
             // additions on every rank (fixed point: any order gives the same bits anyway)
-            long long ls[RLB_MAX_RANKS];
-            int lc[RLB_MAX_RANKS];
             const int W = peers->world;
-#pragma unroll
-            for (int r = 0; r < RLB_MAX_RANKS; r++) {
-                ls[r] = 0;
-                lc[r] = 0;
-                if (r < W) {
-                    const long long* ps = xw_stage(peers, r) + so;
-                    const int32_t* pc = reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride);
-                    ls[r] = __ldcv(ps + o);   // peer memory: never through L1
-                    lc[r] = __ldcv(pc + o);
+            if (peers->seq_loads) {
+                for (int r = 0; r < W; r++) {
+                    vS += __ldcv(xw_stage(peers, r) + so + o);
+                    vC += __ldcv(reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride) + o);
                 }
-            }
+            } else {
+                long long ls[RLB_MAX_RANKS];
+                int lc[RLB_MAX_RANKS];
 #pragma unroll
-            for (int r = 0; r < RLB_MAX_RANKS; r++) {
-                vS += ls[r];
-                vC += lc[r];
+                for (int r = 0; r < RLB_MAX_RANKS; r++) {
+                    ls[r] = 0;
+                    lc[r] = 0;
+                    if (r < W) {
+                        const long long* ps = xw_stage(peers, r) + so;
+                        const int32_t* pc = reinterpret_cast<const int32_t*>(xw_stage(peers, r) + so + hist_stride);
+                        ls[r] = __ldcv(ps + o);   // peer memory: never through L1
+                        lc[r] = __ldcv(pc + o);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RLB_MAX_RANKS; r++) {
+                    vS += ls[r];
+                    vC += lc[r];
+                }
             }
         } else {
             vS = stageSum[o];

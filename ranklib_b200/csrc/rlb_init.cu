@@ -307,6 +307,7 @@ int rlb_p2p_setup(rlb_ctx* c) {
     memset(&tab, 0, sizeof(tab));
     tab.world = c->world;
     tab.rank = c->rank;
+    if (const char* e = getenv("RLB_XW_SEQ_LOADS")) tab.seq_loads = atoi(e) != 0;
     if (ok) {
         for (int r = 0; r < c->world; r++) {
             if (r == c->rank) {

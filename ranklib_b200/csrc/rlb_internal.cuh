@@ -111,6 +111,7 @@ struct XWin {
 struct PeerTab {
     char* win[RLB_MAX_RANKS];      // every rank's window in THIS process's address space (own entry = local pointer)
     int32_t world, rank;
+    int32_t seq_loads, pad_;       // RLB_XW_SEQ_LOADS=1 (measurement aid): reductions over the peers add as they load
     unsigned long long off_root;   // byte offset of the raw root histogram (i64[F * RLB_T])
     unsigned long long off_stage;  // byte offset of the two per-split staging blocks (i64[2][stage_elems])
 };
