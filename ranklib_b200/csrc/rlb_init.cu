@@ -32,50 +32,78 @@ __device__ __forceinline__ float canon_value(float v) {
     return v;
 }
 
-// Row-tiled and coalesced: thread = feature, CTA = a slice of rows; every feature owns a hash set of HASH_CAP
-// slots in GLOBAL memory (F x 8 KB).  A value already present costs one plain load; inserts are atomicCAS.
+// Row-tiled and coalesced: CTA = a slice of rows; thread = (feature, row sub-slice) — with F < blockDim the block's lanes
+// are split into blockDim / F sub-slices that interleave rows, so a 1024-thread block keeps 952 lanes busy at F = 136.
+// Every feature owns a hash set of HASH_CAP slots in GLOBAL memory (F x 8 KB).  Entries only ever go EMPTY -> key, so the
+// presence test may use a plain (L1-cached, possibly stale) load: a stale EMPTY merely sends the thread to the slow path,
+// which re-reads volatile and inserts with atomicCAS.  Rows are taken four at a time with their loads issued together:
+// low-cardinality features keep their set open for all N rows, and a dependent L2 round trip per row per thread (with the
+// 31 other lanes of the warp waiting on it) was what this kernel's time consisted of.
 // Once a feature has more than `limit` distinct values its set is abandoned (only min / max matter then).
-__global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ X, int64_t N, int F, int limit,
-                                                   unsigned int* __restrict__ table, int* __restrict__ nDistinct,
-                                                   unsigned int* __restrict__ minBits, unsigned int* __restrict__ maxBits) {
+__device__ __noinline__ bool colstats_insert(unsigned int* tab, unsigned int key, int* nDistinct, int f, int limit) {
+    const unsigned int h = (key * 2654435761u) >> 21;  // 11 bits
+    for (int probe = 0; probe < HASH_CAP; probe++) {
+        const unsigned int slot = (h + probe) & (HASH_CAP - 1);
+        unsigned int cur = ((volatile unsigned int*)tab)[slot];
+        if (cur == key) return true;
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&tab[slot], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) return atomicAdd(&nDistinct[f], 1) + 1 <= limit;
+            if (cur == key) return true;
+        }
+        if ((probe & 15) == 15 && ((volatile int*)nDistinct)[f] > limit) return false;
+    }
+    return false;   // table full: only reachable once the feature has overflowed `limit`
+}
+
+__global__ void __launch_bounds__(1024) k_colstats(const float* __restrict__ X, int64_t N, int F, int limit,
+                                                    unsigned int* __restrict__ table, int* __restrict__ nDistinct,
+                                                    unsigned int* __restrict__ minBits, unsigned int* __restrict__ maxBits) {
+    const int L = blockDim.x;
+    const int S = max(1, L / F);
     const int64_t rowsPer = (N + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = blockIdx.x * rowsPer, r1 = min(N, r0 + rowsPer);
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    // order-preserving float -> uint map so that atomicMin / atomicMax on integers order like floats
+    auto enc = [](float x) -> unsigned int {
+        const unsigned int b = __float_as_uint(x);
+        return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    };
+    for (int ff = threadIdx.x; ff < F * S; ff += L) {
+        const int f = ff % F, sub = ff / F;
         float mn = FLT_MAX, mx = -INFINITY;  // LambdaMART.java:112-113
         unsigned int* tab = table + (size_t)f * HASH_CAP;
         bool open_set = ((volatile int*)nDistinct)[f] <= limit;
-        for (int64_t k = r0; k < r1; k++) {
+        int64_t k = r0 + sub;
+        int batch = 0;
+        for (; k + 3 * (int64_t)S < r1; k += 4 * (int64_t)S, batch++) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = canon_value(X[(k + (int64_t)u * S) * F + f]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (mx < v[u]) mx = v[u];
+                if (mn > v[u]) mn = v[u];
+            }
+            if (open_set) {
+                if ((batch & 15) == 15 && ((volatile int*)nDistinct)[f] > limit) {
+                    open_set = false;
+                    continue;
+                }
+                unsigned int cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) cur[u] = tab[((__float_as_uint(v[u]) * 2654435761u) >> 21) & (HASH_CAP - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (open_set && cur[u] != __float_as_uint(v[u])) open_set = colstats_insert(tab, __float_as_uint(v[u]), nDistinct, f, limit);
+            }
+        }
+        for (; k < r1; k += S) {
             const float v = canon_value(X[k * F + f]);
             if (mx < v) mx = v;
             if (mn > v) mn = v;
-            if (open_set) {
-                const unsigned int key = __float_as_uint(v);
-                const unsigned int h = (key * 2654435761u) >> 21;  // 11 bits
-                for (int probe = 0; probe < HASH_CAP; probe++) {
-                    const unsigned int slot = (h + probe) & (HASH_CAP - 1);
-                    unsigned int cur = ((volatile unsigned int*)tab)[slot];
-                    if (cur == key) break;
-                    if (cur == EMPTY_KEY) {
-                        cur = atomicCAS(&tab[slot], EMPTY_KEY, key);
-                        if (cur == EMPTY_KEY) {
-                            if (atomicAdd(&nDistinct[f], 1) + 1 > limit) open_set = false;
-                            break;
-                        }
-                        if (cur == key) break;
-                    }
-                    if ((probe & 15) == 15 && ((volatile int*)nDistinct)[f] > limit) {
-                        open_set = false;
-                        break;
-                    }
-                }
-            }
+            if (open_set) open_set = colstats_insert(tab, __float_as_uint(v), nDistinct, f, limit);
         }
-        // order-preserving float -> uint map so that atomicMin / atomicMax on integers order like floats
-        auto enc = [](float x) -> unsigned int {
-            const unsigned int b = __float_as_uint(x);
-            return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-        };
-        if (r1 > r0) {
+        if (r0 + sub < r1) {
             atomicMin(&minBits[f], enc(mn));
             atomicMax(&maxBits[f], enc(mx));
         }
@@ -111,51 +139,92 @@ __global__ void k_colstats_finish(const unsigned int* __restrict__ table, const 
 // binning: bins[k][f] = first t with value <= thresholds[f][t]  (FeatureHistogram.java:89-103);
 // also the raw (non-cumulative) root counts.
 // ------------------------------------------------------------------------------------------------
-// CTA = a block of BIN_ROWS consecutive rows x all features.  The bins of the block are computed into shared memory (reads
-// of X coalesced along the row), then written twice, both times coalesced: row-major (`bins`, rows of Fp entries) and
-// feature-major (`binsT`: for every feature the BIN_ROWS consecutive rows are one contiguous run) — writing binsT element by
-// element from a row-major loop costs one 32-byte sector per 2-byte value (5 GB of write traffic at the MSLR shape).
-#define BIN_ROWS 64
+// CTA = (feature group g of 16 features, a strided set of 192-row tiles) — the unit of the root histogram's layout.  The
+// group's thresholds are staged in shared memory once per CTA (16 x 257 floats); every tile's bins are computed into shared
+// memory (X read as 64-byte row segments) and written three times from there, all coalesced: row-major (`bins`, one 32-byte
+// sector per row), feature-major (`binsT`, runs of 192 rows) and the swizzled tile of k_hist_root (`tiles`, 6 KB contiguous).
+// The search is lower_bound (FeatureHistogram.java:89-103) for ANY non-decreasing threshold array; for the usual one —
+// fmin + j * step (LambdaMART.java:135-149) — a guess from (v - th[0]) / step followed by at most three neighbour steps lands
+// it with 2-3 shared-memory reads instead of 8; when the neighbour steps do not verify it, the binary search runs.
 __global__ void __launch_bounds__(256) k_binning(const float* __restrict__ X, int64_t N, int F, int Fp,
                                                   const float* __restrict__ thr, const int* __restrict__ nthr,
                                                   uint16_t* __restrict__ bins, uint16_t* __restrict__ binsT,
-                                                  int brows) {
-    extern __shared__ uint16_t sb[];   // [brows][Fp + 2]
-    const int pitch = Fp + 2;
-    const int64_t nBlocks = (N + brows - 1) / brows;
-    for (int64_t blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
-        const int64_t k0 = blk * brows;
-        const int rows = (int)min((int64_t)brows, N - k0);
-        __syncthreads();   // the previous block's tile has been written out
-        for (int e = threadIdx.x; e < rows * Fp; e += blockDim.x) {
-            const int r = e / Fp, f = e - r * Fp;
-            uint16_t b = 0;
-            if (f < F) {
-                const float v = canon_value(X[(k0 + r) * F + f]);
-                const float* th = thr + (size_t)f * RLB_T;
-                int lo = 0, hi = nthr[f] - 1;  // the last threshold is Float.MAX_VALUE: every finite value lands
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (v <= th[mid])
-                        hi = mid;
-                    else
-                        lo = mid + 1;
+                                                  uint16_t* __restrict__ tiles, int64_t NB, int nGroups) {
+    constexpr int R = RLB_ROOT_R;
+    constexpr int PITCH = R + 8;                       // 400 bytes per feature row: 16-byte aligned chunks
+    __shared__ float sThr[16][RLB_T];                  // 257 floats per feature: odd pitch spreads the features over the banks
+    __shared__ __align__(16) uint16_t sB[16][PITCH];   // the tile's bins, feature-major
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x % nGroups, sl = blockIdx.x / nGroups;
+    const int slices = (gridDim.x - g + nGroups - 1) / nGroups;
+    for (int i = tid; i < 16 * RLB_T; i += 256) {
+        const int fi = i / RLB_T, t = i - fi * RLB_T, f = g * 16 + fi;
+        sThr[fi][t] = (f < F) ? thr[(size_t)f * RLB_T + t] : FLT_MAX;
+    }
+    __syncthreads();
+    // a thread always works on the same feature of the group (256 % 16 == 0)
+    const int fi = tid & 15, f = g * 16 + fi;
+    const float* th = sThr[fi];
+    const int n = (f < F) ? nthr[f] : 1;               // the last threshold is Float.MAX_VALUE: every finite value lands
+    const float th0 = th[0];
+    float inv = 0.f;
+    if (n >= 4) {
+        const float step = (th[n - 2] - th0) / (float)(n - 2);
+        if (step > 0.f && step < FLT_MAX) inv = 1.f / step;
+    }
+    for (int64_t B = sl; B < NB; B += slices) {
+        const int64_t row0 = B * R;
+        for (int e = tid; e < R * 16; e += 256) {
+            const int r = e >> 4;
+            const int64_t row = row0 + r;
+            int j = 0;
+            if (row < N && f < F) {
+                const float v = canon_value(X[row * F + f]);
+                j = min(max(__float2int_rz((v - th0) * inv), 0), n - 1);
+                int steps = 0;
+                while (j > 0 && v <= th[j - 1] && steps < 3) { j--; steps++; }
+                while (j < n - 1 && v > th[j] && steps < 3) { j++; steps++; }
+                if (!((j == 0 || v > th[j - 1]) && (j == n - 1 || v <= th[j]))) {
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (v <= th[mid])
+                            hi = mid;
+                        else
+                            lo = mid + 1;
+                    }
+                    j = lo;
                 }
-                b = (uint16_t)lo;
             }
-            sb[r * pitch + f] = b;
+            sB[fi][r] = (uint16_t)j;
         }
         __syncthreads();
-        // row-major: the block's rows are contiguous in `bins`
-        for (int e = threadIdx.x; e < rows * Fp; e += blockDim.x) {
-            const int r = e / Fp, f = e - r * Fp;
-            bins[(k0 + r) * Fp + f] = sb[r * pitch + f];
+        // (1) row-major: the group's 16 entries of a row are one 32-byte sector of `bins`; a thread writes half of it
+        for (int e = tid; e < R * 2; e += 256) {
+            const int r = e >> 1, h = e & 1;
+            const int64_t row = row0 + r;
+            if (row < N) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    w[q] = (uint32_t)sB[h * 8 + 2 * q][r] | ((uint32_t)sB[h * 8 + 2 * q + 1][r] << 16);
+                *reinterpret_cast<uint4*>(bins + row * Fp + g * 16 + h * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        // feature-major: for feature f the rows k0 .. k0 + rows - 1 are contiguous in `binsT`
-        for (int e = threadIdx.x; e < F * brows; e += blockDim.x) {
-            const int f = e / brows, r = e - f * brows;
-            if (r < rows) binsT[(size_t)f * N + k0 + r] = sb[r * pitch + f];
+        // (2) feature-major: for feature f the tile's rows are one contiguous run of `binsT`
+        for (int e = tid; e < 16 * R; e += 256) {
+            const int ff = e / R, r = e - ff * R;
+            if (g * 16 + ff < F && row0 + r < N) binsT[(size_t)(g * 16 + ff) * N + row0 + r] = sB[ff][r];
         }
+        // (3) the root histogram's tile: chunk c (rows 8c .. 8c+7) of feature ff sits at chunk position c ^ (ff & 7)
+        {
+            uint4* dst = reinterpret_cast<uint4*>(tiles + ((size_t)g * NB + B) * (16 * R));
+            for (int e = tid; e < 16 * (R / 8); e += 256) {
+                const int ff = e / (R / 8), cp = e - ff * (R / 8);
+                dst[e] = *reinterpret_cast<const uint4*>(&sB[ff][(cp ^ (ff & 7)) * 8]);
+            }
+        }
+        __syncthreads();   // the tile has been written out before the next one overwrites sB
     }
 }
 
@@ -876,7 +945,7 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
             rlb_fill_u32(dMinB, F, 0xffffffffu, c->stream);
             RLB_CUDA(c, cudaMemsetAsync(dMaxB, 0, F * 4, c->stream));
             RLB_CUDA(c, cudaMemsetAsync(dCnt, 0, F * 4, c->stream));
-            k_colstats<<<c->sm_count * 4, 256, 0, c->stream>>>(c->dX, N, F, p->n_threshold, dTab, dCnt, dMinB, dMaxB);
+            k_colstats<<<c->sm_count * 2, 1024, 0, c->stream>>>(c->dX, N, F, p->n_threshold, dTab, dCnt, dMinB, dMaxB);
             RLB_CHECK_LAUNCH(c);
             k_colstats_finish<<<(F + 127) / 128, 128, 0, c->stream>>>(dTab, dCnt, F, p->n_threshold, dMinB, dMaxB, dMin, dMax, dND, dDist);
             RLB_CHECK_LAUNCH(c);
@@ -1038,11 +1107,10 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
     tm.mark("allocations + clears");
     // ---- binning + root counts ----
     {
-        // rows per block: BIN_ROWS, fewer for very wide matrices (the block's bins must fit 96 KB of shared memory)
-        const int brows = (int)std::max<size_t>(1, std::min<size_t>(BIN_ROWS, (96 * 1024) / ((size_t)(Fp + 2) * sizeof(uint16_t))));
-        const size_t sm = (size_t)brows * (Fp + 2) * sizeof(uint16_t);
-        if (sm > 48 * 1024) RLB_CUDA(c, cudaFuncSetAttribute(k_binning, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_binning<<<c->grid_rows, 256, sm, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, brows);
+        // one launch bins the matrix into all three layouts (row-major, feature-major, root-histogram tiles)
+        const int nGroups = Fp / 16;
+        const int grid = nGroups * std::max(1, (c->sm_count * 8) / nGroups);
+        k_binning<<<grid, 256, 0, c->stream>>>(c->dX, N, F, Fp, c->dThr, c->dNThr, c->dBins, c->dBinsT, c->dBinsTile, c->root_nb, nGroups);
         RLB_CHECK_LAUNCH(c);
     }
     {
@@ -1050,8 +1118,6 @@ int rlb_impl_init(rlb_ctx* c, const rlb_params* p) {
         k_root_counts<<<F * slices, 256, 0, c->stream>>>(c->dBinsT, N, F, slices, c->dHistCnt);
         RLB_CHECK_LAUNCH(c);
     }
-    k_tile_bins<<<c->grid_rows, 256, 0, c->stream>>>(c->dBins, Fp, F, N, c->root_nb, c->dBinsTile);
-    RLB_CHECK_LAUNCH(c);
     if (c->world > 1) {   // this rank's own root counts, kept next to the global ones
         RLB_CUDA(c, cudaMemcpyAsync(c->dHistCntL, c->dHistCnt, c->hist_stride * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
         k_cumsum_counts<<<(F + 127) / 128, 128, 0, c->stream>>>(c->dHistCntL, F);
