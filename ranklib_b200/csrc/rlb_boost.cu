@@ -1091,6 +1091,25 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the producer's wait for a free stage: the stage in question is released a whole pipeline depth from now, so polling
+// the mbarrier back to back only puts try_wait traffic on the shared-memory pipe the consumers live on (k_hist_root:
+// one poll every 4.7 cycles per SM in the ncu capture of round 2); sleep between polls instead
+__device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(void* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void cpasync16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -1208,6 +1227,14 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 // completed on an mbarrier; the three consumer warps never touch global memory.
 //   CTA = (group g, a contiguous range of tiles).  Thread (fi, ph) owns private histogram column tid.
 // ------------------------------------------------------------------------------------------------
+// V (bit mask, RLB_HIST_VARIANT): 0 = the kernel as measured in round 2.
+//   bit 0: the last stage of a CTA is peeled off the stage loop.  With the `if (k + 1 < nst)` around the next stage's first
+//          tile read inside the loop, ptxas kept `cur` / `nxt` in fixed registers across the branch and paid 25 moves per
+//          stage (5.6 % of the consumer's instructions, ncu source view of round 2); without it the two chunks alternate
+//          between two register sets.
+//   bit 1: the producer sleeps between polls of a stage's `empty` barrier (mbar_wait_sleep).
+// Combinations that are not instantiated fall back to 0 (hist_root_fn / hist_child_fn).
+template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_root(const uint16_t* __restrict__ tiles, const long long* __restrict__ vfix, int64_t NB, int F, int nGroups,
                 long long* __restrict__ sum) {
@@ -1250,7 +1277,10 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             const long long* gv = vfix + B0 * R;
             for (int k = 0; k < nst; k++) {
                 const int s2 = k % STAGES;
-                if (k >= STAGES) mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
+                if (k >= STAGES) {
+                    if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / STAGES) + 1) & 1, 64);
+                    else mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
+                }
                 unsigned char* st = stage0 + (size_t)s2 * STAGE_BYTES;
                 mbar_expect_tx(&full[s2], STAGE_BYTES);
                 bulk_g2s(st, gt + (size_t)k * TILE_BYTES, TILE_BYTES, &full[s2]);
@@ -1279,6 +1309,31 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         HChunk cur, nxt;
         mbar_wait(&full[0], 0);
         load(cur, st0, ph);
+        if constexpr ((V & 1) != 0) {
+            // one stage: CPS chunks; the last chunk's read-ahead is the first chunk of stage k + 1 unless the stage is the CTA's last
+            auto stage = [&](int k, auto lastTag) {
+                constexpr bool LAST = decltype(lastTag)::value;
+                const int s2 = k % STAGES;
+                const uint32_t sb = st0 + s2 * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < CPS; j++) {
+                    if (j + 1 < CPS) {
+                        load(nxt, sb, ph + PH * (j + 1));
+                    } else {
+                        if constexpr (!LAST) {
+                            const int s1 = (k + 1) % STAGES;
+                            mbar_wait(&full[s1], ((k + 1) / STAGES) & 1);
+                            load(nxt, st0 + s1 * STAGE_BYTES, ph);
+                        }
+                        mbar_arrive(&empty[s2]);   // per thread, as below
+                    }
+                    hist_rmw8(cur);
+                    cur = nxt;
+                }
+            };
+            for (int k = 0; k + 1 < nst; k++) stage(k, std::false_type{});
+            stage(nst - 1, std::true_type{});
+        } else
         for (int k = 0; k < nst; k++) {
             const int s2 = k % STAGES;
             const uint32_t sb = st0 + s2 * STAGE_BYTES;
@@ -1316,6 +1371,12 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 // The row count rides in the top 12 bits of the same accumulator (v + 2^52, decoded at flush; a private bin holds at
 // most 2032 rows between flushes).  CTAs whose row range is empty return before touching shared memory.
 // ------------------------------------------------------------------------------------------------
+// V (bit mask, RLB_HIST_VARIANT): 0 = the kernel as measured in round 2; bits 0 and 1 as in k_hist_root (peeled last full
+// stage: 24 moves per stage less; sleeping producer poll);
+//   bit 2: the producer stores the response of row 16 b + 2 w + odd at slot 16 b + 8 odd + w of the stage, so the eight
+//          responses of a thread's chunk are 64 contiguous bytes: four LDS.128 instead of eight LDS.64 (the short-scoreboard
+//          stalls on these loads were 16 % of the kernel's samples).
+template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
                  const int32_t* __restrict__ samples0, const int32_t* __restrict__ samples1, long long* __restrict__ sum,
@@ -1338,6 +1399,11 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     unsigned long long* empty = full + HSTAGES;
     int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
+    // slot of stage row j's response (bit 2 of V: the rows of a (16-row block, phase parity) are stored together)
+    auto vslot = [](int j) -> int {
+        if constexpr ((V & 4) != 0) return (j & ~15) | ((j & 1) << 3) | ((j & 15) >> 1);
+        else return j;
+    };
     pdl_trigger();
     pdl_wait();
     if (!st->split_active) return;
@@ -1390,7 +1456,10 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         for (int d = 0; d < HIDX; d++) fetch_idx(d);   // stages past the end commit empty groups: the count stays uniform
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
-            if (k >= HSTAGES) mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
+            if (k >= HSTAGES) {
+                if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / HSTAGES) + 1) & 1, 32);
+                else mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
+            }
             const int64_t base = r0 + (int64_t)k * R;
             const int nr = (int)min((int64_t)R, r1 - base);
             unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
@@ -1410,7 +1479,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                     const uint16_t* src = bins + row * Fp + g * HG;
                     cpasync16(bt + j * 32, src);
                     cpasync16(bt + j * 32 + 16, src + 8);
-                    cpasync8(vt + j, vfixc + row);
+                    cpasync8(vt + vslot(j), vfixc + row);
                 }
             }
             cpasync_arrive(&full[s2]);
@@ -1426,11 +1495,21 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         // rows of block b owned by this thread: 16 b + 2 w + odd, w = 0..7
         auto load = [&](HChunk& c, uint32_t sb, int blk) {
             const uint32_t ba = sb + (blk * 16 + odd) * 32 + fi * 2;
-            const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
+            if constexpr ((V & 4) != 0) {
+                const uint32_t va = sb + R * 32 + (blk * 16 + odd * 8) * 8;
+                lds128ll(va, c.v[0], c.v[1]);
+                lds128ll(va + 16, c.v[2], c.v[3]);
+                lds128ll(va + 32, c.v[4], c.v[5]);
+                lds128ll(va + 48, c.v[6], c.v[7]);
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
-                c.v[w] = lds64(va + w * 16);
+                for (int w = 0; w < 8; w++) c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+            } else {
+                const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+                    c.v[w] = lds64(va + w * 16);
+                }
             }
         };
         // threads of an absent feature (last group: its bins are stored as 0) run along into their own column, which
@@ -1439,6 +1518,32 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             HChunk cur, nxt;
             mbar_wait(&full[0], 0);
             load(cur, st0, pp);
+            if constexpr ((V & 1) != 0) {
+                auto stage = [&](int k, auto lastTag) {
+                    constexpr bool LAST = decltype(lastTag)::value;
+                    const int s2 = k % HSTAGES;
+                    const uint32_t sb = st0 + s2 * STAGE_BYTES;
+                    // the packed (count, sum) accumulators hold at most 2^11 rows
+                    if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+#pragma unroll
+                    for (int j = 0; j < BPP; j++) {
+                        if (j + 1 < BPP) {
+                            load(nxt, sb, pp + (PH / 2) * (j + 1));
+                        } else {
+                            if constexpr (!LAST) {
+                                const int s1 = (k + 1) % HSTAGES;
+                                mbar_wait(&full[s1], ((k + 1) / HSTAGES) & 1);
+                                load(nxt, st0 + s1 * STAGE_BYTES, pp);
+                            }
+                            mbar_arrive(&empty[s2]);   // this thread's reads of stage s2 are behind it
+                        }
+                        hist_rmw8(cur);
+                        cur = nxt;
+                    }
+                };
+                for (int k = 0; k + 1 < nfull; k++) stage(k, std::false_type{});
+                stage(nfull - 1, std::true_type{});
+            } else
             for (int k = 0; k < nfull; k++) {
                 const int s2 = k % HSTAGES;
                 const uint32_t sb = st0 + s2 * STAGE_BYTES;
@@ -1474,7 +1579,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 long long* Hme = H + tid;
                 for (int rr = ph; rr < nr; rr += PH) {
                     const int b = btile[rr * HG + fi];
-                    Hme[b * T] += vt[rr];
+                    Hme[b * T] += vt[vslot(rr)];
                 }
             }
         }
@@ -3652,6 +3757,29 @@ static constexpr size_t hist_smem_child() {
 }
 static constexpr int hist_threads() { return 32 * ((HG * HPH + 31) / 32 + 1); }
 
+// the instantiation c->hist_variant selects (RLB_HIST_VARIANT, see the kernels' headers)
+using HistRootFn = void (*)(const uint16_t*, const long long*, int64_t, int, int, long long*);
+using HistChildFn = void (*)(const uint16_t*, int, int, const long long*, const int32_t*, const int32_t*, long long*, int32_t*,
+                             DevState*, int, size_t);
+static HistRootFn hist_root_fn(const rlb_ctx* c) {
+    switch (c->hist_variant & 3) {   // bit 2 is a child-kernel variant
+        case 1: return k_hist_root<1>;
+        case 2: return k_hist_root<2>;
+        case 3: return k_hist_root<3>;
+        default: return k_hist_root<0>;
+    }
+}
+static HistChildFn hist_child_fn(const rlb_ctx* c) {
+    switch (c->hist_variant & 7) {
+        case 1: return k_hist_child<1>;
+        case 2: return k_hist_child<2>;
+        case 3: return k_hist_child<3>;
+        case 4: return k_hist_child<4>;
+        case 5: return k_hist_child<5>;
+        case 7: return k_hist_child<7>;
+        default: return k_hist_child<0>;
+    }
+}
 static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
 static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
 
@@ -3665,8 +3793,8 @@ int rlb_impl_hist_update(rlb_ctx* c) {
     c->identity_fresh = true;
     rlb_prof_begin(c, 0);
     if (c->N >= c->hist_min_rows) {
-        k_hist_root<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
-                                                                                    hist_groups(c), c->dRootRaw);
+        hist_root_fn(c)<<<hist_grid(c), hist_threads(), hist_smem_root(), c->stream>>>(c->dBinsTile, c->dVfix, c->root_nb, c->F,
+                                                                                        hist_groups(c), c->dRootRaw);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
     } else {
@@ -3714,7 +3842,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             RLB_CHECK_LAUNCH(c);
         }
         rlb_prof_begin(c, 1);
-        launch_pdl(c, k_hist_child, dim3(hist_grid(c)), dim3(hist_threads()), hist_smem_child(), c->dBins, c->Fp, c->F, c->dVfixC,
+        launch_pdl(c, hist_child_fn(c), dim3(hist_grid(c)), dim3(hist_threads()), hist_smem_child(), c->dBins, c->Fp, c->F, c->dVfixC,
                    c->dSamples[0], c->dSamples[1], stageSum, stageCnt, c->dState, hist_groups(c), stageStride);
         rlb_prof_end(c);
         RLB_CHECK_LAUNCH(c);
@@ -3790,8 +3918,8 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
 
 // one-time kernel attributes (must not happen inside a stream capture)
 int rlb_impl_prepare(rlb_ctx* c) {
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_hist_child, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
+    RLB_CUDA(c, cudaFuncSetAttribute(hist_root_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
+    RLB_CUDA(c, cudaFuncSetAttribute(hist_child_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 44 + 1280 * 16 + 64));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));

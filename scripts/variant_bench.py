@@ -1,0 +1,81 @@
+"""Development aid: the histogram kernels' variants (RLB_HIST_VARIANT, rlb_boost.cu) side by side in ONE process.
+
+    python scripts/variant_bench.py [variants, default 0,1,3,5,7] [repeats, default 3] [steps, default 20]
+
+For every variant: a fresh context on the full C2 workload (synthetic, 1.2 M documents x 136 features), 5 warm-up
+iterations, `steps` timed iterations through rlb_boost_iters (CUDA events on the context's stream), then the same steps with
+the per-kernel event nodes switched on (root / child histogram time).  The variants are interleaved over the repeats so that
+clock or neighbour noise does not land on one of them, and the CRC of the trees of every run is compared: a variant that
+builds other trees than variant 0 is reported as WRONG.  One JSON line per variant on stdout.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import bench
+    from ranklib_b200.host import native
+    variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0,1,3,5,7").split(",")]
+    repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    torch.cuda.set_device(0)
+    X, label, qoff = bench.make_data("c2", float(os.environ.get("VB_SCALE", "1.0")))
+    Xpin = torch.from_numpy(X).pin_memory()   # kept alive: the contexts upload from this pinned buffer
+    Xp = Xpin.numpy()
+    params = native.make_params()
+    res = {v: {"ms": [], "root_ms": [], "child_ms": [], "crc": set()} for v in variants}
+    for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
+        for v in variants:
+            os.environ["RLB_HIST_VARIANT"] = str(v)
+            ctx = native.Context(0)
+            ctx.load_dense(Xp, label, qoff)
+            ctx.init(params)
+            crc = 0
+            for _ in range(5):
+                nodes, _m = ctx.boost_iter(want_tree=True)
+                crc = bench.tree_crc(crc, nodes)
+            ext = torch.cuda.ExternalStream(ctx.stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(ext)
+            ctx.boost_iters(steps, want_trees=False)
+            e1.record(ext)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            ctx.profile(True)
+            ctx.boost_iter(want_tree=False)
+            ctx.profile_read()
+            ctx.profile(True)
+            for _ in range(steps):
+                nodes, _m = ctx.boost_iter(want_tree=True)
+                crc = bench.tree_crc(crc, nodes)
+            prof = ctx.profile_read()
+            ctx.profile(False)
+            ctx.close()
+            if rep == 0:
+                continue
+            r = res[v]
+            r["ms"].append(ms)
+            r["root_ms"].append(prof[0] / max(prof[1], 1))
+            r["child_ms"].append(prof[3] / steps)
+            r["crc"].add(crc & 0xffffffff)
+    ref = res[variants[0]]["crc"]
+    for v in variants:
+        r = res[v]
+        ok = (r["crc"] == ref) and len(r["crc"]) == 1
+        print(json.dumps({"variant": v, "ms_per_step": [round(x, 4) for x in r["ms"]], "ms_per_step_min": round(min(r["ms"]), 4),
+                          "iters_per_s_best": round(1000.0 / min(r["ms"]), 1),
+                          "root_ms": [round(x, 4) for x in r["root_ms"]], "child_ms_per_step": [round(x, 4) for x in r["child_ms"]],
+                          "trees": "same as variant %d" % variants[0] if ok else "WRONG",
+                          "crc": sorted(f"{c:08x}" for c in r["crc"])}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
