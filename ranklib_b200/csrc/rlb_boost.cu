@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -1107,6 +1108,8 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// sleep between two polls, nanoseconds: [0] root kernel, [1] child kernel (RLB_HIST_SLEEP_ROOT / RLB_HIST_SLEEP_CHILD)
+__device__ unsigned g_hist_sleep_ns[2] = {64u, 32u};
 __device__ __forceinline__ void mbar_wait_sleep(void* bar, uint32_t parity, unsigned ns) {
     while (!mbar_try(bar, parity)) __nanosleep(ns);
 }
@@ -1275,10 +1278,12 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         if (lane == 0) {
             const unsigned char* gt = reinterpret_cast<const unsigned char*>(tiles) + ((size_t)g * NB + B0) * TILE_BYTES;
             const long long* gv = vfix + B0 * R;
+            unsigned sleep_ns = 0;
+            if constexpr ((V & 2) != 0) sleep_ns = g_hist_sleep_ns[0];
             for (int k = 0; k < nst; k++) {
                 const int s2 = k % STAGES;
                 if (k >= STAGES) {
-                    if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / STAGES) + 1) & 1, 64);
+                    if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / STAGES) + 1) & 1, sleep_ns);
                     else mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
                 }
                 unsigned char* st = stage0 + (size_t)s2 * STAGE_BYTES;
@@ -1453,11 +1458,13 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        unsigned sleep_ns = 0;
+        if constexpr ((V & 2) != 0) sleep_ns = g_hist_sleep_ns[1];
         for (int d = 0; d < HIDX; d++) fetch_idx(d);   // stages past the end commit empty groups: the count stays uniform
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
             if (k >= HSTAGES) {
-                if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / HSTAGES) + 1) & 1, 32);
+                if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / HSTAGES) + 1) & 1, sleep_ns);
                 else mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
             }
             const int64_t base = r0 + (int64_t)k * R;
@@ -3918,6 +3925,16 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
 
 // one-time kernel attributes (must not happen inside a stream capture)
 int rlb_impl_prepare(rlb_ctx* c) {
+    {
+        const char* er = getenv("RLB_HIST_SLEEP_ROOT");
+        const char* ec = getenv("RLB_HIST_SLEEP_CHILD");
+        if (er || ec) {
+            unsigned ns[2] = {64u, 32u};
+            if (er) ns[0] = (unsigned)std::max(0, atoi(er));
+            if (ec) ns[1] = (unsigned)std::max(0, atoi(ec));
+            RLB_CUDA(c, cudaMemcpyToSymbol(g_hist_sleep_ns, ns, sizeof(ns)));
+        }
+    }
     RLB_CUDA(c, cudaFuncSetAttribute(hist_root_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
     RLB_CUDA(c, cudaFuncSetAttribute(hist_child_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));

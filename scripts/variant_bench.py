@@ -2,6 +2,8 @@
 
     python scripts/variant_bench.py [variants, default 0,1,3,5,7] [repeats, default 3] [steps, default 20]
 
+A variant is `mask` or `mask:root_ns:child_ns` (sleep between two polls of the producers, RLB_HIST_SLEEP_ROOT / _CHILD).
+
 For every variant: a fresh context on the full C2 workload (synthetic, 1.2 M documents x 136 features), 5 warm-up
 iterations, `steps` timed iterations through rlb_boost_iters (CUDA events on the context's stream), then the same steps with
 the per-kernel event nodes switched on (root / child histogram time).  The variants are interleaved over the repeats so that
@@ -22,7 +24,7 @@ def main():
     import torch
     import bench
     from ranklib_b200.host import native
-    variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0,1,3,5,7").split(",")]
+    variants = (sys.argv[1] if len(sys.argv) > 1 else "0,1,3,5,7").split(",")
     repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     torch.cuda.set_device(0)
@@ -33,7 +35,8 @@ def main():
     res = {v: {"ms": [], "root_ms": [], "child_ms": [], "crc": set()} for v in variants}
     for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
         for v in variants:
-            os.environ["RLB_HIST_VARIANT"] = str(v)
+            spec = (v.split(":") + ["64", "32"])[:3] if ":" in v else [v, "64", "32"]
+            os.environ["RLB_HIST_VARIANT"], os.environ["RLB_HIST_SLEEP_ROOT"], os.environ["RLB_HIST_SLEEP_CHILD"] = spec
             ctx = native.Context(0)
             ctx.load_dense(Xp, label, qoff)
             ctx.init(params)
@@ -73,7 +76,7 @@ def main():
         print(json.dumps({"variant": v, "ms_per_step": [round(x, 4) for x in r["ms"]], "ms_per_step_min": round(min(r["ms"]), 4),
                           "iters_per_s_best": round(1000.0 / min(r["ms"]), 1),
                           "root_ms": [round(x, 4) for x in r["root_ms"]], "child_ms_per_step": [round(x, 4) for x in r["child_ms"]],
-                          "trees": "same as variant %d" % variants[0] if ok else "WRONG",
+                          "trees": "same as variant %s" % variants[0] if ok else "WRONG",
                           "crc": sorted(f"{c:08x}" for c in r["crc"])}), flush=True)
 
 
