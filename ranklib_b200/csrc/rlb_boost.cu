@@ -1186,9 +1186,89 @@ __device__ __forceinline__ void hist_rmw8(HChunk& c) {
     }
 }
 
+// ---- variants of the merge / read-modify-write step (bits 3 and 5 of RLB_HIST_VARIANT) ----
+// The consumers run one warp per scheduler and issue 0.5 instructions per cycle (ncu, round 2): 58 % of their
+// instructions are ALU-pipe operations (SEL / IADD3 / ISETP / LOP3 / SHF, one per two cycles per scheduler) and only
+// 20 % go to the FMA pipe.
+//   bit 3: the merge as multiply-adds by a 0 / 1 mask, v += m * x = IMAD.WIDE.U32 + IMAD (FMA pipe), instead of
+//          2 SEL + IADD3 + IADD3.X: per quad 13 ALU + 12 FMA instead of 21 ALU + 3 FMA instructions.
+//   bit 5: software pipelining by hand: the merge of chunk k + 1 sits between the loads and the stores of chunk k's
+//          read-modify-writes, i.e. in the shadow of their shared-memory latency (hist_rmw8_pipe).
+// v += m * x (mod 2^64) for m in {0, 1}
+__device__ __forceinline__ void add_masked(long long& v, uint32_t m, long long x) {
+    const uint32_t xlo = (uint32_t)(unsigned long long)x, xhi = (uint32_t)((unsigned long long)x >> 32);
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(m), "r"(xlo), "l"((unsigned long long)v));
+    uint32_t rhi = (uint32_t)(r >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(rhi) : "r"(m), "r"(xhi));
+    v = (long long)(((unsigned long long)rhi << 32) | (uint32_t)r);
+}
+// equal bins inside the quad p..p+3: row j takes the merged addend of the NEAREST earlier row with its address
+template <int V>
+__device__ __forceinline__ void merge_quad(HChunk& c, const int p) {
+    const bool e10 = c.a[p + 1] == c.a[p], e21 = c.a[p + 2] == c.a[p + 1], e20 = c.a[p + 2] == c.a[p];
+    const bool e32 = c.a[p + 3] == c.a[p + 2], e31 = c.a[p + 3] == c.a[p + 1], e30 = c.a[p + 3] == c.a[p];
+    if constexpr ((V & 8) != 0) {
+        const uint32_t m10 = e10 ? 1u : 0u, m21 = e21 ? 1u : 0u, m20 = (e20 && !e21) ? 1u : 0u;
+        const uint32_t m32 = e32 ? 1u : 0u, m31 = (e31 && !e32) ? 1u : 0u, m30 = (e30 && !e32 && !e31) ? 1u : 0u;
+        add_masked(c.v[p + 1], m10, c.v[p]);
+        add_masked(c.v[p + 2], m20, c.v[p]);       // the terms that do not wait for a merged addend first
+        add_masked(c.v[p + 3], m30, c.v[p]);
+        add_masked(c.v[p + 2], m21, c.v[p + 1]);
+        add_masked(c.v[p + 3], m31, c.v[p + 1]);
+        add_masked(c.v[p + 3], m32, c.v[p + 2]);
+    } else {
+        c.v[p + 1] += e10 ? c.v[p] : 0LL;
+        c.v[p + 2] += e21 ? c.v[p + 1] : (e20 ? c.v[p] : 0LL);
+        c.v[p + 3] += e32 ? c.v[p + 2] : (e31 ? c.v[p + 1] : (e30 ? c.v[p] : 0LL));
+    }
+}
+template <int V>
+__device__ __forceinline__ void hist_merge8(HChunk& c) {
+    merge_quad<V>(c, 0);
+    merge_quad<V>(c, 4);
+}
+// the read-modify-writes of a chunk whose addends are merged already
+__device__ __forceinline__ void hist_rmw_quad(const HChunk& c, const int p) {
+    const long long h0 = lds64(c.a[p]), h1 = lds64(c.a[p + 1]), h2 = lds64(c.a[p + 2]), h3 = lds64(c.a[p + 3]);
+    sts64(c.a[p], h0 + c.v[p]);
+    sts64(c.a[p + 1], h1 + c.v[p + 1]);
+    sts64(c.a[p + 2], h2 + c.v[p + 2]);
+    sts64(c.a[p + 3], h3 + c.v[p + 3]);
+}
+// cur: merged; nxt: loaded, merged here between cur's loads and stores
+template <int V>
+__device__ __forceinline__ void hist_rmw8_pipe(const HChunk& cur, HChunk& nxt) {
+#pragma unroll
+    for (int p = 0; p < 8; p += 4) {
+        const long long h0 = lds64(cur.a[p]), h1 = lds64(cur.a[p + 1]), h2 = lds64(cur.a[p + 2]), h3 = lds64(cur.a[p + 3]);
+        merge_quad<V>(nxt, p);
+        sts64(cur.a[p], h0 + cur.v[p]);
+        sts64(cur.a[p + 1], h1 + cur.v[p + 1]);
+        sts64(cur.a[p + 2], h2 + cur.v[p + 2]);
+        sts64(cur.a[p + 3], h3 + cur.v[p + 3]);
+    }
+}
+// one chunk step of the stage loops: V without bits 3 / 5 is hist_rmw8 unchanged
+template <int V>
+__device__ __forceinline__ void hist_step(HChunk& cur, HChunk& nxt) {
+    if constexpr ((V & 32) != 0) {
+        hist_rmw8_pipe<V>(cur, nxt);
+    } else if constexpr ((V & 8) != 0) {
+        hist_merge8<V>(cur);
+        hist_rmw_quad(cur, 0);
+        hist_rmw_quad(cur, 4);
+    } else {
+        hist_rmw8(cur);
+    }
+}
+
 // Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
 // per non-empty entry and clear the private copies.  Consumer threads only (named barrier 1).
-template <bool CHILD, int PH, bool CLEAR = true>
+// FAST (bit 6 of RLB_HIST_VARIANT): the packed (count, sum) copies of a child build are decoded with two 32-bit
+// operations per copy: count = (hi32(pk) + 2^19) >> 20 (arithmetic) — the same number as ((pk - sv) >> 52) below, because
+// adding 2^51 does not touch the low word — and the sums are recovered once per entry as (sum of pk) - (sum of counts << 52).
+template <bool CHILD, int PH, bool CLEAR = true, bool FAST = false>
 __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, long long* __restrict__ sum,
                                            int32_t* __restrict__ cnt) {
     constexpr int T = HG * PH;
@@ -1203,7 +1283,11 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
         for (int q = 0; q < PH; q++) {
             const long long pk = H[bin * T + q * HG + ff];
             if (CLEAR) H[bin * T + q * HG + ff] = 0;   // the kernel's last flush leaves the copies as they are
-            if (CHILD) {
+            if (CHILD && FAST) {
+                static_assert(CNT_SHIFT == 52, "count field starts at bit 20 of the high word");
+                sacc += pk;
+                c += ((int)(uint32_t)((unsigned long long)pk >> 32) + (1 << 19)) >> 20;
+            } else if (CHILD) {
                 const long long sv = ((pk + (1LL << (CNT_SHIFT - 1))) & (CNT_ONE - 1)) - (1LL << (CNT_SHIFT - 1));
                 sacc += sv;
                 c += (int)((pk - sv) >> CNT_SHIFT);
@@ -1211,6 +1295,7 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
                 sacc += pk;
             }
         }
+        if (CHILD && FAST) sacc = (long long)((unsigned long long)sacc - ((unsigned long long)(unsigned int)c << CNT_SHIFT));
         if (fo < F) {
             if (sacc != 0) atomicAdd((unsigned long long*)&sum[(size_t)fo * RLB_T + bin], (unsigned long long)sacc);
             if (CHILD && c != 0) atomicAdd(&cnt[(size_t)fo * RLB_T + bin], c);
@@ -1236,6 +1321,7 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 //          stage (5.6 % of the consumer's instructions, ncu source view of round 2); without it the two chunks alternate
 //          between two register sets.
 //   bit 1: the producer sleeps between polls of a stage's `empty` barrier (mbar_wait_sleep).
+//   bits 3, 5 (need bit 0): see hist_step.   bit 6: private histograms cleared with 16-byte stores.
 // Combinations that are not instantiated fall back to 0 (hist_root_fn / hist_child_fn).
 template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
@@ -1264,7 +1350,13 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     const int64_t B0 = NB * idx / nCta, B1 = NB * (idx + 1) / nCta;
     const int nst = (int)(B1 - B0);
     if (nst == 0) return;
-    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if constexpr ((V & 64) != 0) {   // 16 bytes per store
+        static_assert((RLB_T * T) % 2 == 0, "whole uint4");
+        uint4* H4 = reinterpret_cast<uint4*>(H);
+        for (int i = tid; i < RLB_T * T / 2; i += blockDim.x) H4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    }
     if (tid == 0) {
         for (int s2 = 0; s2 < STAGES; s2++) {
             mbar_init(&full[s2], 1u);
@@ -1332,10 +1424,11 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                         }
                         mbar_arrive(&empty[s2]);   // per thread, as below
                     }
-                    hist_rmw8(cur);
+                    hist_step<V>(cur, nxt);   // (bit 5: the CTA's very last step merges a stale nxt, which nobody uses)
                     cur = nxt;
                 }
             };
+            if constexpr ((V & 32) != 0) hist_merge8<V>(cur);
             for (int k = 0; k + 1 < nst; k++) stage(k, std::false_type{});
             stage(nst - 1, std::true_type{});
         } else
@@ -1380,7 +1473,9 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 // stage: 24 moves per stage less; sleeping producer poll);
 //   bit 2: the producer stores the response of row 16 b + 2 w + odd at slot 16 b + 8 odd + w of the stage, so the eight
 //          responses of a thread's chunk are 64 contiguous bytes: four LDS.128 instead of eight LDS.64 (the short-scoreboard
-//          stalls on these loads were 16 % of the kernel's samples).
+//          stalls on these loads were 16 % of the kernel's samples);
+//   bit 4 (needs bit 2): private-histogram address as one multiply-add;  bits 3, 5 (need bit 0): see hist_step;
+//   bit 6: 16-byte clears and the two-operation count decode of hist_flush<.., FAST>.
 template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
@@ -1432,7 +1527,13 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
     const int nfull = (int)((r1 - r0) / R);
 
-    for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    if constexpr ((V & 64) != 0) {   // 16 bytes per store
+        static_assert((RLB_T * T) % 2 == 0, "whole uint4");
+        uint4* H4 = reinterpret_cast<uint4*>(H);
+        for (int i = tid; i < RLB_T * T / 2; i += blockDim.x) H4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = tid; i < RLB_T * T; i += blockDim.x) H[i] = 0;
+    }
     if (tid == 0) {
         for (int s2 = 0; s2 < HSTAGES; s2++) {
             mbar_init(&full[s2], 32u);   // one cp.async-completion arrival per producer lane
@@ -1509,7 +1610,15 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 lds128ll(va + 32, c.v[4], c.v[5]);
                 lds128ll(va + 48, c.v[6], c.v[7]);
 #pragma unroll
-                for (int w = 0; w < 8; w++) c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+                for (int w = 0; w < 8; w++) {
+                    if constexpr ((V & 16) != 0) {
+                        // one IMAD: ptxas otherwise keeps bin * 768 for the equality tests and adds hme separately (24 more
+                        // instructions per stage)
+                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c.a[w]) : "r"(lds16(ba + w * 64)), "r"((uint32_t)(T * 8)), "r"(hme));
+                    } else {
+                        c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
+                    }
+                }
             } else {
                 const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
 #pragma unroll
@@ -1531,7 +1640,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                     const int s2 = k % HSTAGES;
                     const uint32_t sb = st0 + s2 * STAGE_BYTES;
                     // the packed (count, sum) accumulators hold at most 2^11 rows
-                    if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+                    if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
 #pragma unroll
                     for (int j = 0; j < BPP; j++) {
                         if (j + 1 < BPP) {
@@ -1544,10 +1653,11 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                             }
                             mbar_arrive(&empty[s2]);   // this thread's reads of stage s2 are behind it
                         }
-                        hist_rmw8(cur);
+                        hist_step<V>(cur, nxt);
                         cur = nxt;
                     }
                 };
+                if constexpr ((V & 32) != 0) hist_merge8<V>(cur);
                 for (int k = 0; k + 1 < nfull; k++) stage(k, std::false_type{});
                 stage(nfull - 1, std::true_type{});
             } else
@@ -1555,7 +1665,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 const int s2 = k % HSTAGES;
                 const uint32_t sb = st0 + s2 * STAGE_BYTES;
                 // the packed (count, sum) accumulators hold at most 2^11 rows
-                if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+                if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
 #pragma unroll
                 for (int j = 0; j < BPP; j++) {
                     if (j + 1 < BPP) {
@@ -1576,7 +1686,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         if (nst > nfull) {  // the partial last stage, row by row
             const int k = nfull;
             const int s2 = k % HSTAGES;
-            if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH>(H, tid, g, F, sum, cnt);
+            if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
             mbar_wait(&full[s2], (k / HSTAGES) & 1);
             const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
@@ -1590,7 +1700,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 }
             }
         }
-        hist_flush<true, PH, false>(H, tid, g, F, sum, cnt);
+        hist_flush<true, PH, false, (V & 64) != 0>(H, tid, g, F, sum, cnt);
     }
 }
 
@@ -3769,21 +3879,24 @@ using HistRootFn = void (*)(const uint16_t*, const long long*, int64_t, int, int
 using HistChildFn = void (*)(const uint16_t*, int, int, const long long*, const int32_t*, const int32_t*, long long*, int32_t*,
                              DevState*, int, size_t);
 static HistRootFn hist_root_fn(const rlb_ctx* c) {
-    switch (c->hist_variant & 3) {   // bit 2 is a child-kernel variant
+    switch (c->hist_variant & (1 | 2 | 8 | 32 | 64)) {   // bits 2 and 4 are child-kernel variants
         case 1: return k_hist_root<1>;
-        case 2: return k_hist_root<2>;
         case 3: return k_hist_root<3>;
+        case 33: return k_hist_root<33>;
+        case 65: return k_hist_root<65>;
         default: return k_hist_root<0>;
     }
 }
 static HistChildFn hist_child_fn(const rlb_ctx* c) {
-    switch (c->hist_variant & 7) {
+    switch (c->hist_variant & 127) {
         case 1: return k_hist_child<1>;
-        case 2: return k_hist_child<2>;
         case 3: return k_hist_child<3>;
-        case 4: return k_hist_child<4>;
         case 5: return k_hist_child<5>;
         case 7: return k_hist_child<7>;
+        case 21: return k_hist_child<21>;
+        case 37: return k_hist_child<37>;
+        case 69: return k_hist_child<69>;
+        case 85: return k_hist_child<85>;
         default: return k_hist_child<0>;
     }
 }
