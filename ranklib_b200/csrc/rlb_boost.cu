@@ -1092,27 +1092,6 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// the producer's wait for a free stage: the stage in question is released a whole pipeline depth from now, so polling
-// the mbarrier back to back only puts try_wait traffic on the shared-memory pipe the consumers live on (k_hist_root:
-// one poll every 4.7 cycles per SM in the ncu capture of round 2); sleep between polls instead
-__device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// sleep between two polls, nanoseconds: [0] root kernel, [1] child kernel (RLB_HIST_SLEEP_ROOT / RLB_HIST_SLEEP_CHILD)
-__device__ unsigned g_hist_sleep_ns[2] = {64u, 32u};
-__device__ __forceinline__ void mbar_wait_sleep(void* bar, uint32_t parity, unsigned ns) {
-    while (!mbar_try(bar, parity)) __nanosleep(ns);
-}
 __device__ __forceinline__ void cpasync16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -1186,86 +1165,7 @@ __device__ __forceinline__ void hist_rmw8(HChunk& c) {
     }
 }
 
-// ---- variants of the merge / read-modify-write step (bits 3 and 5 of RLB_HIST_VARIANT) ----
-// The consumers run one warp per scheduler and issue 0.5 instructions per cycle (ncu, round 2): 58 % of their
-// instructions are ALU-pipe operations (SEL / IADD3 / ISETP / LOP3 / SHF, one per two cycles per scheduler) and only
-// 20 % go to the FMA pipe.
-//   bit 3: the merge as multiply-adds by a 0 / 1 mask, v += m * x = IMAD.WIDE.U32 + IMAD (FMA pipe), instead of
-//          2 SEL + IADD3 + IADD3.X: per quad 13 ALU + 12 FMA instead of 21 ALU + 3 FMA instructions.
-//   bit 5: software pipelining by hand: the merge of chunk k + 1 sits between the loads and the stores of chunk k's
-//          read-modify-writes, i.e. in the shadow of their shared-memory latency (hist_rmw8_pipe).
-// v += m * x (mod 2^64) for m in {0, 1}
-__device__ __forceinline__ void add_masked(long long& v, uint32_t m, long long x) {
-    const uint32_t xlo = (uint32_t)(unsigned long long)x, xhi = (uint32_t)((unsigned long long)x >> 32);
-    unsigned long long r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(m), "r"(xlo), "l"((unsigned long long)v));
-    uint32_t rhi = (uint32_t)(r >> 32);
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(rhi) : "r"(m), "r"(xhi));
-    v = (long long)(((unsigned long long)rhi << 32) | (uint32_t)r);
-}
-// equal bins inside the quad p..p+3: row j takes the merged addend of the NEAREST earlier row with its address
-template <int V>
-__device__ __forceinline__ void merge_quad(HChunk& c, const int p) {
-    const bool e10 = c.a[p + 1] == c.a[p], e21 = c.a[p + 2] == c.a[p + 1], e20 = c.a[p + 2] == c.a[p];
-    const bool e32 = c.a[p + 3] == c.a[p + 2], e31 = c.a[p + 3] == c.a[p + 1], e30 = c.a[p + 3] == c.a[p];
-    if constexpr ((V & 8) != 0) {
-        const uint32_t m10 = e10 ? 1u : 0u, m21 = e21 ? 1u : 0u, m20 = (e20 && !e21) ? 1u : 0u;
-        const uint32_t m32 = e32 ? 1u : 0u, m31 = (e31 && !e32) ? 1u : 0u, m30 = (e30 && !e32 && !e31) ? 1u : 0u;
-        add_masked(c.v[p + 1], m10, c.v[p]);
-        add_masked(c.v[p + 2], m20, c.v[p]);       // the terms that do not wait for a merged addend first
-        add_masked(c.v[p + 3], m30, c.v[p]);
-        add_masked(c.v[p + 2], m21, c.v[p + 1]);
-        add_masked(c.v[p + 3], m31, c.v[p + 1]);
-        add_masked(c.v[p + 3], m32, c.v[p + 2]);
-    } else {
-        c.v[p + 1] += e10 ? c.v[p] : 0LL;
-        c.v[p + 2] += e21 ? c.v[p + 1] : (e20 ? c.v[p] : 0LL);
-        c.v[p + 3] += e32 ? c.v[p + 2] : (e31 ? c.v[p + 1] : (e30 ? c.v[p] : 0LL));
-    }
-}
-template <int V>
-__device__ __forceinline__ void hist_merge8(HChunk& c) {
-    merge_quad<V>(c, 0);
-    merge_quad<V>(c, 4);
-}
-// the read-modify-writes of a chunk whose addends are merged already
-__device__ __forceinline__ void hist_rmw_quad(const HChunk& c, const int p) {
-    const long long h0 = lds64(c.a[p]), h1 = lds64(c.a[p + 1]), h2 = lds64(c.a[p + 2]), h3 = lds64(c.a[p + 3]);
-    sts64(c.a[p], h0 + c.v[p]);
-    sts64(c.a[p + 1], h1 + c.v[p + 1]);
-    sts64(c.a[p + 2], h2 + c.v[p + 2]);
-    sts64(c.a[p + 3], h3 + c.v[p + 3]);
-}
-// cur: merged; nxt: loaded, merged here between cur's loads and stores
-template <int V>
-__device__ __forceinline__ void hist_rmw8_pipe(const HChunk& cur, HChunk& nxt) {
-#pragma unroll
-    for (int p = 0; p < 8; p += 4) {
-        const long long h0 = lds64(cur.a[p]), h1 = lds64(cur.a[p + 1]), h2 = lds64(cur.a[p + 2]), h3 = lds64(cur.a[p + 3]);
-        merge_quad<V>(nxt, p);
-        sts64(cur.a[p], h0 + cur.v[p]);
-        sts64(cur.a[p + 1], h1 + cur.v[p + 1]);
-        sts64(cur.a[p + 2], h2 + cur.v[p + 2]);
-        sts64(cur.a[p + 3], h3 + cur.v[p + 3]);
-    }
-}
-// one chunk step of the stage loops: V without bits 3 / 5 is hist_rmw8 unchanged
-template <int V>
-__device__ __forceinline__ void hist_step(HChunk& cur, HChunk& nxt) {
-    if constexpr ((V & 32) != 0) {
-        hist_rmw8_pipe<V>(cur, nxt);
-    } else if constexpr ((V & 8) != 0) {
-        hist_merge8<V>(cur);
-        hist_rmw_quad(cur, 0);
-        hist_rmw_quad(cur, 4);
-    } else {
-        hist_rmw8(cur);
-    }
-}
-
-// Sum the PH private copies of every (bin, feature) of this CTA, publish with one global reduction
-// per non-empty entry and clear the private copies.  Consumer threads only (named barrier 1).
-// FAST (bit 6 of RLB_HIST_VARIANT): the packed (count, sum) copies of a child build are decoded with two 32-bit
+// FAST (RLB_HIST_VARIANT 1): the packed (count, sum) copies of a child build are decoded with two 32-bit
 // operations per copy: count = (hi32(pk) + 2^19) >> 20 (arithmetic) — the same number as ((pk - sv) >> 52) below, because
 // adding 2^51 does not touch the low word — and the sums are recovered once per entry as (sum of pk) - (sum of counts << 52).
 template <bool CHILD, int PH, bool CLEAR = true, bool FAST = false>
@@ -1315,14 +1215,13 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 // completed on an mbarrier; the three consumer warps never touch global memory.
 //   CTA = (group g, a contiguous range of tiles).  Thread (fi, ph) owns private histogram column tid.
 // ------------------------------------------------------------------------------------------------
-// V (bit mask, RLB_HIST_VARIANT): 0 = the kernel as measured in round 2.
-//   bit 0: the last stage of a CTA is peeled off the stage loop.  With the `if (k + 1 < nst)` around the next stage's first
-//          tile read inside the loop, ptxas kept `cur` / `nxt` in fixed registers across the branch and paid 25 moves per
-//          stage (5.6 % of the consumer's instructions, ncu source view of round 2); without it the two chunks alternate
-//          between two register sets.
-//   bit 1: the producer sleeps between polls of a stage's `empty` barrier (mbar_wait_sleep).
-//   bits 3, 5 (need bit 0): see hist_step.   bit 6: private histograms cleared with 16-byte stores.
-// Combinations that are not instantiated fall back to 0 (hist_root_fn / hist_child_fn).
+// V (RLB_HIST_VARIANT): 0 = the kernel as first measured in round 2 (kept selectable: the "before" arm of
+// profiles/r2x_variants.jsonl); 1 (default) =
+//   * the last stage of a CTA is peeled off the stage loop.  With the `if (k + 1 < nst)` around the next stage's first tile
+//     read inside the loop, ptxas kept `cur` / `nxt` in fixed registers across the branch and paid 25 moves per stage
+//     (ncu source view); without it the two chunks alternate between two register sets: 442 -> 418 instructions and
+//     735 -> 649 issue cycles (sum of the SASS stall fields) per stage, 0.195 -> 0.174 ms per root pass on the B200;
+//   * the private histograms are cleared with 16-byte stores.
 template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_root(const uint16_t* __restrict__ tiles, const long long* __restrict__ vfix, int64_t NB, int F, int nGroups,
@@ -1350,7 +1249,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     const int64_t B0 = NB * idx / nCta, B1 = NB * (idx + 1) / nCta;
     const int nst = (int)(B1 - B0);
     if (nst == 0) return;
-    if constexpr ((V & 64) != 0) {   // 16 bytes per store
+    if constexpr (V != 0) {   // 16 bytes per store
         static_assert((RLB_T * T) % 2 == 0, "whole uint4");
         uint4* H4 = reinterpret_cast<uint4*>(H);
         for (int i = tid; i < RLB_T * T / 2; i += blockDim.x) H4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1370,14 +1269,9 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         if (lane == 0) {
             const unsigned char* gt = reinterpret_cast<const unsigned char*>(tiles) + ((size_t)g * NB + B0) * TILE_BYTES;
             const long long* gv = vfix + B0 * R;
-            unsigned sleep_ns = 0;
-            if constexpr ((V & 2) != 0) sleep_ns = g_hist_sleep_ns[0];
             for (int k = 0; k < nst; k++) {
                 const int s2 = k % STAGES;
-                if (k >= STAGES) {
-                    if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / STAGES) + 1) & 1, sleep_ns);
-                    else mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
-                }
+                if (k >= STAGES) mbar_wait(&empty[s2], ((k / STAGES) + 1) & 1);
                 unsigned char* st = stage0 + (size_t)s2 * STAGE_BYTES;
                 mbar_expect_tx(&full[s2], STAGE_BYTES);
                 bulk_g2s(st, gt + (size_t)k * TILE_BYTES, TILE_BYTES, &full[s2]);
@@ -1406,7 +1300,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         HChunk cur, nxt;
         mbar_wait(&full[0], 0);
         load(cur, st0, ph);
-        if constexpr ((V & 1) != 0) {
+        if constexpr (V != 0) {
             // one stage: CPS chunks; the last chunk's read-ahead is the first chunk of stage k + 1 unless the stage is the CTA's last
             auto stage = [&](int k, auto lastTag) {
                 constexpr bool LAST = decltype(lastTag)::value;
@@ -1424,11 +1318,10 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                         }
                         mbar_arrive(&empty[s2]);   // per thread, as below
                     }
-                    hist_step<V>(cur, nxt);   // (bit 5: the CTA's very last step merges a stale nxt, which nobody uses)
+                    hist_rmw8(cur);
                     cur = nxt;
                 }
             };
-            if constexpr ((V & 32) != 0) hist_merge8<V>(cur);
             for (int k = 0; k + 1 < nst; k++) stage(k, std::false_type{});
             stage(nst - 1, std::true_type{});
         } else
@@ -1469,13 +1362,16 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 // The row count rides in the top 12 bits of the same accumulator (v + 2^52, decoded at flush; a private bin holds at
 // most 2032 rows between flushes).  CTAs whose row range is empty return before touching shared memory.
 // ------------------------------------------------------------------------------------------------
-// V (bit mask, RLB_HIST_VARIANT): 0 = the kernel as measured in round 2; bits 0 and 1 as in k_hist_root (peeled last full
-// stage: 24 moves per stage less; sleeping producer poll);
-//   bit 2: the producer stores the response of row 16 b + 2 w + odd at slot 16 b + 8 odd + w of the stage, so the eight
-//          responses of a thread's chunk are 64 contiguous bytes: four LDS.128 instead of eight LDS.64 (the short-scoreboard
-//          stalls on these loads were 16 % of the kernel's samples);
-//   bit 4 (needs bit 2): private-histogram address as one multiply-add;  bits 3, 5 (need bit 0): see hist_step;
-//   bit 6: 16-byte clears and the two-operation count decode of hist_flush<.., FAST>.
+// V (RLB_HIST_VARIANT): 0 = the kernel as first measured in round 2; 1 (default) =
+//   * last full stage peeled off the stage loop, as in k_hist_root (24 register moves per stage less);
+//   * the producer stores the response of row 16 b + 2 w + odd at slot 16 b + 8 odd + w of the stage, so the eight
+//     responses of a thread's chunk are 64 contiguous bytes: four LDS.128 instead of eight LDS.64 (the short-scoreboard
+//     stalls on these loads were 16 % of the kernel's samples);
+//   * private-histogram address as ONE multiply-add (ptxas otherwise keeps bin * 768 for the equality tests and adds the
+//     column offset separately: 24 more instructions per stage);
+//   * 16-byte clears and the two-operation count decode of hist_flush<.., FAST> (the flush is a third of a small node's
+//     launch).
+//   Together 0.493 -> 0.443 ms of child histograms per iteration at the C2 shape (profiles/r2x_variants.jsonl).
 template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,
@@ -1499,9 +1395,9 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     unsigned long long* empty = full + HSTAGES;
     int32_t* iring = reinterpret_cast<int32_t*>(empty + HSTAGES);                  // HIDX x R sample indices
 
-    // slot of stage row j's response (bit 2 of V: the rows of a (16-row block, phase parity) are stored together)
+    // slot of stage row j's response (V = 1: the rows of a (16-row block, phase parity) are stored together)
     auto vslot = [](int j) -> int {
-        if constexpr ((V & 4) != 0) return (j & ~15) | ((j & 1) << 3) | ((j & 15) >> 1);
+        if constexpr (V != 0) return (j & ~15) | ((j & 1) << 3) | ((j & 15) >> 1);
         else return j;
     };
     pdl_trigger();
@@ -1527,7 +1423,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     if (nst == 0) return;  // nothing to add (small nodes leave most CTAs without rows): skip the 197 KB clear + flush
     const int nfull = (int)((r1 - r0) / R);
 
-    if constexpr ((V & 64) != 0) {   // 16 bytes per store
+    if constexpr (V != 0) {   // 16 bytes per store
         static_assert((RLB_T * T) % 2 == 0, "whole uint4");
         uint4* H4 = reinterpret_cast<uint4*>(H);
         for (int i = tid; i < RLB_T * T / 2; i += blockDim.x) H4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1559,15 +1455,10 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        unsigned sleep_ns = 0;
-        if constexpr ((V & 2) != 0) sleep_ns = g_hist_sleep_ns[1];
         for (int d = 0; d < HIDX; d++) fetch_idx(d);   // stages past the end commit empty groups: the count stays uniform
         for (int k = 0; k < nst; k++) {
             const int s2 = k % HSTAGES;
-            if (k >= HSTAGES) {
-                if constexpr ((V & 2) != 0) mbar_wait_sleep(&empty[s2], ((k / HSTAGES) + 1) & 1, sleep_ns);
-                else mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
-            }
+            if (k >= HSTAGES) mbar_wait(&empty[s2], ((k / HSTAGES) + 1) & 1);
             const int64_t base = r0 + (int64_t)k * R;
             const int nr = (int)min((int64_t)R, r1 - base);
             unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
@@ -1603,22 +1494,15 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         // rows of block b owned by this thread: 16 b + 2 w + odd, w = 0..7
         auto load = [&](HChunk& c, uint32_t sb, int blk) {
             const uint32_t ba = sb + (blk * 16 + odd) * 32 + fi * 2;
-            if constexpr ((V & 4) != 0) {
+            if constexpr (V != 0) {
                 const uint32_t va = sb + R * 32 + (blk * 16 + odd * 8) * 8;
                 lds128ll(va, c.v[0], c.v[1]);
                 lds128ll(va + 16, c.v[2], c.v[3]);
                 lds128ll(va + 32, c.v[4], c.v[5]);
                 lds128ll(va + 48, c.v[6], c.v[7]);
 #pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    if constexpr ((V & 16) != 0) {
-                        // one IMAD: ptxas otherwise keeps bin * 768 for the equality tests and adds hme separately (24 more
-                        // instructions per stage)
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c.a[w]) : "r"(lds16(ba + w * 64)), "r"((uint32_t)(T * 8)), "r"(hme));
-                    } else {
-                        c.a[w] = hme + lds16(ba + w * 64) * (T * 8);
-                    }
-                }
+                for (int w = 0; w < 8; w++)
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c.a[w]) : "r"(lds16(ba + w * 64)), "r"((uint32_t)(T * 8)), "r"(hme));
             } else {
                 const uint32_t va = sb + R * 32 + (blk * 16 + odd) * 8;
 #pragma unroll
@@ -1634,13 +1518,13 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
             HChunk cur, nxt;
             mbar_wait(&full[0], 0);
             load(cur, st0, pp);
-            if constexpr ((V & 1) != 0) {
+            if constexpr (V != 0) {
                 auto stage = [&](int k, auto lastTag) {
                     constexpr bool LAST = decltype(lastTag)::value;
                     const int s2 = k % HSTAGES;
                     const uint32_t sb = st0 + s2 * STAGE_BYTES;
                     // the packed (count, sum) accumulators hold at most 2^11 rows
-                    if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
+                    if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, V != 0>(H, tid, g, F, sum, cnt);
 #pragma unroll
                     for (int j = 0; j < BPP; j++) {
                         if (j + 1 < BPP) {
@@ -1653,11 +1537,10 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                             }
                             mbar_arrive(&empty[s2]);   // this thread's reads of stage s2 are behind it
                         }
-                        hist_step<V>(cur, nxt);
+                        hist_rmw8(cur);
                         cur = nxt;
                     }
                 };
-                if constexpr ((V & 32) != 0) hist_merge8<V>(cur);
                 for (int k = 0; k + 1 < nfull; k++) stage(k, std::false_type{});
                 stage(nfull - 1, std::true_type{});
             } else
@@ -1665,7 +1548,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 const int s2 = k % HSTAGES;
                 const uint32_t sb = st0 + s2 * STAGE_BYTES;
                 // the packed (count, sum) accumulators hold at most 2^11 rows
-                if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
+                if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, V != 0>(H, tid, g, F, sum, cnt);
 #pragma unroll
                 for (int j = 0; j < BPP; j++) {
                     if (j + 1 < BPP) {
@@ -1686,7 +1569,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
         if (nst > nfull) {  // the partial last stage, row by row
             const int k = nfull;
             const int s2 = k % HSTAGES;
-            if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, (V & 64) != 0>(H, tid, g, F, sum, cnt);
+            if (k > 0 && (k % FLUSH_STAGES) == 0) hist_flush<true, PH, true, V != 0>(H, tid, g, F, sum, cnt);
             mbar_wait(&full[s2], (k / HSTAGES) & 1);
             const unsigned char* bt = tiles + (size_t)s2 * STAGE_BYTES;
             const unsigned short* btile = reinterpret_cast<const unsigned short*>(bt);
@@ -1700,7 +1583,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
                 }
             }
         }
-        hist_flush<true, PH, false, (V & 64) != 0>(H, tid, g, F, sum, cnt);
+        hist_flush<true, PH, false, V != 0>(H, tid, g, F, sum, cnt);
     }
 }
 
@@ -3874,32 +3757,12 @@ static constexpr size_t hist_smem_child() {
 }
 static constexpr int hist_threads() { return 32 * ((HG * HPH + 31) / 32 + 1); }
 
-// the instantiation c->hist_variant selects (RLB_HIST_VARIANT, see the kernels' headers)
+// the instantiation c->hist_variant selects (RLB_HIST_VARIANT: 1 = default, 0 = the kernels as first measured in round 2)
 using HistRootFn = void (*)(const uint16_t*, const long long*, int64_t, int, int, long long*);
 using HistChildFn = void (*)(const uint16_t*, int, int, const long long*, const int32_t*, const int32_t*, long long*, int32_t*,
                              DevState*, int, size_t);
-static HistRootFn hist_root_fn(const rlb_ctx* c) {
-    switch (c->hist_variant & (1 | 2 | 8 | 32 | 64)) {   // bits 2 and 4 are child-kernel variants
-        case 1: return k_hist_root<1>;
-        case 3: return k_hist_root<3>;
-        case 33: return k_hist_root<33>;
-        case 65: return k_hist_root<65>;
-        default: return k_hist_root<0>;
-    }
-}
-static HistChildFn hist_child_fn(const rlb_ctx* c) {
-    switch (c->hist_variant & 127) {
-        case 1: return k_hist_child<1>;
-        case 3: return k_hist_child<3>;
-        case 5: return k_hist_child<5>;
-        case 7: return k_hist_child<7>;
-        case 21: return k_hist_child<21>;
-        case 37: return k_hist_child<37>;
-        case 69: return k_hist_child<69>;
-        case 85: return k_hist_child<85>;
-        default: return k_hist_child<0>;
-    }
-}
+static HistRootFn hist_root_fn(const rlb_ctx* c) { return c->hist_variant ? k_hist_root<1> : k_hist_root<0>; }
+static HistChildFn hist_child_fn(const rlb_ctx* c) { return c->hist_variant ? k_hist_child<1> : k_hist_child<0>; }
 static int hist_groups(const rlb_ctx* c) { return (c->F + HG - 1) / HG; }
 static int hist_grid(const rlb_ctx* c) { return std::max(c->sm_count, hist_groups(c)); }
 
@@ -4038,16 +3901,6 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
 
 // one-time kernel attributes (must not happen inside a stream capture)
 int rlb_impl_prepare(rlb_ctx* c) {
-    {
-        const char* er = getenv("RLB_HIST_SLEEP_ROOT");
-        const char* ec = getenv("RLB_HIST_SLEEP_CHILD");
-        if (er || ec) {
-            unsigned ns[2] = {64u, 32u};
-            if (er) ns[0] = (unsigned)std::max(0, atoi(er));
-            if (ec) ns[1] = (unsigned)std::max(0, atoi(ec));
-            RLB_CUDA(c, cudaMemcpyToSymbol(g_hist_sleep_ns, ns, sizeof(ns)));
-        }
-    }
     RLB_CUDA(c, cudaFuncSetAttribute(hist_root_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
     RLB_CUDA(c, cudaFuncSetAttribute(hist_child_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
     RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));

@@ -14,7 +14,7 @@
 #include "../../include/ranklib_b200.h"
 
 #ifndef RLB_HIST_VARIANT_DEFAULT
-#define RLB_HIST_VARIANT_DEFAULT 0
+#define RLB_HIST_VARIANT_DEFAULT 1
 #endif
 
 // NCCL is bound at run time (dlopen) the first time a communicator is needed: a single-GPU user never loads
@@ -200,7 +200,7 @@ struct rlb_ctx {
     int64_t N = 0, N_total = 0, Q_total = 0;
     int32_t F = 0, Fp = 0, Q = 0, max_query = 0;
     bool loaded = false, inited = false, have_thr = false, tree_ready = false, tree_output_ready = false;
-    int hist_variant = RLB_HIST_VARIANT_DEFAULT;   // bit mask of the histogram kernels' variants (RLB_HIST_VARIANT; rlb_boost.cu)
+    int hist_variant = RLB_HIST_VARIANT_DEFAULT;   // 1 = current histogram kernels, 0 = as first measured in round 2 (RLB_HIST_VARIANT)
     bool thr_user = false;          // h_thr was imposed by rlb_set_thresholds (kept across re-inits); else derived from the data
     int32_t thr_built_for = 0;      // n_threshold the derived thresholds were built with
     bool lambda_fresh = false;      // dLambda / dWeight / scales belong to the current dScore

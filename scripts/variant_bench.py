@@ -1,8 +1,11 @@
 """Development aid: the histogram kernels' variants (RLB_HIST_VARIANT, rlb_boost.cu) side by side in ONE process.
 
-    python scripts/variant_bench.py [variants, default 0,1,3,5,7] [repeats, default 3] [steps, default 20]
+    python scripts/variant_bench.py [variants, default 0,1] [repeats, default 3] [steps, default 20]
 
-A variant is `mask` or `mask:root_ns:child_ns` (sleep between two polls of the producers, RLB_HIST_SLEEP_ROOT / _CHILD).
+RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2, 1 = the current default.  (While the default was being chosen
+the value was a bit mask of the individual changes — profiles/r2x_variants*.jsonl: 1 peeled last stage, 2 sleeping producer
+poll, 4 child response layout, 8 multiply-add merge, 16 fused child address, 32 hand-pipelined merge, 64 16-byte clears +
+fast count decode; 85 = 1 + 4 + 16 + 64 is what became variant 1.)
 
 For every variant: a fresh context on the full C2 workload (synthetic, 1.2 M documents x 136 features), 5 warm-up
 iterations, `steps` timed iterations through rlb_boost_iters (CUDA events on the context's stream), then the same steps with
@@ -24,7 +27,7 @@ def main():
     import torch
     import bench
     from ranklib_b200.host import native
-    variants = (sys.argv[1] if len(sys.argv) > 1 else "0,1,3,5,7").split(",")
+    variants = (sys.argv[1] if len(sys.argv) > 1 else "0,1").split(",")
     repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     torch.cuda.set_device(0)
@@ -35,8 +38,7 @@ def main():
     res = {v: {"ms": [], "root_ms": [], "child_ms": [], "crc": set()} for v in variants}
     for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
         for v in variants:
-            spec = (v.split(":") + ["64", "32"])[:3] if ":" in v else [v, "64", "32"]
-            os.environ["RLB_HIST_VARIANT"], os.environ["RLB_HIST_SLEEP_ROOT"], os.environ["RLB_HIST_SLEEP_CHILD"] = spec
+            os.environ["RLB_HIST_VARIANT"] = v
             ctx = native.Context(0)
             ctx.load_dense(Xp, label, qoff)
             ctx.init(params)
