@@ -676,7 +676,12 @@ __device__ __forceinline__ void group_sync() {
         __syncthreads();
 }
 
-template <int G>
+// LV (RLB_LAMBDA_VARIANT): 0 = the accumulation loops as first measured in round 2 (a branch per visited pair: the lanes of a
+// warp own different documents, so the branch diverges on almost every iteration and pays BSSY / BSYNC around a body
+// that runs anyway); 1 = branch-free: the table entry is always read and a pair that does not count contributes +0.0.
+// Bit-identical: acc starts as +0.0 and a sum of doubles is -0.0 only when every term is -0.0, so acc is never -0.0
+// and acc + (+0.0) == acc exactly; entries of equal-label pairs are never written, but they are never SELECTED either.
+template <int G, int LV>
 __device__ __forceinline__ void query_fast(int q, int gt, const double* __restrict__ score, const float* __restrict__ label,
                                            const int32_t* __restrict__ qoff, int cutoff, int metric,
                                            const double* __restrict__ disc, const double* __restrict__ idealIn,
@@ -802,7 +807,32 @@ __device__ __forceinline__ void query_fast(int q, int gt, const double* __restri
             const double* T = isW ? tW : tL;
             const float lp = sLabel[p];
             double acc = 0.0;
-            if (size > 0) {
+            if (LV != 0 && size > 0) {
+                const int j1 = min(p, size);
+                for (int j = 0; j < j1; j++) {  // (1) outer j < p: p loses to every better-labelled j in the top `size`
+                    const double t = T[j * n + p];
+                    acc += (sLabel[j] > lp) ? (isW ? t : -t) : 0.0;
+                }
+                if (p < size) {
+                    for (int k = 0; k < p; k++) {  // (2) outer j == p: p wins over every worse-labelled k (k < p, then k > p)
+                        const double t = T[k * n + p];
+                        acc += (lp > sLabel[k]) ? t : 0.0;
+                    }
+                    for (int k = p + 1; k < n; k++) {
+                        const double t = T[p * n + k];
+                        acc += (lp > sLabel[k]) ? t : 0.0;
+                    }
+                    for (int j = p + 1; j < n; j++) {  // (3) outer j > p
+                        const double t = T[p * n + j];
+                        acc += (sLabel[j] > lp) ? (isW ? t : -t) : 0.0;
+                    }
+                } else {
+                    for (int k = 0; k < size; k++) {
+                        const double t = T[k * n + p];
+                        acc += (lp > sLabel[k]) ? t : 0.0;
+                    }
+                }
+            } else if (size > 0) {
                 const int j1 = min(p, size);
                 for (int j = 0; j < j1; j++)  // (1) outer j < p: p loses to every better-labelled j in the top `size`
                     if (sLabel[j] > lp) {
@@ -847,6 +877,7 @@ __device__ __forceinline__ void publish_max(double thrMax, DevState* st) {
     if ((threadIdx.x & 31) == 0 && b) atomicMax(&st->max_abs_bits, b);
 }
 
+template <int LV>
 __global__ void __launch_bounds__(256) k_query_warp(const double* __restrict__ score, const float* __restrict__ label,
                                                      const int32_t* __restrict__ qoff, const int32_t* __restrict__ qlist, int nq,
                                                      int cutoff, int metric, const double* __restrict__ disc,
@@ -868,12 +899,12 @@ __global__ void __launch_bounds__(256) k_query_warp(const double* __restrict__ s
     double thrMax = 0.0;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
     for (int i = gw; i < nq; i += nw)
-        query_fast<32>(qlist[i], lane, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw, sScore,
+        query_fast<32, LV>(qlist[i], lane, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw, sScore,
                        sLabel, sDoc, tL, tW, auxD, auxI, sAux, QA_N, thrMax);
     if (lambda) publish_max(thrMax, st);
 }
 
-template <int G>
+template <int G, int LV>
 __global__ void __launch_bounds__(G) k_query_block(const double* __restrict__ score, const float* __restrict__ label,
                                                     const int32_t* __restrict__ qoff, const int32_t* __restrict__ qlist, int nq,
                                                     int cutoff, int metric, const double* __restrict__ disc,
@@ -892,7 +923,7 @@ __global__ void __launch_bounds__(G) k_query_block(const double* __restrict__ sc
     int* auxI = sDoc + capN;
     double thrMax = 0.0;
     for (int i = blockIdx.x; i < nq; i += gridDim.x)
-        query_fast<G>(qlist[i], threadIdx.x, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw,
+        query_fast<G, LV>(qlist[i], threadIdx.x, score, label, qoff, cutoff, metric, disc, idealIn, lambda, weight, qmetric, sRaw,
                       sScore, sLabel, sDoc, tL, tW, auxD, auxI, sAux, capN, thrMax);
     if (lambda) publish_max(thrMax, st);
 }
@@ -3661,6 +3692,7 @@ static int launch_queries(rlb_ctx* c, const QuerySet& qs, bool want_lambda, doub
     double* lam = want_lambda ? c->dLambda : nullptr;
     double* wgt = want_lambda ? c->dWeight : nullptr;
     const int k = c->prm.metric_k, m = c->prm.metric;
+    const bool lv = c->lambda_variant != 0;
     // The size classes are independent: run them as parallel branches (fork / join with events; inside a stream
     // capture this becomes parallel graph branches).  The warp-path kernel stays on the main stream.
     int nside = 0;
@@ -3674,21 +3706,21 @@ static int launch_queries(rlb_ctx* c, const QuerySet& qs, bool want_lambda, doub
     };
     if (qs.nqB0 > 0) {   // 65 .. 128 documents: two warps per query (a 128-thread CTA mostly waits at its barriers here)
         const int grid = std::min(qs.nqB0, c->sm_count * 8);
-        k_query_block<64><<<grid, 64, smB0, branch(3)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA, qs.nqB0, k, m, c->dDisc,
+        (lv ? k_query_block<64, 1> : k_query_block<64, 0>)<<<grid, 64, smB0, branch(3)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA, qs.nqB0, k, m, c->dDisc,
                                                          qs.dIdeal, lam, wgt, qmetric, c->dState, B0N, B0T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[3], c->side[3]));
     }
     if (qs.nqB1 > 0) {
         const int grid = std::min(qs.nqB1, c->sm_count * 4);
-        k_query_block<128><<<grid, 128, smB1, branch(0)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0, qs.nqB1, k, m, c->dDisc,
+        (lv ? k_query_block<128, 1> : k_query_block<128, 0>)<<<grid, 128, smB1, branch(0)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0, qs.nqB1, k, m, c->dDisc,
                                                            qs.dIdeal, lam, wgt, qmetric, c->dState, B1N, B1T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
     }
     if (qs.nqB2 > 0) {
         const int grid = std::min(qs.nqB2, c->sm_count);
-        k_query_block<256><<<grid, 256, smB2, branch(1)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0 + qs.nqB1, qs.nqB2, k, m,
+        (lv ? k_query_block<256, 1> : k_query_block<256, 0>)<<<grid, 256, smB2, branch(1)>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList + qs.nqA + qs.nqB0 + qs.nqB1, qs.nqB2, k, m,
                                                            c->dDisc, qs.dIdeal, lam, wgt, qmetric, c->dState, B2N, B2T);
         RLB_CHECK_LAUNCH(c);
         if (fork) RLB_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
@@ -3710,7 +3742,7 @@ static int launch_queries(rlb_ctx* c, const QuerySet& qs, bool want_lambda, doub
     }
     if (qs.nqA > 0) {
         const int grid = std::min((qs.nqA + 7) / 8, c->sm_count * 2);
-        k_query_warp<<<grid, 256, smA, c->stream>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList, qs.nqA, k, m, c->dDisc, qs.dIdeal, lam, wgt,
+        (lv ? k_query_warp<1> : k_query_warp<0>)<<<grid, 256, smA, c->stream>>>(qs.dScore, qs.dLabel, qs.dQoff, qs.dQList, qs.nqA, k, m, c->dDisc, qs.dIdeal, lam, wgt,
                                                     qmetric, c->dState);
         RLB_CHECK_LAUNCH(c);
     }
@@ -3903,10 +3935,17 @@ int rlb_impl_tree_fit(rlb_ctx* c) {
 int rlb_impl_prepare(rlb_ctx* c) {
     RLB_CUDA(c, cudaFuncSetAttribute(hist_root_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_root()));
     RLB_CUDA(c, cudaFuncSetAttribute(hist_child_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_child()));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 44 + 1280 * 16 + 64));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));
-    RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 44 + 10240 * 16 + 64));
+    if (c->lambda_variant) {
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 44 + 1280 * 16 + 64));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 44 + 10240 * 16 + 64));
+    } else {
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * QA_WARP_BYTES));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 44 + 1280 * 16 + 64));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 44 + 2560 * 16 + 64));
+        RLB_CUDA(c, cudaFuncSetAttribute(k_query_block<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 44 + 10240 * 16 + 64));
+    }
     return RLB_OK;
 }
 

@@ -15,7 +15,9 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 echo "== variants"
 timeout 240 python scripts/variant_bench.py "$LIST" 3 20 > "$OUT/${TAG}_variants.jsonl" 2> "$OUT/${TAG}_variants.err"
 echo "rc=$?"; cat "$OUT/${TAG}_variants.jsonl"; tail -3 "$OUT/${TAG}_variants.err"
+if [ "$V" != "notest" ]; then
 echo "== tests with RLB_HIST_VARIANT=$V"
 RLB_HIST_VARIANT=$V timeout 240 python -m pytest tests -m gpu -x -q > "$OUT/${TAG}_tests_v${V}.log" 2>&1
 echo "rc=$?"; tail -3 "$OUT/${TAG}_tests_v${V}.log"
+fi
 echo "== done"

@@ -2,7 +2,8 @@
 
     python scripts/variant_bench.py [variants, default 0,1] [repeats, default 3] [steps, default 20]
 
-RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2, 1 = the current default.  (While the default was being chosen
+A variant is "<RLB_HIST_VARIANT>[:<RLB_LAMBDA_VARIANT>]".  RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2,
+1 = the current default; RLB_LAMBDA_VARIANT: 0 = branchy accumulation loops, 1 = branch-free (query_fast, rlb_boost.cu).  (While the default was being chosen
 the value was a bit mask of the individual changes — profiles/r2x_variants*.jsonl: 1 peeled last stage, 2 sleeping producer
 poll, 4 child response layout, 8 multiply-add merge, 16 fused child address, 32 hand-pipelined merge, 64 16-byte clears +
 fast count decode; 85 = 1 + 4 + 16 + 64 is what became variant 1.)
@@ -35,10 +36,12 @@ def main():
     Xpin = torch.from_numpy(X).pin_memory()   # kept alive: the contexts upload from this pinned buffer
     Xp = Xpin.numpy()
     params = native.make_params()
-    res = {v: {"ms": [], "root_ms": [], "child_ms": [], "crc": set()} for v in variants}
+    res = {v: {"ms": [], "root_ms": [], "child_ms": [], "lambda_ms": [], "crc": set()} for v in variants}
     for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
         for v in variants:
-            os.environ["RLB_HIST_VARIANT"] = v
+            hv, _, lv = v.partition(":")          # "<histogram variant>[:<lambda variant>]"
+            os.environ["RLB_HIST_VARIANT"] = hv
+            os.environ["RLB_LAMBDA_VARIANT"] = lv or "0"
             ctx = native.Context(0)
             ctx.load_dense(Xp, label, qoff)
             ctx.init(params)
@@ -70,6 +73,7 @@ def main():
             r["ms"].append(ms)
             r["root_ms"].append(prof[0] / max(prof[1], 1))
             r["child_ms"].append(prof[3] / steps)
+            r["lambda_ms"].append(prof[6] / steps)
             r["crc"].add(crc & 0xffffffff)
     ref = res[variants[0]]["crc"]
     for v in variants:
@@ -78,6 +82,7 @@ def main():
         print(json.dumps({"variant": v, "ms_per_step": [round(x, 4) for x in r["ms"]], "ms_per_step_min": round(min(r["ms"]), 4),
                           "iters_per_s_best": round(1000.0 / min(r["ms"]), 1),
                           "root_ms": [round(x, 4) for x in r["root_ms"]], "child_ms_per_step": [round(x, 4) for x in r["child_ms"]],
+                          "lambda_ms_per_step": [round(x, 4) for x in r["lambda_ms"]],
                           "trees": "same as variant %s" % variants[0] if ok else "WRONG",
                           "crc": sorted(f"{c:08x}" for c in r["crc"])}), flush=True)
 
