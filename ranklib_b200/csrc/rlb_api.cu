@@ -332,6 +332,7 @@ int rlb_lambdamart_init(rlb_ctx* c, const rlb_params* params) {
     c->Q_total = q;
     if (const char* e = getenv("RLB_NO_GRAPH")) c->use_graph = (atoi(e) == 0);
     if (const char* e = getenv("RLB_PDL")) c->pdl = (atoi(e) != 0);
+    if (const char* e = getenv("RLB_ITER_VARIANT")) c->iter_variant = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("RLB_LAMBDA_VARIANT")) c->lambda_variant = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("RLB_HIST_VARIANT")) c->hist_variant = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("RLB_GRAPH_MULTI")) c->graph_multi = (atoi(e) != 0);

@@ -2026,6 +2026,10 @@ __global__ void __launch_bounds__(288) k_scan(DevState* __restrict__ st, TreePar
 // scatters.  Tile states carry the split ordinal as an epoch, so nothing has to be cleared between steps.
 // Also: clears the staging histogram slot, accumulates the squared responses of the rows on the scanned side,
 // creates the two child records.
+// PV (RLB_ITER_VARIANT): 0 = as first measured in round 2: the squared response of a row is fetched only once its side is
+// known (sample index -> bin -> squared response: three dependent memory round trips per tile); 1 = bin and squared
+// response are fetched together and the side selects afterwards (two round trips; integer sums, so nothing else changes).
+template <int PV>
 __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, const uint16_t* __restrict__ binsT, int64_t Nrows,
                                                      int32_t* __restrict__ samples0, int32_t* __restrict__ samples1,
                                                      unsigned long long* __restrict__ tileState, long long* __restrict__ stageSum,
@@ -2100,6 +2104,27 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
             const int i = base + k;
             doc[k] = (i < n) ? src[lo + i] : -1;
         }
+        if constexpr (PV != 0) {
+            int bv[8];
+            long long sv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int d = doc[k] >= 0 ? doc[k] : 0;   // rows past the node's end read row 0 and are discarded below
+                bv[k] = bcol[d];
+                sv[k] = sqfix[d];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (doc[k] >= 0) {
+                    const bool left = bv[k] <= btv;
+                    if (left) {
+                        mask |= 1u << k;
+                        c++;
+                    }
+                    sq += (left == smallLeft) ? sv[k] : 0LL;  // squared responses of the scanned (smaller) child
+                }
+            }
+        } else {
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (doc[k] >= 0) {
@@ -2110,6 +2135,7 @@ __global__ void __launch_bounds__(256) k_part_fused(DevState* __restrict__ st, c
                 }
                 if (left == smallLeft) sq += sqfix[doc[k]];  // squared responses of the scanned (smaller) child
             }
+        }
         }
         for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
         if (lane == 0 && sq != 0) atomicAdd((unsigned long long*)stageSq, (unsigned long long)sq);
@@ -2334,6 +2360,9 @@ __global__ void __launch_bounds__(256) k_part_scatter(DevState* __restrict__ st,
 // derive the sibling by subtraction from the parent (:222-234, exact in fixed point), then the last
 // CTA computes the children's deviances (:349-350), inserts them in the queue and selects the next
 // node (RegressionTree.java:69-85).
+// PV (RLB_ITER_VARIANT, as k_part_fused): 1 = the parent's cumulative histogram entry is fetched together with the staged
+// child entry instead of behind the block scan (one global round trip less on the kernel's critical path).
+template <int PV>
 __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeParams tp, long long* __restrict__ histSum,
                                                  int32_t* __restrict__ histCnt, size_t hist_stride,
                                                  const long long* __restrict__ stageSum,
@@ -2374,6 +2403,12 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
     long long vS = 0, oS = 0;
     int vC = 0, oC = 0;
     int lC = 0;   // this rank's own raw count of the scanned child (N GPUs: kept cumulative per node for the one-pass partition)
+    long long pS0 = 0;
+    int pC0 = 0;
+    if (PV != 0 && t < RLB_T) {
+        pS0 = histSum[(size_t)parent * hist_stride + o];
+        pC0 = histCnt[(size_t)parent * hist_stride + o];
+    }
     if (t < RLB_T) {
         if (peers) {
             lC = stageCnt[o];
@@ -2432,8 +2467,8 @@ __global__ void __launch_bounds__(288) k_finish(DevState* __restrict__ st, TreeP
         histCntL[(size_t)other * hist_stride + o] = pL - lC;
     }
     if (t < RLB_T) {
-        const long long pS = histSum[(size_t)parent * hist_stride + o];
-        const int pC = histCnt[(size_t)parent * hist_stride + o];
+        const long long pS = PV != 0 ? pS0 : histSum[(size_t)parent * hist_stride + o];
+        const int pC = PV != 0 ? pC0 : histCnt[(size_t)parent * hist_stride + o];
         histSum[(size_t)small * hist_stride + o] = vS;
         histCnt[(size_t)small * hist_stride + o] = vC;
         histSum[(size_t)other * hist_stride + o] = pS - vS;
@@ -3538,13 +3573,47 @@ __global__ void k_leaf_finalize(DevState* st, int kind, const PeerTab* peers) {
 
 // K8: modelScores[k] += learningRate * leaf output (LambdaMART.java:203-210); also records the node
 // of every doc for rlb_read.
+// PV (RLB_ITER_VARIANT): 1 = the leaf table (segment starts, sample buffer, lr * output) is staged in shared memory once per
+// CTA and searched there; 0 = every row walks the table in global memory (five dependent loads per row).
+template <int PV>
 __global__ void __launch_bounds__(256) k_score_update(DevState* __restrict__ st, const int32_t* __restrict__ samples0,
                                                        const int32_t* __restrict__ samples1, double* __restrict__ score,
                                                        int32_t* __restrict__ nodeOf, int64_t N, float lr, int apply) {
     const int nl = st->n_leaves_out;
     if (nl == 0) return;  // unfinished tree (see k_tree_end)
+    constexpr int LCAP = 1024;
+    __shared__ int sLo[PV != 0 ? LCAP : 1];
+    __shared__ int sNode[PV != 0 ? LCAP : 1];
+    __shared__ double sAdd[PV != 0 ? LCAP : 1];
+    __shared__ unsigned char sBuf[PV != 0 ? LCAP : 1];
+    const bool staged = PV != 0 && nl <= LCAP;
+    if (staged) {
+        for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+            const int node = st->leaf_nodes[i];
+            const NodeRec& r = st->nodes[node];
+            sLo[i] = (int)st->leaf_lo[i];
+            sNode[i] = node;
+            sAdd[i] = (double)lr * (double)r.output;
+            sBuf[i] = (unsigned char)(r.buf ? 1 : 0);
+        }
+        __syncthreads();
+    }
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = nl - 1;  // last leaf with leaf_lo <= p
+        if (staged) {
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sLo[mid] <= p)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            while (lo + 1 < nl && sLo[lo + 1] <= p) lo++;
+            const int doc = (sBuf[lo] ? samples1 : samples0)[p];
+            if (apply) score[doc] += sAdd[lo];
+            nodeOf[doc] = sNode[lo];
+            continue;
+        }
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (st->leaf_lo[mid] <= p)
@@ -3846,7 +3915,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
         if (c->world == 1 || c->p2p) {
             // one pass: the number of this rank's rows going left is known beforehand (N GPUs: from the rank's own cumulative
             // counts, which the peer-memory path keeps per node)
-            launch_pdl(c, k_part_fused, dim3(c->grid_rows), dim3(256), 0, c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1],
+            launch_pdl(c, c->iter_variant ? k_part_fused<1> : k_part_fused<0>, dim3(c->grid_rows), dim3(256), 0, c->dState, c->dBinsT, c->N, c->dSamples[0], c->dSamples[1],
                        c->dTileState, stageSum, stageCnt, c->hist_stride, c->dSqfix, stageSq, stageStride, c->p2p ? 1 : 0);
             RLB_CHECK_LAUNCH(c);
         } else {  // NCCL path: local left counts are not known in advance: count pass + scatter pass
@@ -3866,7 +3935,7 @@ static int enqueue_split_steps(rlb_ctx* c, int steps) {
             // and its squared-sum scalar, at fixed addresses
             if (int rc = rlb_allreduce_i64(c, c->dStage, c->hist_stride + (c->hist_stride + 1) / 2 + 1)) return rc;
         }
-        launch_pdl(c, k_finish, dim3(c->F), dim3(288), 0, c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt,
+        launch_pdl(c, c->iter_variant ? k_finish<1> : k_finish<0>, dim3(c->F), dim3(288), 0, c->dState, tp, c->dHistSum, c->dHistCnt, c->hist_stride, stageSum, stageCnt,
                    c->dUsed, c->dUsed + c->F, c->dNThr, c->dNodeFeatS, c->dNodeFeatT, stageSq, (c->world == 1 || c->p2p) ? 1 : 0,
                    stageStride, c->p2p ? c->dPeers : nullptr, c->p2p ? c->dHistCntL : nullptr);
         RLB_CHECK_LAUNCH(c);
@@ -4098,8 +4167,8 @@ int rlb_impl_update_scores(rlb_ctx* c) {
         rlb_set_error(c, RLB_E_INVALID, "rlb_update_scores", "leaf outputs not computed");
         return RLB_E_INVALID;
     }
-    k_score_update<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N,
-                                                        c->prm.learning_rate, 1);
+    (c->iter_variant ? k_score_update<1> : k_score_update<0>)<<<c->grid_rows, 256, 0, c->stream>>>(
+        c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N, c->prm.learning_rate, 1);
     RLB_CHECK_LAUNCH(c);
     c->tree_output_ready = false;  // a second call must not add the tree twice
     c->lambda_fresh = false;       // the pseudo responses belong to the old scores
@@ -4108,8 +4177,8 @@ int rlb_impl_update_scores(rlb_ctx* c) {
 
 // node id of every doc of the last tree without touching the scores (rlb_read)
 int rlb_impl_assign_nodes(rlb_ctx* c) {
-    k_score_update<<<c->grid_rows, 256, 0, c->stream>>>(c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N,
-                                                        c->prm.learning_rate, 0);
+    (c->iter_variant ? k_score_update<1> : k_score_update<0>)<<<c->grid_rows, 256, 0, c->stream>>>(
+        c->dState, c->dSamples[0], c->dSamples[1], c->dScore, c->dNodeOf, c->N, c->prm.learning_rate, 0);
     RLB_CHECK_LAUNCH(c);
     RLB_CUDA(c, cudaStreamSynchronize(c->stream));
     return RLB_OK;

@@ -2,7 +2,7 @@
 
     python scripts/variant_bench.py [variants, default 0,1] [repeats, default 3] [steps, default 20]
 
-A variant is "<RLB_HIST_VARIANT>[:<RLB_LAMBDA_VARIANT>]".  RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2,
+A variant is "<RLB_HIST_VARIANT>[:<RLB_LAMBDA_VARIANT>[:<RLB_ITER_VARIANT>]]".  RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2,
 1 = the current default; RLB_LAMBDA_VARIANT: 0 = branchy accumulation loops, 1 = branch-free (query_fast, rlb_boost.cu).  (While the default was being chosen
 the value was a bit mask of the individual changes — profiles/r2x_variants*.jsonl: 1 peeled last stage, 2 sleeping producer
 poll, 4 child response layout, 8 multiply-add merge, 16 fused child address, 32 hand-pipelined merge, 64 16-byte clears +
@@ -39,9 +39,10 @@ def main():
     res = {v: {"ms": [], "root_ms": [], "child_ms": [], "lambda_ms": [], "crc": set()} for v in variants}
     for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
         for v in variants:
-            hv, _, lv = v.partition(":")          # "<histogram variant>[:<lambda variant>]"
-            os.environ["RLB_HIST_VARIANT"] = hv
-            os.environ["RLB_LAMBDA_VARIANT"] = lv or "0"
+            spec = (v.split(":") + ["", ""])[:3]     # "<histogram variant>[:<lambda variant>[:<partition variant>]]"
+            os.environ["RLB_HIST_VARIANT"] = spec[0]
+            os.environ["RLB_LAMBDA_VARIANT"] = spec[1] or "0"
+            os.environ["RLB_ITER_VARIANT"] = spec[2] or "0"
             ctx = native.Context(0)
             ctx.load_dense(Xp, label, qoff)
             ctx.init(params)
