@@ -1247,7 +1247,7 @@ __device__ __forceinline__ void hist_flush(long long* H, int tid, int g, int F, 
 //   CTA = (group g, a contiguous range of tiles).  Thread (fi, ph) owns private histogram column tid.
 // ------------------------------------------------------------------------------------------------
 // V (RLB_HIST_VARIANT): 0 = the kernel as first measured in round 2 (kept selectable: the "before" arm of
-// profiles/r2x_variants.jsonl); 1 (default) =
+// profiles/r2x_variants_hist_b.jsonl); 1 (default) =
 //   * the last stage of a CTA is peeled off the stage loop.  With the `if (k + 1 < nst)` around the next stage's first tile
 //     read inside the loop, ptxas kept `cur` / `nxt` in fixed registers across the branch and paid 25 moves per stage
 //     (ncu source view); without it the two chunks alternate between two register sets: 442 -> 418 instructions and
@@ -1402,7 +1402,7 @@ __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
 //     column offset separately: 24 more instructions per stage);
 //   * 16-byte clears and the two-operation count decode of hist_flush<.., FAST> (the flush is a third of a small node's
 //     launch).
-//   Together 0.493 -> 0.443 ms of child histograms per iteration at the C2 shape (profiles/r2x_variants.jsonl).
+//   Together 0.493 -> 0.443 ms of child histograms per iteration at the C2 shape (profiles/r2x_variants_hist_b.jsonl).
 template <int V>
 __global__ void __launch_bounds__(32 * ((HG * HPH + 31) / 32 + 1), 1)
     k_hist_child(const uint16_t* __restrict__ bins, int Fp, int F, const long long* __restrict__ vfixc,

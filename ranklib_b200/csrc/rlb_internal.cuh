@@ -201,8 +201,8 @@ struct rlb_ctx {
     int32_t F = 0, Fp = 0, Q = 0, max_query = 0;
     bool loaded = false, inited = false, have_thr = false, tree_ready = false, tree_output_ready = false;
     int hist_variant = RLB_HIST_VARIANT_DEFAULT;   // 1 = current histogram kernels, 0 = as first measured in round 2 (RLB_HIST_VARIANT)
-    int iter_variant = 0;           // k_part_fused / k_finish / k_score_update variants (RLB_ITER_VARIANT; rlb_boost.cu)
-    int lambda_variant = 0;         // accumulation loops of the lambda kernels (RLB_LAMBDA_VARIANT; query_fast in rlb_boost.cu)
+    int iter_variant = 1;           // k_part_fused / k_finish / k_score_update variants (RLB_ITER_VARIANT; rlb_boost.cu)
+    int lambda_variant = 1;         // accumulation loops of the lambda kernels (RLB_LAMBDA_VARIANT; query_fast in rlb_boost.cu)
     bool thr_user = false;          // h_thr was imposed by rlb_set_thresholds (kept across re-inits); else derived from the data
     int32_t thr_built_for = 0;      // n_threshold the derived thresholds were built with
     bool lambda_fresh = false;      // dLambda / dWeight / scales belong to the current dScore

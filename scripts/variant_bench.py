@@ -1,18 +1,21 @@
-"""Development aid: the histogram kernels' variants (RLB_HIST_VARIANT, rlb_boost.cu) side by side in ONE process.
+"""Development aid: kernel variants side by side in ONE process, on the full C2 workload.
 
-    python scripts/variant_bench.py [variants, default 0,1] [repeats, default 3] [steps, default 20]
+    python scripts/variant_bench.py [variants, default 0:0:0,1:1:1] [repeats, default 3] [steps, default 20]
 
-A variant is "<RLB_HIST_VARIANT>[:<RLB_LAMBDA_VARIANT>[:<RLB_ITER_VARIANT>]]".  RLB_HIST_VARIANT: 0 = the kernels as first measured in round 2,
-1 = the current default; RLB_LAMBDA_VARIANT: 0 = branchy accumulation loops, 1 = branch-free (query_fast, rlb_boost.cu).  (While the default was being chosen
-the value was a bit mask of the individual changes — profiles/r2x_variants*.jsonl: 1 peeled last stage, 2 sleeping producer
-poll, 4 child response layout, 8 multiply-add merge, 16 fused child address, 32 hand-pipelined merge, 64 16-byte clears +
-fast count decode; 85 = 1 + 4 + 16 + 64 is what became variant 1.)
+A variant is "<RLB_HIST_VARIANT>[:<RLB_LAMBDA_VARIANT>[:<RLB_ITER_VARIANT>]]" (a missing field is 0); 0 always selects the
+kernels as first measured in round 2, 1 the current default:
+  RLB_HIST_VARIANT    k_hist_root / k_hist_child (peeled last stage, child response layout, fused address, flush decode)
+  RLB_LAMBDA_VARIANT  branch-free accumulation loops of the lambda kernels (query_fast)
+  RLB_ITER_VARIANT    k_part_fused / k_finish (loads fetched together), k_score_update (leaf table in shared memory)
+While the histogram default was being chosen RLB_HIST_VARIANT was a bit mask of the individual changes
+(profiles/r2x_variants_hist_*.jsonl: 1 peeled last stage, 2 sleeping producer poll, 4 child response layout, 8 multiply-add merge,
+16 fused child address, 32 hand-pipelined merge, 64 16-byte clears + fast count decode; 85 = 1 + 4 + 16 + 64 became 1).
 
-For every variant: a fresh context on the full C2 workload (synthetic, 1.2 M documents x 136 features), 5 warm-up
-iterations, `steps` timed iterations through rlb_boost_iters (CUDA events on the context's stream), then the same steps with
-the per-kernel event nodes switched on (root / child histogram time).  The variants are interleaved over the repeats so that
-clock or neighbour noise does not land on one of them, and the CRC of the trees of every run is compared: a variant that
-builds other trees than variant 0 is reported as WRONG.  One JSON line per variant on stdout.
+For every variant: a fresh context (synthetic C2: 1.2 M documents x 136 features), 5 warm-up iterations, `steps` timed
+iterations through rlb_boost_iters (CUDA events on the context's stream), then the same steps with the per-kernel event nodes
+switched on (root / child histogram and lambda time).  The variants are interleaved over the repeats so that clock or
+neighbour noise does not land on one of them, and the CRC of the trees of every run is compared: a variant that builds other
+trees than the first one listed is reported as WRONG.  One JSON line per variant on stdout.
 """
 import json
 import os
@@ -28,7 +31,7 @@ def main():
     import torch
     import bench
     from ranklib_b200.host import native
-    variants = (sys.argv[1] if len(sys.argv) > 1 else "0,1").split(",")
+    variants = (sys.argv[1] if len(sys.argv) > 1 else "0:0:0,1:1:1").split(",")
     repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     torch.cuda.set_device(0)
@@ -39,7 +42,7 @@ def main():
     res = {v: {"ms": [], "root_ms": [], "child_ms": [], "lambda_ms": [], "crc": set()} for v in variants}
     for rep in range(repeats + 1):          # pass 0 is the process warm-up (module load, allocator) and is dropped
         for v in variants:
-            spec = (v.split(":") + ["", ""])[:3]     # "<histogram variant>[:<lambda variant>[:<partition variant>]]"
+            spec = (v.split(":") + ["", ""])[:3]     # "<histogram>[:<lambda>[:<iteration>]]" variants
             os.environ["RLB_HIST_VARIANT"] = spec[0]
             os.environ["RLB_LAMBDA_VARIANT"] = spec[1] or "0"
             os.environ["RLB_ITER_VARIANT"] = spec[2] or "0"
