@@ -5,7 +5,9 @@
 
 C1 (1k docs x 50 features, private-histogram path) and a 12k-doc MSLR-shaped slice (tiled root-histogram kernel), two
 LambdaMART iterations each without the CUDA graph, one MART iteration, ERR as a second metric, Ensemble.eval, the metric
-scorer and the float-chain hook.  Prints SANITIZE_SMALL DONE when every call returned RLB_OK."""
+scorer and the float-chain hook.  Prints SANITIZE_SMALL DONE when every call returned RLB_OK.
+`python scripts/sanitize_small.py slice` runs the MSLR-shaped slice only (the histogram, lambda, partition, finish and
+score-update kernels with their shared-memory stages reused): the short form for the last GPU minutes of a round."""
 import os
 import sys
 
@@ -40,6 +42,11 @@ def run(X, label, qoff, iters, valid=None, **kw):
     return m
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "slice":
+    X, label, qoff = synth.c2(0.025)
+    print("mslr slice", run(X, label, qoff, 2))
+    print("SANITIZE_SMALL DONE")
+    sys.exit(0)
 X, label, qoff = synth.c1()
 print("c1 LambdaMART", run(X, label, qoff, 2))
 print("c1 MART", run(X, label, qoff, 1, kind=native.KIND_MART))
